@@ -1,0 +1,155 @@
+/*
+ * r4d.h — C ABI of the B200-native query-by-pool scoring + top-K engine (libr4d.so).
+ *
+ * The reference (YuxiaWu/RAG4DyG) has no FFI; its boundary for this path is a set of Python
+ * functions.  Each export below names the reference interface it replaces (file:line relative to
+ * the reference root).  INTEGRATION.md shows the ctypes stub a maintainer would add.
+ *
+ * Conventions
+ *  - every pointer marked [dev] is a device pointer owned by the caller (a torch allocation);
+ *    [host] pointers are host memory.  The library never allocates device memory: scratch comes
+ *    from a caller-provided workspace sized by the matching *_workspace_bytes() query.
+ *  - every call only ENQUEUES work on `stream` (a cudaStream_t); it never synchronises.
+ *  - return value: 0 = OK, negative = error (R4D_E_*); r4d_last_error() gives a thread-local text.
+ *  - indices are int32 (pool sizes < 2^31).  R4D_IDX_NONE marks "no candidate" (pool shorter than k).
+ *  - canonical order everywhere: (score descending, pool index ascending) == np.argsort(-s, kind='stable').
+ *  - sm_100a only.  There is no CPU fallback: with no usable device every call returns R4D_E_CUDA.
+ */
+#ifndef R4D_H_
+#define R4D_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* r4d_stream_t; /* cudaStream_t */
+
+#define R4D_OK 0
+#define R4D_E_ARG (-1)     /* bad argument (null pointer, k out of range, misaligned pitch ...) */
+#define R4D_E_CUDA (-2)    /* CUDA runtime / driver error, or no sm_100 device */
+#define R4D_E_WORKSPACE (-3) /* workspace too small */
+#define R4D_IDX_NONE 0x7fffffff
+#define R4D_TOPK_MAX 32    /* fused top-K width limit (one list entry per lane) */
+
+/* dense scorer epilogue modes (r4d_dense_*) */
+#define R4D_DENSE_HALF_COS 0       /* (cos+1)/2                  train/train_retriever.py:437-438 */
+#define R4D_DENSE_COS_DECAY 1      /* cos * exp(-lambda*|dt|)    train/train_retriever.py:47-55   */
+#define R4D_DENSE_HALF_COS_DECAY 2 /* ((cos+1)/2) * exp(-lambda*|dt|)                              */
+/* dense contraction precision */
+#define R4D_PREC_BF16 0   /* one tcgen05 kind::f16 pass on bf16-rounded operands                  */
+#define R4D_PREC_BF16X3 1 /* hi/lo split: hi*hi + hi*lo + lo*hi, fp32 accumulate (fp32-faithful)   */
+
+int r4d_version(void);
+const char* r4d_last_error(void);
+/* 1 when a CUDA device of compute capability 10.x is visible, else 0 (never touches the device otherwise). */
+int r4d_device_ok(void);
+
+/* ---------------------------------------------------------------- set encoder (subsystem 1)
+ * Replaces the per-pair `set(seq_i)`, `set(seq_j)` construction of co_occurrence_ratio
+ * (retrieval_data_annotation.py:12-13): each row's token set becomes a fixed-width bitset. */
+
+/* words per row for n_bits (ceil(n_bits/32)) and the row pitch (words, multiple of 32 => 128 B rows). */
+int32_t r4d_bitset_words(int32_t n_bits);
+int32_t r4d_bitset_pitch_words(int32_t n_bits);
+
+/* CSR -> bitsets.  bit_pos[row_off[r] .. row_off[r+1]) are the bit positions (duplicates allowed,
+ * each < n_bits) of row r.  Writes bits[n_rows][pitch_words] (fully, including zero padding) and
+ * card[n_rows] = |set| (popcount).  All pointers [dev]. */
+int r4d_bitset_encode(const int32_t* bit_pos, const int64_t* row_off, int64_t n_rows, int32_t n_bits,
+                      int32_t pitch_words, uint32_t* bits, uint32_t* card, r4d_stream_t stream);
+
+/* ---------------------------------------------------------------- Jaccard scorer (subsystem 2)
+ * Replaces occurrence_matrix / co_occurrence_ratio (retrieval_data_annotation.py:36-41, :5-15). */
+
+/* Full matrix: inter[q][p] = |Q_q & P_p| (uint32, row stride ld_inter elements) and, if score != NULL,
+ * score[q][p] = inter/union as float64 (0.0 when either set is empty; row stride ld_score).
+ * zero_diag != 0 forces the entry with query_base+q == pool_base+p to 0
+ * (np.fill_diagonal, retrieval_data_annotation.py:172-173).  All pointers [dev]. */
+int r4d_jaccard_full(const uint32_t* qbits, const uint32_t* qcard, int64_t nq, const uint32_t* pbits,
+                     const uint32_t* pcard, int64_t np, int32_t words, int32_t pitch_words, int32_t zero_diag,
+                     int64_t query_base, int64_t pool_base, uint32_t* inter, int64_t ld_inter, double* score,
+                     int64_t ld_score, r4d_stream_t stream);
+
+/* Fused scorer + top-K (subsystem 4): never materialises [nq, np].
+ * Replaces occurrence_matrix + np.argsort(-row)[:k] (retrieval_data_annotation.py:97-103).
+ * Outputs [nq][k]: exact integer counts (score = inter/union) and GLOBAL pool index pool_base+p,
+ * ordered (score desc, index asc).  1 <= k <= R4D_TOPK_MAX.  Rows short of k are padded with
+ * (0, 1, R4D_IDX_NONE). */
+size_t r4d_jaccard_topk_workspace_bytes(int64_t nq, int64_t np, int32_t k);
+int r4d_jaccard_topk(const uint32_t* qbits, const uint32_t* qcard, int64_t nq, const uint32_t* pbits,
+                     const uint32_t* pcard, int64_t np, int32_t words, int32_t pitch_words, int32_t k,
+                     int32_t zero_diag, int64_t query_base, int64_t pool_base, uint32_t* top_inter,
+                     uint32_t* top_union, int32_t* top_idx, void* workspace, size_t workspace_bytes,
+                     r4d_stream_t stream);
+
+/* Merge n_lists candidate lists per query (layout [n_lists][nq][k_in], e.g. the all-gather of the
+ * per-shard outputs of r4d_jaccard_topk) into [nq][k_out]; exact rational compare, index tiebreak, so
+ * the result does not depend on how the pool was sharded. */
+int r4d_jaccard_topk_merge(const uint32_t* inter, const uint32_t* uni, const int32_t* idx, int32_t n_lists,
+                           int64_t nq, int32_t k_in, int32_t k_out, uint32_t* out_inter, uint32_t* out_union,
+                           int32_t* out_idx, r4d_stream_t stream);
+
+/* ---------------------------------------------------------------- ranking of score matrices
+ * Full descending STABLE ranking of every row: order[q][:] = np.argsort(-scores[q], kind='stable').
+ * Replaces np.argsort(-M, axis=1) in save_index_score (retrieval_data_annotation.py:89,
+ * train/train_retriever.py:358).  NaN sorts last.  workspace from the *_workspace_bytes query. */
+size_t r4d_rank_rows_workspace_bytes(int64_t nq, int64_t n, int32_t elem_bytes);
+int r4d_rank_rows_f64(const double* scores, int64_t nq, int64_t n, int64_t ld, int32_t* order, void* workspace,
+                      size_t workspace_bytes, r4d_stream_t stream);
+int r4d_rank_rows_f32(const float* scores, int64_t nq, int64_t n, int64_t ld, int32_t* order, void* workspace,
+                      size_t workspace_bytes, r4d_stream_t stream);
+
+/* Top-k of every row of an explicit float64 matrix, canonical order
+ * (save_score_file_train on a caller-provided matrix, retrieval_data_annotation.py:97-103). */
+int r4d_topk_rows_f64(const double* scores, int64_t nq, int64_t n, int64_t ld, int32_t k, double* top_score,
+                      int32_t* top_idx, r4d_stream_t stream);
+
+/* ---------------------------------------------------------------- triplet mining
+ * Device part of save_train_annotation (retrieval_data_annotation.py:54-71): for every row i of the
+ * [n, n] float64 matrices `out` (label-set Jaccard) and `in` (history-set Jaccard):
+ *   n_pos[i]          = #{j : out[i,j] > thr}
+ *   neg[i][0..n_neg)  = the first neg_num indices j, in descending-in[i,j] (stable) order, with
+ *                       out[i,j] <= thr and out[i,j] > 0; if fewer than neg_num, continued in the same
+ *                       order with out[i,j] == 0.
+ * The host then lists positives (np.where) and replays np.random.choice (:79).  neg_num <= 32. */
+int r4d_triplet_mine_f64(const double* out, const double* in, int64_t n, int64_t ld, double thr,
+                         int32_t neg_num, int32_t* n_pos, int32_t* neg /*[n][neg_num]*/, int32_t* n_neg,
+                         r4d_stream_t stream);
+
+/* ---------------------------------------------------------------- dense scorer (subsystem 3)
+ * Replaces the scoring block of test() (train/train_retriever.py:433-438) and, optionally, the
+ * exp(-lambda*|dt|) factor of CLtime_loss (train/train_retriever.py:50-55).
+ *
+ * r4d_dense_prepare: rows of x[n][d] (fp32) are L2-normalised (x / ||x||, no epsilon: a zero row gives
+ * NaN exactly like :433,:436) and written as bf16 planes hi[n][d_pad] and (prec == BF16X3) lo[n][d_pad],
+ * d_pad = r4d_dense_dpad(d) (multiple of 64, zero padded). */
+int32_t r4d_dense_dpad(int32_t d);
+int r4d_dense_prepare(const float* x, int64_t n, int32_t d, int64_t ld, int32_t prec, void* hi, void* lo,
+                      r4d_stream_t stream);
+
+/* Fused tcgen05 contraction + epilogue + top-K over prepared operands.
+ * q_time/p_time may be NULL for mode R4D_DENSE_HALF_COS.  Outputs [nq][k] float32 scores and global
+ * pool indices, ordered (score desc, index asc). */
+size_t r4d_dense_topk_workspace_bytes(int64_t nq, int64_t np, int32_t k);
+int r4d_dense_topk(const void* q_hi, const void* q_lo, int64_t nq, const void* p_hi, const void* p_lo, int64_t np,
+                   int32_t d_pad, int32_t prec, const float* q_time, const float* p_time, float lambda,
+                   int32_t mode, int32_t k, int64_t pool_base, float* top_score, int32_t* top_idx,
+                   void* workspace, size_t workspace_bytes, r4d_stream_t stream);
+
+/* Same contraction + epilogue, full score rows scores[nq][ld] (the `.gen` score files need them,
+ * train/train_retriever.py:357-368). */
+int r4d_dense_full(const void* q_hi, const void* q_lo, int64_t nq, const void* p_hi, const void* p_lo, int64_t np,
+                   int32_t d_pad, int32_t prec, const float* q_time, const float* p_time, float lambda,
+                   int32_t mode, float* scores, int64_t ld, r4d_stream_t stream);
+
+/* Merge [n_lists][nq][k_in] dense candidate lists into [nq][k_out] (score desc, index asc). */
+int r4d_dense_topk_merge(const float* score, const int32_t* idx, int32_t n_lists, int64_t nq, int32_t k_in,
+                         int32_t k_out, float* out_score, int32_t* out_idx, r4d_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* R4D_H_ */

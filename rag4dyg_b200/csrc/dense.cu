@@ -1,0 +1,617 @@
+// dense.cu — subsystem 3 (+4): query x pool embedding contraction on tcgen05 tensor cores with the
+// (cos+1)/2 / exp(-lambda*|dt|) epilogue and a fused top-K, never materialising [nq, np] in top-K mode.
+//
+// Replaces the scoring block of test() (train/train_retriever.py:433-438: row L2-normalise, matmul, (x+1)/2) and
+// optionally applies the CLtime_loss decay factor (train/train_retriever.py:50-55).
+//
+// Kernel anatomy (sm_100a, one CTA per SM, 320 threads):
+//   warp 0      TMA producer: per 64-wide k-block loads the Q tile [128 x 64] and P tile [256 x 64] (bf16,
+//               SWIZZLE_128B) — plus the lo planes in BF16X3 mode — into an mbarrier-guarded smem ring.
+//   warp 1      MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=256, K=16),
+//               fp32 accumulators in TMEM; two 256-column accumulator buffers ping-pong with the epilogue.
+//               BF16X3: D += Qhi*Phi + Qhi*Plo + Qlo*Phi  (fp32-faithful ranking, 3x tensor work).
+//   warps 2..9  epilogue: tcgen05.ld (32x32b.x32) — thread t owns query row t of the tile, so the running
+//               K-th-best threshold is a private register; scores are (x+1)/2, x*2^(-l|dt|) ...; a column enters
+//               the thread's sorted smem list only if it beats the threshold (rare after warm-up).
+//   Per-(stripe, column-half) lists are merged by dense_merge_kernel with the canonical comparator.
+#include <cuda_bf16.h>
+
+#include "r4d_common.cuh"
+
+namespace r4d {
+
+constexpr int DQ = 128;          // query rows per tile  (UMMA M)
+constexpr int DP = 256;          // pool rows per tile   (UMMA N)
+constexpr int DKB = 64;          // bf16 elements per k-block (128 B rows: one swizzle atom)
+constexpr int Q_TILE_BYTES = DQ * DKB * 2;  // 16 KB
+constexpr int P_TILE_BYTES = DP * DKB * 2;  // 32 KB
+constexpr int D_THREADS = 320;
+constexpr int D_EPI_WARPS = 8;
+constexpr int D_EPI_THREADS = D_EPI_WARPS * 32;
+
+constexpr int DMODE_TOPK = 0;
+constexpr int DMODE_FULL = 1;
+
+struct DenseParams {
+    int64_t nq, np;
+    int32_t n_kblocks;  // d_pad / 64
+    int32_t prec;       // R4D_PREC_*
+    int32_t mode;       // R4D_DENSE_*
+    int32_t k;
+    int32_t n_stages;
+    int32_t stage_bytes;
+    float neg_lambda_log2e;  // -lambda * log2(e)
+    int64_t pool_base;
+    const float* q_time;
+    const float* p_time;
+    int32_t n_qtiles, n_ptiles, n_stripes, ptiles_per_stripe;
+    float* part_score;  // [2*n_stripes][nq][k]
+    int32_t* part_idx;
+    float* scores;  // full mode
+    int64_t ld;
+};
+
+// ---- tcgen05 wrappers
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+                 "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major, SWIZZLE_128B operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (=1), version 1.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+        "%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// sorted insertion into this thread's list (column-major in smem: slot t of thread `tid` at [t*D_EPI_THREADS+tid]).
+// Returns the new k-th best score.
+__device__ __noinline__ float list_insert(float* ls, int32_t* li, int k, float s, int32_t idx) {
+    int t = k - 1;
+    while (t > 0) {
+        const float prev = ls[(t - 1) * D_EPI_THREADS];
+        if (!(prev < s)) break;  // strict: an equal earlier (smaller index) entry stays ahead
+        ls[t * D_EPI_THREADS] = prev;
+        li[t * D_EPI_THREADS] = li[(t - 1) * D_EPI_THREADS];
+        --t;
+    }
+    ls[t * D_EPI_THREADS] = s;
+    li[t * D_EPI_THREADS] = idx;
+    return ls[(k - 1) * D_EPI_THREADS];
+}
+
+template <int DMODE>
+__global__ void __launch_bounds__(D_THREADS, 1)
+dense_kernel(const __grid_constant__ CUtensorMap tm_qh, const __grid_constant__ CUtensorMap tm_ql,
+             const __grid_constant__ CUtensorMap tm_ph, const __grid_constant__ CUtensorMap tm_pl,
+             const DenseParams prm) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* stages = smem;
+    uint8_t* after = smem + (size_t)prm.n_stages * prm.stage_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(after);      // [n_stages]
+    uint64_t* empty_bar = full_bar + 8;                           // [n_stages]  (n_stages <= 8)
+    uint64_t* tfull_bar = empty_bar + 8;                          // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;                         // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float* ptime_s = reinterpret_cast<float*>(tmem_slot + 4);     // [2][DP]
+    float* list_s = ptime_s + 2 * DP;                             // [k][D_EPI_THREADS]   (top-K mode)
+    int32_t* list_i = reinterpret_cast<int32_t*>(list_s + (size_t)prm.k * D_EPI_THREADS);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const bool x3 = prm.prec == R4D_PREC_BF16X3;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tm_qh);
+        tma_prefetch_desc(&tm_ph);
+        if (x3) {
+            tma_prefetch_desc(&tm_ql);
+            tma_prefetch_desc(&tm_pl);
+        }
+        for (int s = 0; s < prm.n_stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tfull_bar[b], 1);
+            mbar_init(&tempty_bar[b], D_EPI_WARPS);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int n_items = prm.n_qtiles * prm.n_stripes;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int stripe = item / prm.n_qtiles;
+                const int qtile = item - stripe * prm.n_qtiles;
+                const int pt_beg = stripe * prm.ptiles_per_stripe;
+                const int pt_end = min(pt_beg + prm.ptiles_per_stripe, prm.n_ptiles);
+                for (int pt = pt_beg; pt < pt_end; ++pt) {
+                    for (int kb = 0; kb < prm.n_kblocks; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* dst = stages + (size_t)stage * prm.stage_bytes;
+                        mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)prm.stage_bytes);
+                        tma_load_2d(dst, &tm_qh, &full_bar[stage], kb * DKB, qtile * DQ);
+                        tma_load_2d(dst + Q_TILE_BYTES, &tm_ph, &full_bar[stage], kb * DKB, pt * DP);
+                        if (x3) {
+                            tma_load_2d(dst + Q_TILE_BYTES + P_TILE_BYTES, &tm_ql, &full_bar[stage], kb * DKB,
+                                        qtile * DQ);
+                            tma_load_2d(dst + 2 * Q_TILE_BYTES + P_TILE_BYTES, &tm_pl, &full_bar[stage], kb * DKB,
+                                        pt * DP);
+                        }
+                        if (++stage == prm.n_stages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (one elected lane)
+        if (lane == 0) {
+            // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7, 10), K-major both, N>>3 at 17, M>>4 at 24
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(DP >> 3) << 17) |
+                                   ((uint32_t)(DQ >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t tile_seq = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int stripe = item / prm.n_qtiles;
+                const int pt_beg = stripe * prm.ptiles_per_stripe;
+                const int pt_end = min(pt_beg + prm.ptiles_per_stripe, prm.n_ptiles);
+                for (int pt = pt_beg; pt < pt_end; ++pt, ++tile_seq) {
+                    const uint32_t buf = tile_seq & 1u;
+                    mbar_wait(&tempty_bar[buf], ((tile_seq >> 1) & 1u) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + buf * DP;
+                    for (int kb = 0; kb < prm.n_kblocks; ++kb) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint32_t sbase = smem_u32(stages + (size_t)stage * prm.stage_bytes);
+                        const uint64_t qh = make_smem_desc(sbase);
+                        const uint64_t ph = make_smem_desc(sbase + Q_TILE_BYTES);
+#pragma unroll
+                        for (int ks = 0; ks < DKB / 16; ++ks) {
+                            // advance 16 bf16 = 32 B inside the 128 B swizzle atom: +2 in (addr >> 4) units
+                            umma_bf16(tmem_d, qh + (uint64_t)(2 * ks), ph + (uint64_t)(2 * ks), idesc,
+                                      (kb | ks) != 0 ? 1u : 0u);
+                        }
+                        if (x3) {
+                            const uint64_t ql = make_smem_desc(sbase + Q_TILE_BYTES + P_TILE_BYTES);
+                            const uint64_t pl = make_smem_desc(sbase + 2 * Q_TILE_BYTES + P_TILE_BYTES);
+#pragma unroll
+                            for (int ks = 0; ks < DKB / 16; ++ks) {
+                                umma_bf16(tmem_d, qh + (uint64_t)(2 * ks), pl + (uint64_t)(2 * ks), idesc, 1u);
+                                umma_bf16(tmem_d, ql + (uint64_t)(2 * ks), ph + (uint64_t)(2 * ks), idesc, 1u);
+                            }
+                        }
+                        tc_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+                        if (++stage == prm.n_stages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                    tc_commit(&tfull_bar[buf]);  // accumulator complete
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue warps 2..9
+        const int ew = warp - 2;             // 0..7
+        const int quarter = warp & 3;        // TMEM lane quarter this warp may access
+        const int half = ew >> 2;            // column half of the 256-wide tile
+        const int etid = threadIdx.x - 64;   // 0..255
+        const int row_in_tile = quarter * 32 + lane;
+        float* ls = list_s + (half * 128 + row_in_tile);   // this thread's list column
+        int32_t* li = list_i + (half * 128 + row_in_tile);
+        uint32_t tile_seq = 0;
+
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int stripe = item / prm.n_qtiles;
+            const int qtile = item - stripe * prm.n_qtiles;
+            const int pt_beg = stripe * prm.ptiles_per_stripe;
+            const int pt_end = min(pt_beg + prm.ptiles_per_stripe, prm.n_ptiles);
+            const int64_t gq = (int64_t)qtile * DQ + row_in_tile;
+            const bool q_ok = gq < prm.nq;
+            const float tq = (prm.mode != R4D_DENSE_HALF_COS && q_ok) ? prm.q_time[gq] : 0.f;
+            float thr = -INFINITY;
+            if (DMODE == DMODE_TOPK) {
+                for (int t = 0; t < prm.k; ++t) {
+                    ls[t * D_EPI_THREADS] = -INFINITY;
+                    li[t * D_EPI_THREADS] = R4D_IDX_NONE;
+                }
+            }
+            for (int pt = pt_beg; pt < pt_end; ++pt, ++tile_seq) {
+                const uint32_t buf = tile_seq & 1u;
+                if (prm.mode != R4D_DENSE_HALF_COS) {
+                    // stage this tile's 256 pool times for broadcast reads
+                    const int64_t gp = (int64_t)pt * DP + etid;
+                    ptime_s[buf * DP + etid] = gp < prm.np ? prm.p_time[gp] : 0.f;
+                    named_bar_sync(2, D_EPI_THREADS);
+                }
+                mbar_wait(&tfull_bar[buf], (tile_seq >> 1) & 1u);
+                tc_fence_after();
+#pragma unroll 1
+                for (int ch = 0; ch < 4; ++ch) {
+                    const int col0 = half * 128 + ch * 32;
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * DP + col0, v);
+                    tmem_ld_wait();
+                    const int64_t gp0 = (int64_t)pt * DP + col0;
+                    float s[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float x = __uint_as_float(v[j]);
+                        float sc;
+                        if (prm.mode == R4D_DENSE_HALF_COS) {
+                            sc = (x + 1.0f) * 0.5f;
+                        } else {
+                            const float dt = fabsf(tq - ptime_s[buf * DP + col0 + j]);
+                            const float dec = ex2_approx(prm.neg_lambda_log2e * dt);
+                            sc = (prm.mode == R4D_DENSE_COS_DECAY) ? x * dec : (x + 1.0f) * 0.5f * dec;
+                        }
+                        s[j] = sc;
+                    }
+                    if (DMODE == DMODE_FULL) {
+                        if (q_ok) {
+                            float* dst = prm.scores + gq * prm.ld + gp0;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (gp0 + j < prm.np) dst[j] = s[j];
+                        }
+                    } else {
+                        if (gp0 + 32 > prm.np) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (gp0 + j >= prm.np) s[j] = -INFINITY;
+                        }
+                        float m = s[0];
+#pragma unroll
+                        for (int j = 1; j < 32; ++j) m = fmaxf(m, s[j]);
+                        if (q_ok && m > thr) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (s[j] > thr) thr = list_insert(ls, li, prm.k, s[j], (int32_t)(prm.pool_base + gp0 + j));
+                        }
+                    }
+                }
+                // all TMEM reads of this buffer are done: hand it back to the MMA warp
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+            }
+            if (DMODE == DMODE_TOPK && q_ok) {
+                const int64_t o = ((int64_t)(stripe * 2 + half) * prm.nq + gq) * prm.k;
+                for (int t = 0; t < prm.k; ++t) {
+                    prm.part_score[o + t] = ls[t * D_EPI_THREADS];
+                    prm.part_idx[o + t] = li[t * D_EPI_THREADS];
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---------------------------------------------------------------------------- row normalisation + bf16 split
+// one warp per row: n = sqrt(sum x^2) (fp32), y = x / n, hi = bf16(y), lo = bf16(y - hi)
+__global__ void __launch_bounds__(256)
+dense_prepare_kernel(const float* __restrict__ x, int64_t n, int32_t d, int64_t ld, int32_t d_pad, int32_t want_lo,
+                     __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wpg = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n; r += wpg) {
+        const float* row = x + r * ld;
+        float ss = 0.f;
+        for (int c = lane; c < d; c += 32) {
+            const float v = row[c];
+            ss = fmaf(v, v, ss);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        const float nrm = sqrtf(ss);
+        for (int c = lane; c < d_pad; c += 32) {
+            float y = 0.f;
+            if (c < d) y = row[c] / nrm;  // no epsilon: a zero row gives NaN like the reference (:433,:436)
+            const __nv_bfloat16 h = __float2bfloat16_rn(y);
+            hi[r * d_pad + c] = h;
+            if (want_lo) lo[r * d_pad + c] = __float2bfloat16_rn(y - __bfloat162float(h));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+dense_merge_kernel(const float* __restrict__ score, const int32_t* __restrict__ idx, int32_t n_lists, int64_t nq,
+                   int32_t k_in, int32_t k_out, float* __restrict__ out_score, int32_t* __restrict__ out_idx) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wpg = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); q < nq; q += wpg) {
+        WarpTopK<FEntry<float>> tk;
+        tk.init(k_out);
+        for (int l = 0; l < n_lists; ++l) {
+            const int64_t base = ((int64_t)l * nq + q) * k_in;
+            for (int e0 = 0; e0 < k_in; e0 += 32) {
+                const int e = e0 + lane;
+                FEntry<float> c = FEntry<float>::worst();
+                if (e < k_in) c = FEntry<float>{score[base + e], idx[base + e]};
+                uint32_t m = __ballot_sync(0xffffffffu,
+                                           e < k_in && c.idx != R4D_IDX_NONE && FEntry<float>::better(c, tk.kth));
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    tk.insert(c.shfl(src));
+                }
+            }
+        }
+        if (lane < k_out) {
+            out_score[q * k_out + lane] = tk.mine.s;
+            out_idx[q * k_out + lane] = tk.mine.idx;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------- host side
+struct DensePlan {
+    int32_t n_qtiles, n_ptiles, n_stripes, ptiles_per_stripe;
+};
+
+static DensePlan dense_plan(int64_t nq, int64_t np, bool topk) {
+    DensePlan pl;
+    pl.n_qtiles = (int32_t)((nq + DQ - 1) / DQ);
+    pl.n_ptiles = (int32_t)((np + DP - 1) / DP);
+    if (pl.n_qtiles < 1) pl.n_qtiles = 1;
+    if (pl.n_ptiles < 1) pl.n_ptiles = 1;
+    if (!topk) {
+        pl.n_stripes = pl.n_ptiles;
+        pl.ptiles_per_stripe = 1;
+        return pl;
+    }
+    // long stripes keep the per-thread top-K warm-up (K*ln(L/K) insertions) negligible; ~8 items per SM
+    const int64_t target = (int64_t)num_sms() * 8;
+    int64_t stripes = (target + pl.n_qtiles - 1) / pl.n_qtiles;
+    const int64_t max_stripes = (pl.n_ptiles + 15) / 16;  // at least 16 pool tiles (4096 rows) per stripe
+    if (stripes > max_stripes) stripes = max_stripes;
+    if (stripes < 1) stripes = 1;
+    pl.ptiles_per_stripe = (int32_t)((pl.n_ptiles + stripes - 1) / stripes);
+    pl.n_stripes = (pl.n_ptiles + pl.ptiles_per_stripe - 1) / pl.ptiles_per_stripe;
+    return pl;
+}
+
+static int dense_launch(int dmode, const void* q_hi, const void* q_lo, int64_t nq, const void* p_hi, const void* p_lo,
+                        int64_t np, int32_t d_pad, int32_t prec, DenseParams& prm, cudaStream_t st) {
+    const bool x3 = prec == R4D_PREC_BF16X3;
+    CUtensorMap tm_qh, tm_ql, tm_ph, tm_pl;
+    int rc;
+    const uint64_t rs = (uint64_t)d_pad * 2;
+    if ((rc = make_tmap_2d(&tm_qh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, q_hi, d_pad, nq, rs, DKB, DQ,
+                           CU_TENSOR_MAP_SWIZZLE_128B)))
+        return rc;
+    if ((rc = make_tmap_2d(&tm_ph, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p_hi, d_pad, np, rs, DKB, DP,
+                           CU_TENSOR_MAP_SWIZZLE_128B)))
+        return rc;
+    if (x3) {
+        if ((rc = make_tmap_2d(&tm_ql, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, q_lo, d_pad, nq, rs, DKB, DQ,
+                               CU_TENSOR_MAP_SWIZZLE_128B)))
+            return rc;
+        if ((rc = make_tmap_2d(&tm_pl, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p_lo, d_pad, np, rs, DKB, DP,
+                               CU_TENSOR_MAP_SWIZZLE_128B)))
+            return rc;
+    } else {
+        tm_ql = tm_qh;
+        tm_pl = tm_ph;
+    }
+    prm.n_kblocks = d_pad / DKB;
+    prm.prec = prec;
+    prm.stage_bytes = (Q_TILE_BYTES + P_TILE_BYTES) * (x3 ? 2 : 1);
+    const size_t fixed = 1024 + 20 * sizeof(uint64_t) + 16 + 2 * DP * sizeof(float) +
+                         (dmode == DMODE_TOPK ? (size_t)prm.k * D_EPI_THREADS * 8 : 0);
+    int n_stages = (int)((227 * 1024 - fixed) / prm.stage_bytes);
+    if (n_stages > 8) n_stages = 8;
+    if (n_stages < 2) {
+        set_error("dense: not enough shared memory for a 2-stage pipeline (k=%d)", prm.k);
+        return R4D_E_ARG;
+    }
+    prm.n_stages = n_stages;
+    const size_t smem = fixed + (size_t)n_stages * prm.stage_bytes;
+    const int64_t n_items = (int64_t)prm.n_qtiles * prm.n_stripes;
+    int grid = num_sms();
+    if (n_items < grid) grid = (int)n_items;
+    if (dmode == DMODE_TOPK) {
+        R4D_CUDA(cudaFuncSetAttribute(dense_kernel<DMODE_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dense_kernel<DMODE_TOPK><<<grid, D_THREADS, smem, st>>>(tm_qh, tm_ql, tm_ph, tm_pl, prm);
+    } else {
+        R4D_CUDA(cudaFuncSetAttribute(dense_kernel<DMODE_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dense_kernel<DMODE_FULL><<<grid, D_THREADS, smem, st>>>(tm_qh, tm_ql, tm_ph, tm_pl, prm);
+    }
+    R4D_CUDA(cudaGetLastError());
+    return R4D_OK;
+}
+
+static int dense_check(const void* q_hi, const void* q_lo, int64_t nq, const void* p_hi, const void* p_lo, int64_t np,
+                       int32_t d_pad, int32_t prec, const float* q_time, const float* p_time, int32_t mode) {
+    R4D_REQUIRE(nq >= 0 && np >= 0 && nq < ((int64_t)1 << 31) && np < ((int64_t)1 << 31), "dense: bad sizes");
+    R4D_REQUIRE(d_pad > 0 && d_pad % DKB == 0, "dense: d_pad=%d must be a positive multiple of %d", d_pad, DKB);
+    R4D_REQUIRE(prec == R4D_PREC_BF16 || prec == R4D_PREC_BF16X3, "dense: unknown precision %d", prec);
+    R4D_REQUIRE(mode >= 0 && mode <= 2, "dense: unknown mode %d", mode);
+    if (nq > 0 && np > 0) {
+        R4D_REQUIRE(q_hi && p_hi, "dense: null operand");
+        R4D_REQUIRE(prec != R4D_PREC_BF16X3 || (q_lo && p_lo), "dense: BF16X3 needs the lo planes");
+        R4D_REQUIRE(mode == R4D_DENSE_HALF_COS || (q_time && p_time), "dense: decay modes need q_time and p_time");
+    }
+    return R4D_OK;
+}
+
+}  // namespace r4d
+
+extern "C" {
+
+int32_t r4d_dense_dpad(int32_t d) { return d <= 0 ? r4d::DKB : (d + r4d::DKB - 1) / r4d::DKB * r4d::DKB; }
+
+int r4d_dense_prepare(const float* x, int64_t n, int32_t d, int64_t ld, int32_t prec, void* hi, void* lo,
+                      r4d_stream_t stream) {
+    using namespace r4d;
+    R4D_REQUIRE(n >= 0 && d > 0 && ld >= d, "dense_prepare: n=%lld d=%d ld=%lld", (long long)n, d, (long long)ld);
+    R4D_REQUIRE(prec == R4D_PREC_BF16 || prec == R4D_PREC_BF16X3, "dense_prepare: unknown precision %d", prec);
+    if (n == 0) return R4D_OK;
+    R4D_REQUIRE(x && hi && (prec == R4D_PREC_BF16 || lo), "dense_prepare: null pointer");
+    int64_t blocks = (n + 7) / 8;
+    const int64_t cap = (int64_t)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    dense_prepare_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
+        x, n, d, ld, r4d_dense_dpad(d), prec == R4D_PREC_BF16X3 ? 1 : 0, reinterpret_cast<__nv_bfloat16*>(hi),
+        reinterpret_cast<__nv_bfloat16*>(lo));
+    R4D_CUDA(cudaGetLastError());
+    return R4D_OK;
+}
+
+size_t r4d_dense_topk_workspace_bytes(int64_t nq, int64_t np, int32_t k) {
+    using namespace r4d;
+    if (nq <= 0 || np <= 0 || k <= 0) return 256;
+    const DensePlan pl = dense_plan(nq, np, true);
+    return (size_t)pl.n_stripes * 2 * (size_t)nq * (size_t)k * 8 + 256;
+}
+
+int r4d_dense_topk(const void* q_hi, const void* q_lo, int64_t nq, const void* p_hi, const void* p_lo, int64_t np,
+                   int32_t d_pad, int32_t prec, const float* q_time, const float* p_time, float lambda, int32_t mode,
+                   int32_t k, int64_t pool_base, float* top_score, int32_t* top_idx, void* workspace,
+                   size_t workspace_bytes, r4d_stream_t stream) {
+    using namespace r4d;
+    int rc = dense_check(q_hi, q_lo, nq, p_hi, p_lo, np, d_pad, prec, q_time, p_time, mode);
+    if (rc) return rc;
+    R4D_REQUIRE(k >= 1 && k <= R4D_TOPK_MAX, "dense_topk: k=%d out of range [1, %d]", k, R4D_TOPK_MAX);
+    R4D_REQUIRE(pool_base >= 0 && pool_base + np < (int64_t)R4D_IDX_NONE, "dense_topk: pool_base+np exceeds int32");
+    if (nq == 0) return R4D_OK;
+    R4D_REQUIRE(top_score && top_idx, "dense_topk: null output");
+    const DensePlan pl = dense_plan(nq, np, true);
+    const size_t per = (size_t)pl.n_stripes * 2 * (size_t)nq * (size_t)k;
+    if (np > 0 && (workspace_bytes < per * 8 || !workspace)) {
+        set_error("dense_topk: workspace %zu B < required %zu B", workspace_bytes, per * 8);
+        return R4D_E_WORKSPACE;
+    }
+    if (np == 0)
+        return r4d_dense_topk_merge(nullptr, nullptr, 0, nq, k, k, top_score, top_idx, stream);
+    DenseParams prm{};
+    prm.nq = nq;
+    prm.np = np;
+    prm.mode = mode;
+    prm.k = k;
+    prm.neg_lambda_log2e = -lambda * 1.4426950408889634f;
+    prm.pool_base = pool_base;
+    prm.q_time = q_time;
+    prm.p_time = p_time;
+    prm.n_qtiles = pl.n_qtiles;
+    prm.n_ptiles = pl.n_ptiles;
+    prm.n_stripes = pl.n_stripes;
+    prm.ptiles_per_stripe = pl.ptiles_per_stripe;
+    prm.part_score = reinterpret_cast<float*>(workspace);
+    prm.part_idx = reinterpret_cast<int32_t*>(prm.part_score + per);
+    rc = dense_launch(DMODE_TOPK, q_hi, q_lo, nq, p_hi, p_lo, np, d_pad, prec, prm, as_stream(stream));
+    if (rc) return rc;
+    return r4d_dense_topk_merge(prm.part_score, prm.part_idx, pl.n_stripes * 2, nq, k, k, top_score, top_idx, stream);
+}
+
+int r4d_dense_full(const void* q_hi, const void* q_lo, int64_t nq, const void* p_hi, const void* p_lo, int64_t np,
+                   int32_t d_pad, int32_t prec, const float* q_time, const float* p_time, float lambda, int32_t mode,
+                   float* scores, int64_t ld, r4d_stream_t stream) {
+    using namespace r4d;
+    int rc = dense_check(q_hi, q_lo, nq, p_hi, p_lo, np, d_pad, prec, q_time, p_time, mode);
+    if (rc) return rc;
+    if (nq == 0 || np == 0) return R4D_OK;
+    R4D_REQUIRE(scores && ld >= np, "dense_full: scores null or ld < np");
+    const DensePlan pl = dense_plan(nq, np, false);
+    DenseParams prm{};
+    prm.nq = nq;
+    prm.np = np;
+    prm.mode = mode;
+    prm.k = 0;
+    prm.neg_lambda_log2e = -lambda * 1.4426950408889634f;
+    prm.pool_base = 0;
+    prm.q_time = q_time;
+    prm.p_time = p_time;
+    prm.n_qtiles = pl.n_qtiles;
+    prm.n_ptiles = pl.n_ptiles;
+    prm.n_stripes = pl.n_stripes;
+    prm.ptiles_per_stripe = pl.ptiles_per_stripe;
+    prm.scores = scores;
+    prm.ld = ld;
+    return dense_launch(DMODE_FULL, q_hi, q_lo, nq, p_hi, p_lo, np, d_pad, prec, prm, as_stream(stream));
+}
+
+int r4d_dense_topk_merge(const float* score, const int32_t* idx, int32_t n_lists, int64_t nq, int32_t k_in,
+                         int32_t k_out, float* out_score, int32_t* out_idx, r4d_stream_t stream) {
+    using namespace r4d;
+    R4D_REQUIRE(n_lists >= 0 && nq >= 0 && k_in >= 1 && k_out >= 1 && k_out <= R4D_TOPK_MAX,
+                "dense_topk_merge: n_lists=%d k_in=%d k_out=%d", n_lists, k_in, k_out);
+    if (nq == 0) return R4D_OK;
+    R4D_REQUIRE(out_score && out_idx, "dense_topk_merge: null output");
+    R4D_REQUIRE(n_lists == 0 || (score && idx), "dense_topk_merge: null input");
+    int64_t blocks = (nq + 7) / 8;
+    const int64_t cap = (int64_t)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    dense_merge_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(score, idx, n_lists, nq, k_in, k_out, out_score,
+                                                                       out_idx);
+    R4D_CUDA(cudaGetLastError());
+    return R4D_OK;
+}
+
+}  // extern "C"

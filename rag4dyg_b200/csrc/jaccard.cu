@@ -1,0 +1,487 @@
+// jaccard.cu — subsystems 2 + 4: all-pairs Jaccard on bitsets, full-matrix mode and fused top-K mode.
+//
+// Replaces occurrence_matrix / co_occurrence_ratio (retrieval_data_annotation.py:36-41, :5-15) and, in
+// top-K mode, also np.argsort(-row)[:k] (retrieval_data_annotation.py:97-103).
+//
+// Design (B200, sm_100a)
+//  * CTA tile 128 queries x 128 pool rows, persistent CTAs (one per SM) walking a static list of
+//    (pool stripe, query tile) work items.
+//  * warp 0 = TMA producer: per 32-word chunk it issues two cp.async.bulk.tensor.2d loads (128 rows x 128 B,
+//    SWIZZLE_128B) into a 3-stage smem ring guarded by full/empty mbarriers.
+//  * warps 1..8 = consumers: each thread owns an 8x8 micro-tile of intersection counters; per 16-byte group it
+//    issues 8+8 conflict-free LDS.128 (the 128B swizzle spreads the 8 rows a quarter-warp touches over all
+//    banks) and 256 LOP3(AND)+POPC+IADD3.  The POPC pipe is the binding unit.
+//  * counts are exact integers; union = |q| + |p| - inter.  Scores are compared as rationals by 64-bit
+//    cross-multiplication (JEntry::better), so ranking is exact and ties break by ascending pool index.
+//  * top-K mode: the 128x128 count tile goes through smem once, each consumer warp scans 16 query rows,
+//    ballots the entries that beat the row's current k-th candidate and inserts them into a one-entry-per-lane
+//    sorted list (WarpTopK).  Per-stripe lists are merged by jaccard_merge_kernel.
+#include "r4d_common.cuh"
+
+namespace r4d {
+
+constexpr int TQ = 128;
+constexpr int TP = 128;
+constexpr int CHUNK_WORDS = 32;                   // 128 B of each row per pipeline stage
+constexpr int OPER_BYTES = TQ * CHUNK_WORDS * 4;  // 16 KB per operand per stage
+constexpr int STAGE_BYTES = 2 * OPER_BYTES;
+constexpr int NSTAGES = 3;
+constexpr int N_CONSUMER_WARPS = 8;
+constexpr int N_CONSUMERS = 32 * N_CONSUMER_WARPS;
+constexpr int N_THREADS = 32 + N_CONSUMERS;
+constexpr int TILE_LD = TP + 8;  // padded pitch (words) of the count tile: conflict-free register->smem spill
+constexpr int LIST_LD = 32;      // one list slot per lane
+
+constexpr int MODE_TOPK = 0;
+constexpr int MODE_FULL = 1;
+
+struct JaccardParams {
+    const uint32_t* qcard;
+    const uint32_t* pcard;
+    int64_t nq, np;
+    int32_t n_chunks;     // ceil(words / 32)
+    int32_t last_groups;  // 16-byte groups holding real words in the last chunk (1..8)
+    int32_t k;
+    int32_t zero_diag;
+    int64_t query_base, pool_base;
+    int32_t n_qtiles, n_ptiles, n_stripes, ptiles_per_stripe;
+    // top-K partial lists [n_stripes][nq][k]
+    uint32_t* part_inter;
+    uint32_t* part_union;
+    int32_t* part_idx;
+    // full-matrix outputs
+    uint32_t* inter;
+    int64_t ld_inter;
+    double* score;
+    int64_t ld_score;
+};
+
+constexpr size_t smem_bytes_for(int mode) {
+    size_t b = 1024 /*alignment slack*/ + (size_t)NSTAGES * STAGE_BYTES + 2 * NSTAGES * sizeof(uint64_t);
+    if (mode == MODE_TOPK) b += (size_t)TQ * TILE_LD * 4 + 3 * (size_t)TQ * LIST_LD * 4;
+    return b;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(N_THREADS, 1)
+jaccard_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_p,
+               const JaccardParams prm) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* stages = smem;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)NSTAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + NSTAGES;
+    uint32_t* tilebuf = reinterpret_cast<uint32_t*>(empty_bar + NSTAGES);  // [TQ][TILE_LD]      (top-K mode)
+    uint32_t* l_inter = tilebuf + TQ * TILE_LD;                           // [TQ][LIST_LD] x 3  (top-K mode)
+    uint32_t* l_union = l_inter + TQ * LIST_LD;
+    int32_t* l_idx = reinterpret_cast<int32_t*>(l_union + TQ * LIST_LD);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tm_q);
+        tma_prefetch_desc(&tm_p);
+        for (int s = 0; s < NSTAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], N_CONSUMER_WARPS);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    const int n_items = prm.n_qtiles * prm.n_stripes;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer (one elected lane)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int stripe = item / prm.n_qtiles;
+                const int qtile = item - stripe * prm.n_qtiles;
+                const int pt_beg = stripe * prm.ptiles_per_stripe;
+                const int pt_end = min(pt_beg + prm.ptiles_per_stripe, prm.n_ptiles);
+                for (int pt = pt_beg; pt < pt_end; ++pt) {
+                    for (int c = 0; c < prm.n_chunks; ++c) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* dst = stages + (size_t)stage * STAGE_BYTES;
+                        mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+                        tma_load_2d(dst, &tm_q, &full_bar[stage], c * CHUNK_WORDS, qtile * TQ);
+                        tma_load_2d(dst + OPER_BYTES, &tm_p, &full_bar[stage], c * CHUNK_WORDS, pt * TP);
+                        if (++stage == NSTAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------- consumers (warps 1..8)
+    const int cw = warp - 1;    // 0..7
+    const int wq = cw >> 1;     // 0..3 : 32-query slab
+    const int wp = cw & 1;      // 0..1 : 64-pool-row slab
+    const int lq = lane >> 3;   // 0..3
+    const int lp = lane & 7;    // 0..7
+    // rows owned by this thread: q(i) = wq*32 + i*4 + lq, p(j) = wp*64 + j*8 + lp  (i, j in 0..7)
+    const uint32_t q_off = (uint32_t)(wq * 32 + lq) * 128u;             // + i*512
+    const uint32_t p_off = OPER_BYTES + (uint32_t)(wp * 64 + lp) * 128u;  // + j*1024
+    const uint32_t q_xor_even = (uint32_t)lq << 4;                      // (row & 7) << 4 for even i
+    const uint32_t q_xor_odd = (uint32_t)(lq + 4) << 4;                 //                    odd i
+    const uint32_t p_xor = (uint32_t)lp << 4;
+    const uint32_t stages_u32 = smem_u32(stages);
+
+    int stage = 0;
+    uint32_t phase = 0;
+
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int stripe = item / prm.n_qtiles;
+        const int qtile = item - stripe * prm.n_qtiles;
+        const int pt_beg = stripe * prm.ptiles_per_stripe;
+        const int pt_end = min(pt_beg + prm.ptiles_per_stripe, prm.n_ptiles);
+
+        if (MODE == MODE_TOPK) {
+            // reset the 16 lists this warp owns
+            for (int qq = 0; qq < 16; ++qq) {
+                const int q = cw * 16 + qq;
+                l_inter[q * LIST_LD + lane] = 0u;
+                l_union[q * LIST_LD + lane] = 1u;
+                l_idx[q * LIST_LD + lane] = R4D_IDX_NONE;
+            }
+            __syncwarp();
+        }
+
+        for (int pt = pt_beg; pt < pt_end; ++pt) {
+            uint32_t acc[8][8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = 0u;
+
+            for (int c = 0; c < prm.n_chunks; ++c) {
+                mbar_wait(&full_bar[stage], phase);
+                const uint32_t sbase = stages_u32 + (uint32_t)stage * STAGE_BYTES;
+                const int ngroups = (c == prm.n_chunks - 1) ? prm.last_groups : 8;
+#pragma unroll 1
+                for (int g = 0; g < ngroups; ++g) {
+                    const uint32_t gq_e = sbase + q_off + (((uint32_t)g << 4) ^ q_xor_even);
+                    const uint32_t gq_o = sbase + q_off + (((uint32_t)g << 4) ^ q_xor_odd);
+                    const uint32_t gp = sbase + p_off + (((uint32_t)g << 4) ^ p_xor);
+                    uint4 qv[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const uint32_t a = ((i & 1) ? gq_o : gq_e) + (uint32_t)i * 512u;
+                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                     : "=r"(qv[i].x), "=r"(qv[i].y), "=r"(qv[i].z), "=r"(qv[i].w)
+                                     : "r"(a));
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        uint4 pv;
+                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                     : "=r"(pv.x), "=r"(pv.y), "=r"(pv.z), "=r"(pv.w)
+                                     : "r"(gp + (uint32_t)j * 1024u));
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            acc[i][j] += __popc(qv[i].x & pv.x) + __popc(qv[i].y & pv.y) +
+                                         __popc(qv[i].z & pv.z) + __popc(qv[i].w & pv.w);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[stage]);
+                if (++stage == NSTAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+
+            // -------------------------------------------------------- epilogue
+            if (MODE == MODE_FULL) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int64_t gq = (int64_t)qtile * TQ + wq * 32 + i * 4 + lq;
+                    if (gq >= prm.nq) continue;
+                    const uint32_t cq = prm.qcard[gq];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int64_t gp_row = (int64_t)pt * TP + wp * 64 + j * 8 + lp;
+                        if (gp_row >= prm.np) continue;
+                        uint32_t in = acc[i][j];
+                        if (prm.zero_diag && (prm.query_base + gq == prm.pool_base + gp_row)) in = 0u;
+                        prm.inter[gq * prm.ld_inter + gp_row] = in;
+                        if (prm.score) {
+                            const uint32_t un = cq + prm.pcard[gp_row] - in;
+                            prm.score[gq * prm.ld_score + gp_row] = in ? (double)in / (double)un : 0.0;
+                        }
+                    }
+                }
+            } else {
+                named_bar_sync(1, N_CONSUMERS);  // previous tile's scan is finished
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        tilebuf[(wq * 32 + i * 4 + lq) * TILE_LD + wp * 64 + j * 8 + lp] = acc[i][j];
+                named_bar_sync(1, N_CONSUMERS);  // count tile complete
+
+                // pool-side constants of the 4 columns this lane scans
+                uint32_t cp[4];
+                int64_t gpi[4];
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    gpi[s] = (int64_t)pt * TP + s * 32 + lane;
+                    cp[s] = gpi[s] < prm.np ? prm.pcard[gpi[s]] : 0u;
+                }
+                for (int qq = 0; qq < 16; ++qq) {
+                    const int q = cw * 16 + qq;
+                    const int64_t gq = (int64_t)qtile * TQ + q;
+                    if (gq >= prm.nq) break;  // warp-uniform
+                    const uint32_t cq = prm.qcard[gq];
+                    WarpTopK<JEntry> tk;
+                    tk.k = prm.k;
+                    tk.mine = JEntry{l_inter[q * LIST_LD + lane], l_union[q * LIST_LD + lane], l_idx[q * LIST_LD + lane]};
+                    tk.refresh_kth();
+                    bool changed = false;
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        uint32_t in = tilebuf[q * TILE_LD + s * 32 + lane];
+                        const bool valid = gpi[s] < prm.np;
+                        if (prm.zero_diag && (prm.query_base + gq == prm.pool_base + gpi[s])) in = 0u;
+                        // both sets empty: union 0 -> score 0, represented as 0/1 so cross-multiplication stays valid
+                        JEntry c{in, max(cq + cp[s] - in, 1u), (int32_t)(prm.pool_base + gpi[s])};
+                        uint32_t m = __ballot_sync(0xffffffffu, valid && JEntry::better(c, tk.kth));
+                        while (m) {
+                            const int src = __ffs(m) - 1;
+                            m &= m - 1;
+                            tk.insert(c.shfl(src));
+                            changed = true;
+                        }
+                    }
+                    if (changed) {
+                        l_inter[q * LIST_LD + lane] = tk.mine.inter;
+                        l_union[q * LIST_LD + lane] = tk.mine.uni;
+                        l_idx[q * LIST_LD + lane] = tk.mine.idx;
+                    }
+                }
+            }
+        }
+
+        if (MODE == MODE_TOPK) {
+            __syncwarp();
+            // flush this warp's 16 lists to the stripe's partial slot
+            for (int qq = 0; qq < 16; ++qq) {
+                const int q = cw * 16 + qq;
+                const int64_t gq = (int64_t)qtile * TQ + q;
+                if (gq >= prm.nq) break;
+                if (lane < prm.k) {
+                    const int64_t o = ((int64_t)stripe * prm.nq + gq) * prm.k + lane;
+                    prm.part_inter[o] = l_inter[q * LIST_LD + lane];
+                    prm.part_union[o] = l_union[q * LIST_LD + lane];
+                    prm.part_idx[o] = l_idx[q * LIST_LD + lane];
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// Merge n_lists lists of k_in candidates per query into the best k_out.  One warp per query.
+__global__ void __launch_bounds__(256)
+jaccard_merge_kernel(const uint32_t* __restrict__ inter, const uint32_t* __restrict__ uni,
+                     const int32_t* __restrict__ idx, int32_t n_lists, int64_t nq, int32_t k_in, int32_t k_out,
+                     uint32_t* __restrict__ out_inter, uint32_t* __restrict__ out_union, int32_t* __restrict__ out_idx) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wpg = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); q < nq; q += wpg) {
+        WarpTopK<JEntry> tk;
+        tk.init(k_out);
+        for (int l = 0; l < n_lists; ++l) {
+            const int64_t base = ((int64_t)l * nq + q) * k_in;
+            for (int e0 = 0; e0 < k_in; e0 += 32) {
+                const int e = e0 + lane;
+                JEntry c = JEntry::worst();
+                if (e < k_in) c = JEntry{inter[base + e], uni[base + e], idx[base + e]};
+                uint32_t m = __ballot_sync(0xffffffffu, e < k_in && c.idx != R4D_IDX_NONE && JEntry::better(c, tk.kth));
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    tk.insert(c.shfl(src));
+                }
+            }
+        }
+        if (lane < k_out) {
+            out_inter[q * k_out + lane] = tk.mine.inter;
+            out_union[q * k_out + lane] = tk.mine.uni;
+            out_idx[q * k_out + lane] = tk.mine.idx;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------- host side
+struct JaccardPlan {
+    int32_t n_qtiles, n_ptiles, n_stripes, ptiles_per_stripe;
+};
+
+static JaccardPlan plan_topk(int64_t nq, int64_t np) {
+    JaccardPlan pl;
+    pl.n_qtiles = (int32_t)((nq + TQ - 1) / TQ);
+    pl.n_ptiles = (int32_t)((np + TP - 1) / TP);
+    if (pl.n_qtiles < 1) pl.n_qtiles = 1;
+    if (pl.n_ptiles < 1) pl.n_ptiles = 1;
+    // enough (stripe, query-tile) items for ~32 per SM so the static round-robin tail stays below ~3 %
+    const int64_t target = (int64_t)num_sms() * 32;
+    int64_t stripes = (target + pl.n_qtiles - 1) / pl.n_qtiles;
+    if (stripes > pl.n_ptiles) stripes = pl.n_ptiles;
+    if (stripes < 1) stripes = 1;
+    pl.ptiles_per_stripe = (int32_t)((pl.n_ptiles + stripes - 1) / stripes);
+    pl.n_stripes = (pl.n_ptiles + pl.ptiles_per_stripe - 1) / pl.ptiles_per_stripe;
+    return pl;
+}
+
+static int check_common(const uint32_t* qbits, const uint32_t* qcard, int64_t nq, const uint32_t* pbits,
+                        const uint32_t* pcard, int64_t np, int32_t words, int32_t pitch_words) {
+    R4D_REQUIRE(nq >= 0 && np >= 0, "jaccard: negative size");
+    R4D_REQUIRE(words > 0 && pitch_words >= words && pitch_words % 4 == 0,
+                "jaccard: words=%d pitch_words=%d (pitch must be >= words and a multiple of 4)", words, pitch_words);
+    R4D_REQUIRE(nq < (int64_t)1 << 31 && np < (int64_t)1 << 31, "jaccard: sizes must be < 2^31");
+    if (nq > 0 && np > 0) R4D_REQUIRE(qbits && qcard && pbits && pcard, "jaccard: null pointer");
+    return R4D_OK;
+}
+
+template <int MODE>
+static int launch(const uint32_t* qbits, int64_t nq, const uint32_t* pbits, int64_t np, int32_t words,
+                  int32_t pitch_words, JaccardParams& prm, cudaStream_t st) {
+    CUtensorMap tm_q, tm_p;
+    int rc = make_tmap_2d(&tm_q, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, qbits, (uint64_t)pitch_words, (uint64_t)nq,
+                          (uint64_t)pitch_words * 4, CHUNK_WORDS, TQ, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = make_tmap_2d(&tm_p, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, pbits, (uint64_t)pitch_words, (uint64_t)np,
+                      (uint64_t)pitch_words * 4, CHUNK_WORDS, TP, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    prm.n_chunks = (words + CHUNK_WORDS - 1) / CHUNK_WORDS;
+    const int rem = words - (prm.n_chunks - 1) * CHUNK_WORDS;  // 1..32 real words in the last chunk
+    prm.last_groups = (rem + 3) / 4;
+    const size_t smem = smem_bytes_for(MODE);
+    static bool attr_done[2] = {false, false};
+    if (!attr_done[MODE]) {
+        R4D_CUDA(cudaFuncSetAttribute(jaccard_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done[MODE] = true;
+    }
+    const int64_t n_items = (int64_t)prm.n_qtiles * prm.n_stripes;
+    int grid = num_sms();
+    if (n_items < grid) grid = (int)n_items;
+    jaccard_kernel<MODE><<<grid, N_THREADS, smem, st>>>(tm_q, tm_p, prm);
+    R4D_CUDA(cudaGetLastError());
+    return R4D_OK;
+}
+
+}  // namespace r4d
+
+extern "C" {
+
+int r4d_jaccard_full(const uint32_t* qbits, const uint32_t* qcard, int64_t nq, const uint32_t* pbits,
+                     const uint32_t* pcard, int64_t np, int32_t words, int32_t pitch_words, int32_t zero_diag,
+                     int64_t query_base, int64_t pool_base, uint32_t* inter, int64_t ld_inter, double* score,
+                     int64_t ld_score, r4d_stream_t stream) {
+    using namespace r4d;
+    int rc = check_common(qbits, qcard, nq, pbits, pcard, np, words, pitch_words);
+    if (rc) return rc;
+    if (nq == 0 || np == 0) return R4D_OK;
+    R4D_REQUIRE(inter && ld_inter >= np, "jaccard_full: inter null or ld_inter < np");
+    R4D_REQUIRE(!score || ld_score >= np, "jaccard_full: ld_score < np");
+    JaccardParams prm{};
+    prm.qcard = qcard;
+    prm.pcard = pcard;
+    prm.nq = nq;
+    prm.np = np;
+    prm.k = 0;
+    prm.zero_diag = zero_diag;
+    prm.query_base = query_base;
+    prm.pool_base = pool_base;
+    prm.n_qtiles = (int32_t)((nq + TQ - 1) / TQ);
+    prm.n_ptiles = (int32_t)((np + TP - 1) / TP);
+    prm.n_stripes = prm.n_ptiles;  // one pool tile per work item
+    prm.ptiles_per_stripe = 1;
+    prm.inter = inter;
+    prm.ld_inter = ld_inter;
+    prm.score = score;
+    prm.ld_score = ld_score;
+    return launch<MODE_FULL>(qbits, nq, pbits, np, words, pitch_words, prm, as_stream(stream));
+}
+
+size_t r4d_jaccard_topk_workspace_bytes(int64_t nq, int64_t np, int32_t k) {
+    using namespace r4d;
+    if (nq <= 0 || np <= 0 || k <= 0) return 256;
+    const JaccardPlan pl = plan_topk(nq, np);
+    return (size_t)pl.n_stripes * (size_t)nq * (size_t)k * 12 + 256;
+}
+
+int r4d_jaccard_topk(const uint32_t* qbits, const uint32_t* qcard, int64_t nq, const uint32_t* pbits,
+                     const uint32_t* pcard, int64_t np, int32_t words, int32_t pitch_words, int32_t k,
+                     int32_t zero_diag, int64_t query_base, int64_t pool_base, uint32_t* top_inter,
+                     uint32_t* top_union, int32_t* top_idx, void* workspace, size_t workspace_bytes,
+                     r4d_stream_t stream) {
+    using namespace r4d;
+    int rc = check_common(qbits, qcard, nq, pbits, pcard, np, words, pitch_words);
+    if (rc) return rc;
+    R4D_REQUIRE(k >= 1 && k <= R4D_TOPK_MAX, "jaccard_topk: k=%d out of range [1, %d]", k, R4D_TOPK_MAX);
+    R4D_REQUIRE(pool_base >= 0 && pool_base + np < (int64_t)R4D_IDX_NONE, "jaccard_topk: pool_base+np exceeds int32");
+    if (nq == 0) return R4D_OK;
+    R4D_REQUIRE(top_inter && top_union && top_idx, "jaccard_topk: null output");
+    cudaStream_t st = as_stream(stream);
+    const JaccardPlan pl = plan_topk(nq, np);
+    const size_t per = (size_t)pl.n_stripes * (size_t)nq * (size_t)k;
+    if (workspace_bytes < per * 12 || (!workspace && per)) {
+        set_error("jaccard_topk: workspace %zu B < required %zu B", workspace_bytes, per * 12);
+        return R4D_E_WORKSPACE;
+    }
+    JaccardParams prm{};
+    prm.qcard = qcard;
+    prm.pcard = pcard;
+    prm.nq = nq;
+    prm.np = np;
+    prm.k = k;
+    prm.zero_diag = zero_diag;
+    prm.query_base = query_base;
+    prm.pool_base = pool_base;
+    prm.n_qtiles = pl.n_qtiles;
+    prm.n_ptiles = pl.n_ptiles;
+    prm.n_stripes = pl.n_stripes;
+    prm.ptiles_per_stripe = pl.ptiles_per_stripe;
+    prm.part_inter = reinterpret_cast<uint32_t*>(workspace);
+    prm.part_union = prm.part_inter + per;
+    prm.part_idx = reinterpret_cast<int32_t*>(prm.part_union + per);
+    if (np == 0) {
+        // no pool rows: every list is padding; the merge of zero lists writes it
+        return r4d_jaccard_topk_merge(prm.part_inter, prm.part_union, prm.part_idx, 0, nq, k, k, top_inter, top_union,
+                                      top_idx, stream);
+    }
+    rc = launch<MODE_TOPK>(qbits, nq, pbits, np, words, pitch_words, prm, st);
+    if (rc) return rc;
+    return r4d_jaccard_topk_merge(prm.part_inter, prm.part_union, prm.part_idx, pl.n_stripes, nq, k, k, top_inter,
+                                  top_union, top_idx, stream);
+}
+
+int r4d_jaccard_topk_merge(const uint32_t* inter, const uint32_t* uni, const int32_t* idx, int32_t n_lists,
+                           int64_t nq, int32_t k_in, int32_t k_out, uint32_t* out_inter, uint32_t* out_union,
+                           int32_t* out_idx, r4d_stream_t stream) {
+    using namespace r4d;
+    R4D_REQUIRE(n_lists >= 0 && nq >= 0 && k_in >= 1 && k_out >= 1 && k_out <= R4D_TOPK_MAX,
+                "jaccard_topk_merge: n_lists=%d k_in=%d k_out=%d", n_lists, k_in, k_out);
+    if (nq == 0) return R4D_OK;
+    R4D_REQUIRE(out_inter && out_union && out_idx, "jaccard_topk_merge: null output");
+    R4D_REQUIRE(n_lists == 0 || (inter && uni && idx), "jaccard_topk_merge: null input");
+    int64_t blocks = (nq + 7) / 8;
+    const int64_t cap = (int64_t)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    jaccard_merge_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(inter, uni, idx, n_lists, nq, k_in, k_out,
+                                                                         out_inter, out_union, out_idx);
+    R4D_CUDA(cudaGetLastError());
+    return R4D_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,105 @@
+// r4d_host.cu — error plumbing, device probe, TMA descriptor factory.
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+
+#include "r4d_common.cuh"
+
+namespace r4d {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    return R4D_E_CUDA;
+}
+
+int num_sms() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static encode_tiled_fn get_encode_fn() {
+    static encode_tiled_fn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<encode_tiled_fn>(p);
+    });
+    return fn;
+}
+
+int make_tmap_2d(CUtensorMap* map, CUtensorMapDataType dtype, int elem_bytes, const void* base, uint64_t dim0,
+                 uint64_t dim1, uint64_t row_stride_bytes, uint32_t box0, uint32_t box1, CUtensorMapSwizzle swz) {
+    encode_tiled_fn fn = get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled not available from the CUDA driver");
+        return R4D_E_CUDA;
+    }
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (row_stride_bytes & 15) != 0) {
+        set_error("TMA operand must be 16-byte aligned (base %p, row stride %llu B)", base,
+                  (unsigned long long)row_stride_bytes);
+        return R4D_E_ARG;
+    }
+    (void)elem_bytes;
+    cuuint64_t dims[2] = {dim0, dim1};
+    cuuint64_t strides[1] = {row_stride_bytes};
+    cuuint32_t box[2] = {box0, box1};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, dtype, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (dims %llu x %llu, stride %llu, box %u x %u)", (int)r,
+                  (unsigned long long)dim0, (unsigned long long)dim1, (unsigned long long)row_stride_bytes, box0, box1);
+        return R4D_E_CUDA;
+    }
+    return R4D_OK;
+}
+
+}  // namespace r4d
+
+extern "C" {
+
+int r4d_version(void) { return 100; }
+
+const char* r4d_last_error(void) { return r4d::g_err; }
+
+int r4d_device_ok(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        r4d::set_error("no CUDA device visible");
+        return 0;
+    }
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+    if (major != 10) {
+        r4d::set_error("device %d has compute capability %d.x; libr4d is built for sm_100a only", dev, major);
+        return 0;
+    }
+    return 1;
+}
+
+}  // extern "C"

@@ -1,0 +1,285 @@
+"""Thin torch-tensor front end of the C ABI (include/r4d.h).
+
+Every function here takes CUDA tensors, passes raw device pointers + the current CUDA stream to libr4d.so and returns
+CUDA tensors.  Nothing is computed in Python/torch: a missing library or device raises (no CPU fallback).
+"""
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+from ._lib import (DENSE_COS_DECAY, DENSE_HALF_COS, DENSE_HALF_COS_DECAY, PREC_BF16, PREC_BF16X3, R4D_IDX_NONE,
+                   R4D_TOPK_MAX, R4DError, check)
+
+__all__ = [
+    "BitsetMatrix", "encode_bitsets", "jaccard_full", "jaccard_topk", "jaccard_topk_merge", "rank_rows", "topk_rows",
+    "triplet_mine", "DensePlanes", "dense_prepare", "dense_topk", "dense_full", "dense_topk_merge", "R4D_IDX_NONE",
+    "R4D_TOPK_MAX", "DENSE_HALF_COS", "DENSE_COS_DECAY", "DENSE_HALF_COS_DECAY", "PREC_BF16", "PREC_BF16X3",
+    "launch_count", "reset_launch_count",
+]
+
+_launches = 0  # kernels of OURS enqueued through this module (bench.py reports it as gpu_launches)
+
+
+def launch_count():
+    return _launches
+
+
+def reset_launch_count():
+    global _launches
+    _launches = 0
+
+
+def _count(n):
+    global _launches
+    _launches += n
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _dev_tensor(t, dtype, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise R4DError(f"{name}: expected a CUDA tensor (this path has no CPU implementation)")
+    if t.dtype != dtype:
+        raise R4DError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise R4DError(f"{name}: tensor must be contiguous")
+    return t
+
+
+@dataclass
+class BitsetMatrix:
+    """Rows of fixed-width uint32 bitsets in HBM: bits[n_rows, pitch_words] (int32 storage), card[n_rows] = |set|."""
+    bits: torch.Tensor
+    card: torch.Tensor
+    n_bits: int
+    words: int
+    pitch_words: int
+
+    @property
+    def n_rows(self):
+        return self.bits.shape[0]
+
+    def rows(self, start, stop):
+        """Contiguous row slice (a pool shard); shares storage."""
+        return BitsetMatrix(self.bits[start:stop], self.card[start:stop], self.n_bits, self.words, self.pitch_words)
+
+
+def encode_bitsets(bit_pos, row_off, n_bits):
+    """CSR (int32 bit positions, int64 row offsets; CUDA tensors) -> BitsetMatrix.  r4d_bitset_encode."""
+    lib = _lib.load()
+    bit_pos = _dev_tensor(bit_pos, torch.int32, "bit_pos")
+    row_off = _dev_tensor(row_off, torch.int64, "row_off")
+    n_rows = row_off.numel() - 1
+    if n_rows < 0:
+        raise R4DError("row_off must hold n_rows+1 offsets")
+    words = lib.r4d_bitset_words(n_bits)
+    pitch = lib.r4d_bitset_pitch_words(n_bits)
+    dev = row_off.device
+    bits = torch.empty((n_rows, pitch), dtype=torch.int32, device=dev)
+    card = torch.empty((n_rows,), dtype=torch.int32, device=dev)
+    check(lib.r4d_bitset_encode(_ptr(bit_pos), _ptr(row_off), n_rows, n_bits, pitch, _ptr(bits), _ptr(card), _stream()),
+          "r4d_bitset_encode")
+    _count(1 if n_rows else 0)
+    return BitsetMatrix(bits, card, n_bits, words, pitch)
+
+
+def _check_pair(q, p):
+    if q.words != p.words or q.pitch_words != p.pitch_words:
+        raise R4DError("query and pool bitsets must share the same universe (words/pitch differ)")
+
+
+def jaccard_full(q, p, zero_diag=False, want_score=True, query_base=0, pool_base=0):
+    """All-pairs intersection counts (int32 [nq, np]) and float64 Jaccard scores.  r4d_jaccard_full."""
+    lib = _lib.load()
+    _check_pair(q, p)
+    nq, np_ = q.n_rows, p.n_rows
+    dev = q.bits.device
+    inter = torch.empty((nq, np_), dtype=torch.int32, device=dev)
+    score = torch.empty((nq, np_), dtype=torch.float64, device=dev) if want_score else None
+    check(lib.r4d_jaccard_full(_ptr(q.bits), _ptr(q.card), nq, _ptr(p.bits), _ptr(p.card), np_, q.words, q.pitch_words,
+                               int(bool(zero_diag)), query_base, pool_base, _ptr(inter), np_, _ptr(score), np_,
+                               _stream()), "r4d_jaccard_full")
+    _count(1 if nq and np_ else 0)
+    return inter, score
+
+
+def jaccard_topk(q, p, k, zero_diag=False, query_base=0, pool_base=0, workspace=None):
+    """Fused scorer + top-K: (inter, union, idx) int32 [nq, k], order (score desc, idx asc).  r4d_jaccard_topk."""
+    lib = _lib.load()
+    _check_pair(q, p)
+    nq, np_ = q.n_rows, p.n_rows
+    dev = q.bits.device
+    need = lib.r4d_jaccard_topk_workspace_bytes(nq, np_, k)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty((need,), dtype=torch.uint8, device=dev)
+    top_inter = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    top_union = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    top_idx = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    check(lib.r4d_jaccard_topk(_ptr(q.bits), _ptr(q.card), nq, _ptr(p.bits), _ptr(p.card), np_, q.words, q.pitch_words,
+                               k, int(bool(zero_diag)), query_base, pool_base, _ptr(top_inter), _ptr(top_union),
+                               _ptr(top_idx), _ptr(workspace), workspace.numel(), _stream()), "r4d_jaccard_topk")
+    _count(2 if nq and np_ else (1 if nq else 0))
+    return top_inter, top_union, top_idx
+
+
+def jaccard_topk_merge(inter, uni, idx, k_out):
+    """Merge candidate lists [n_lists, nq, k_in] -> [nq, k_out].  r4d_jaccard_topk_merge."""
+    lib = _lib.load()
+    inter = _dev_tensor(inter, torch.int32, "inter")
+    uni = _dev_tensor(uni, torch.int32, "uni")
+    idx = _dev_tensor(idx, torch.int32, "idx")
+    n_lists, nq, k_in = inter.shape
+    dev = inter.device
+    o_i = torch.empty((nq, k_out), dtype=torch.int32, device=dev)
+    o_u = torch.empty((nq, k_out), dtype=torch.int32, device=dev)
+    o_x = torch.empty((nq, k_out), dtype=torch.int32, device=dev)
+    check(lib.r4d_jaccard_topk_merge(_ptr(inter), _ptr(uni), _ptr(idx), n_lists, nq, k_in, k_out, _ptr(o_i), _ptr(o_u),
+                                     _ptr(o_x), _stream()), "r4d_jaccard_topk_merge")
+    _count(1 if nq else 0)
+    return o_i, o_u, o_x
+
+
+def rank_rows(scores):
+    """order[q] = argsort(-scores[q], stable) as int32 [nq, n].  float64 or float32 CUDA matrix."""
+    lib = _lib.load()
+    if scores.dtype == torch.float64:
+        fn, eb = lib.r4d_rank_rows_f64, 8
+    elif scores.dtype == torch.float32:
+        fn, eb = lib.r4d_rank_rows_f32, 4
+    else:
+        raise R4DError(f"rank_rows: unsupported dtype {scores.dtype}")
+    scores = _dev_tensor(scores, scores.dtype, "scores")
+    nq, n = scores.shape
+    dev = scores.device
+    order = torch.empty((nq, n), dtype=torch.int32, device=dev)
+    need = lib.r4d_rank_rows_workspace_bytes(nq, n, eb)
+    ws = torch.empty((need,), dtype=torch.uint8, device=dev)
+    check(fn(_ptr(scores), nq, n, n, _ptr(order), _ptr(ws), ws.numel(), _stream()), "r4d_rank_rows")
+    _count(1 if nq and n else 0)
+    return order
+
+
+def topk_rows(scores, k):
+    """Top-k of each row of an explicit float64 matrix: (scores f64 [nq,k], idx int32 [nq,k])."""
+    lib = _lib.load()
+    scores = _dev_tensor(scores, torch.float64, "scores")
+    nq, n = scores.shape
+    dev = scores.device
+    ts = torch.empty((nq, k), dtype=torch.float64, device=dev)
+    ti = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    check(lib.r4d_topk_rows_f64(_ptr(scores), nq, n, n, k, _ptr(ts), _ptr(ti), _stream()), "r4d_topk_rows_f64")
+    _count(1 if nq else 0)
+    return ts, ti
+
+
+def triplet_mine(out, inn, thr, neg_num):
+    """Device part of save_train_annotation: (n_pos [n], neg [n, neg_num], n_neg [n]) int32."""
+    lib = _lib.load()
+    out = _dev_tensor(out, torch.float64, "out")
+    inn = _dev_tensor(inn, torch.float64, "in")
+    n = out.shape[0]
+    if out.shape != (n, n) or inn.shape != (n, n):
+        raise R4DError("triplet_mine: out/in must be square matrices of the same size")
+    dev = out.device
+    n_pos = torch.empty((n,), dtype=torch.int32, device=dev)
+    neg = torch.empty((n, neg_num), dtype=torch.int32, device=dev)
+    n_neg = torch.empty((n,), dtype=torch.int32, device=dev)
+    check(lib.r4d_triplet_mine_f64(_ptr(out), _ptr(inn), n, n, float(thr), neg_num, _ptr(n_pos), _ptr(neg), _ptr(n_neg),
+                                   _stream()), "r4d_triplet_mine_f64")
+    _count(1 if n else 0)
+    return n_pos, neg, n_neg
+
+
+# ---------------------------------------------------------------------------------------------- dense scorer
+@dataclass
+class DensePlanes:
+    """L2-normalised embeddings in the scorer's layout: bf16 hi plane [n, d_pad] (+ lo plane for BF16X3)."""
+    hi: torch.Tensor
+    lo: torch.Tensor  # None for PREC_BF16
+    d: int
+    d_pad: int
+    prec: int
+
+    @property
+    def n_rows(self):
+        return self.hi.shape[0]
+
+    def rows(self, start, stop):
+        return DensePlanes(self.hi[start:stop], None if self.lo is None else self.lo[start:stop], self.d, self.d_pad,
+                           self.prec)
+
+
+def dense_prepare(x, prec=PREC_BF16X3):
+    """fp32 [n, d] -> row-normalised bf16 planes.  r4d_dense_prepare."""
+    lib = _lib.load()
+    x = _dev_tensor(x, torch.float32, "x")
+    n, d = x.shape
+    d_pad = lib.r4d_dense_dpad(d)
+    hi = torch.empty((n, d_pad), dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty((n, d_pad), dtype=torch.bfloat16, device=x.device) if prec == PREC_BF16X3 else None
+    check(lib.r4d_dense_prepare(_ptr(x), n, d, d, prec, _ptr(hi), _ptr(lo), _stream()), "r4d_dense_prepare")
+    _count(1 if n else 0)
+    return DensePlanes(hi, lo, d, d_pad, prec)
+
+
+def _check_dense(q, p, q_time, p_time, mode):
+    if q.d_pad != p.d_pad or q.prec != p.prec:
+        raise R4DError("dense: query/pool planes differ in width or precision")
+    if mode != DENSE_HALF_COS:
+        if q_time is None or p_time is None:
+            raise R4DError("dense: decay modes need q_time and p_time")
+        _dev_tensor(q_time, torch.float32, "q_time")
+        _dev_tensor(p_time, torch.float32, "p_time")
+        if q_time.numel() != q.n_rows or p_time.numel() != p.n_rows:
+            raise R4DError("dense: time vectors must have one entry per row")
+
+
+def dense_topk(q, p, k, mode=DENSE_HALF_COS, q_time=None, p_time=None, lam=0.0, pool_base=0, workspace=None):
+    """Fused tcgen05 contraction + epilogue + top-K: (score f32 [nq,k], idx int32 [nq,k]).  r4d_dense_topk."""
+    lib = _lib.load()
+    _check_dense(q, p, q_time, p_time, mode)
+    nq, np_ = q.n_rows, p.n_rows
+    dev = q.hi.device
+    need = lib.r4d_dense_topk_workspace_bytes(nq, np_, k)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty((need,), dtype=torch.uint8, device=dev)
+    ts = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    ti = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    check(lib.r4d_dense_topk(_ptr(q.hi), _ptr(q.lo), nq, _ptr(p.hi), _ptr(p.lo), np_, q.d_pad, q.prec, _ptr(q_time),
+                             _ptr(p_time), float(lam), mode, k, pool_base, _ptr(ts), _ptr(ti), _ptr(workspace),
+                             workspace.numel(), _stream()), "r4d_dense_topk")
+    _count(2 if nq and np_ else (1 if nq else 0))
+    return ts, ti
+
+
+def dense_full(q, p, mode=DENSE_HALF_COS, q_time=None, p_time=None, lam=0.0):
+    """Full score rows f32 [nq, np].  r4d_dense_full."""
+    lib = _lib.load()
+    _check_dense(q, p, q_time, p_time, mode)
+    nq, np_ = q.n_rows, p.n_rows
+    scores = torch.empty((nq, np_), dtype=torch.float32, device=q.hi.device)
+    check(lib.r4d_dense_full(_ptr(q.hi), _ptr(q.lo), nq, _ptr(p.hi), _ptr(p.lo), np_, q.d_pad, q.prec, _ptr(q_time),
+                             _ptr(p_time), float(lam), mode, _ptr(scores), np_, _stream()), "r4d_dense_full")
+    _count(1 if nq and np_ else 0)
+    return scores
+
+
+def dense_topk_merge(score, idx, k_out):
+    """Merge [n_lists, nq, k_in] dense candidate lists -> [nq, k_out]."""
+    lib = _lib.load()
+    score = _dev_tensor(score, torch.float32, "score")
+    idx = _dev_tensor(idx, torch.int32, "idx")
+    n_lists, nq, k_in = score.shape
+    o_s = torch.empty((nq, k_out), dtype=torch.float32, device=score.device)
+    o_i = torch.empty((nq, k_out), dtype=torch.int32, device=score.device)
+    check(lib.r4d_dense_topk_merge(_ptr(score), _ptr(idx), n_lists, nq, k_in, k_out, _ptr(o_s), _ptr(o_i), _stream()),
+          "r4d_dense_topk_merge")
+    _count(1 if nq else 0)
+    return o_s, o_i

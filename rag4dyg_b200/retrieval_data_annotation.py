@@ -1,0 +1,215 @@
+"""Drop-in for the reference's retrieval-pool annotation stage, computed on a B200 through libr4d.so.
+
+Same surface as /root/reference/retrieval_data_annotation.py:
+  * CLI      python retrieval_data_annotation.py <dataset> <timestep> <threshold>      (:111-113)
+  * functions co_occurrence_ratio, get_input_seq, get_output_seq, get_inout_list, occurrence_matrix,
+              save_train_annotation, save_index_score, save_score_file_train           (same positional arguments)
+  * files    resources/<ds>/<T>/train_retrieval/{train,val,test}_{index,score}.retrieval and
+             resources/train_generator/<ds>/<T>/train_gt_topk/train_{index,score}.gen  (:117-135)
+
+What differs, on purpose:
+  * every `np.argsort(-x)` of the reference is unstable and therefore machine-dependent on ties;
+    this engine always emits the canonical order (score descending, pool index ascending) == kind='stable'.
+  * all scoring / ranking / mining runs on the GPU; there is no CPU path (a missing library or device raises).
+The random negative per positive still comes from the legacy global numpy RNG, called exactly as the reference calls
+it (:79), so seeding `np.random.seed(s)` before `main()` reproduces a seeded reference run byte for byte.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+from . import engine, set_encoder, writers
+
+_DEVICE = "cuda"
+
+
+# ------------------------------------------------------------------------------------------------ parsing
+def _between(text, start, end):
+    # text after the first `start` (up to a second one, as str.split would cut), then up to the first `end`
+    parts = text.split(start)
+    if len(parts) < 2:
+        raise IndexError(f"marker {start!r} not found")
+    return parts[1].split(end)[0]
+
+
+def get_input_seq(seq):
+    """History tokens: ego id, `<|timeN|>` markers and neighbour ids, duplicates kept (reference :17-20)."""
+    return [tok for tok in _between(seq, "<|history|>", "<|endofhistory|>").split(" ") if tok != ""]
+
+
+def get_output_seq(seq):
+    """Label (y) tokens; anything containing 'time' is dropped (reference :22-26)."""
+    return [tok for tok in _between(seq, "<|pre|>", "<|endofpre|>").split(" ") if tok != "" and "time" not in tok]
+
+
+def get_inout_list(data, gt):
+    """(history lists, label lists) for parallel line lists (reference :28-34)."""
+    in_list = [get_input_seq(data[n]) for n in range(len(data))]
+    out_list = [get_output_seq(gt[n]) for n in range(len(data))]
+    return in_list, out_list
+
+
+# ------------------------------------------------------------------------------------------------ scoring
+def _encode_pair(target, source):
+    uni = set_encoder.Universe().add(source).add(target)
+    same = target is source
+    p = set_encoder.encode_sequences(source, uni, _DEVICE)
+    q = p if same else set_encoder.encode_sequences(target, uni, _DEVICE)
+    return q, p
+
+
+def occurrence_matrix(target, source):
+    """All-pairs Jaccard, float64 [len(target), len(source)] on the host (reference :36-41), computed by
+    r4d_bitset_encode + r4d_jaccard_full."""
+    if len(target) == 0 or len(source) == 0:
+        return np.zeros((len(target), len(source)))
+    q, p = _encode_pair(target, source)
+    _, score = engine.jaccard_full(q, p, zero_diag=False, want_score=True)
+    return score.cpu().numpy()
+
+
+def co_occurrence_ratio(seq_i, seq_j):
+    """|A & B| / |A | B| of two token lists; 0 when either is empty/None (reference :5-15)."""
+    if type(seq_j) is not list:
+        seq_j = [seq_j]
+    if seq_i is None or seq_j is None:
+        return 0
+    if len(seq_i) == 0 or len(seq_j) == 0:
+        return 0
+    return float(occurrence_matrix([list(seq_i)], [seq_j])[0, 0])
+
+
+def _to_device_f64(m):
+    if isinstance(m, torch.Tensor):
+        return m.to(device=_DEVICE, dtype=torch.float64).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(m, dtype=np.float64)).to(_DEVICE)
+
+
+def _write_triplets(save_file, save_file_score, n_rows, pos_rows, pos_cols, pos_scores, neg, n_neg, neg_scores):
+    """Host tail of save_train_annotation: dialog truncation, np.random.choice replay, text output (:72-85)."""
+    cnt = 0
+    is_dialog = "dialog" in dataset  # noqa: F821  module global set by main(), exactly like the reference (:73)
+    starts = np.searchsorted(pos_rows, np.arange(n_rows + 1))
+    with open(save_file, "w") as f, open(save_file_score, "w") as g:
+        for i in range(n_rows):
+            lo, hi = starts[i], starts[i + 1]
+            if hi == lo:
+                continue
+            if is_dialog:
+                hi = min(hi, lo + 4)
+            cand = neg[i, : n_neg[i]]
+            cand_scores = neg_scores[i]
+            for t in range(lo, hi):
+                neg_i = np.random.choice(cand)
+                s_neg = cand_scores[int(np.nonzero(cand == neg_i)[0][0])]
+                f.write(f"{i} {pos_cols[t]} {neg_i}\n")
+                g.write(f"{i} {writers.fmt_str(pos_scores[t])} {writers.fmt_str(s_neg)}\n")
+                cnt += 1
+    print("Number of original instances:", n_rows)
+    print("Number of positive samples:", cnt)
+
+
+def _mine_and_write(out_d, in_d, save_file, save_file_score, threshold, neg_num):
+    n = out_d.shape[0]
+    n_pos, neg, n_neg = engine.triplet_mine(out_d, in_d, threshold, neg_num)
+    pos = torch.nonzero(out_d > threshold)  # row-major == np.where per row in ascending order (:54)
+    pos_scores = out_d[pos[:, 0], pos[:, 1]]
+    neg_scores = torch.gather(out_d, 1, neg.clamp(min=0).to(torch.int64))
+    pos_h = pos.cpu().numpy()
+    _write_triplets(save_file, save_file_score, n, pos_h[:, 0], pos_h[:, 1], pos_scores.cpu().numpy(),
+                    neg.cpu().numpy(), n_neg.cpu().numpy(), neg_scores.cpu().numpy())
+    return n_pos
+
+
+def save_train_annotation(scores_matrix, scores_matrix_in, save_file, save_file_score, threshold=0.8, neg_num=5):
+    """Positive / negative triplets for the retriever (reference :43-85).  Matrices may be numpy or CUDA tensors."""
+    _mine_and_write(_to_device_f64(scores_matrix), _to_device_f64(scores_matrix_in), save_file, save_file_score,
+                    threshold, neg_num)
+
+
+def save_index_score(score_matrix, save_index_file, save_score_file):
+    """Full descending ranking + raw score rows (reference :88-93)."""
+    s = _to_device_f64(score_matrix)
+    order = engine.rank_rows(s)
+    writers.write_int_rows(save_index_file, order.cpu().numpy())
+    writers.write_float_rows(save_score_file, s.cpu().numpy(), writers.fmt_str)
+
+
+def save_score_file_train(scores_matrix, save_file_index, save_file_score, topk=10):
+    """Top-k indices and scores per row (reference :97-103)."""
+    s = _to_device_f64(scores_matrix)
+    k = min(topk, s.shape[1])
+    ts, ti = engine.topk_rows(s, k)
+    writers.write_int_rows(save_file_index, ti.cpu().numpy())
+    writers.write_float_rows(save_file_score, ts.cpu().numpy(), writers.fmt_str)
+
+
+# ------------------------------------------------------------------------------------------------ CLI
+def _read_lines(path):
+    with open(path, "r") as f:
+        return [line for line in f.read().splitlines() if (len(line) > 0 and not line.isspace())]
+
+
+def annotate(dataset_name, timestamp, threshold, neg_num=5, topk=10):
+    """The whole stage on the device (reference __main__, :109-200): bitsets stay in HBM, the train top-k comes
+    from the fused scorer+top-K kernel (no [N, N] ranking), only what is written to disk crosses to the host."""
+    global dataset
+    dataset = dataset_name
+    save_path = os.path.join("./resources/", dataset, str(timestamp), "train_retrieval")
+    os.makedirs(save_path, exist_ok=True)
+    save_path_gen = os.path.join("./resources/train_generator", dataset, str(timestamp), "train_gt_topk")
+    os.makedirs(save_path_gen, exist_ok=True)
+
+    base = os.path.join("resources", dataset, timestamp)
+    train_data = _read_lines(os.path.join(base, "train.link_prediction"))
+    test_data = _read_lines(os.path.join(base, "test.link_prediction"))
+    test_gt = _read_lines(os.path.join(base, "test_gt.link_prediction"))
+    val_data = _read_lines(os.path.join(base, "val.link_prediction"))
+    val_gt = _read_lines(os.path.join(base, "val_gt.link_prediction"))
+
+    train_in, train_out = get_inout_list(train_data, train_data)
+    _, test_out = get_inout_list(test_data, test_gt)
+    _, val_out = get_inout_list(val_data, val_gt)
+
+    # subsystem 1: set encoder.  One universe for label sets (train/test/val), one for history sets.
+    uni_out = set_encoder.Universe().add(train_out).add(test_out).add(val_out)
+    uni_in = set_encoder.Universe().add(train_in)
+    b_train_out = set_encoder.encode_sequences(train_out, uni_out, _DEVICE)
+    b_test_out = set_encoder.encode_sequences(test_out, uni_out, _DEVICE)
+    b_val_out = set_encoder.encode_sequences(val_out, uni_out, _DEVICE)
+    b_train_in = set_encoder.encode_sequences(train_in, uni_in, _DEVICE)
+
+    # subsystem 2: Jaccard matrices (diagonals zeroed as :172-173)
+    _, s_train_out = engine.jaccard_full(b_train_out, b_train_out, zero_diag=True)
+    _, s_train_in = engine.jaccard_full(b_train_in, b_train_in, zero_diag=True)
+    _mine_and_write(s_train_out, s_train_in, os.path.join(save_path, "train_index.retrieval"),
+                    os.path.join(save_path, "train_score.retrieval"), threshold, neg_num)
+    del s_train_in
+
+    for name, b in (("test", b_test_out), ("val", b_val_out)):
+        _, s = engine.jaccard_full(b, b_train_out, zero_diag=False)
+        order = engine.rank_rows(s)
+        writers.write_int_rows(os.path.join(save_path, f"{name}_index.retrieval"), order.cpu().numpy())
+        writers.write_float_rows(os.path.join(save_path, f"{name}_score.retrieval"), s.cpu().numpy(), writers.fmt_str)
+
+    # subsystem 4: fused scorer + top-K for the generator's train_gt_topk (never ranks the [N, N] matrix)
+    k = min(topk, b_train_out.n_rows)
+    t_inter, t_union, t_idx = engine.jaccard_topk(b_train_out, b_train_out, k, zero_diag=True)
+    writers.write_int_rows(os.path.join(save_path_gen, "train_index.gen"), t_idx.cpu().numpy())
+    writers.write_float_rows(os.path.join(save_path_gen, "train_score.gen"),
+                             writers.jaccard_scores_f64(t_inter.cpu().numpy(), t_union.cpu().numpy()), writers.fmt_str)
+    print("Done!")
+
+
+def main(argv=None):
+    argv = sys.argv if argv is None else argv
+    dataset_name = argv[1]
+    timestamp = argv[2]
+    threshold = float(argv[3])
+    annotate(dataset_name, timestamp, threshold)
+
+
+if __name__ == "__main__":
+    main()
