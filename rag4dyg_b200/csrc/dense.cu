@@ -467,8 +467,8 @@ static int dense_launch(int dmode, const void* q_hi, const void* q_lo, int64_t n
                          (dmode == DMODE_TOPK ? (size_t)prm.k * D_EPI_THREADS * 8 : 0);
     int n_stages = (int)((227 * 1024 - fixed) / prm.stage_bytes);
     if (n_stages > 8) n_stages = 8;
-    if (n_stages < 2) {
-        set_error("dense: not enough shared memory for a 2-stage pipeline (k=%d)", prm.k);
+    if (n_stages < 1) {  // (1 stage = no load/compute overlap; only BF16X3 with k > 16 lands there)
+        set_error("dense: not enough shared memory for one pipeline stage (k=%d)", prm.k);
         return R4D_E_ARG;
     }
     prm.n_stages = n_stages;
