@@ -1,0 +1,446 @@
+#!/usr/bin/env python
+"""bench.py — query-pool pairs scored + top-K'd per second (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scorers jaccard,dense]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workloads (BASELINE.json configs[3] and [4]), synthetic data, fixed TOTAL size (strong
+scaling: the pool is sharded row-wise over the N ranks, queries replicated, local top-K lists all-gathered over NCCL
+and merged):
+  jaccard : 1,000,000-set pool x 100,000 queries, 20,000-node vocab (W = 625 words), K = 10.
+            A step = one 8,192-query batch scored against the WHOLE 1M pool + top-K (+ all-gather + merge).
+  dense   : 10,000,000 x 768 pool embeddings x 100,000 queries, K = 10, exp(-lambda|dt|) epilogue, bf16 tensor cores.
+            A step = one 8,192-query batch against the whole 10M pool.
+One JSON line: the Jaccard scorer is the headline (`value`), the dense scorer is reported under "dense".
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+V_BITS = 20000
+POOL_N = 1_000_000
+QUERY_N = 100_000
+TOPK = 10
+Q_STEP = 8192
+DENSE_POOL_N = 10_000_000
+DENSE_D = 768
+DENSE_LAMBDA = 1e-4
+SEED_POOL, SEED_QUERY = 1234, 5678
+SEED_DPOOL, SEED_DQUERY = 4321, 8765
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scorers", default="jaccard,dense")
+    ap.add_argument("--pool", type=int, default=POOL_N)
+    ap.add_argument("--dense-pool", type=int, default=DENSE_POOL_N)
+    ap.add_argument("--queries-per-step", type=int, default=Q_STEP)
+    ap.add_argument("--mean-set", type=float, default=1.0 / 0.45, help="mean set size (y-like 2.2; x-like 20)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------ synthetic data
+def synth_sets(n, seed, mean, vocab=V_BITS, max_len=64):
+    """CSR id lists: |set| = min(64, Geometric(1/mean)) (support 1.., as the shipped label sets), ids uniform.
+    (Drawn with replacement; the rare duplicate collapses in the set encoder exactly like Python's set().)"""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    p = 1.0 / mean
+    u = torch.rand(n, generator=g, dtype=torch.float64).clamp_(min=1e-300)
+    lens = torch.floor(torch.log(u) / math.log(1.0 - p)).to(torch.int64) + 1
+    lens.clamp_(min=1, max=max_len)
+    off = torch.zeros(n + 1, dtype=torch.int64)
+    torch.cumsum(lens, 0, out=off[1:])
+    ids = torch.randint(0, vocab, (int(off[-1]),), generator=g, dtype=torch.int32)
+    return ids, off
+
+
+def csr_rows(ids, off, a, b):
+    o = off[a:b + 1]
+    return ids[int(o[0]):int(o[-1])].contiguous(), (o - o[0]).contiguous()
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                pass
+        sm, smax, reasons = [], 0.0, set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = max(smax, float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU baselines
+def _token_lists(ids, off, a, b):
+    ids = ids.numpy() if hasattr(ids, "numpy") else ids
+    off = off.numpy() if hasattr(off, "numpy") else off
+    return [[str(t) for t in ids[off[r]:off[r + 1]]] for r in range(a, b)]
+
+
+def _cpu_port_job(args):
+    """One worker: the reference's algorithm on its query slice (Python sets, retrieval_data_annotation.py:36-41,
+    then np.argsort(-row)[:k], :101)."""
+    q_lists, p_lists, k = args
+    from oracle import jaccard_oracle as jo
+    t0 = time.perf_counter()
+    m = jo.occurrence_matrix(q_lists, p_lists)
+    jo.topk_stable(m, k)
+    return time.perf_counter() - t0
+
+
+def cpu_port_sample(pool_ids, pool_off, q_ids, q_off, n_q, n_p, procs):
+    """pairs/s of the oracle port on `procs` host processes over disjoint query slices (bounded sample)."""
+    p_lists = _token_lists(pool_ids, pool_off, 0, n_p)
+    per = max(1, n_q // procs)
+    jobs = [(_token_lists(q_ids, q_off, w * per, (w + 1) * per), p_lists, TOPK) for w in range(procs)]
+    t0 = time.perf_counter()
+    if procs == 1:
+        _cpu_port_job(jobs[0])
+    else:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(procs) as pool:
+            pool.map(_cpu_port_job, jobs)
+    dt = time.perf_counter() - t0
+    return per * procs * n_p / dt, dt, per * procs
+
+
+def cpu_c_port_sample(pool_ids, pool_off, q_ids, q_off, n_q, n_p):
+    from oracle import jaccard_oracle as jo
+    qi, qo = csr_rows(q_ids, q_off, 0, n_q)
+    pi, po = csr_rows(pool_ids, pool_off, 0, n_p)
+    t0 = time.perf_counter()
+    jo.c_topk(qi.numpy(), qo.numpy(), pi.numpy(), po.numpy(), TOPK)
+    dt = time.perf_counter() - t0
+    return n_q * n_p / dt, dt
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference is pure Python
+    (nothing to compile into oracle/_ref), so this times the oracle port — the same Python-set double loop +
+    argsort — on all host cores.  Rank 0 only."""
+    if rank != 0:
+        return
+    procs = os.cpu_count() or 1
+    n_p_sample, q_per_worker = 100_000, 4
+    pool_ids, pool_off = synth_sets(n_p_sample, SEED_POOL, args.mean_set)
+    q_ids, q_off = synth_sets(args.queries_per_step, SEED_QUERY, args.mean_set)
+    times = []
+    for step in range(args.warmup + args.steps):
+        rate, dt, nq = cpu_port_sample(pool_ids, pool_off, q_ids, q_off, q_per_worker * procs, n_p_sample, procs)
+        if step >= args.warmup:
+            times.append(dt)
+    pairs = q_per_worker * procs * n_p_sample
+    total = sum(times)
+    value = pairs * args.steps / total
+    sample = (f"{q_per_worker * procs} queries x {n_p_sample} pool sets per step (same distribution/seeds as the GPU "
+              f"workload), Python-set Jaccard + stable argsort top-{TOPK}, {procs} processes on disjoint query slices")
+    print(json.dumps({
+        "impl": "reference", "metric": "query-pool pairs scored+top-K/sec (Jaccard)", "value": value,
+        "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "int (Python set algebra) / float64 divide", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": procs, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": f"synthetic Jaccard top-K: {args.pool:,}-set pool x {QUERY_N:,} queries, vocab {V_BITS:,} "
+                        f"(W=625 uint32 words), K={TOPK}; step = {args.queries_per_step:,}-query batch vs the whole pool",
+            "pool": args.pool, "queries_total": QUERY_N, "queries_per_step": args.queries_per_step, "vocab": V_BITS,
+            "k": TOPK, "mean_set_size": round(args.mean_set, 3), "parallelism": f"pool-sharded x{world}",
+            "l2": "inputs larger than L2 (pool bitsets 2.56 GB / n_gpus; a different query batch every step)"}
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from rag4dyg_b200 import _lib, engine, set_encoder, sharded
+
+    _lib.require_device()  # fail loudly: no CPU fallback
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    scorers = args.scorers.split(",")
+    K, W = args.steps, args.warmup
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(step_fn, sampler=None):
+        for i in range(W):
+            step_fn(i)
+        barrier()
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        engine.reset_launch_count()
+        e0.record()
+        for i in range(K):
+            step_fn(W + i)
+        e1.record()
+        barrier()
+        launches = engine.launch_count()
+        clocks = sampler.stop() if sampler else None
+        return max_over_ranks(e0.elapsed_time(e1)), launches, clocks
+
+    out = {}
+    # =============================================================== Jaccard
+    if "jaccard" in scorers:
+        n_pool, qs = args.pool, args.queries_per_step
+        lo, hi = rank * n_pool // world, (rank + 1) * n_pool // world
+        pool_ids, pool_off = synth_sets(n_pool, SEED_POOL, args.mean_set)
+        q_ids, q_off = synth_sets(QUERY_N, SEED_QUERY, args.mean_set)
+        sh_ids, sh_off = csr_rows(pool_ids, pool_off, lo, hi)
+        sh_ids_pin, sh_off_pin = sh_ids.pin_memory(), sh_off.pin_memory()
+        bp = set_encoder.encode_csr(sh_ids_pin, sh_off_pin, V_BITS, dev)      # pool shard resident in HBM
+        bq_all = set_encoder.encode_csr(q_ids, q_off, V_BITS, dev)            # all 100k queries resident (250 MB)
+        n_batches = QUERY_N // qs
+        ws = torch.empty(_lib.load().r4d_jaccard_topk_workspace_bytes(qs, hi - lo, TOPK), dtype=torch.uint8, device=dev)
+        result = {}
+
+        def step_resident(i):
+            b = i % n_batches
+            bq = bq_all.rows(b * qs, (b + 1) * qs)
+            # local fused top-K on the shard, then ONE exchange: all-gather of [Q, K] candidates + merge
+            result["last"] = sharded.jaccard_topk_sharded(bq, bp, TOPK, pool_base=lo, workspace=ws)
+
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        ms, launches, clocks = timed(step_resident, sampler)
+        pairs_per_step = qs * n_pool
+        value = pairs_per_step * K / (ms * 1e-3)
+
+        # kernel-only timing of the dominant kernel (r4d_jaccard_topk on this rank's shard), CUDA events on its stream
+        def kernel_only(i):
+            b = i % n_batches
+            engine.jaccard_topk(bq_all.rows(b * qs, (b + 1) * qs), bp, TOPK, pool_base=lo, workspace=ws)
+        k_ms, _, _ = timed(kernel_only)
+        k_s = k_ms * 1e-3 / K
+        words = 625
+        word_ops = qs * (hi - lo) * words                      # algorithmic AND+POPC word-ops per launch (W per pair)
+        sm_max = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz", 1965.0)
+        popc_peak = 148 * 16 * sm_max * 1e6                    # 16 POPC lanes/clk/SM
+        hbm_alg = ((hi - lo) + qs) * words * 4 + qs * TOPK * 12  # compulsory bytes per launch
+        roofline = {"bound": "int-pipe (POPC issue; the path is not HBM- or tensor-bound, SURVEY.md 8d)",
+                    "achieved": word_ops / k_s / 1e12, "peak": popc_peak / 1e12, "unit": "T word-op/s (32-bit AND+POPC)",
+                    "frac": word_ops / k_s / popc_peak, "traffic": None,
+                    "kernel": "r4d::jaccard_kernel<MODE_TOPK>", "kernel_ms": k_ms / K,
+                    "peak_source": f"148 SM x 16 POPC/clk x {sm_max:.0f} MHz (clocks.max.sm)",
+                    "hbm": {"algorithmic_bytes": hbm_alg, "achieved_GBps": hbm_alg / k_s / 1e9,
+                            "peak_GBps": peaks.get("hbm_gbs", 6650.0),
+                            "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
+
+        e2e = None
+        if not args.no_e2e:
+            q_pins = []
+            for b in range(n_batches):
+                qi, qo = csr_rows(q_ids, q_off, b * qs, (b + 1) * qs)
+                q_pins.append((qi.pin_memory(), qo.pin_memory()))
+            host_out = {}
+
+            def step_e2e(i):
+                qi, qo = q_pins[i % n_batches]
+                bq = set_encoder.encode_csr(qi, qo, V_BITS, dev)                     # H2D + encode (queries)
+                bpool = set_encoder.encode_csr(sh_ids_pin, sh_off_pin, V_BITS, dev)   # H2D + encode (pool shard)
+                r = sharded.jaccard_topk_sharded(bq, bpool, TOPK, pool_base=lo, workspace=ws)
+                host_out["r"] = [t.cpu() for t in r]                                  # D2H of the step's result
+            e_ms, _, _ = timed(step_e2e)
+            h2d = (q_pins[0][0].numel() * 4 + q_pins[0][1].numel() * 8 + sh_ids.numel() * 4 + sh_off.numel() * 8)
+            e2e = {"value": pairs_per_step * K / (e_ms * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d) * world,
+                   "d2h_bytes_per_step": qs * TOPK * 12, "ms_per_step": e_ms / K,
+                   "what": "host CSR id lists (pinned) of the query batch AND the pool shard -> H2D -> set encoder -> "
+                           "fused Jaccard top-K (-> all-gather + merge) -> D2H of [Q,K] (inter, union, idx)"}
+
+        cpu_baseline = None
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            n_p_s, n_q_s = 100_000, 64
+            rate, dt, nq_s = cpu_port_sample(pool_ids, pool_off, q_ids, q_off, n_q_s, n_p_s, 1)
+            c_rate, c_dt = cpu_c_port_sample(pool_ids, pool_off, q_ids, q_off, 512, n_p_s)
+            cpu_baseline = {"value": rate, "unit": "pairs/s", "cores": 1, "kind": "port",
+                            "sample": f"{nq_s} queries x {n_p_s} pool sets of the same workload ({dt:.1f} s): Python-set "
+                                      f"Jaccard double loop + stable argsort top-{TOPK} (the reference is single-threaded)",
+                            "c_port": {"value": c_rate, "unit": "pairs/s", "cores": 1,
+                                       "sample": f"512 x {n_p_s} (sorted-list merge in C, {c_dt:.1f} s)"}}
+        out = {"metric": "query-pool pairs scored+top-K/sec (Jaccard)", "value": value, "unit": "pairs/s",
+               "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+               "scaling": "strong", "vs_baseline": None, "dtype": "u32 (bitset AND+POPC, exact integer counts)",
+               "data": "synthetic", "config": workload_config(args, world), "roofline": roofline,
+               "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches * world, "clocks": clocks}
+        del bp, bq_all, ws
+        torch.cuda.empty_cache()
+
+    # =============================================================== dense
+    if "dense" in scorers:
+        n_pool, qs = args.dense_pool, args.queries_per_step
+        lo, hi = rank * n_pool // world, (rank + 1) * n_pool // world
+        g = torch.Generator(device=dev).manual_seed(SEED_DPOOL + rank)
+        hi_plane = torch.empty((hi - lo, DENSE_D), dtype=torch.bfloat16, device=dev)
+        chunk = 500_000
+        for a in range(0, hi - lo, chunk):
+            b = min(a + chunk, hi - lo)
+            x = torch.randn((b - a, DENSE_D), generator=g, device=dev)
+            hi_plane[a:b] = engine.dense_prepare(x, engine.PREC_BF16).hi
+            del x
+        pool = engine.DensePlanes(hi_plane, None, DENSE_D, DENSE_D, engine.PREC_BF16)
+        p_time = torch.rand(hi - lo, generator=g, device=dev) * 110.0
+        gq = torch.Generator().manual_seed(SEED_DQUERY)
+        n_batches = 4                                           # distinct query batches cycled through
+        q_host = [torch.randn((qs, DENSE_D), generator=gq).pin_memory() for _ in range(n_batches)]
+        qt_host = [(torch.rand(qs, generator=gq) * 110.0).pin_memory() for _ in range(n_batches)]
+        q_planes = [engine.dense_prepare(q.to(dev), engine.PREC_BF16) for q in q_host]
+        q_times = [t.to(dev) for t in qt_host]
+        ws = torch.empty(_lib.load().r4d_dense_topk_workspace_bytes(qs, hi - lo, TOPK), dtype=torch.uint8, device=dev)
+        mode = engine.DENSE_COS_DECAY
+
+        def dstep(i):
+            b = i % n_batches
+            sharded.dense_topk_sharded(q_planes[b], pool, TOPK, pool_base=lo, mode=mode, q_time=q_times[b], p_time=p_time,
+                                       lam=DENSE_LAMBDA, workspace=ws)
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        d_ms, d_launch, d_clocks = timed(dstep, sampler)
+        pairs = qs * n_pool
+        d_value = pairs * K / (d_ms * 1e-3)
+
+        def dkernel(i):
+            b = i % n_batches
+            engine.dense_topk(q_planes[b], pool, TOPK, mode, q_times[b], p_time, DENSE_LAMBDA, pool_base=lo, workspace=ws)
+        dk_ms, _, _ = timed(dkernel)
+        dk_s = dk_ms * 1e-3 / K
+        flops = 2.0 * DENSE_D * qs * (hi - lo)
+        peak_tf = peaks.get("bf16_tflops", 1590.0)
+        d_roof = {"bound": "tensor", "achieved": flops / dk_s / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+                  "frac": flops / dk_s / 1e12 / peak_tf, "traffic": None, "kernel": "r4d::dense_kernel<DMODE_TOPK>",
+                  "kernel_ms": dk_ms / K,
+                  "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1.59 PFLOP/s"}
+        d_e2e = None
+        if not args.no_e2e:
+            host = {}
+
+            def dstep_e2e(i):
+                b = i % n_batches
+                qd = q_host[b].to(dev, non_blocking=True)                     # H2D fp32 query embeddings + times
+                qt = qt_host[b].to(dev, non_blocking=True)
+                r = sharded.dense_topk_sharded(engine.dense_prepare(qd, engine.PREC_BF16), pool, TOPK, pool_base=lo, mode=mode,
+                                               q_time=qt, p_time=p_time, lam=DENSE_LAMBDA, workspace=ws)
+                host["r"] = [t.cpu() for t in r]
+            de_ms, _, _ = timed(dstep_e2e)
+            d_e2e = {"value": pairs * K / (de_ms * 1e-3), "unit": "pairs/s",
+                     "h2d_bytes_per_step": (qs * DENSE_D * 4 + qs * 4) * world, "d2h_bytes_per_step": qs * TOPK * 8,
+                     "ms_per_step": de_ms / K,
+                     "what": "fp32 query embeddings + times from pinned host memory -> H2D -> normalise/bf16 -> tcgen05 "
+                             "top-K -> D2H; pool embeddings stay resident in HBM (the reference keeps train_embeddings "
+                             "on the GPU too, train/train_retriever.py:423,435)"}
+        d_cpu = None
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            from oracle import dense_oracle
+            torch.manual_seed(0)
+            nqc, npc = 256, 200_000
+            qc, pc = torch.randn(nqc, DENSE_D), torch.randn(npc, DENSE_D)
+            tqc, tpc = torch.rand(nqc) * 110, torch.rand(npc) * 110
+            t0 = time.perf_counter()
+            sc = dense_oracle.scores(qc, pc, 1, tqc, tpc, DENSE_LAMBDA).numpy()
+            dense_oracle.rank_stable(sc)
+            dt = time.perf_counter() - t0
+            d_cpu = {"value": nqc * npc / dt, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
+                     "sample": f"{nqc} x {npc} x {DENSE_D} fp32 torch-CPU restatement of train_retriever.py:433-438 + "
+                               f"decay + full stable argsort ({dt:.1f} s)"}
+        dense = {"metric": "query-pool pairs scored+top-K/sec (dense)", "value": d_value, "unit": "pairs/s",
+                 "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": d_ms / K, "higher_is_better": True,
+                 "scaling": "strong", "dtype": "bf16 operands, fp32 accumulate (tcgen05 kind::f16)", "data": "synthetic",
+                 "config": {"workload": f"synthetic dense top-K: {n_pool:,} x {DENSE_D} pool x {QUERY_N:,} queries, K={TOPK}, "
+                                        f"cos*exp(-{DENSE_LAMBDA}|dt|) epilogue; step = {qs:,}-query batch vs the whole pool",
+                            "parallelism": f"pool-sharded x{world}", "l2": "inputs larger than L2 (pool 15.4 GB / n_gpus)"},
+                 "roofline": d_roof, "cpu_baseline": d_cpu, "e2e": d_e2e, "gpu_launches": d_launch * world,
+                 "clocks": d_clocks}
+        if out:
+            out["dense"] = dense
+        else:
+            out = dense
+
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
