@@ -14,16 +14,11 @@
 //               K-th-best threshold is a private register; scores are (x+1)/2, x*2^(-l|dt|) ...; a column enters
 //               the thread's sorted smem list only if it beats the threshold (rare after warm-up).
 //   Per-(stripe, column-half) lists are merged by dense_merge_kernel with the canonical comparator.
-#include <cuda_bf16.h>
-
-#include "r4d_common.cuh"
+#include "dense_common.cuh"
 
 namespace r4d {
 
-constexpr int DQ = 128;          // query rows per tile  (UMMA M)
 constexpr int DP = 256;          // pool rows per tile   (UMMA N)
-constexpr int DKB = 64;          // bf16 elements per k-block (128 B rows: one swizzle atom)
-constexpr int Q_TILE_BYTES = DQ * DKB * 2;  // 16 KB
 constexpr int P_TILE_BYTES = DP * DKB * 2;  // 32 KB
 constexpr int D_THREADS = 320;
 constexpr int D_EPI_WARPS = 8;
@@ -50,59 +45,6 @@ struct DenseParams {
     float* scores;  // full mode
     int64_t ld;
 };
-
-// ---- tcgen05 wrappers
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
-                 "r"(ncols)
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_relinquish() {
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// K-major, SWIZZLE_128B operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (=1), version 1.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
-           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
-        "%29,%30,%31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ float ex2_approx(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
 
 // sorted insertion into this thread's list (column-major in smem: slot t of thread `tid` at [t*D_EPI_THREADS+tid]).
 // Returns the new k-th best score.
@@ -296,16 +238,8 @@ dense_kernel(const __grid_constant__ CUtensorMap tm_qh, const __grid_constant__ 
                     float s[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const float x = __uint_as_float(v[j]);
-                        float sc;
-                        if (prm.mode == R4D_DENSE_HALF_COS) {
-                            sc = (x + 1.0f) * 0.5f;
-                        } else {
-                            const float dt = fabsf(tq - ptime_s[buf * DP + col0 + j]);
-                            const float dec = ex2_approx(prm.neg_lambda_log2e * dt);
-                            sc = (prm.mode == R4D_DENSE_COS_DECAY) ? x * dec : (x + 1.0f) * 0.5f * dec;
-                        }
-                        s[j] = sc;
+                        const float tp = prm.mode == R4D_DENSE_HALF_COS ? 0.f : ptime_s[buf * DP + col0 + j];
+                        s[j] = dense_score(__uint_as_float(v[j]), prm.mode, tq, tp, prm.neg_lambda_log2e);
                     }
                     if (DMODE == DMODE_FULL) {
                         if (q_ok) {
@@ -528,7 +462,16 @@ size_t r4d_dense_topk_workspace_bytes(int64_t nq, int64_t np, int32_t k) {
     using namespace r4d;
     if (nq <= 0 || np <= 0 || k <= 0) return 256;
     const DensePlan pl = dense_plan(nq, np, true);
-    return (size_t)pl.n_stripes * 2 * (size_t)nq * (size_t)k * 8 + 256;
+    size_t need = (size_t)pl.n_stripes * 2 * (size_t)nq * (size_t)k * 8 + 256;
+    // the CTA-pair kernel (dense2.cu) plans its own stripes; d_pad is not known here, so bound it over the widths
+    // it supports (multiples of 64 up to 768)
+    if (k <= 16)
+        for (int d = 64; d <= 768; d += 64)
+            if (dense2_supported(nq, np, d, R4D_PREC_BF16, k)) {
+                const size_t n2 = dense2_workspace_bytes(nq, np, d, k);
+                if (n2 > need) need = n2;
+            }
+    return need;
 }
 
 int r4d_dense_topk(const void* q_hi, const void* q_lo, int64_t nq, const void* p_hi, const void* p_lo, int64_t np,
@@ -542,6 +485,21 @@ int r4d_dense_topk(const void* q_hi, const void* q_lo, int64_t nq, const void* p
     R4D_REQUIRE(pool_base >= 0 && pool_base + np < (int64_t)R4D_IDX_NONE, "dense_topk: pool_base+np exceeds int32");
     if (nq == 0) return R4D_OK;
     R4D_REQUIRE(top_score && top_idx, "dense_topk: null output");
+    if (np > 0 && dense2_supported(nq, np, d_pad, prec, k)) {
+        // throughput path: CTA pairs (cta_group::2), resident query tile, register top-K (dense2.cu)
+        const size_t need2 = dense2_workspace_bytes(nq, np, d_pad, k);
+        if (workspace_bytes < need2 || !workspace) {
+            set_error("dense_topk: workspace %zu B < required %zu B", workspace_bytes, need2);
+            return R4D_E_WORKSPACE;
+        }
+        int32_t n_lists = 0;
+        float* ps = reinterpret_cast<float*>(workspace);
+        int32_t* pi = reinterpret_cast<int32_t*>(ps + (need2 - 256) / 8);
+        rc = dense2_topk(q_hi, nq, p_hi, np, d_pad, q_time, p_time, lambda, mode, k, pool_base, ps, pi, &n_lists,
+                         as_stream(stream));
+        if (rc) return rc;
+        return r4d_dense_topk_merge(ps, pi, n_lists, nq, k, k, top_score, top_idx, stream);
+    }
     const DensePlan pl = dense_plan(nq, np, true);
     const size_t per = (size_t)pl.n_stripes * 2 * (size_t)nq * (size_t)k;
     if (np > 0 && (workspace_bytes < per * 8 || !workspace)) {

@@ -1,0 +1,458 @@
+// dense2.cu — dense scorer, throughput kernel: CTA pairs (cta_group::2, UMMA M = 256), query tile resident in smem.
+//
+// Why: dense.cu streams both operands per k-block (96 B/clk/SM of L2->smem traffic at full MMA rate), which is what
+// caps it near half of the tensor peak.  Here each CTA of a 2-CTA cluster keeps its 128 query rows x D resident in
+// shared memory for a whole work item and streams only ITS HALF of each pool tile; the pair's single
+// tcgen05.mma.cta_group::2 consumes A = 256 query rows (128 per CTA) and B = N pool rows (N/2 per CTA), so the
+// streamed traffic drops to 32 B/clk/SM.
+//
+// Roles per CTA (320 threads): warp 0 TMA producer (both CTAs; cp.async.bulk.tensor ... .cta_group::2 signals the
+// LEADER's full barrier), warp 1 MMA issuer (leader CTA only; commits multicast to both CTAs' barriers), warps 2..9
+// epilogue on the CTA's own 128 TMEM lanes, with the running top-K of each (row, column-half) in REGISTERS
+// (16 slots, branch-free compare-swap insertion) — shared memory is fully spent on the resident query tile.
+//
+// Supports: PREC_BF16, top-K with k <= 16, D such that the query tile + >= 2 pool stages fit in 227 KB (D <= 768 at
+// N = 128).  Everything else goes through dense.cu.
+#include "dense_common.cuh"
+
+namespace r4d {
+
+constexpr int D2_THREADS = 320;
+constexpr int D2_EPI_WARPS = 8;
+constexpr int D2_EPI_THREADS = 256;
+constexpr int D2_KR = 16;  // register-resident list slots per thread
+
+struct Dense2Params {
+    int64_t nq, np;
+    int32_t n_kblocks;
+    int32_t mode;
+    int32_t k;
+    int32_t n_stages;
+    float neg_lambda_log2e;
+    int64_t pool_base;
+    const float* q_time;
+    const float* p_time;
+    int32_t n_qpairs, n_ptiles, n_stripes, ptiles_per_stripe;
+    float* part_score;  // [2*n_stripes][nq][k]
+    int32_t* part_idx;
+};
+
+// ---- cluster / 2-SM PTX wrappers
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA tile load into this CTA's smem whose completion is signalled on a barrier that may live in the peer CTA
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst_smem, const CUtensorMap* map, uint32_t mbar_cluster_addr,
+                                                int32_t c0, int32_t c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+        "[%2];" ::"r"(dst_smem),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(mbar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+                 "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t addr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// commit all prior MMAs of this thread; arrive on the barrier at the same smem offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc_commit_2sm_mc(uint64_t* bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"((uint16_t)3)
+        : "memory");
+}
+
+// ---- register-resident sorted list (descending score; equal scores keep insertion order = ascending index)
+struct RegList {
+    float s[D2_KR];
+    int32_t i[D2_KR];
+};
+__device__ __forceinline__ void reg_insert(RegList& L, float s, int32_t idx) {
+#pragma unroll
+    for (int t = 0; t < D2_KR; ++t) {
+        const bool sw = s > L.s[t];
+        const float ts = sw ? L.s[t] : s;
+        const int32_t ti = sw ? L.i[t] : idx;
+        L.s[t] = sw ? s : L.s[t];
+        L.i[t] = sw ? idx : L.i[t];
+        s = ts;
+        idx = ti;
+    }
+}
+__device__ __forceinline__ float reg_kth(const RegList& L, int k) {
+    float t = L.s[0];
+#pragma unroll
+    for (int j = 1; j < D2_KR; ++j) t = (j == k - 1) ? L.s[j] : t;
+    return t;
+}
+
+template <int DPN>  // pool rows per pair tile (UMMA N): 256 or 128; each CTA streams DPN/2 rows per k-block
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D2_THREADS, 1)
+dense2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_p,
+              const Dense2Params prm) {
+    constexpr int P_STAGE_BYTES = (DPN / 2) * DKB * 2;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* q_res = smem;                                              // [n_kblocks][128 x 64 bf16]  resident
+    uint8_t* stages = smem + (size_t)prm.n_kblocks * Q_TILE_BYTES;      // [n_stages][DPN/2 x 64 bf16]
+    uint8_t* after = stages + (size_t)prm.n_stages * P_STAGE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(after);            // [8]  used in the LEADER (count 2)
+    uint64_t* empty_bar = full_bar + 8;                                 // [8]  per CTA (multicast commit)
+    uint64_t* tfull_bar = empty_bar + 8;                                // [2]  per CTA (multicast commit)
+    uint64_t* tempty_bar = tfull_bar + 2;                               // [2]  LEADER (count 16: both CTAs' epilogue warps)
+    uint64_t* qfull_bar = tempty_bar + 2;                               // [1]  LEADER (count 2)
+    uint64_t* qempty_bar = qfull_bar + 1;                               // [1]  per CTA (multicast commit)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(qempty_bar + 1);
+    float* ptime_s = reinterpret_cast<float*>(tmem_slot + 4);           // [2][DPN]
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B tiles need a 1024-byte aligned base
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tm_q);
+        tma_prefetch_desc(&tm_p);
+        for (int s = 0; s < 8; ++s) {
+            mbar_init(&full_bar[s], 2);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tfull_bar[b], 1);
+            mbar_init(&tempty_bar[b], 2 * D2_EPI_WARPS);
+        }
+        mbar_init(qfull_bar, 2);
+        mbar_init(qempty_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc_2sm(tmem_slot, 512);
+        tmem_relinquish_2sm();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int n_items = prm.n_qpairs * prm.n_stripes;
+    const int n_clusters = gridDim.x >> 1;
+    const int cluster_id = blockIdx.x >> 1;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer (both CTAs)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0, item_seq = 0;
+            const uint32_t qfull_leader = mapa_shared(smem_u32(qfull_bar), 0);
+            for (int item = cluster_id; item < n_items; item += n_clusters, ++item_seq) {
+                const int stripe = item / prm.n_qpairs;
+                const int qtile = (item - stripe * prm.n_qpairs) * 2 + (int)rank;
+                const int pt_beg = stripe * prm.ptiles_per_stripe;
+                const int pt_end = min(pt_beg + prm.ptiles_per_stripe, prm.n_ptiles);
+                // resident query tile: wait until the previous item's MMAs have released it
+                mbar_wait(qempty_bar, (item_seq & 1u) ^ 1u);
+                mbar_arrive_expect_tx_cluster(qfull_leader, (uint32_t)(prm.n_kblocks * Q_TILE_BYTES));
+                for (int kb = 0; kb < prm.n_kblocks; ++kb)
+                    tma_load_2d_2sm(smem_u32(q_res + (size_t)kb * Q_TILE_BYTES), &tm_q, qfull_leader, kb * DKB, qtile * DQ);
+                for (int pt = pt_beg; pt < pt_end; ++pt) {
+                    for (int kb = 0; kb < prm.n_kblocks; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[stage]), 0);
+                        mbar_arrive_expect_tx_cluster(full_leader, (uint32_t)P_STAGE_BYTES);
+                        tma_load_2d_2sm(smem_u32(stages + (size_t)stage * P_STAGE_BYTES), &tm_p, full_leader, kb * DKB,
+                                        pt * DPN + (int)rank * (DPN / 2));
+                        if (++stage == prm.n_stages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (leader CTA, one lane)
+        if (leader && lane == 0) {
+            // D=f32, A=B=bf16, K-major; N>>3 at bit 17; M = 256 (pair) -> M>>4 at bit 24
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(DPN >> 3) << 17) |
+                                   ((uint32_t)(256 >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0, tile_seq = 0, item_seq = 0;
+            for (int item = cluster_id; item < n_items; item += n_clusters, ++item_seq) {
+                const int stripe = item / prm.n_qpairs;
+                const int pt_beg = stripe * prm.ptiles_per_stripe;
+                const int pt_end = min(pt_beg + prm.ptiles_per_stripe, prm.n_ptiles);
+                mbar_wait(qfull_bar, item_seq & 1u);  // both CTAs' query tiles have landed
+                tc_fence_after();
+                const uint32_t qbase = smem_u32(q_res);
+                for (int pt = pt_beg; pt < pt_end; ++pt, ++tile_seq) {
+                    const uint32_t buf = tile_seq & 1u;
+                    mbar_wait(&tempty_bar[buf], ((tile_seq >> 1) & 1u) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + buf * DPN;
+                    for (int kb = 0; kb < prm.n_kblocks; ++kb) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint64_t qd = make_smem_desc(qbase + (uint32_t)kb * Q_TILE_BYTES);
+                        const uint64_t pd = make_smem_desc(smem_u32(stages + (size_t)stage * P_STAGE_BYTES));
+#pragma unroll
+                        for (int ks = 0; ks < DKB / 16; ++ks)
+                            umma_bf16_2sm(tmem_d, qd + (uint64_t)(2 * ks), pd + (uint64_t)(2 * ks), idesc,
+                                          (kb | ks) != 0 ? 1u : 0u);
+                        tc_commit_2sm_mc(&empty_bar[stage]);  // pool stage free in both CTAs
+                        if (++stage == prm.n_stages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                    tc_commit_2sm_mc(&tfull_bar[buf]);  // accumulator complete in both CTAs
+                }
+                tc_commit_2sm_mc(qempty_bar);  // resident query tiles may be overwritten
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue warps 2..9 (own 128 TMEM lanes)
+        const int ew = warp - 2;
+        const int quarter = warp & 3;
+        const int half = ew >> 2;
+        const int etid = threadIdx.x - 64;
+        const int row_in_tile = quarter * 32 + lane;
+        constexpr int COLS_PER_THREAD = DPN / 2;
+        uint32_t tile_seq = 0;
+        uint32_t tempty_leader[2];
+        tempty_leader[0] = mapa_shared(smem_u32(&tempty_bar[0]), 0);
+        tempty_leader[1] = mapa_shared(smem_u32(&tempty_bar[1]), 0);
+
+        for (int item = cluster_id; item < n_items; item += n_clusters) {
+            const int stripe = item / prm.n_qpairs;
+            const int qtile = (item - stripe * prm.n_qpairs) * 2 + (int)rank;
+            const int pt_beg = stripe * prm.ptiles_per_stripe;
+            const int pt_end = min(pt_beg + prm.ptiles_per_stripe, prm.n_ptiles);
+            const int64_t gq = (int64_t)qtile * DQ + row_in_tile;
+            const bool q_ok = gq < prm.nq;
+            const float tq = (prm.mode != R4D_DENSE_HALF_COS && q_ok) ? prm.q_time[gq] : 0.f;
+            RegList L;
+#pragma unroll
+            for (int t = 0; t < D2_KR; ++t) {
+                L.s[t] = -INFINITY;
+                L.i[t] = R4D_IDX_NONE;
+            }
+            float thr = -INFINITY;
+            for (int pt = pt_beg; pt < pt_end; ++pt, ++tile_seq) {
+                const uint32_t buf = tile_seq & 1u;
+                if (prm.mode != R4D_DENSE_HALF_COS) {
+                    if (etid < DPN) {
+                        const int64_t gp = (int64_t)pt * DPN + etid;
+                        ptime_s[buf * DPN + etid] = gp < prm.np ? prm.p_time[gp] : 0.f;
+                    }
+                    named_bar_sync(2, D2_EPI_THREADS);
+                }
+                mbar_wait(&tfull_bar[buf], (tile_seq >> 1) & 1u);
+                tc_fence_after();
+#pragma unroll 1
+                for (int ch = 0; ch < COLS_PER_THREAD / 32; ++ch) {
+                    const int col0 = half * COLS_PER_THREAD + ch * 32;
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * DPN + col0, v);
+                    tmem_ld_wait();
+                    const int64_t gp0 = (int64_t)pt * DPN + col0;
+                    float s[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float tp = prm.mode == R4D_DENSE_HALF_COS ? 0.f : ptime_s[buf * DPN + col0 + j];
+                        s[j] = dense_score(__uint_as_float(v[j]), prm.mode, tq, tp, prm.neg_lambda_log2e);
+                    }
+                    if (gp0 + 32 > prm.np) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (gp0 + j >= prm.np) s[j] = -INFINITY;
+                    }
+                    float m = s[0];
+#pragma unroll
+                    for (int j = 1; j < 32; ++j) m = fmaxf(m, s[j]);
+                    // rare path: extract candidates in descending order (first occurrence on ties => ascending index)
+                    while (q_ok && m > thr) {
+                        float best = s[0];
+                        int bj = 0;
+#pragma unroll
+                        for (int j = 1; j < 32; ++j)
+                            if (s[j] > best) {
+                                best = s[j];
+                                bj = j;
+                            }
+                        reg_insert(L, best, (int32_t)(prm.pool_base + gp0 + bj));
+                        thr = reg_kth(L, prm.k);
+                        m = -INFINITY;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            s[j] = (j == bj) ? -INFINITY : s[j];
+                            m = fmaxf(m, s[j]);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(tempty_leader[buf]);
+            }
+            if (q_ok) {
+                const int64_t o = ((int64_t)(stripe * 2 + half) * prm.nq + gq) * prm.k;
+#pragma unroll
+                for (int t = 0; t < D2_KR; ++t)
+                    if (t < prm.k) {
+                        prm.part_score[o + t] = L.s[t];
+                        prm.part_idx[o + t] = L.i[t];
+                    }
+            }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();  // no CTA may exit while its peer can still signal its barriers / read its smem
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, 512);
+    }
+}
+
+// ---------------------------------------------------------------------------- host side
+struct Dense2Plan {
+    int32_t n_qpairs, n_ptiles, n_stripes, ptiles_per_stripe, dpn, n_stages;
+    bool ok;
+};
+
+static Dense2Plan dense2_plan(int64_t nq, int64_t np, int32_t d_pad, int32_t k) {
+    Dense2Plan pl{};
+    pl.ok = false;
+    if (k > D2_KR || nq <= 0 || np <= 0) return pl;
+    const int n_kblocks = d_pad / DKB;
+    const long q_bytes = (long)n_kblocks * Q_TILE_BYTES;
+    const long total = 227 * 1024;
+    const long fixed256 = 23 * 8 + 16 + 2 * 256 * 4 + 64, fixed128 = 23 * 8 + 16 + 2 * 128 * 4 + 64;
+    long avail = total - q_bytes - fixed256;
+    if (avail >= 4 * 16384) {
+        pl.dpn = 256;
+        pl.n_stages = (int)(avail / 16384);
+    } else {
+        avail = total - q_bytes - fixed128;
+        pl.dpn = 128;
+        pl.n_stages = (int)(avail / 8192);
+    }
+    if (pl.n_stages > 8) pl.n_stages = 8;
+    if (pl.n_stages < 3) return pl;
+    pl.n_qpairs = (int32_t)((nq + 2 * DQ - 1) / (2 * DQ));
+    pl.n_ptiles = (int32_t)((np + pl.dpn - 1) / pl.dpn);
+    const int n_clusters = num_sms() / 2;
+    const int64_t target = (int64_t)n_clusters * 8;
+    int64_t stripes = (target + pl.n_qpairs - 1) / pl.n_qpairs;
+    const int64_t min_tiles = 16384 / pl.dpn;  // >= 16 K pool rows per stripe keeps the top-K warm-up negligible
+    const int64_t max_stripes = (pl.n_ptiles + min_tiles - 1) / min_tiles;
+    if (stripes > max_stripes) stripes = max_stripes;
+    if (stripes < 1) stripes = 1;
+    pl.ptiles_per_stripe = (int32_t)((pl.n_ptiles + stripes - 1) / stripes);
+    pl.n_stripes = (pl.n_ptiles + pl.ptiles_per_stripe - 1) / pl.ptiles_per_stripe;
+    pl.ok = true;
+    return pl;
+}
+
+// exported to dense.cu
+bool dense2_supported(int64_t nq, int64_t np, int32_t d_pad, int32_t prec, int32_t k) {
+    static const bool disabled = [] {
+        const char* e = getenv("R4D_DENSE_V1");
+        return e && atoi(e) != 0;
+    }();
+    if (disabled || prec != R4D_PREC_BF16) return false;
+    return dense2_plan(nq, np, d_pad, k).ok;
+}
+
+size_t dense2_workspace_bytes(int64_t nq, int64_t np, int32_t d_pad, int32_t k) {
+    const Dense2Plan pl = dense2_plan(nq, np, d_pad, k);
+    return (size_t)pl.n_stripes * 2 * (size_t)nq * (size_t)k * 8 + 256;
+}
+
+int dense2_topk(const void* q_hi, int64_t nq, const void* p_hi, int64_t np, int32_t d_pad, const float* q_time,
+                const float* p_time, float lambda, int32_t mode, int32_t k, int64_t pool_base, float* part_score,
+                int32_t* part_idx, int32_t* n_lists_out, cudaStream_t st) {
+    const Dense2Plan pl = dense2_plan(nq, np, d_pad, k);
+    if (!pl.ok) {
+        set_error("dense2: unsupported shape");
+        return R4D_E_ARG;
+    }
+    CUtensorMap tm_q, tm_p;
+    int rc;
+    const uint64_t rs = (uint64_t)d_pad * 2;
+    if ((rc = make_tmap_2d(&tm_q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, q_hi, d_pad, nq, rs, DKB, DQ,
+                           CU_TENSOR_MAP_SWIZZLE_128B)))
+        return rc;
+    if ((rc = make_tmap_2d(&tm_p, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p_hi, d_pad, np, rs, DKB, pl.dpn / 2,
+                           CU_TENSOR_MAP_SWIZZLE_128B)))
+        return rc;
+    Dense2Params prm{};
+    prm.nq = nq;
+    prm.np = np;
+    prm.n_kblocks = d_pad / DKB;
+    prm.mode = mode;
+    prm.k = k;
+    prm.n_stages = pl.n_stages;
+    prm.neg_lambda_log2e = -lambda * 1.4426950408889634f;
+    prm.pool_base = pool_base;
+    prm.q_time = q_time;
+    prm.p_time = p_time;
+    prm.n_qpairs = pl.n_qpairs;
+    prm.n_ptiles = pl.n_ptiles;
+    prm.n_stripes = pl.n_stripes;
+    prm.ptiles_per_stripe = pl.ptiles_per_stripe;
+    prm.part_score = part_score;
+    prm.part_idx = part_idx;
+    const size_t smem = (size_t)prm.n_kblocks * Q_TILE_BYTES + (size_t)pl.n_stages * (pl.dpn / 2) * DKB * 2 + 23 * 8 + 16 +
+                        2 * (size_t)pl.dpn * 4 + 64;
+    const int64_t n_items = (int64_t)pl.n_qpairs * pl.n_stripes;
+    int n_clusters = num_sms() / 2;
+    if (n_items < n_clusters) n_clusters = (int)n_items;
+    if (pl.dpn == 256) {
+        R4D_CUDA(cudaFuncSetAttribute(dense2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dense2_kernel<256><<<2 * n_clusters, D2_THREADS, smem, st>>>(tm_q, tm_p, prm);
+    } else {
+        R4D_CUDA(cudaFuncSetAttribute(dense2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dense2_kernel<128><<<2 * n_clusters, D2_THREADS, smem, st>>>(tm_q, tm_p, prm);
+    }
+    R4D_CUDA(cudaGetLastError());
+    *n_lists_out = pl.n_stripes * 2;
+    return R4D_OK;
+}
+
+}  // namespace r4d

@@ -6,16 +6,19 @@
 // Design (B200, sm_100a)
 //  * CTA tile 128 queries x 128 pool rows, persistent CTAs (one per SM) walking a static list of
 //    (pool stripe, query tile) work items.
-//  * warp 0 = TMA producer: per 32-word chunk it issues two cp.async.bulk.tensor.2d loads (128 rows x 128 B,
-//    SWIZZLE_128B) into a 3-stage smem ring guarded by full/empty mbarriers.
-//  * warps 1..8 = consumers: each thread owns an 8x8 micro-tile of intersection counters; per 16-byte group it
-//    issues 8+8 conflict-free LDS.128 (the 128B swizzle spreads the 8 rows a quarter-warp touches over all
-//    banks) and 256 LOP3(AND)+POPC+IADD3.  The POPC pipe is the binding unit.
+//  * TMA: per 32-word chunk two cp.async.bulk.tensor.2d loads (128 rows x 128 B, SWIZZLE_128B) land in a 3-stage
+//    smem ring guarded by full/empty mbarriers; one elected consumer lane issues them two stages ahead.
+//  * 8 or 16 consumer warps: each thread owns an 8x8 (or 4x8) micro-tile of intersection counters; per pair of
+//    16-byte groups it issues conflict-free LDS.128 (the 128B swizzle spreads the 8 rows a quarter-warp touches
+//    over all banks), ANDs 8 words, compresses 7 of them with a LOP3 carry-save tree and issues 4 POPC
+//    (the POPC/XU pipe, 16 lanes/clk/SM, is the scarce unit; LOP3 runs at 64 lanes/clk/SM — DESIGN.md).
 //  * counts are exact integers; union = |q| + |p| - inter.  Scores are compared as rationals by 64-bit
 //    cross-multiplication (JEntry::better), so ranking is exact and ties break by ascending pool index.
 //  * top-K mode: the 128x128 count tile goes through smem once, each consumer warp scans 16 query rows,
 //    ballots the entries that beat the row's current k-th candidate and inserts them into a one-entry-per-lane
 //    sorted list (WarpTopK).  Per-stripe lists are merged by jaccard_merge_kernel.
+#include <cstdlib>
+
 #include "r4d_common.cuh"
 
 namespace r4d {
@@ -26,9 +29,7 @@ constexpr int CHUNK_WORDS = 32;                   // 128 B of each row per pipel
 constexpr int OPER_BYTES = TQ * CHUNK_WORDS * 4;  // 16 KB per operand per stage
 constexpr int STAGE_BYTES = 2 * OPER_BYTES;
 constexpr int NSTAGES = 3;
-constexpr int N_CONSUMER_WARPS = 8;
-constexpr int N_CONSUMERS = 32 * N_CONSUMER_WARPS;
-constexpr int N_THREADS = 32 + N_CONSUMERS;
+// consumer warps per CTA: 8 (8x8 counters per thread) or 16 (4x8 counters per thread, 4 warps per scheduler)
 constexpr int TILE_LD = TP + 8;  // padded pitch (words) of the count tile: conflict-free register->smem spill
 constexpr int LIST_LD = 32;      // one list slot per lane
 
@@ -56,14 +57,45 @@ struct JaccardParams {
     int64_t ld_score;
 };
 
+
+__device__ __forceinline__ void lds128(uint4& v, uint32_t addr) {
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+}
+// carry-save adder on 32 independent bit columns: sum = a^b^c, carry = majority(a,b,c) — one LOP3 each
+__device__ __forceinline__ uint32_t csa_sum(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ uint32_t csa_carry(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xe8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+// |q & p| over 8 words with 4 POPC instead of 8: the POPC unit (16 lanes/clk/SM) is the saturated pipe, LOP3 runs
+// at 64 lanes/clk/SM, so 7 of the 8 AND words are compressed by a carry-save tree (ones, twos, fours) first.
+//   8 AND + 8 LOP3(CSA) + 4 POPC + 1 IADD3 + 2 IMAD   vs   8 AND + 8 POPC + 4 IADD3
+__device__ __forceinline__ uint32_t popc8_csa(const uint4& qa, const uint4& qb, const uint4& pa, const uint4& pb) {
+    const uint32_t a0 = qa.x & pa.x, a1 = qa.y & pa.y, a2 = qa.z & pa.z, a3 = qa.w & pa.w;
+    const uint32_t a4 = qb.x & pb.x, a5 = qb.y & pb.y, a6 = qb.z & pb.z, a7 = qb.w & pb.w;
+    const uint32_t s1 = csa_sum(a0, a1, a2), c1 = csa_carry(a0, a1, a2);
+    const uint32_t s2 = csa_sum(s1, a3, a4), c2 = csa_carry(s1, a3, a4);
+    const uint32_t s3 = csa_sum(s2, a5, a6), c3 = csa_carry(s2, a5, a6);
+    const uint32_t t = csa_sum(c1, c2, c3), f = csa_carry(c1, c2, c3);
+    return __popc(s3) + __popc(a7) + 2u * __popc(t) + 4u * __popc(f);
+}
+
 constexpr size_t smem_bytes_for(int mode) {
     size_t b = 1024 /*alignment slack*/ + (size_t)NSTAGES * STAGE_BYTES + 2 * NSTAGES * sizeof(uint64_t);
     if (mode == MODE_TOPK) b += (size_t)TQ * TILE_LD * 4 + 3 * (size_t)TQ * LIST_LD * 4;
     return b;
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(N_THREADS, 1)
+// No dedicated producer warp: registers are split per SM sub-partition (16 K each), so a 9th / 17th warp would put a
+// third / fifth warp on one scheduler and cut the per-thread budget to 168 / 96.  With exactly 8 or 16 warps the
+// budget is 255 / 128; lane 0 of warp 0 issues the TMA refills inline, two stages ahead of consumption.
+template <int MODE, int NCW>
+__global__ void __launch_bounds__(32 * NCW, 1)
 jaccard_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_p,
                const JaccardParams prm) {
     extern __shared__ uint8_t smem_raw[];
@@ -76,6 +108,11 @@ jaccard_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     uint32_t* l_union = l_inter + TQ * LIST_LD;
     int32_t* l_idx = reinterpret_cast<int32_t*>(l_union + TQ * LIST_LD);
 
+    constexpr int N_CONSUMER_WARPS = NCW;
+    constexpr int N_CONSUMERS = 32 * NCW;
+    constexpr int RQ = 64 / NCW;          // query rows per thread: 8 or 4
+    constexpr int SLAB = 4 * RQ;          // query rows per warp slab: 32 or 16
+    constexpr int SCAN_ROWS = TQ / NCW;   // query rows each warp scans in the top-K epilogue: 16 or 8
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
@@ -92,42 +129,53 @@ jaccard_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 
     const int n_items = prm.n_qtiles * prm.n_stripes;
 
-    if (warp == 0) {
-        // ------------------------------------------------------------ TMA producer (one elected lane)
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int stripe = item / prm.n_qtiles;
-                const int qtile = item - stripe * prm.n_qtiles;
-                const int pt_beg = stripe * prm.ptiles_per_stripe;
-                const int pt_end = min(pt_beg + prm.ptiles_per_stripe, prm.n_ptiles);
-                for (int pt = pt_beg; pt < pt_end; ++pt) {
-                    for (int c = 0; c < prm.n_chunks; ++c) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
-                        uint8_t* dst = stages + (size_t)stage * STAGE_BYTES;
-                        mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-                        tma_load_2d(dst, &tm_q, &full_bar[stage], c * CHUNK_WORDS, qtile * TQ);
-                        tma_load_2d(dst + OPER_BYTES, &tm_p, &full_bar[stage], c * CHUNK_WORDS, pt * TP);
-                        if (++stage == NSTAGES) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
-                    }
-                }
+    // ---------------------------------------------------------------- inline TMA producer (thread 0 only)
+    // The loads of this CTA form one linear stream of chunks (item -> pool tile -> 32-word chunk); the cursor below
+    // walks it NSTAGES-1 chunks ahead of the consumers.
+    const bool is_producer = threadIdx.x == 0;
+    int p_item = blockIdx.x, p_qtile = 0, p_pt = 0, p_pt_end = 0, p_c = 0, p_stage = 0;
+    uint32_t p_phase = 0;
+    auto p_open_item = [&]() {
+        if (p_item < n_items) {
+            const int stripe = p_item / prm.n_qtiles;
+            p_qtile = p_item - stripe * prm.n_qtiles;
+            p_pt = stripe * prm.ptiles_per_stripe;
+            p_pt_end = min(p_pt + prm.ptiles_per_stripe, prm.n_ptiles);
+            p_c = 0;
+        }
+    };
+    auto p_issue = [&]() {
+        if (p_item >= n_items) return;
+        mbar_wait(&empty_bar[p_stage], p_phase ^ 1);
+        uint8_t* dst = stages + (size_t)p_stage * STAGE_BYTES;
+        mbar_arrive_expect_tx(&full_bar[p_stage], STAGE_BYTES);
+        tma_load_2d(dst, &tm_q, &full_bar[p_stage], p_c * CHUNK_WORDS, p_qtile * TQ);
+        tma_load_2d(dst + OPER_BYTES, &tm_p, &full_bar[p_stage], p_c * CHUNK_WORDS, p_pt * TP);
+        if (++p_stage == NSTAGES) {
+            p_stage = 0;
+            p_phase ^= 1;
+        }
+        if (++p_c == prm.n_chunks) {
+            p_c = 0;
+            if (++p_pt == p_pt_end) {
+                p_item += gridDim.x;
+                p_open_item();
             }
         }
-        return;
+    };
+    if (is_producer) {
+        p_open_item();
+        for (int i = 0; i < NSTAGES - 1; ++i) p_issue();
     }
 
-    // ---------------------------------------------------------------- consumers (warps 1..8)
-    const int cw = warp - 1;    // 0..7
-    const int wq = cw >> 1;     // 0..3 : 32-query slab
+    // ---------------------------------------------------------------- consumers (all NCW warps)
+    const int cw = warp;        // 0..NCW-1
+    const int wq = cw >> 1;     // query slab of SLAB rows
     const int wp = cw & 1;      // 0..1 : 64-pool-row slab
     const int lq = lane >> 3;   // 0..3
     const int lp = lane & 7;    // 0..7
-    // rows owned by this thread: q(i) = wq*32 + i*4 + lq, p(j) = wp*64 + j*8 + lp  (i, j in 0..7)
-    const uint32_t q_off = (uint32_t)(wq * 32 + lq) * 128u;             // + i*512
+    // rows owned by this thread: q(i) = wq*SLAB + i*4 + lq (i < RQ), p(j) = wp*64 + j*8 + lp (j < 8)
+    const uint32_t q_off = (uint32_t)(wq * SLAB + lq) * 128u;           // + i*512
     const uint32_t p_off = OPER_BYTES + (uint32_t)(wp * 64 + lp) * 128u;  // + j*1024
     const uint32_t q_xor_even = (uint32_t)lq << 4;                      // (row & 7) << 4 for even i
     const uint32_t q_xor_odd = (uint32_t)(lq + 4) << 4;                 //                    odd i
@@ -144,9 +192,9 @@ jaccard_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         const int pt_end = min(pt_beg + prm.ptiles_per_stripe, prm.n_ptiles);
 
         if (MODE == MODE_TOPK) {
-            // reset the 16 lists this warp owns
-            for (int qq = 0; qq < 16; ++qq) {
-                const int q = cw * 16 + qq;
+            // reset the lists this warp owns
+            for (int qq = 0; qq < SCAN_ROWS; ++qq) {
+                const int q = cw * SCAN_ROWS + qq;
                 l_inter[q * LIST_LD + lane] = 0u;
                 l_union[q * LIST_LD + lane] = 1u;
                 l_idx[q * LIST_LD + lane] = R4D_IDX_NONE;
@@ -155,40 +203,41 @@ jaccard_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         }
 
         for (int pt = pt_beg; pt < pt_end; ++pt) {
-            uint32_t acc[8][8];
+            uint32_t acc[RQ][8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < RQ; ++i)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) acc[i][j] = 0u;
 
             for (int c = 0; c < prm.n_chunks; ++c) {
+                if (is_producer) p_issue();  // refill the stage released one chunk ago
                 mbar_wait(&full_bar[stage], phase);
                 const uint32_t sbase = stages_u32 + (uint32_t)stage * STAGE_BYTES;
-                const int ngroups = (c == prm.n_chunks - 1) ? prm.last_groups : 8;
+                // 16-byte groups are consumed in pairs (8 words per counter update).  Words past W are zero in
+                // both operands (encoder padding / TMA zero fill), so rounding the group count up to even is exact.
+                const int npairs = ((c == prm.n_chunks - 1) ? prm.last_groups + 1 : 8) >> 1;
 #pragma unroll 1
-                for (int g = 0; g < ngroups; ++g) {
-                    const uint32_t gq_e = sbase + q_off + (((uint32_t)g << 4) ^ q_xor_even);
-                    const uint32_t gq_o = sbase + q_off + (((uint32_t)g << 4) ^ q_xor_odd);
-                    const uint32_t gp = sbase + p_off + (((uint32_t)g << 4) ^ p_xor);
-                    uint4 qv[8];
+                for (int g2 = 0; g2 < npairs; ++g2) {
+                    const uint32_t g = (uint32_t)g2 << 5;  // byte offset of the first group of the pair (2 x 16 B)
+                    const uint32_t gq_e0 = sbase + q_off + (g ^ q_xor_even);
+                    const uint32_t gq_e1 = sbase + q_off + ((g + 16u) ^ q_xor_even);
+                    const uint32_t gq_o0 = sbase + q_off + (g ^ q_xor_odd);
+                    const uint32_t gq_o1 = sbase + q_off + ((g + 16u) ^ q_xor_odd);
+                    const uint32_t gp0 = sbase + p_off + (g ^ p_xor);
+                    const uint32_t gp1 = sbase + p_off + ((g + 16u) ^ p_xor);
+                    uint4 qa[RQ], qb[RQ];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const uint32_t a = ((i & 1) ? gq_o : gq_e) + (uint32_t)i * 512u;
-                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                                     : "=r"(qv[i].x), "=r"(qv[i].y), "=r"(qv[i].z), "=r"(qv[i].w)
-                                     : "r"(a));
+                    for (int i = 0; i < RQ; ++i) {
+                        lds128(qa[i], ((i & 1) ? gq_o0 : gq_e0) + (uint32_t)i * 512u);
+                        lds128(qb[i], ((i & 1) ? gq_o1 : gq_e1) + (uint32_t)i * 512u);
                     }
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        uint4 pv;
-                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                                     : "=r"(pv.x), "=r"(pv.y), "=r"(pv.z), "=r"(pv.w)
-                                     : "r"(gp + (uint32_t)j * 1024u));
+                        uint4 pa, pb;
+                        lds128(pa, gp0 + (uint32_t)j * 1024u);
+                        lds128(pb, gp1 + (uint32_t)j * 1024u);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            acc[i][j] += __popc(qv[i].x & pv.x) + __popc(qv[i].y & pv.y) +
-                                         __popc(qv[i].z & pv.z) + __popc(qv[i].w & pv.w);
-                        }
+                        for (int i = 0; i < RQ; ++i) acc[i][j] += popc8_csa(qa[i], qb[i], pa, pb);
                     }
                 }
                 __syncwarp();
@@ -202,8 +251,8 @@ jaccard_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             // -------------------------------------------------------- epilogue
             if (MODE == MODE_FULL) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int64_t gq = (int64_t)qtile * TQ + wq * 32 + i * 4 + lq;
+                for (int i = 0; i < RQ; ++i) {
+                    const int64_t gq = (int64_t)qtile * TQ + wq * SLAB + i * 4 + lq;
                     if (gq >= prm.nq) continue;
                     const uint32_t cq = prm.qcard[gq];
 #pragma unroll
@@ -222,10 +271,10 @@ jaccard_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             } else {
                 named_bar_sync(1, N_CONSUMERS);  // previous tile's scan is finished
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
+                for (int i = 0; i < RQ; ++i)
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        tilebuf[(wq * 32 + i * 4 + lq) * TILE_LD + wp * 64 + j * 8 + lp] = acc[i][j];
+                        tilebuf[(wq * SLAB + i * 4 + lq) * TILE_LD + wp * 64 + j * 8 + lp] = acc[i][j];
                 named_bar_sync(1, N_CONSUMERS);  // count tile complete
 
                 // pool-side constants of the 4 columns this lane scans
@@ -236,8 +285,8 @@ jaccard_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                     gpi[s] = (int64_t)pt * TP + s * 32 + lane;
                     cp[s] = gpi[s] < prm.np ? prm.pcard[gpi[s]] : 0u;
                 }
-                for (int qq = 0; qq < 16; ++qq) {
-                    const int q = cw * 16 + qq;
+                for (int qq = 0; qq < SCAN_ROWS; ++qq) {
+                    const int q = cw * SCAN_ROWS + qq;
                     const int64_t gq = (int64_t)qtile * TQ + q;
                     if (gq >= prm.nq) break;  // warp-uniform
                     const uint32_t cq = prm.qcard[gq];
@@ -272,9 +321,9 @@ jaccard_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 
         if (MODE == MODE_TOPK) {
             __syncwarp();
-            // flush this warp's 16 lists to the stripe's partial slot
-            for (int qq = 0; qq < 16; ++qq) {
-                const int q = cw * 16 + qq;
+            // flush this warp's lists to the stripe's partial slot
+            for (int qq = 0; qq < SCAN_ROWS; ++qq) {
+                const int q = cw * SCAN_ROWS + qq;
                 const int64_t gq = (int64_t)qtile * TQ + q;
                 if (gq >= prm.nq) break;
                 if (lane < prm.k) {
@@ -352,6 +401,31 @@ static int check_common(const uint32_t* qbits, const uint32_t* qcard, int64_t nq
     return R4D_OK;
 }
 
+static int consumer_warps() {
+    // debug / tuning knob; 16 warps (4 per scheduler) hide the AND->CSA->POPC dependency chains better
+    static int v = [] {
+        const char* e = getenv("R4D_JACCARD_WARPS");
+        return (e && atoi(e) == 8) ? 8 : 16;
+    }();
+    return v;
+}
+
+template <int MODE, int NCW>
+static int launch_ncw(const CUtensorMap& tm_q, const CUtensorMap& tm_p, const JaccardParams& prm, cudaStream_t st) {
+    const size_t smem = smem_bytes_for(MODE);
+    static bool attr_done = false;
+    if (!attr_done) {
+        R4D_CUDA(cudaFuncSetAttribute(jaccard_kernel<MODE, NCW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    const int64_t n_items = (int64_t)prm.n_qtiles * prm.n_stripes;
+    int grid = num_sms();
+    if (n_items < grid) grid = (int)n_items;
+    jaccard_kernel<MODE, NCW><<<grid, 32 * NCW, smem, st>>>(tm_q, tm_p, prm);
+    R4D_CUDA(cudaGetLastError());
+    return R4D_OK;
+}
+
 template <int MODE>
 static int launch(const uint32_t* qbits, int64_t nq, const uint32_t* pbits, int64_t np, int32_t words,
                   int32_t pitch_words, JaccardParams& prm, cudaStream_t st) {
@@ -365,18 +439,7 @@ static int launch(const uint32_t* qbits, int64_t nq, const uint32_t* pbits, int6
     prm.n_chunks = (words + CHUNK_WORDS - 1) / CHUNK_WORDS;
     const int rem = words - (prm.n_chunks - 1) * CHUNK_WORDS;  // 1..32 real words in the last chunk
     prm.last_groups = (rem + 3) / 4;
-    const size_t smem = smem_bytes_for(MODE);
-    static bool attr_done[2] = {false, false};
-    if (!attr_done[MODE]) {
-        R4D_CUDA(cudaFuncSetAttribute(jaccard_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done[MODE] = true;
-    }
-    const int64_t n_items = (int64_t)prm.n_qtiles * prm.n_stripes;
-    int grid = num_sms();
-    if (n_items < grid) grid = (int)n_items;
-    jaccard_kernel<MODE><<<grid, N_THREADS, smem, st>>>(tm_q, tm_p, prm);
-    R4D_CUDA(cudaGetLastError());
-    return R4D_OK;
+    return consumer_warps() == 8 ? launch_ncw<MODE, 8>(tm_q, tm_p, prm, st) : launch_ncw<MODE, 16>(tm_q, tm_p, prm, st);
 }
 
 }  // namespace r4d
