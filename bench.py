@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--dense-pool", type=int, default=DENSE_POOL_N)
     ap.add_argument("--queries-per-step", type=int, default=Q_STEP)
     ap.add_argument("--mean-set", type=float, default=1.0 / 0.45, help="mean set size (y-like 2.2; x-like 20)")
+    ap.add_argument("--dense-d", type=int, default=DENSE_D, help="embedding width (experiments; the metric uses 768)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -89,7 +90,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None
@@ -350,6 +351,7 @@ def main():
     # =============================================================== dense
     if "dense" in scorers:
         n_pool, qs = args.dense_pool, args.queries_per_step
+        DENSE_D = args.dense_d
         lo, hi = rank * n_pool // world, (rank + 1) * n_pool // world
         g = torch.Generator(device=dev).manual_seed(SEED_DPOOL + rank)
         hi_plane = torch.empty((hi - lo, DENSE_D), dtype=torch.bfloat16, device=dev)

@@ -11,8 +11,11 @@
 // epilogue on the CTA's own 128 TMEM lanes, with the running top-K of each (row, column-half) in REGISTERS
 // (16 slots, branch-free compare-swap insertion) — shared memory is fully spent on the resident query tile.
 //
-// Supports: PREC_BF16, top-K with k <= 16, D such that the query tile + >= 2 pool stages fit in 227 KB (D <= 768 at
-// N = 128).  Everything else goes through dense.cu.
+// At D = 768 the resident tile (192 KB) would leave only 32 KB of pool stages in flight per CTA, which is TMA-latency
+// bound (measured: no gain over dense.cu), so wide D uses QRES = false: the pair streams both k-blocks (64 B/clk/SM,
+// 7-stage ring) and still halves the pool traffic per MMA.
+//
+// Supports: PREC_BF16, top-K with k <= 16.  Everything else goes through dense.cu.
 #include "dense_common.cuh"
 
 namespace r4d {
@@ -51,13 +54,15 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
     return r;
 }
+// NOTE: deliberately without .release.cluster — that form compiles to MEMBAR.ALL.GPU + ERRBAR per call and
+// serialises the TMA pipeline; the data itself is published by the TMA's complete_tx, not by this arrive.
 __device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr),
+    asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr),
                  "r"(bytes)
                  : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA tile load into this CTA's smem whose completion is signalled on a barrier that may live in the peer CTA
 __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst_smem, const CUtensorMap* map, uint32_t mbar_cluster_addr,
@@ -121,14 +126,19 @@ __device__ __forceinline__ float reg_kth(const RegList& L, int k) {
     return t;
 }
 
-template <int DPN>  // pool rows per pair tile (UMMA N): 256 or 128; each CTA streams DPN/2 rows per k-block
+// DPN : pool rows per pair tile (UMMA N), 256 or 128; each CTA streams DPN/2 rows per k-block.
+// QRES: true  = this CTA's query tile (128 x D) stays resident in smem for the whole work item (32 B/clk/SM streamed);
+//              needs D small enough to leave >= 4 pool stages (D <= 512).
+//       false = the query k-block is streamed next to the pool k-block (64 B/clk/SM, deep ring) — wide D.
+template <int DPN, bool QRES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D2_THREADS, 1)
 dense2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_p,
               const Dense2Params prm) {
-    constexpr int P_STAGE_BYTES = (DPN / 2) * DKB * 2;
+    constexpr int P_TILE_BYTES_ = (DPN / 2) * DKB * 2;
+    constexpr int P_STAGE_BYTES = P_TILE_BYTES_ + (QRES ? 0 : Q_TILE_BYTES);  // streamed Q k-block sits after the P tile
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* q_res = smem;                                              // [n_kblocks][128 x 64 bf16]  resident
-    uint8_t* stages = smem + (size_t)prm.n_kblocks * Q_TILE_BYTES;      // [n_stages][DPN/2 x 64 bf16]
+    uint8_t* q_res = smem;                                              // [n_kblocks][128 x 64 bf16]  resident (QRES)
+    uint8_t* stages = smem + (QRES ? (size_t)prm.n_kblocks * Q_TILE_BYTES : 0);  // [n_stages][stage]
     uint8_t* after = stages + (size_t)prm.n_stages * P_STAGE_BYTES;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(after);            // [8]  used in the LEADER (count 2)
     uint64_t* empty_bar = full_bar + 8;                                 // [8]  per CTA (multicast commit)
@@ -185,18 +195,22 @@ dense2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                 const int qtile = (item - stripe * prm.n_qpairs) * 2 + (int)rank;
                 const int pt_beg = stripe * prm.ptiles_per_stripe;
                 const int pt_end = min(pt_beg + prm.ptiles_per_stripe, prm.n_ptiles);
-                // resident query tile: wait until the previous item's MMAs have released it
-                mbar_wait(qempty_bar, (item_seq & 1u) ^ 1u);
-                mbar_arrive_expect_tx_cluster(qfull_leader, (uint32_t)(prm.n_kblocks * Q_TILE_BYTES));
-                for (int kb = 0; kb < prm.n_kblocks; ++kb)
-                    tma_load_2d_2sm(smem_u32(q_res + (size_t)kb * Q_TILE_BYTES), &tm_q, qfull_leader, kb * DKB, qtile * DQ);
+                if (QRES) {
+                    // resident query tile: wait until the previous item's MMAs have released it
+                    mbar_wait(qempty_bar, (item_seq & 1u) ^ 1u);
+                    mbar_arrive_expect_tx_cluster(qfull_leader, (uint32_t)(prm.n_kblocks * Q_TILE_BYTES));
+                    for (int kb = 0; kb < prm.n_kblocks; ++kb)
+                        tma_load_2d_2sm(smem_u32(q_res + (size_t)kb * Q_TILE_BYTES), &tm_q, qfull_leader, kb * DKB,
+                                        qtile * DQ);
+                }
                 for (int pt = pt_beg; pt < pt_end; ++pt) {
                     for (int kb = 0; kb < prm.n_kblocks; ++kb) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[stage]), 0);
+                        const uint32_t sdst = smem_u32(stages + (size_t)stage * P_STAGE_BYTES);
                         mbar_arrive_expect_tx_cluster(full_leader, (uint32_t)P_STAGE_BYTES);
-                        tma_load_2d_2sm(smem_u32(stages + (size_t)stage * P_STAGE_BYTES), &tm_p, full_leader, kb * DKB,
-                                        pt * DPN + (int)rank * (DPN / 2));
+                        tma_load_2d_2sm(sdst, &tm_p, full_leader, kb * DKB, pt * DPN + (int)rank * (DPN / 2));
+                        if (!QRES) tma_load_2d_2sm(sdst + P_TILE_BYTES_, &tm_q, full_leader, kb * DKB, qtile * DQ);
                         if (++stage == prm.n_stages) {
                             stage = 0;
                             phase ^= 1;
@@ -217,8 +231,10 @@ dense2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                 const int stripe = item / prm.n_qpairs;
                 const int pt_beg = stripe * prm.ptiles_per_stripe;
                 const int pt_end = min(pt_beg + prm.ptiles_per_stripe, prm.n_ptiles);
-                mbar_wait(qfull_bar, item_seq & 1u);  // both CTAs' query tiles have landed
-                tc_fence_after();
+                if (QRES) {
+                    mbar_wait(qfull_bar, item_seq & 1u);  // both CTAs' query tiles have landed
+                    tc_fence_after();
+                }
                 const uint32_t qbase = smem_u32(q_res);
                 for (int pt = pt_beg; pt < pt_end; ++pt, ++tile_seq) {
                     const uint32_t buf = tile_seq & 1u;
@@ -228,8 +244,9 @@ dense2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                     for (int kb = 0; kb < prm.n_kblocks; ++kb) {
                         mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
-                        const uint64_t qd = make_smem_desc(qbase + (uint32_t)kb * Q_TILE_BYTES);
-                        const uint64_t pd = make_smem_desc(smem_u32(stages + (size_t)stage * P_STAGE_BYTES));
+                        const uint32_t sbase = smem_u32(stages + (size_t)stage * P_STAGE_BYTES);
+                        const uint64_t qd = make_smem_desc(QRES ? qbase + (uint32_t)kb * Q_TILE_BYTES : sbase + P_TILE_BYTES_);
+                        const uint64_t pd = make_smem_desc(sbase);
 #pragma unroll
                         for (int ks = 0; ks < DKB / 16; ++ks)
                             umma_bf16_2sm(tmem_d, qd + (uint64_t)(2 * ks), pd + (uint64_t)(2 * ks), idesc,
@@ -242,7 +259,7 @@ dense2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                     }
                     tc_commit_2sm_mc(&tfull_bar[buf]);  // accumulator complete in both CTAs
                 }
-                tc_commit_2sm_mc(qempty_bar);  // resident query tiles may be overwritten
+                if (QRES) tc_commit_2sm_mc(qempty_bar);  // resident query tiles may be overwritten
             }
         }
     } else {
@@ -352,7 +369,9 @@ dense2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
 // ---------------------------------------------------------------------------- host side
 struct Dense2Plan {
     int32_t n_qpairs, n_ptiles, n_stripes, ptiles_per_stripe, dpn, n_stages;
+    bool qres;
     bool ok;
+    size_t smem;
 };
 
 static Dense2Plan dense2_plan(int64_t nq, int64_t np, int32_t d_pad, int32_t k) {
@@ -360,20 +379,24 @@ static Dense2Plan dense2_plan(int64_t nq, int64_t np, int32_t d_pad, int32_t k) 
     pl.ok = false;
     if (k > D2_KR || nq <= 0 || np <= 0) return pl;
     const int n_kblocks = d_pad / DKB;
-    const long q_bytes = (long)n_kblocks * Q_TILE_BYTES;
     const long total = 227 * 1024;
-    const long fixed256 = 23 * 8 + 16 + 2 * 256 * 4 + 64, fixed128 = 23 * 8 + 16 + 2 * 128 * 4 + 64;
-    long avail = total - q_bytes - fixed256;
-    if (avail >= 4 * 16384) {
-        pl.dpn = 256;
-        pl.n_stages = (int)(avail / 16384);
+    const long fixed = 22 * 8 + 16 + 2 * 256 * 4 + 64;
+    pl.dpn = 256;
+    const long q_bytes = (long)n_kblocks * Q_TILE_BYTES;
+    static const int force = [] {
+        const char* e = getenv("R4D_DENSE2_QRES");  // tuning knob: 0 = always stream, 1 = resident when it fits
+        return e ? atoi(e) : -1;
+    }();
+    const long avail_res = total - fixed - q_bytes;
+    pl.qres = avail_res >= 4 * 16384 && force != 0;
+    if (pl.qres) {
+        pl.n_stages = (int)(avail_res / 16384);
     } else {
-        avail = total - q_bytes - fixed128;
-        pl.dpn = 128;
-        pl.n_stages = (int)(avail / 8192);
+        pl.n_stages = (int)((total - fixed) / (16384 + Q_TILE_BYTES));
     }
     if (pl.n_stages > 8) pl.n_stages = 8;
     if (pl.n_stages < 3) return pl;
+    pl.smem = (size_t)fixed + (size_t)pl.n_stages * (16384 + (pl.qres ? 0 : Q_TILE_BYTES)) + (pl.qres ? (size_t)q_bytes : 0);
     pl.n_qpairs = (int32_t)((nq + 2 * DQ - 1) / (2 * DQ));
     pl.n_ptiles = (int32_t)((np + pl.dpn - 1) / pl.dpn);
     const int n_clusters = num_sms() / 2;
@@ -438,17 +461,16 @@ int dense2_topk(const void* q_hi, int64_t nq, const void* p_hi, int64_t np, int3
     prm.ptiles_per_stripe = pl.ptiles_per_stripe;
     prm.part_score = part_score;
     prm.part_idx = part_idx;
-    const size_t smem = (size_t)prm.n_kblocks * Q_TILE_BYTES + (size_t)pl.n_stages * (pl.dpn / 2) * DKB * 2 + 23 * 8 + 16 +
-                        2 * (size_t)pl.dpn * 4 + 64;
+    const size_t smem = pl.smem;
     const int64_t n_items = (int64_t)pl.n_qpairs * pl.n_stripes;
     int n_clusters = num_sms() / 2;
     if (n_items < n_clusters) n_clusters = (int)n_items;
-    if (pl.dpn == 256) {
-        R4D_CUDA(cudaFuncSetAttribute(dense2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dense2_kernel<256><<<2 * n_clusters, D2_THREADS, smem, st>>>(tm_q, tm_p, prm);
+    if (pl.qres) {
+        R4D_CUDA(cudaFuncSetAttribute(dense2_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dense2_kernel<256, true><<<2 * n_clusters, D2_THREADS, smem, st>>>(tm_q, tm_p, prm);
     } else {
-        R4D_CUDA(cudaFuncSetAttribute(dense2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dense2_kernel<128><<<2 * n_clusters, D2_THREADS, smem, st>>>(tm_q, tm_p, prm);
+        R4D_CUDA(cudaFuncSetAttribute(dense2_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dense2_kernel<256, false><<<2 * n_clusters, D2_THREADS, smem, st>>>(tm_q, tm_p, prm);
     }
     R4D_CUDA(cudaGetLastError());
     *n_lists_out = pl.n_stripes * 2;

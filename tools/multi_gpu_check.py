@@ -1,0 +1,68 @@
+#!/usr/bin/env python
+"""Multi-GPU parity check, run under torchrun (one process per GPU, NCCL):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/multi_gpu_check.py
+Every rank encodes/prepares only its pool shard, runs the sharded top-K (local fused kernel + all-gather + merge)
+and rank 0 compares with (a) the single-GPU result over the whole pool and (b) the CPU oracle.  Bit-exact for Jaccard,
+exact equality with the unsharded kernel result for dense (same arithmetic per pair)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    from conftest import random_sets, to_csr
+    from oracle import jaccard_oracle as jo
+    from rag4dyg_b200 import engine, set_encoder, sharded
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    rng = np.random.default_rng(2024)        # same data on every rank
+    n_bits, nq, npool, k = 20000, 700, 60001, 10
+    q = random_sets(rng, nq, n_bits, mean=2.2)
+    p = random_sets(rng, npool, n_bits, mean=2.2)
+    lo, hi = sharded.my_shard(npool)
+    bq = set_encoder.encode_csr(*to_csr(q), n_bits, dev)
+    bp_shard = set_encoder.encode_csr(*to_csr(p[lo:hi]), n_bits, dev)
+    got = sharded.jaccard_topk_sharded(bq, bp_shard, k, pool_base=lo)
+    ok = True
+    if rank == 0:
+        bp_all = set_encoder.encode_csr(*to_csr(p), n_bits, dev)
+        ref = engine.jaccard_topk(bq, bp_all, k)
+        ok &= all(torch.equal(a, b) for a, b in zip(got, ref))
+        oi, ou, ox = jo.c_topk(*to_csr(q[:200]), *to_csr(p), k)
+        ok &= np.array_equal(got[2][:200].cpu().numpy(), ox) and np.array_equal(got[0][:200].cpu().numpy(), oi)
+        print(f"[multi_gpu_check] world={world} jaccard sharded == single-GPU == oracle: {ok}", flush=True)
+
+    g = torch.Generator().manual_seed(7)
+    pe, qe = torch.randn(50000, 256, generator=g), torch.randn(300, 256, generator=g)
+    tp, tq = torch.rand(50000, generator=g) * 110, torch.rand(300, generator=g) * 110
+    lo, hi = sharded.my_shard(50000)
+    for prec in (engine.PREC_BF16, engine.PREC_BF16X3):
+        qp = engine.dense_prepare(qe.to(dev), prec)
+        pp = engine.dense_prepare(pe[lo:hi].to(dev), prec)
+        gs, gi = sharded.dense_topk_sharded(qp, pp, k, pool_base=lo, mode=engine.DENSE_COS_DECAY, q_time=tq.to(dev),
+                                            p_time=tp[lo:hi].to(dev), lam=0.01)
+        if rank == 0:
+            pa = engine.dense_prepare(pe.to(dev), prec)
+            rs, ri = engine.dense_topk(qp, pa, k, engine.DENSE_COS_DECAY, tq.to(dev), tp.to(dev), 0.01)
+            same = torch.equal(gi, ri) and torch.equal(gs, rs)
+            ok &= same
+            print(f"[multi_gpu_check] world={world} dense prec={prec} sharded == single-GPU: {same}", flush=True)
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.broadcast(flag, 0)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
