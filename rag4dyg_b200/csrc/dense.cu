@@ -22,7 +22,6 @@ constexpr int DP = 256;          // pool rows per tile   (UMMA N)
 constexpr int P_TILE_BYTES = DP * DKB * 2;  // 32 KB
 constexpr int D_THREADS = 320;
 constexpr int D_EPI_WARPS = 8;
-constexpr int D_EPI_THREADS = D_EPI_WARPS * 32;
 
 constexpr int DMODE_TOPK = 0;
 constexpr int DMODE_FULL = 1;
@@ -45,22 +44,6 @@ struct DenseParams {
     float* scores;  // full mode
     int64_t ld;
 };
-
-// sorted insertion into this thread's list (column-major in smem: slot t of thread `tid` at [t*D_EPI_THREADS+tid]).
-// Returns the new k-th best score.
-__device__ __noinline__ float list_insert(float* ls, int32_t* li, int k, float s, int32_t idx) {
-    int t = k - 1;
-    while (t > 0) {
-        const float prev = ls[(t - 1) * D_EPI_THREADS];
-        if (!(prev < s)) break;  // strict: an equal earlier (smaller index) entry stays ahead
-        ls[t * D_EPI_THREADS] = prev;
-        li[t * D_EPI_THREADS] = li[(t - 1) * D_EPI_THREADS];
-        --t;
-    }
-    ls[t * D_EPI_THREADS] = s;
-    li[t * D_EPI_THREADS] = idx;
-    return ls[(k - 1) * D_EPI_THREADS];
-}
 
 template <int DMODE>
 __global__ void __launch_bounds__(D_THREADS, 1)

@@ -8,14 +8,18 @@
 //
 // Roles per CTA (320 threads): warp 0 TMA producer (both CTAs; cp.async.bulk.tensor ... .cta_group::2 signals the
 // LEADER's full barrier), warp 1 MMA issuer (leader CTA only; commits multicast to both CTAs' barriers), warps 2..9
-// epilogue on the CTA's own 128 TMEM lanes, with the running top-K of each (row, column-half) in REGISTERS
-// (16 slots, branch-free compare-swap insertion) — shared memory is fully spent on the resident query tile.
+// epilogue on the CTA's own 128 TMEM lanes: per 32-column chunk the raw cosines give an upper bound on every score
+// (decay <= 1), so chunks that cannot beat the row's k-th best skip the MUFU/decay work entirely; survivors go into
+// per-thread sorted smem lists; the two column halves of a row share their thresholds.
 //
 // At D = 768 the resident tile (192 KB) would leave only 32 KB of pool stages in flight per CTA, which is TMA-latency
 // bound (measured: no gain over dense.cu), so wide D uses QRES = false: the pair streams both k-blocks (64 B/clk/SM,
 // 7-stage ring) and still halves the pool traffic per MMA.
 //
 // Supports: PREC_BF16, top-K with k <= 16.  Everything else goes through dense.cu.
+#include <cmath>
+#include <cstdlib>
+
 #include "dense_common.cuh"
 
 namespace r4d {
@@ -23,7 +27,7 @@ namespace r4d {
 constexpr int D2_THREADS = 320;
 constexpr int D2_EPI_WARPS = 8;
 constexpr int D2_EPI_THREADS = 256;
-constexpr int D2_KR = 16;  // register-resident list slots per thread
+constexpr int D2_KMAX = 16;  // top-K width served by this kernel (wider K -> dense.cu)
 
 struct Dense2Params {
     int64_t nq, np;
@@ -102,30 +106,6 @@ __device__ __forceinline__ void tc_commit_2sm_mc(uint64_t* bar) {
         : "memory");
 }
 
-// ---- register-resident sorted list (descending score; equal scores keep insertion order = ascending index)
-struct RegList {
-    float s[D2_KR];
-    int32_t i[D2_KR];
-};
-__device__ __forceinline__ void reg_insert(RegList& L, float s, int32_t idx) {
-#pragma unroll
-    for (int t = 0; t < D2_KR; ++t) {
-        const bool sw = s > L.s[t];
-        const float ts = sw ? L.s[t] : s;
-        const int32_t ti = sw ? L.i[t] : idx;
-        L.s[t] = sw ? s : L.s[t];
-        L.i[t] = sw ? idx : L.i[t];
-        s = ts;
-        idx = ti;
-    }
-}
-__device__ __forceinline__ float reg_kth(const RegList& L, int k) {
-    float t = L.s[0];
-#pragma unroll
-    for (int j = 1; j < D2_KR; ++j) t = (j == k - 1) ? L.s[j] : t;
-    return t;
-}
-
 // DPN : pool rows per pair tile (UMMA N), 256 or 128; each CTA streams DPN/2 rows per k-block.
 // QRES: true  = this CTA's query tile (128 x D) stays resident in smem for the whole work item (32 B/clk/SM streamed);
 //              needs D small enough to leave >= 4 pool stages (D <= 512).
@@ -148,6 +128,9 @@ dense2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     uint64_t* qempty_bar = qfull_bar + 1;                               // [1]  per CTA (multicast commit)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(qempty_bar + 1);
     float* ptime_s = reinterpret_cast<float*>(tmem_slot + 4);           // [2][DPN]
+    float* thr_s = ptime_s + 2 * DPN;                                   // [256] k-th best per (row, column half)
+    float* list_s = thr_s + D2_EPI_THREADS;                             // [k][256] per-thread sorted lists
+    int32_t* list_i = reinterpret_cast<int32_t*>(list_s + (size_t)prm.k * D2_EPI_THREADS);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -283,13 +266,20 @@ dense2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
             const int64_t gq = (int64_t)qtile * DQ + row_in_tile;
             const bool q_ok = gq < prm.nq;
             const float tq = (prm.mode != R4D_DENSE_HALF_COS && q_ok) ? prm.q_time[gq] : 0.f;
-            RegList L;
-#pragma unroll
-            for (int t = 0; t < D2_KR; ++t) {
-                L.s[t] = -INFINITY;
-                L.i[t] = R4D_IDX_NONE;
+            float* ls = list_s + (half * 128 + row_in_tile);
+            int32_t* li = list_i + (half * 128 + row_in_tile);
+            for (int t = 0; t < prm.k; ++t) {
+                ls[t * D2_EPI_THREADS] = -INFINITY;
+                li[t * D2_EPI_THREADS] = R4D_IDX_NONE;
             }
-            float thr = -INFINITY;
+            float thr = -INFINITY;  // this thread's k-th best
+            // the other column half of the same query row shares its threshold (stored one ulp low so that the strict
+            // test below keeps equal scores, whose index order across halves is not monotone)
+            thr_s[half * 128 + row_in_tile] = -INFINITY;
+            named_bar_sync(3, D2_EPI_THREADS);
+            const float* thr_partner = thr_s + ((half ^ 1) * 128 + row_in_tile);
+            // decay in (0, 1] lets the raw cosine bound every score of a chunk from above (lambda >= 0 only)
+            const bool can_bound = prm.neg_lambda_log2e <= 0.f;
             for (int pt = pt_beg; pt < pt_end; ++pt, ++tile_seq) {
                 const uint32_t buf = tile_seq & 1u;
                 if (prm.mode != R4D_DENSE_HALF_COS) {
@@ -299,6 +289,7 @@ dense2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                     }
                     named_bar_sync(2, D2_EPI_THREADS);
                 }
+                float cut = fmaxf(thr, *thr_partner);  // candidates must beat both halves' k-th best
                 mbar_wait(&tfull_bar[buf], (tile_seq >> 1) & 1u);
                 tc_fence_after();
 #pragma unroll 1
@@ -308,6 +299,12 @@ dense2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                     tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * DPN + col0, v);
                     tmem_ld_wait();
                     const int64_t gp0 = (int64_t)pt * DPN + col0;
+                    // fast reject: upper bound of the chunk's scores from the raw cosines (no MUFU, no pool times)
+                    float xm = __uint_as_float(v[0]);
+#pragma unroll
+                    for (int j = 1; j < 32; ++j) xm = fmaxf(xm, __uint_as_float(v[j]));
+                    const float ub = prm.mode == R4D_DENSE_COS_DECAY ? fmaxf(xm, 0.f) : fmaxf((xm + 1.0f) * 0.5f, 0.f);
+                    if (!q_ok || (can_bound && !(ub > cut))) continue;
                     float s[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
@@ -322,38 +319,26 @@ dense2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                     float m = s[0];
 #pragma unroll
                     for (int j = 1; j < 32; ++j) m = fmaxf(m, s[j]);
-                    // rare path: extract candidates in descending order (first occurrence on ties => ascending index)
-                    while (q_ok && m > thr) {
-                        float best = s[0];
-                        int bj = 0;
+                    if (m > cut) {
 #pragma unroll
-                        for (int j = 1; j < 32; ++j)
-                            if (s[j] > best) {
-                                best = s[j];
-                                bj = j;
+                        for (int j = 0; j < 32; ++j)
+                            if (s[j] > cut) {
+                                thr = list_insert(ls, li, prm.k, s[j], (int32_t)(prm.pool_base + gp0 + j));
+                                cut = fmaxf(cut, thr);
                             }
-                        reg_insert(L, best, (int32_t)(prm.pool_base + gp0 + bj));
-                        thr = reg_kth(L, prm.k);
-                        m = -INFINITY;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            s[j] = (j == bj) ? -INFINITY : s[j];
-                            m = fmaxf(m, s[j]);
-                        }
                     }
                 }
+                thr_s[half * 128 + row_in_tile] = nextafterf(thr, -INFINITY);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(tempty_leader[buf]);
             }
             if (q_ok) {
                 const int64_t o = ((int64_t)(stripe * 2 + half) * prm.nq + gq) * prm.k;
-#pragma unroll
-                for (int t = 0; t < D2_KR; ++t)
-                    if (t < prm.k) {
-                        prm.part_score[o + t] = L.s[t];
-                        prm.part_idx[o + t] = L.i[t];
-                    }
+                for (int t = 0; t < prm.k; ++t) {
+                    prm.part_score[o + t] = ls[t * D2_EPI_THREADS];
+                    prm.part_idx[o + t] = li[t * D2_EPI_THREADS];
+                }
             }
         }
     }
@@ -377,10 +362,10 @@ struct Dense2Plan {
 static Dense2Plan dense2_plan(int64_t nq, int64_t np, int32_t d_pad, int32_t k) {
     Dense2Plan pl{};
     pl.ok = false;
-    if (k > D2_KR || nq <= 0 || np <= 0) return pl;
+    if (k > D2_KMAX || nq <= 0 || np <= 0) return pl;
     const int n_kblocks = d_pad / DKB;
     const long total = 227 * 1024;
-    const long fixed = 22 * 8 + 16 + 2 * 256 * 4 + 64;
+    const long fixed = 22 * 8 + 16 + 2 * 256 * 4 + 64 + 256 * 4 + (long)k * 256 * 8;  // barriers, times, thr, lists
     pl.dpn = 256;
     const long q_bytes = (long)n_kblocks * Q_TILE_BYTES;
     static const int force = [] {
@@ -399,14 +384,28 @@ static Dense2Plan dense2_plan(int64_t nq, int64_t np, int32_t d_pad, int32_t k) 
     pl.smem = (size_t)fixed + (size_t)pl.n_stages * (16384 + (pl.qres ? 0 : Q_TILE_BYTES)) + (pl.qres ? (size_t)q_bytes : 0);
     pl.n_qpairs = (int32_t)((nq + 2 * DQ - 1) / (2 * DQ));
     pl.n_ptiles = (int32_t)((np + pl.dpn - 1) / pl.dpn);
+    // Stripe count by a small cost model: rounds(items / clusters) x (tile time + top-K warm-up per stripe).  A stripe
+    // of L columns costs ~24 cycles per column (MMA bound) plus ~32*k*(1 + ln(L / (32*k))) list insertions per warp.
     const int n_clusters = num_sms() / 2;
-    const int64_t target = (int64_t)n_clusters * 8;
-    int64_t stripes = (target + pl.n_qpairs - 1) / pl.n_qpairs;
-    const int64_t min_tiles = 16384 / pl.dpn;  // >= 16 K pool rows per stripe keeps the top-K warm-up negligible
-    const int64_t max_stripes = (pl.n_ptiles + min_tiles - 1) / min_tiles;
-    if (stripes > max_stripes) stripes = max_stripes;
-    if (stripes < 1) stripes = 1;
-    pl.ptiles_per_stripe = (int32_t)((pl.n_ptiles + stripes - 1) / stripes);
+    const int64_t max_stripes = pl.n_ptiles < 4096 ? pl.n_ptiles : 4096;
+    double best_cost = 0;
+    int64_t best = 1;
+    for (int64_t st = 1; st <= max_stripes; ++st) {
+        const int64_t tiles = (pl.n_ptiles + st - 1) / st;
+        const int64_t real_st = (pl.n_ptiles + tiles - 1) / tiles;
+        if (real_st != st) continue;
+        const double L = (double)tiles * pl.dpn;
+        const double ev = 32.0 * k * (1.0 + (L > 32.0 * k ? log(L / (32.0 * k)) : 0.0));
+        const double per_item = 24.0 * L + 150.0 * ev + 3000.0;
+        const int64_t items = (int64_t)pl.n_qpairs * st;
+        const int64_t rounds = (items + n_clusters - 1) / n_clusters;
+        const double cost = (double)rounds * per_item;
+        if (st == 1 || cost < best_cost) {
+            best_cost = cost;
+            best = st;
+        }
+    }
+    pl.ptiles_per_stripe = (int32_t)((pl.n_ptiles + best - 1) / best);
     pl.n_stripes = (pl.n_ptiles + pl.ptiles_per_stripe - 1) / pl.ptiles_per_stripe;
     pl.ok = true;
     return pl;

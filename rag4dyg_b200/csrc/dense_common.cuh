@@ -71,6 +71,24 @@ __device__ __forceinline__ float dense_score(float x, int mode, float tq, float 
     return (mode == R4D_DENSE_COS_DECAY) ? x * dec : (x + 1.0f) * 0.5f * dec;
 }
 
+constexpr int D_EPI_THREADS = 256;  // 8 epilogue warps in both dense kernels
+
+// sorted insertion into this thread's list (column-major in smem: slot t of thread `tid` at [t*D_EPI_THREADS+tid]).
+// Returns the new k-th best score.
+static __device__ __noinline__ float list_insert(float* ls, int32_t* li, int k, float s, int32_t idx) {
+    int t = k - 1;
+    while (t > 0) {
+        const float prev = ls[(t - 1) * D_EPI_THREADS];
+        if (!(prev < s)) break;  // strict: an equal earlier (smaller index) entry stays ahead
+        ls[t * D_EPI_THREADS] = prev;
+        li[t * D_EPI_THREADS] = li[(t - 1) * D_EPI_THREADS];
+        --t;
+    }
+    ls[t * D_EPI_THREADS] = s;
+    li[t * D_EPI_THREADS] = idx;
+    return ls[(k - 1) * D_EPI_THREADS];
+}
+
 // dense2.cu (CTA-pair kernel) entry points used by the C ABI in dense.cu
 bool dense2_supported(int64_t nq, int64_t np, int32_t d_pad, int32_t prec, int32_t k);
 size_t dense2_workspace_bytes(int64_t nq, int64_t np, int32_t d_pad, int32_t k);
