@@ -297,16 +297,27 @@ def main():
             engine.jaccard_topk(bq_all.rows(b * qs, (b + 1) * qs), bp, TOPK, pool_base=lo, workspace=ws)
         k_ms, _, _ = timed(kernel_only)
         k_s = k_ms * 1e-3 / K
+        # dense case: the same kernel with zero-span skipping disabled executes every algorithmic word-op
+        _lib.set_option("jaccard_skip_zero", 0)
+        kd_ms, _, _ = timed(kernel_only)
+        _lib.set_option("jaccard_skip_zero", 1)
+        kd_s = kd_ms * 1e-3 / K
         words = 625
         word_ops = qs * (hi - lo) * words                      # algorithmic AND+POPC word-ops per launch (W per pair)
         sm_max = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz", 1965.0)
-        popc_peak = 148 * 16 * sm_max * 1e6                    # 16 POPC lanes/clk/SM
+        popc_peak = 148 * 16 * sm_max * 1e6                    # 16 POPC lanes/clk/SM (measured 15.8, tools/microbench.cu)
+        two_pipe = 148 * (64 / 2.125) * sm_max * 1e6           # CSA kernel: 17 ALU ops (64 lanes/clk/SM) + 4 POPC per 8 words
         hbm_alg = ((hi - lo) + qs) * words * 4 + qs * TOPK * 12  # compulsory bytes per launch
-        roofline = {"bound": "int-pipe (POPC issue; the path is not HBM- or tensor-bound, SURVEY.md 8d)",
-                    "achieved": word_ops / k_s / 1e12, "peak": popc_peak / 1e12, "unit": "T word-op/s (32-bit AND+POPC)",
+        roofline = {"bound": "int-pipe (the path is neither HBM- nor tensor-bound, SURVEY.md 8d)",
+                    "achieved": word_ops / k_s / 1e12, "peak": popc_peak / 1e12, "unit": "T word-op/s (32-bit AND+POPC, algorithmic W per pair)",
                     "frac": word_ops / k_s / popc_peak, "traffic": None,
-                    "kernel": "r4d::jaccard_kernel<MODE_TOPK>", "kernel_ms": k_ms / K,
-                    "peak_source": f"148 SM x 16 POPC/clk x {sm_max:.0f} MHz (clocks.max.sm)",
+                    "kernel": "r4d::jaccard_kernel<MODE_TOPK, 16 warps, SKIP>", "kernel_ms": k_ms / K,
+                    "peak_source": f"148 SM x 16 POPC/clk x {sm_max:.0f} MHz (clocks.max.sm); naive 1-POPC-per-word roof",
+                    "note": "frac > 1 because (a) a carry-save tree issues 4 POPC per 8 words and (b) all-zero 8-word spans "
+                            "are skipped (exact). dense_case = same launch with skipping disabled: every word-op executed.",
+                    "dense_case": {"pairs_per_s": qs * (hi - lo) / kd_s * world, "kernel_ms": kd_ms / K,
+                                   "achieved": word_ops / kd_s / 1e12, "frac_popc_roof": word_ops / kd_s / popc_peak,
+                                   "two_pipe_roof": two_pipe / 1e12, "frac_two_pipe_roof": word_ops / kd_s / two_pipe},
                     "hbm": {"algorithmic_bytes": hbm_alg, "achieved_GBps": hbm_alg / k_s / 1e9,
                             "peak_GBps": peaks.get("hbm_gbs", 6650.0),
                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}

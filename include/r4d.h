@@ -47,6 +47,13 @@ const char* r4d_last_error(void);
 /* 1 when a CUDA device of compute capability 10.x is visible, else 0 (never touches the device otherwise). */
 int r4d_device_ok(void);
 
+/* Tuning / measurement knobs (process-wide; defaults in brackets).  Returns the previous value, or R4D_E_ARG.
+ *   "jaccard_skip_zero" [1]  skip 8-word spans that are all-zero across a warp (exact; 0 = execute every word-op)
+ *   "jaccard_warps"     [16] consumer warps per CTA (8 or 16)
+ *   "dense_pair_kernel" [1]  use the CTA-pair (cta_group::2) kernel for bf16 top-K when it applies
+ *   "dense_pair_qres"   [-1] query tile resident in smem: -1 auto (when >= 4 pool stages fit), 0 never */
+int r4d_set_option(const char* key, int value);
+
 /* ---------------------------------------------------------------- set encoder (subsystem 1)
  * Replaces the per-pair `set(seq_i)`, `set(seq_j)` construction of co_occurrence_ratio
  * (retrieval_data_annotation.py:12-13): each row's token set becomes a fixed-width bitset. */

@@ -31,6 +31,7 @@ PROTOTYPES = {
     "r4d_version": (_c.c_int, []),
     "r4d_last_error": (_c.c_char_p, []),
     "r4d_device_ok": (_c.c_int, []),
+    "r4d_set_option": (_c.c_int, [_c.c_char_p, _c.c_int]),
     "r4d_bitset_words": (_i32, [_i32]),
     "r4d_bitset_pitch_words": (_i32, [_i32]),
     "r4d_bitset_encode": (_c.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
@@ -89,6 +90,14 @@ def last_error():
 def check(rc, what):
     if rc != 0:
         raise R4DError(f"{what} failed (rc={rc}): {last_error()}")
+
+
+def set_option(key, value):
+    """r4d_set_option: returns the previous value."""
+    prev = load().r4d_set_option(key.encode(), int(value))
+    if prev == R4D_E_ARG and key not in ("dense_pair_qres",):
+        raise R4DError(last_error())
+    return prev
 
 
 def require_device():

@@ -368,10 +368,7 @@ static Dense2Plan dense2_plan(int64_t nq, int64_t np, int32_t d_pad, int32_t k) 
     const long fixed = 22 * 8 + 16 + 2 * 256 * 4 + 64 + 256 * 4 + (long)k * 256 * 8;  // barriers, times, thr, lists
     pl.dpn = 256;
     const long q_bytes = (long)n_kblocks * Q_TILE_BYTES;
-    static const int force = [] {
-        const char* e = getenv("R4D_DENSE2_QRES");  // tuning knob: 0 = always stream, 1 = resident when it fits
-        return e ? atoi(e) : -1;
-    }();
+    const int force = options().dense_pair_qres;  // -1 auto, 0 never resident
     const long avail_res = total - fixed - q_bytes;
     pl.qres = avail_res >= 4 * 16384 && force != 0;
     if (pl.qres) {
@@ -413,11 +410,7 @@ static Dense2Plan dense2_plan(int64_t nq, int64_t np, int32_t d_pad, int32_t k) 
 
 // exported to dense.cu
 bool dense2_supported(int64_t nq, int64_t np, int32_t d_pad, int32_t prec, int32_t k) {
-    static const bool disabled = [] {
-        const char* e = getenv("R4D_DENSE_V1");
-        return e && atoi(e) != 0;
-    }();
-    if (disabled || prec != R4D_PREC_BF16) return false;
+    if (!options().dense_pair_kernel || prec != R4D_PREC_BF16) return false;
     return dense2_plan(nq, np, d_pad, k).ok;
 }
 

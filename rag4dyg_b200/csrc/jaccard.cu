@@ -94,7 +94,10 @@ constexpr size_t smem_bytes_for(int mode) {
 // No dedicated producer warp: registers are split per SM sub-partition (16 K each), so a 9th / 17th warp would put a
 // third / fifth warp on one scheduler and cut the per-thread budget to 168 / 96.  With exactly 8 or 16 warps the
 // budget is 255 / 128; lane 0 of warp 0 issues the TMA refills inline, two stages ahead of consumption.
-template <int MODE, int NCW>
+// SKIP: bitsets of real node-id sets are very sparse (2.2 of 20 000 bits set in the headline workload).  An 8-word
+// span whose query words are zero in every lane of the warp (one REDUX.OR), or whose pool words are zero in every lane
+// (one VOTE per pool row), contributes nothing, so its LDS / LOP3 / POPC work is skipped — results are identical.
+template <int MODE, int NCW, bool SKIP>
 __global__ void __launch_bounds__(32 * NCW, 1)
 jaccard_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_p,
                const JaccardParams prm) {
@@ -231,13 +234,32 @@ jaccard_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                         lds128(qa[i], ((i & 1) ? gq_o0 : gq_e0) + (uint32_t)i * 512u);
                         lds128(qb[i], ((i & 1) ? gq_o1 : gq_e1) + (uint32_t)i * 512u);
                     }
+                    uint32_t qmask = (1u << RQ) - 1u;  // bit i: some lane holds a non-zero query word for row slot i
+                    if (SKIP) {
+                        uint32_t mine = 0;
+#pragma unroll
+                        for (int i = 0; i < RQ; ++i) {
+                            const uint32_t nz = (qa[i].x | qa[i].y | qa[i].z) | (qa[i].w | qb[i].x | qb[i].y) | (qb[i].z | qb[i].w);
+                            mine |= (nz != 0u ? 1u : 0u) << i;
+                        }
+                        qmask = __reduce_or_sync(0xffffffffu, mine);
+                        if (qmask == 0u) continue;  // warp-uniform: nothing to intersect in this span
+                    }
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         uint4 pa, pb;
                         lds128(pa, gp0 + (uint32_t)j * 1024u);
                         lds128(pb, gp1 + (uint32_t)j * 1024u);
+                        if (SKIP) {
+                            const uint32_t pnz = (pa.x | pa.y | pa.z) | (pa.w | pb.x | pb.y) | (pb.z | pb.w);
+                            if (!__any_sync(0xffffffffu, pnz != 0u)) continue;
 #pragma unroll
-                        for (int i = 0; i < RQ; ++i) acc[i][j] += popc8_csa(qa[i], qb[i], pa, pb);
+                            for (int i = 0; i < RQ; ++i)
+                                if (qmask & (1u << i)) acc[i][j] += popc8_csa(qa[i], qb[i], pa, pb);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < RQ; ++i) acc[i][j] += popc8_csa(qa[i], qb[i], pa, pb);
+                        }
                     }
                 }
                 __syncwarp();
@@ -401,27 +423,22 @@ static int check_common(const uint32_t* qbits, const uint32_t* qcard, int64_t nq
     return R4D_OK;
 }
 
-static int consumer_warps() {
-    // debug / tuning knob; 16 warps (4 per scheduler) hide the AND->CSA->POPC dependency chains better
-    static int v = [] {
-        const char* e = getenv("R4D_JACCARD_WARPS");
-        return (e && atoi(e) == 8) ? 8 : 16;
-    }();
-    return v;
-}
+static int consumer_warps() { return options().jaccard_warps == 8 ? 8 : 16; }
 
-template <int MODE, int NCW>
+static bool skip_zero_spans() { return options().jaccard_skip_zero != 0; }
+
+template <int MODE, int NCW, bool SKIP>
 static int launch_ncw(const CUtensorMap& tm_q, const CUtensorMap& tm_p, const JaccardParams& prm, cudaStream_t st) {
     const size_t smem = smem_bytes_for(MODE);
-    static bool attr_done = false;
+    static bool attr_done = false;  // one flag per template instantiation
     if (!attr_done) {
-        R4D_CUDA(cudaFuncSetAttribute(jaccard_kernel<MODE, NCW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        R4D_CUDA(cudaFuncSetAttribute(jaccard_kernel<MODE, NCW, SKIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
     const int64_t n_items = (int64_t)prm.n_qtiles * prm.n_stripes;
     int grid = num_sms();
     if (n_items < grid) grid = (int)n_items;
-    jaccard_kernel<MODE, NCW><<<grid, 32 * NCW, smem, st>>>(tm_q, tm_p, prm);
+    jaccard_kernel<MODE, NCW, SKIP><<<grid, 32 * NCW, smem, st>>>(tm_q, tm_p, prm);
     R4D_CUDA(cudaGetLastError());
     return R4D_OK;
 }
@@ -439,7 +456,11 @@ static int launch(const uint32_t* qbits, int64_t nq, const uint32_t* pbits, int6
     prm.n_chunks = (words + CHUNK_WORDS - 1) / CHUNK_WORDS;
     const int rem = words - (prm.n_chunks - 1) * CHUNK_WORDS;  // 1..32 real words in the last chunk
     prm.last_groups = (rem + 3) / 4;
-    return consumer_warps() == 8 ? launch_ncw<MODE, 8>(tm_q, tm_p, prm, st) : launch_ncw<MODE, 16>(tm_q, tm_p, prm, st);
+    if (skip_zero_spans())
+        return consumer_warps() == 8 ? launch_ncw<MODE, 8, true>(tm_q, tm_p, prm, st)
+                                     : launch_ncw<MODE, 16, true>(tm_q, tm_p, prm, st);
+    return consumer_warps() == 8 ? launch_ncw<MODE, 8, false>(tm_q, tm_p, prm, st)
+                                 : launch_ncw<MODE, 16, false>(tm_q, tm_p, prm, st);
 }
 
 }  // namespace r4d

@@ -13,6 +13,14 @@ void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 int num_sms();  // SM count of the current device (cached)
 
+struct Options {
+    int jaccard_skip_zero = 1;
+    int jaccard_warps = 16;
+    int dense_pair_kernel = 1;
+    int dense_pair_qres = -1;
+};
+Options& options();  // process-wide knobs (r4d_set_option); environment variables R4D_* give the initial values
+
 #define R4D_CUDA(expr)                                                        \
     do {                                                                      \
         cudaError_t e__ = (expr);                                             \

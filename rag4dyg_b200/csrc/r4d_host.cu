@@ -1,6 +1,8 @@
 // r4d_host.cu — error plumbing, device probe, TMA descriptor factory.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 
 #include "r4d_common.cuh"
@@ -31,6 +33,18 @@ int num_sms() {
         cached[dev] = n;
     }
     return cached[dev];
+}
+
+Options& options() {
+    static Options o = [] {
+        Options v;
+        if (const char* e = getenv("R4D_JACCARD_NOSKIP")) v.jaccard_skip_zero = atoi(e) ? 0 : 1;
+        if (const char* e = getenv("R4D_JACCARD_WARPS")) v.jaccard_warps = atoi(e) == 8 ? 8 : 16;
+        if (const char* e = getenv("R4D_DENSE_V1")) v.dense_pair_kernel = atoi(e) ? 0 : 1;
+        if (const char* e = getenv("R4D_DENSE2_QRES")) v.dense_pair_qres = atoi(e);
+        return v;
+    }();
+    return o;
 }
 
 typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -84,6 +98,23 @@ extern "C" {
 int r4d_version(void) { return 100; }
 
 const char* r4d_last_error(void) { return r4d::g_err; }
+
+int r4d_set_option(const char* key, int value) {
+    if (!key) return R4D_E_ARG;
+    r4d::Options& o = r4d::options();
+    int* slot = nullptr;
+    if (!strcmp(key, "jaccard_skip_zero")) slot = &o.jaccard_skip_zero;
+    else if (!strcmp(key, "jaccard_warps")) slot = &o.jaccard_warps;
+    else if (!strcmp(key, "dense_pair_kernel")) slot = &o.dense_pair_kernel;
+    else if (!strcmp(key, "dense_pair_qres")) slot = &o.dense_pair_qres;
+    if (!slot || (slot == &o.jaccard_warps && value != 8 && value != 16)) {
+        r4d::set_error("r4d_set_option: unknown key or bad value (%s = %d)", key, value);
+        return R4D_E_ARG;
+    }
+    const int prev = *slot;
+    *slot = value;
+    return prev;
+}
 
 int r4d_device_ok(void) {
     int n = 0;

@@ -150,3 +150,29 @@ def test_synthetic_full_width_properties():
     assert np.all(np.diff(tx, axis=1)[same] > 0)
     oi, ou, ox = jo.c_topk(*to_csr(p[:300]), *to_csr(p), 10)
     assert np.array_equal(tx[:300], ox) and np.array_equal(ti[:300], oi) and np.array_equal(tu[:300], ou)
+
+
+@pytest.mark.parametrize("warps", [8, 16])
+def test_zero_span_skipping_and_warp_variants_are_exact(warps):
+    """Every kernel variant (8/16 consumer warps, zero-span skipping on/off) returns identical bits."""
+    from rag4dyg_b200 import _lib
+    rng = np.random.default_rng(77)
+    n_bits = 20000
+    q = random_sets(rng, 300, n_bits, mean=2.2) + random_sets(rng, 60, n_bits, mean=40, max_len=64)
+    p = random_sets(rng, 3000, n_bits, mean=2.2) + random_sets(rng, 500, n_bits, mean=40, max_len=64)
+    bq, bp = encode(q, n_bits), encode(p, n_bits)
+    prev_w = _lib.set_option("jaccard_warps", warps)
+    try:
+        outs = []
+        for skip in (1, 0):
+            _lib.set_option("jaccard_skip_zero", skip)
+            top = engine.jaccard_topk(bq, bp, 10)
+            inter, score = engine.jaccard_full(bq, bp)
+            outs.append([t.clone() for t in top] + [inter, score])
+        for a, b in zip(*outs):
+            assert torch.equal(a, b)
+        oi, ou, ox = jo.c_topk(*to_csr(q), *to_csr(p), 10)
+        assert np.array_equal(outs[0][2].cpu().numpy(), ox) and np.array_equal(outs[0][0].cpu().numpy(), oi)
+    finally:
+        _lib.set_option("jaccard_skip_zero", 1)
+        _lib.set_option("jaccard_warps", prev_w)
