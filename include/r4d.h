@@ -126,6 +126,13 @@ int r4d_triplet_mine_f64(const double* out, const double* in, int64_t n, int64_t
                          int32_t neg_num, int32_t* n_pos, int32_t* neg /*[n][neg_num]*/, int32_t* n_neg,
                          r4d_stream_t stream);
 
+/* Counter-based replacement of the sequential np.random.choice (:79) — NOT bit-compatible with numpy's RNG, offered
+ * as the deterministic device-side mode of SURVEY.md 8f-2.  For positive pair t (row pos_row[t], its rank within the
+ * row = t - row_start[row]): choice[t] = neg[row][splitmix64(seed, row, rank) % n_neg[row]] (or -1 if n_neg == 0).
+ * pos_row [n_pairs] and row_start [n_rows+1] are int64 [dev]. */
+int r4d_triplet_sample(const int64_t* pos_row, const int64_t* row_start, int64_t n_pairs, const int32_t* neg,
+                       const int32_t* n_neg, int32_t neg_num, uint64_t seed, int32_t* choice, r4d_stream_t stream);
+
 /* ---------------------------------------------------------------- dense scorer (subsystem 3)
  * Replaces the scoring block of test() (train/train_retriever.py:433-438) and, optionally, the
  * exp(-lambda*|dt|) factor of CLtime_loss (train/train_retriever.py:50-55).
@@ -152,9 +159,26 @@ int r4d_dense_full(const void* q_hi, const void* q_lo, int64_t nq, const void* p
                    int32_t d_pad, int32_t prec, const float* q_time, const float* p_time, float lambda,
                    int32_t mode, float* scores, int64_t ld, r4d_stream_t stream);
 
+/* Pool-embedding producer: hidden[batch][len][d] fp32 -> mean over the padded length
+ * (train/train_retriever.py:420, :432) -> L2-normalised bf16 planes exactly as r4d_dense_prepare would give for that
+ * mean; mean_out (nullable) receives the fp32 means [batch][d].  Deterministic (no float atomics). */
+size_t r4d_meanpool_workspace_bytes(int64_t batch, int32_t d);
+int r4d_meanpool_prepare(const float* hidden, int64_t batch, int32_t len, int32_t d, int32_t prec, float* mean_out,
+                         void* hi, void* lo, void* workspace, size_t workspace_bytes, r4d_stream_t stream);
+
 /* Merge [n_lists][nq][k_in] dense candidate lists into [nq][k_out] (score desc, index asc). */
 int r4d_dense_topk_merge(const float* score, const int32_t* idx, int32_t n_lists, int64_t nq, int32_t k_in,
                          int32_t k_out, float* out_score, int32_t* out_idx, r4d_stream_t stream);
+
+/* ---------------------------------------------------------------- host-side text formatters
+ * [host] pointers.  Produce the exact bytes of ' '.join(str(x) for x in row) + '\n' per row
+ * (retrieval_data_annotation.py:92-93,102-103; train/train_retriever.py:362-363).  Return bytes written (>= 0)
+ * or a negative error code.  r4d_format_lut_rows looks every element's text up in a caller-built table
+ * (lut_off has n_codes + 1 entries into lut_blob), so float formatting stays the reference's own. */
+size_t r4d_format_int_rows_bound(int64_t nq, int64_t n);
+int64_t r4d_format_int_rows(const int32_t* rows, int64_t nq, int64_t n, int64_t ld, char* out, size_t cap);
+int64_t r4d_format_lut_rows(const int32_t* codes, int64_t nq, int64_t n, int64_t ld, const char* lut_blob,
+                            const int64_t* lut_off, int32_t n_codes, char* out, size_t cap);
 
 #ifdef __cplusplus
 }

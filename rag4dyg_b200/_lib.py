@@ -46,6 +46,7 @@ PROTOTYPES = {
     "r4d_rank_rows_f32": (_c.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _sz, _vp]),
     "r4d_topk_rows_f64": (_c.c_int, [_vp, _i64, _i64, _i64, _i32, _vp, _vp, _vp]),
     "r4d_triplet_mine_f64": (_c.c_int, [_vp, _vp, _i64, _i64, _f64, _i32, _vp, _vp, _vp, _vp]),
+    "r4d_triplet_sample": (_c.c_int, [_vp, _vp, _i64, _vp, _vp, _i32, _c.c_uint64, _vp, _vp]),
     "r4d_dense_dpad": (_i32, [_i32]),
     "r4d_dense_prepare": (_c.c_int, [_vp, _i64, _i32, _i64, _i32, _vp, _vp, _vp]),
     "r4d_dense_topk_workspace_bytes": (_sz, [_i64, _i64, _i32]),
@@ -53,6 +54,11 @@ PROTOTYPES = {
                                   _vp, _vp, _sz, _vp]),
     "r4d_dense_full": (_c.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _f32, _i32, _vp, _i64, _vp]),
     "r4d_dense_topk_merge": (_c.c_int, [_vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp]),
+    "r4d_meanpool_workspace_bytes": (_sz, [_i64, _i32]),
+    "r4d_meanpool_prepare": (_c.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "r4d_format_int_rows_bound": (_sz, [_i64, _i64]),
+    "r4d_format_int_rows": (_i64, [_vp, _i64, _i64, _i64, _vp, _sz]),
+    "r4d_format_lut_rows": (_i64, [_vp, _i64, _i64, _i64, _vp, _vp, _i32, _vp, _sz]),
 }
 
 _lib = None

@@ -230,6 +230,33 @@ triplet_mine_f64_kernel(const double* __restrict__ out, const double* __restrict
     }
 }
 
+// ---------------------------------------------------------------------------- counter-based negative sampling
+// One thread per positive pair t: neg_choice[t] = neg[row][hash(seed, row, rank-of-t-within-row) % n_neg[row]].
+// Stateless (splitmix64 of a counter), so the triplet list no longer needs the host's sequential np.random.choice.
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9e3779b97f4a7c15ull;
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+    x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+    return x ^ (x >> 31);
+}
+
+__global__ void __launch_bounds__(256)
+triplet_sample_kernel(const int64_t* __restrict__ pos_row, const int64_t* __restrict__ row_start, int64_t n_pairs,
+                      const int32_t* __restrict__ neg, const int32_t* __restrict__ n_neg, int32_t neg_num, uint64_t seed,
+                      int32_t* __restrict__ choice) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_pairs; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = pos_row[t];
+        const int64_t rank = t - row_start[row];
+        const int32_t cnt = n_neg[row];
+        int32_t c = -1;
+        if (cnt > 0) {
+            const uint64_t h = splitmix64(splitmix64(seed ^ (uint64_t)row * 0xd6e8feb86659fd93ull) + (uint64_t)rank);
+            c = neg[row * neg_num + (int32_t)(h % (uint64_t)cnt)];
+        }
+        choice[t] = c;
+    }
+}
+
 template <class T>
 static int rank_rows_impl(const T* scores, int64_t nq, int64_t n, int64_t ld, int32_t* order, void* workspace,
                           size_t workspace_bytes, cudaStream_t st) {
@@ -283,6 +310,21 @@ int r4d_topk_rows_f64(const double* scores, int64_t nq, int64_t n, int64_t ld, i
     const int64_t cap = (int64_t)num_sms() * 16;
     if (blocks > cap) blocks = cap;
     topk_rows_f64_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(scores, nq, n, ld, k, top_score, top_idx);
+    R4D_CUDA(cudaGetLastError());
+    return R4D_OK;
+}
+
+int r4d_triplet_sample(const int64_t* pos_row, const int64_t* row_start, int64_t n_pairs, const int32_t* neg,
+                       const int32_t* n_neg, int32_t neg_num, uint64_t seed, int32_t* choice, r4d_stream_t stream) {
+    using namespace r4d;
+    R4D_REQUIRE(n_pairs >= 0 && neg_num >= 1, "triplet_sample: n_pairs=%lld neg_num=%d", (long long)n_pairs, neg_num);
+    if (n_pairs == 0) return R4D_OK;
+    R4D_REQUIRE(pos_row && row_start && neg && n_neg && choice, "triplet_sample: null pointer");
+    int64_t blocks = (n_pairs + 255) / 256;
+    const int64_t cap = (int64_t)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    triplet_sample_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(pos_row, row_start, n_pairs, neg, n_neg, neg_num,
+                                                                         seed, choice);
     R4D_CUDA(cudaGetLastError());
     return R4D_OK;
 }

@@ -13,7 +13,7 @@ from ._lib import (DENSE_COS_DECAY, DENSE_HALF_COS, DENSE_HALF_COS_DECAY, PREC_B
 
 __all__ = [
     "BitsetMatrix", "encode_bitsets", "jaccard_full", "jaccard_topk", "jaccard_topk_merge", "rank_rows", "topk_rows",
-    "triplet_mine", "DensePlanes", "dense_prepare", "dense_topk", "dense_full", "dense_topk_merge", "R4D_IDX_NONE",
+    "triplet_mine", "triplet_sample", "DensePlanes", "dense_prepare", "dense_topk", "dense_full", "dense_topk_merge", "meanpool_prepare", "R4D_IDX_NONE",
     "R4D_TOPK_MAX", "DENSE_HALF_COS", "DENSE_COS_DECAY", "DENSE_HALF_COS_DECAY", "PREC_BF16", "PREC_BF16X3",
     "launch_count", "reset_launch_count",
 ]
@@ -197,6 +197,21 @@ def triplet_mine(out, inn, thr, neg_num):
     return n_pos, neg, n_neg
 
 
+def triplet_sample(pos_row, row_start, neg, n_neg, seed):
+    """Counter-based negative choice per positive pair (r4d_triplet_sample): int32 [n_pairs]."""
+    lib = _lib.load()
+    pos_row = _dev_tensor(pos_row, torch.int64, "pos_row")
+    row_start = _dev_tensor(row_start, torch.int64, "row_start")
+    neg = _dev_tensor(neg, torch.int32, "neg")
+    n_neg = _dev_tensor(n_neg, torch.int32, "n_neg")
+    n_pairs = pos_row.numel()
+    choice = torch.empty((n_pairs,), dtype=torch.int32, device=pos_row.device)
+    check(lib.r4d_triplet_sample(_ptr(pos_row), _ptr(row_start), n_pairs, _ptr(neg), _ptr(n_neg), neg.shape[1],
+                                 int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(choice), _stream()), "r4d_triplet_sample")
+    _count(1 if n_pairs else 0)
+    return choice
+
+
 # ---------------------------------------------------------------------------------------------- dense scorer
 @dataclass
 class DensePlanes:
@@ -227,6 +242,24 @@ def dense_prepare(x, prec=PREC_BF16X3):
     check(lib.r4d_dense_prepare(_ptr(x), n, d, d, prec, _ptr(hi), _ptr(lo), _stream()), "r4d_dense_prepare")
     _count(1 if n else 0)
     return DensePlanes(hi, lo, d, d_pad, prec)
+
+
+def meanpool_prepare(hidden, prec=PREC_BF16X3, want_mean=False):
+    """hidden fp32 [B, L, D] -> (DensePlanes of the L2-normalised mean over L, fp32 means or None).
+    r4d_meanpool_prepare: replaces torch.mean(h, dim=1) + per-batch normalisation (train_retriever.py:420,433)."""
+    lib = _lib.load()
+    hidden = _dev_tensor(hidden, torch.float32, "hidden")
+    b, l, d = hidden.shape
+    d_pad = lib.r4d_dense_dpad(d)
+    dev = hidden.device
+    hi = torch.empty((b, d_pad), dtype=torch.bfloat16, device=dev)
+    lo = torch.empty((b, d_pad), dtype=torch.bfloat16, device=dev) if prec == PREC_BF16X3 else None
+    mean = torch.empty((b, d), dtype=torch.float32, device=dev) if want_mean else None
+    ws = torch.empty((lib.r4d_meanpool_workspace_bytes(b, d),), dtype=torch.uint8, device=dev)
+    check(lib.r4d_meanpool_prepare(_ptr(hidden), b, l, d, prec, _ptr(mean), _ptr(hi), _ptr(lo), _ptr(ws), ws.numel(),
+                                   _stream()), "r4d_meanpool_prepare")
+    _count(2 if b else 0)
+    return DensePlanes(hi, lo, d, d_pad, prec), mean
 
 
 def _check_dense(q, p, q_time, p_time, mode):

@@ -111,10 +111,38 @@ def _write_triplets(save_file, save_file_score, n_rows, pos_rows, pos_cols, pos_
     print("Number of positive samples:", cnt)
 
 
-def _mine_and_write(out_d, in_d, save_file, save_file_score, threshold, neg_num):
+def _device_sampled_triplets(out_d, pos, neg, n_neg, save_file, save_file_score, seed):
+    """sampler="counter": the whole triplet list is produced on the device (r4d_triplet_sample) and written by the
+    native formatters.  Deterministic in `seed`, NOT the numpy stream."""
+    n = out_d.shape[0]
+    rows, cols = pos[:, 0].contiguous(), pos[:, 1].contiguous()
+    if "dialog" in dataset:  # noqa: F821  (:73-74) keep the first 4 positives of every row
+        start = torch.searchsorted(rows, torch.arange(n + 1, device=rows.device))
+        keep = (torch.arange(rows.numel(), device=rows.device) - start[rows]) < 4
+        rows, cols = rows[keep].contiguous(), cols[keep].contiguous()
+    row_start = torch.searchsorted(rows, torch.arange(n + 1, device=rows.device)).contiguous()
+    choice = engine.triplet_sample(rows, row_start, neg, n_neg, seed)
+    if bool((choice < 0).any()):
+        raise ValueError("'a' cannot be empty unless no samples are taken")  # np.random.choice([]) in the reference
+    s_pos = out_d[rows, cols]
+    s_neg = out_d[rows, choice.long()]
+    trip = torch.stack([rows.int(), cols.int(), choice], dim=1).cpu().numpy()
+    writers.write_int_rows(save_file, trip)
+    sp, sn = s_pos.cpu().numpy(), s_neg.cpu().numpy()
+    with open(save_file_score, "w") as g:
+        for t in range(trip.shape[0]):
+            g.write(f"{trip[t, 0]} {writers.fmt_str(sp[t])} {writers.fmt_str(sn[t])}\n")
+    print("Number of original instances:", n)
+    print("Number of positive samples:", trip.shape[0])
+
+
+def _mine_and_write(out_d, in_d, save_file, save_file_score, threshold, neg_num, sampler="numpy", seed=0):
     n = out_d.shape[0]
     n_pos, neg, n_neg = engine.triplet_mine(out_d, in_d, threshold, neg_num)
     pos = torch.nonzero(out_d > threshold)  # row-major == np.where per row in ascending order (:54)
+    if sampler == "counter":
+        _device_sampled_triplets(out_d, pos, neg, n_neg, save_file, save_file_score, seed)
+        return n_pos
     pos_scores = out_d[pos[:, 0], pos[:, 1]]
     neg_scores = torch.gather(out_d, 1, neg.clamp(min=0).to(torch.int64))
     pos_h = pos.cpu().numpy()
@@ -123,10 +151,12 @@ def _mine_and_write(out_d, in_d, save_file, save_file_score, threshold, neg_num)
     return n_pos
 
 
-def save_train_annotation(scores_matrix, scores_matrix_in, save_file, save_file_score, threshold=0.8, neg_num=5):
-    """Positive / negative triplets for the retriever (reference :43-85).  Matrices may be numpy or CUDA tensors."""
+def save_train_annotation(scores_matrix, scores_matrix_in, save_file, save_file_score, threshold=0.8, neg_num=5,
+                          sampler="numpy", seed=0):
+    """Positive / negative triplets for the retriever (reference :43-85).  Matrices may be numpy or CUDA tensors.
+    sampler="numpy" replays the reference's np.random.choice stream (parity); "counter" samples on the device."""
     _mine_and_write(_to_device_f64(scores_matrix), _to_device_f64(scores_matrix_in), save_file, save_file_score,
-                    threshold, neg_num)
+                    threshold, neg_num, sampler, seed)
 
 
 def save_index_score(score_matrix, save_index_file, save_score_file):

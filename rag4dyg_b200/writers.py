@@ -5,28 +5,34 @@ The reference formats every score with `str(np.float64)` (shortest round-trip re
 matrices hold few distinct values (hard part 6), so each distinct value is formatted once with the
 reference's own formatter and rows are assembled by table lookup.
 """
+import ctypes
+
 import numpy as np
 
-_INT_LUT = np.empty(0, dtype=object)
+from . import _lib
 
-
-def _int_strings(n):
-    """object array with str(i) for i < n (grown on demand)."""
-    global _INT_LUT
-    if _INT_LUT.shape[0] < n:
-        _INT_LUT = np.array([str(i) for i in range(n)], dtype=object)
-    return _INT_LUT
+_CHUNK_BYTES = 64 << 20  # formatting buffer per call into the native formatter
 
 
 def write_int_rows(path, rows, mode="w"):
-    """Each row of the 2-D integer array as space separated decimals (== ' '.join(str(x) for x in row))."""
-    rows = np.asarray(rows)
-    if rows.size and rows.min() < 0:
-        raise ValueError("negative index in an index file")
-    lut = _int_strings(int(rows.max()) + 1 if rows.size else 0)
-    with open(path, mode) as f:
-        for r in rows:
-            f.write(" ".join(lut[r].tolist()) + "\n")
+    """Each row of the 2-D integer array as space separated decimals (== ' '.join(str(x) for x in row)),
+    formatted by the native r4d_format_int_rows."""
+    lib = _lib.load()
+    rows = np.ascontiguousarray(rows, dtype=np.int32)
+    if rows.ndim != 2:
+        raise ValueError("write_int_rows expects a 2-D array")
+    nq, n = rows.shape
+    per_row = max(1, n * 12 + 1)
+    step = max(1, _CHUNK_BYTES // per_row)
+    with open(path, mode + "b") as f:
+        for r0 in range(0, nq, step):
+            blk = rows[r0:r0 + step]
+            cap = lib.r4d_format_int_rows_bound(blk.shape[0], n)
+            buf = ctypes.create_string_buffer(cap)
+            got = lib.r4d_format_int_rows(blk.ctypes.data, blk.shape[0], n, n, ctypes.addressof(buf), cap)
+            if got < 0:
+                raise _lib.R4DError(f"r4d_format_int_rows failed ({got}): {_lib.last_error()}")
+            f.write(memoryview(buf)[:got])
 
 
 def _float_codes(mat, fmt):
@@ -55,11 +61,32 @@ def fmt_4f(v):
 
 
 def write_float_rows(path, mat, fmt=fmt_str, mode="w"):
+    """Rows of floats as text.  Every DISTINCT value is formatted once with `fmt` (the reference's own formatter), the
+    rows are assembled by the native r4d_format_lut_rows."""
+    lib = _lib.load()
     mat = np.asarray(mat)
+    if mat.ndim != 2:
+        raise ValueError("write_float_rows expects a 2-D array")
     codes, strings = _float_codes(mat, fmt)
-    with open(path, mode) as f:
-        for r in codes:
-            f.write(" ".join(strings[r].tolist()) + "\n")
+    codes = np.ascontiguousarray(codes, dtype=np.int32)
+    enc = [s.encode("ascii") for s in strings.tolist()]
+    off = np.zeros(len(enc) + 1, dtype=np.int64)
+    np.cumsum([len(e) for e in enc], out=off[1:])
+    blob = b"".join(enc)
+    max_len = max((len(e) for e in enc), default=1)
+    nq, n = codes.shape
+    per_row = max(1, n * (max_len + 1) + 1)
+    step = max(1, _CHUNK_BYTES // per_row)
+    with open(path, mode + "b") as f:
+        for r0 in range(0, nq, step):
+            blk = codes[r0:r0 + step]
+            cap = blk.shape[0] * per_row + 1
+            buf = ctypes.create_string_buffer(cap)
+            got = lib.r4d_format_lut_rows(blk.ctypes.data, blk.shape[0], n, n, blob, off.ctypes.data, len(enc),
+                                          ctypes.addressof(buf), cap)
+            if got < 0:
+                raise _lib.R4DError(f"r4d_format_lut_rows failed ({got}): {_lib.last_error()}")
+            f.write(memoryview(buf)[:got])
 
 
 def jaccard_scores_f64(inter, union):
