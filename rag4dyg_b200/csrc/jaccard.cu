@@ -517,6 +517,8 @@ int r4d_jaccard_topk(const uint32_t* qbits, const uint32_t* qcard, int64_t nq, c
     if (nq == 0) return R4D_OK;
     R4D_REQUIRE(top_inter && top_union && top_idx, "jaccard_topk: null output");
     cudaStream_t st = as_stream(stream);
+    if (np == 0)  // no pool rows: every list is padding; the merge of zero lists writes it, no workspace needed
+        return r4d_jaccard_topk_merge(nullptr, nullptr, nullptr, 0, nq, k, k, top_inter, top_union, top_idx, stream);
     const JaccardPlan pl = plan_topk(nq, np);
     const size_t per = (size_t)pl.n_stripes * (size_t)nq * (size_t)k;
     if (workspace_bytes < per * 12 || (!workspace && per)) {
@@ -539,11 +541,6 @@ int r4d_jaccard_topk(const uint32_t* qbits, const uint32_t* qcard, int64_t nq, c
     prm.part_inter = reinterpret_cast<uint32_t*>(workspace);
     prm.part_union = prm.part_inter + per;
     prm.part_idx = reinterpret_cast<int32_t*>(prm.part_union + per);
-    if (np == 0) {
-        // no pool rows: every list is padding; the merge of zero lists writes it
-        return r4d_jaccard_topk_merge(prm.part_inter, prm.part_union, prm.part_idx, 0, nq, k, k, top_inter, top_union,
-                                      top_idx, stream);
-    }
     rc = launch<MODE_TOPK>(qbits, nq, pbits, np, words, pitch_words, prm, st);
     if (rc) return rc;
     return r4d_jaccard_topk_merge(prm.part_inter, prm.part_union, prm.part_idx, pl.n_stripes, nq, k, k, top_inter,
