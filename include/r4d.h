@@ -51,7 +51,8 @@ int r4d_device_ok(void);
  *   "jaccard_skip_zero" [1]  skip 8-word spans that are all-zero across a warp (exact; 0 = execute every word-op)
  *   "jaccard_warps"     [16] consumer warps per CTA (8 or 16)
  *   "dense_pair_kernel" [1]  use the CTA-pair (cta_group::2) kernel for bf16 top-K when it applies
- *   "dense_pair_qres"   [-1] query tile resident in smem: -1 auto (when >= 4 pool stages fit), 0 never */
+ *   "dense_pair_qres"   [-1] query tile resident in smem: -1 auto (when >= 4 pool stages fit), 0 never
+ *   "stripe_interleave" [1]  dense pair kernel: stripe s owns pool tiles s, s+S, s+2S, ... (0: contiguous stripes) */
 int r4d_set_option(const char* key, int value);
 
 /* ---------------------------------------------------------------- set encoder (subsystem 1)

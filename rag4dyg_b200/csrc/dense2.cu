@@ -40,6 +40,7 @@ struct Dense2Params {
     const float* q_time;
     const float* p_time;
     int32_t n_qpairs, n_ptiles, n_stripes, ptiles_per_stripe;
+    int32_t interleave;  // 1: stripe s owns tiles s, s+S, ...; 0: tiles [s*T, (s+1)*T)
     float* part_score;  // [2*n_stripes][nq][k]
     int32_t* part_idx;
 };
@@ -175,9 +176,10 @@ dense2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
             const uint32_t qfull_leader = mapa_shared(smem_u32(qfull_bar), 0);
             for (int item = cluster_id; item < n_items; item += n_clusters, ++item_seq) {
                 const int stripe = item / prm.n_qpairs;
+                const int pt_step = prm.interleave ? prm.n_stripes : 1;
+                const int pt0 = prm.interleave ? stripe : stripe * prm.ptiles_per_stripe;
+                const int pt_lim = prm.interleave ? prm.n_ptiles : min(pt0 + prm.ptiles_per_stripe, prm.n_ptiles);
                 const int qtile = (item - stripe * prm.n_qpairs) * 2 + (int)rank;
-                const int pt_beg = stripe * prm.ptiles_per_stripe;
-                const int pt_end = min(pt_beg + prm.ptiles_per_stripe, prm.n_ptiles);
                 if (QRES) {
                     // resident query tile: wait until the previous item's MMAs have released it
                     mbar_wait(qempty_bar, (item_seq & 1u) ^ 1u);
@@ -186,7 +188,7 @@ dense2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                         tma_load_2d_2sm(smem_u32(q_res + (size_t)kb * Q_TILE_BYTES), &tm_q, qfull_leader, kb * DKB,
                                         qtile * DQ);
                 }
-                for (int pt = pt_beg; pt < pt_end; ++pt) {
+                for (int pt = pt0; pt < pt_lim; pt += pt_step) {
                     for (int kb = 0; kb < prm.n_kblocks; ++kb) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[stage]), 0);
@@ -212,14 +214,15 @@ dense2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
             uint32_t phase = 0, tile_seq = 0, item_seq = 0;
             for (int item = cluster_id; item < n_items; item += n_clusters, ++item_seq) {
                 const int stripe = item / prm.n_qpairs;
-                const int pt_beg = stripe * prm.ptiles_per_stripe;
-                const int pt_end = min(pt_beg + prm.ptiles_per_stripe, prm.n_ptiles);
+                const int pt_step = prm.interleave ? prm.n_stripes : 1;
+                const int pt0 = prm.interleave ? stripe : stripe * prm.ptiles_per_stripe;
+                const int pt_lim = prm.interleave ? prm.n_ptiles : min(pt0 + prm.ptiles_per_stripe, prm.n_ptiles);
                 if (QRES) {
                     mbar_wait(qfull_bar, item_seq & 1u);  // both CTAs' query tiles have landed
                     tc_fence_after();
                 }
                 const uint32_t qbase = smem_u32(q_res);
-                for (int pt = pt_beg; pt < pt_end; ++pt, ++tile_seq) {
+                for (int pt = pt0; pt < pt_lim; pt += pt_step, ++tile_seq) {
                     const uint32_t buf = tile_seq & 1u;
                     mbar_wait(&tempty_bar[buf], ((tile_seq >> 1) & 1u) ^ 1u);
                     tc_fence_after();
@@ -260,9 +263,10 @@ dense2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
 
         for (int item = cluster_id; item < n_items; item += n_clusters) {
             const int stripe = item / prm.n_qpairs;
+                const int pt_step = prm.interleave ? prm.n_stripes : 1;
+                const int pt0 = prm.interleave ? stripe : stripe * prm.ptiles_per_stripe;
+                const int pt_lim = prm.interleave ? prm.n_ptiles : min(pt0 + prm.ptiles_per_stripe, prm.n_ptiles);
             const int qtile = (item - stripe * prm.n_qpairs) * 2 + (int)rank;
-            const int pt_beg = stripe * prm.ptiles_per_stripe;
-            const int pt_end = min(pt_beg + prm.ptiles_per_stripe, prm.n_ptiles);
             const int64_t gq = (int64_t)qtile * DQ + row_in_tile;
             const bool q_ok = gq < prm.nq;
             const float tq = (prm.mode != R4D_DENSE_HALF_COS && q_ok) ? prm.q_time[gq] : 0.f;
@@ -280,7 +284,7 @@ dense2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
             const float* thr_partner = thr_s + ((half ^ 1) * 128 + row_in_tile);
             // decay in (0, 1] lets the raw cosine bound every score of a chunk from above (lambda >= 0 only)
             const bool can_bound = prm.neg_lambda_log2e <= 0.f;
-            for (int pt = pt_beg; pt < pt_end; ++pt, ++tile_seq) {
+            for (int pt = pt0; pt < pt_lim; pt += pt_step, ++tile_seq) {
                 const uint32_t buf = tile_seq & 1u;
                 if (prm.mode != R4D_DENSE_HALF_COS) {
                     if (etid < DPN) {
@@ -451,6 +455,7 @@ int dense2_topk(const void* q_hi, int64_t nq, const void* p_hi, int64_t np, int3
     prm.n_ptiles = pl.n_ptiles;
     prm.n_stripes = pl.n_stripes;
     prm.ptiles_per_stripe = pl.ptiles_per_stripe;
+    prm.interleave = options().stripe_interleave ? 1 : 0;
     prm.part_score = part_score;
     prm.part_idx = part_idx;
     const size_t smem = pl.smem;

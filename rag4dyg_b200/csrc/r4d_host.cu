@@ -107,6 +107,7 @@ int r4d_set_option(const char* key, int value) {
     else if (!strcmp(key, "jaccard_warps")) slot = &o.jaccard_warps;
     else if (!strcmp(key, "dense_pair_kernel")) slot = &o.dense_pair_kernel;
     else if (!strcmp(key, "dense_pair_qres")) slot = &o.dense_pair_qres;
+    else if (!strcmp(key, "stripe_interleave")) slot = &o.stripe_interleave;
     if (!slot || (slot == &o.jaccard_warps && value != 8 && value != 16)) {
         r4d::set_error("r4d_set_option: unknown key or bad value (%s = %d)", key, value);
         return R4D_E_ARG;
