@@ -235,6 +235,17 @@ def main():
         peaks = json.load(open(pk))
     scorers = args.scorers.split(",")
     K, W = args.steps, args.warmup
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp))
+
+    def dram_traffic(key, **cfg):
+        # ncu-measured DRAM bytes per launch; only valid for the exact configuration it was captured on
+        t = traffic.get(key)
+        if t and all(t.get(k) == v for k, v in cfg.items()):
+            return t["dram_bytes"]
+        return None
 
     def barrier():
         if world > 1:
@@ -310,7 +321,8 @@ def main():
         hbm_alg = ((hi - lo) + qs) * words * 4 + qs * TOPK * 12  # compulsory bytes per launch
         roofline = {"bound": "int-pipe (the path is neither HBM- nor tensor-bound, SURVEY.md 8d)",
                     "achieved": word_ops / k_s / 1e12, "peak": popc_peak / 1e12, "unit": "T word-op/s (32-bit AND+POPC, algorithmic W per pair)",
-                    "frac": word_ops / k_s / popc_peak, "traffic": None,
+                    "frac": word_ops / k_s / popc_peak,
+                    "traffic": dram_traffic("jaccard_topk", queries=qs, pool=hi - lo) if world == 1 else None,
                     "kernel": "r4d::jaccard_kernel<MODE_TOPK, 16 warps, SKIP>", "kernel_ms": k_ms / K,
                     "peak_source": f"148 SM x 16 POPC/clk x {sm_max:.0f} MHz (clocks.max.sm); naive 1-POPC-per-word roof",
                     "note": "frac > 1 because (a) a carry-save tree issues 4 POPC per 8 words and (b) all-zero 8-word spans "
@@ -416,7 +428,9 @@ def main():
         flops = 2.0 * DENSE_D * qs * (hi - lo)
         peak_tf = peaks.get("bf16_tflops", 1590.0)
         d_roof = {"bound": "tensor", "achieved": flops / dk_s / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
-                  "frac": flops / dk_s / 1e12 / peak_tf, "traffic": None, "kernel": "r4d::dense_kernel<DMODE_TOPK>",
+                  "frac": flops / dk_s / 1e12 / peak_tf,
+                  "traffic": dram_traffic("dense_topk", queries=qs, pool=hi - lo, d=DENSE_D) if world == 1 else None,
+                  "kernel": "r4d::dense2_kernel<256, streaming> (CTA pair, tcgen05.mma.cta_group::2)",
                   "kernel_ms": dk_ms / K,
                   "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1.59 PFLOP/s"}
         d_e2e = None

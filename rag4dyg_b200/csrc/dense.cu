@@ -103,7 +103,9 @@ dense_kernel(const __grid_constant__ CUtensorMap tm_qh, const __grid_constant__ 
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const int stripe = item / prm.n_qtiles;
                 const int qtile = item - stripe * prm.n_qtiles;
-                for (int pt = stripe; pt < prm.n_ptiles; pt += prm.n_stripes) {
+                const int pt_beg = stripe * prm.ptiles_per_stripe;
+                const int pt_end = min(pt_beg + prm.ptiles_per_stripe, prm.n_ptiles);
+                for (int pt = pt_beg; pt < pt_end; ++pt) {
                     for (int kb = 0; kb < prm.n_kblocks; ++kb) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* dst = stages + (size_t)stage * prm.stage_bytes;
@@ -135,7 +137,9 @@ dense_kernel(const __grid_constant__ CUtensorMap tm_qh, const __grid_constant__ 
             uint32_t tile_seq = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const int stripe = item / prm.n_qtiles;
-                for (int pt = stripe; pt < prm.n_ptiles; pt += prm.n_stripes, ++tile_seq) {
+                const int pt_beg = stripe * prm.ptiles_per_stripe;
+                const int pt_end = min(pt_beg + prm.ptiles_per_stripe, prm.n_ptiles);
+                for (int pt = pt_beg; pt < pt_end; ++pt, ++tile_seq) {
                     const uint32_t buf = tile_seq & 1u;
                     mbar_wait(&tempty_bar[buf], ((tile_seq >> 1) & 1u) ^ 1u);
                     tc_fence_after();
@@ -188,6 +192,8 @@ dense_kernel(const __grid_constant__ CUtensorMap tm_qh, const __grid_constant__ 
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int stripe = item / prm.n_qtiles;
             const int qtile = item - stripe * prm.n_qtiles;
+            const int pt_beg = stripe * prm.ptiles_per_stripe;
+            const int pt_end = min(pt_beg + prm.ptiles_per_stripe, prm.n_ptiles);
             const int64_t gq = (int64_t)qtile * DQ + row_in_tile;
             const bool q_ok = gq < prm.nq;
             const float tq = (prm.mode != R4D_DENSE_HALF_COS && q_ok) ? prm.q_time[gq] : 0.f;
@@ -198,7 +204,7 @@ dense_kernel(const __grid_constant__ CUtensorMap tm_qh, const __grid_constant__ 
                     li[t * D_EPI_THREADS] = R4D_IDX_NONE;
                 }
             }
-            for (int pt = stripe; pt < prm.n_ptiles; pt += prm.n_stripes, ++tile_seq) {
+            for (int pt = pt_beg; pt < pt_end; ++pt, ++tile_seq) {
                 const uint32_t buf = tile_seq & 1u;
                 if (prm.mode != R4D_DENSE_HALF_COS) {
                     // stage this tile's 256 pool times for broadcast reads

@@ -5,8 +5,7 @@
 //
 // Design (B200, sm_100a)
 //  * CTA tile 128 queries x 128 pool rows, persistent CTAs (one per SM) walking a static list of
-//    (pool stripe, query tile) work items.  Stripes are INTERLEAVED (stripe s owns pool tiles s, s+S, s+2S, ...), so
-//    all CTAs sweep the pool front to back together and each pool tile is fetched from HBM once and then hits L2.
+//    (pool stripe, query tile) work items.
 //  * TMA: per 32-word chunk two cp.async.bulk.tensor.2d loads (128 rows x 128 B, SWIZZLE_128B) land in a 3-stage
 //    smem ring guarded by full/empty mbarriers; one elected consumer lane issues them two stages ahead.
 //  * 8 or 16 consumer warps: each thread owns an 8x8 (or 4x8) micro-tile of intersection counters; per pair of
@@ -137,13 +136,14 @@ jaccard_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     // The loads of this CTA form one linear stream of chunks (item -> pool tile -> 32-word chunk); the cursor below
     // walks it NSTAGES-1 chunks ahead of the consumers.
     const bool is_producer = threadIdx.x == 0;
-    int p_item = blockIdx.x, p_qtile = 0, p_pt = 0, p_c = 0, p_stage = 0;
+    int p_item = blockIdx.x, p_qtile = 0, p_pt = 0, p_pt_end = 0, p_c = 0, p_stage = 0;
     uint32_t p_phase = 0;
     auto p_open_item = [&]() {
         if (p_item < n_items) {
             const int stripe = p_item / prm.n_qtiles;
             p_qtile = p_item - stripe * prm.n_qtiles;
-            p_pt = stripe;  // interleaved stripes: stripe s owns pool tiles s, s + n_stripes, s + 2 n_stripes, ...
+            p_pt = stripe * prm.ptiles_per_stripe;
+            p_pt_end = min(p_pt + prm.ptiles_per_stripe, prm.n_ptiles);
             p_c = 0;
         }
     };
@@ -160,7 +160,7 @@ jaccard_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         }
         if (++p_c == prm.n_chunks) {
             p_c = 0;
-            if ((p_pt += prm.n_stripes) >= prm.n_ptiles) {
+            if (++p_pt == p_pt_end) {
                 p_item += gridDim.x;
                 p_open_item();
             }
@@ -191,6 +191,8 @@ jaccard_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int stripe = item / prm.n_qtiles;
         const int qtile = item - stripe * prm.n_qtiles;
+        const int pt_beg = stripe * prm.ptiles_per_stripe;
+        const int pt_end = min(pt_beg + prm.ptiles_per_stripe, prm.n_ptiles);
 
         if (MODE == MODE_TOPK) {
             // reset the lists this warp owns
@@ -203,7 +205,7 @@ jaccard_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             __syncwarp();
         }
 
-        for (int pt = stripe; pt < prm.n_ptiles; pt += prm.n_stripes) {
+        for (int pt = pt_beg; pt < pt_end; ++pt) {
             uint32_t acc[RQ][8];
 #pragma unroll
             for (int i = 0; i < RQ; ++i)
