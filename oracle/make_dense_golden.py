@@ -33,10 +33,23 @@ def stub(name, **attrs):
     return m
 
 
-def main():
+# per-dataset retriever configuration: scripts/train_retriever/train_retriever_{UCI_13,hepth,dialog}.sh
+CONFIGS = {
+    "UCI_13": dict(T="12", n_layer=4, n_head=2, n_embed=512, block=512, pool_rows=None, query_rows=None),
+    "hepth": dict(T="11", n_layer=12, n_head=2, n_embed=256, block=1024, pool_rows=1500, query_rows=128),
+    "dialog": dict(T="15", n_layer=2, n_head=2, n_embed=256, block=1024, pool_rows=1500, query_rows=128),
+}
+
+
+def main(ds="UCI_13"):
+    cfg = CONFIGS[ds]
+    T = cfg["T"]
     scratch = tempfile.mkdtemp(prefix="r4d_dense_golden_")
-    os.makedirs(os.path.join(scratch, "resources", "UCI_13"), exist_ok=True)
-    shutil.copytree(os.path.join(REF, "resources", "UCI_13", "12"), os.path.join(scratch, "resources", "UCI_13", "12"))
+    os.makedirs(os.path.join(scratch, "resources", ds), exist_ok=True)
+    shutil.copytree(os.path.join(REF, "resources", ds, T), os.path.join(scratch, "resources", ds, T))
+    if ds == "hepth":
+        shutil.copy(os.path.join(REF, "resources", "hepth", "node_features.npy"), os.path.join(scratch, "resources", "hepth"))
+        torch.Tensor.cuda = lambda self, *a, **k: self   # utils/tokenizer.py:62 hard-codes .cuda(); no GPU here
     shutil.copytree(os.path.join(REF, "vocabs"), os.path.join(scratch, "vocabs"))
     os.chdir(scratch)
 
@@ -74,8 +87,9 @@ def main():
     from torch.nn.utils.rnn import pad_sequence
 
     args = types.SimpleNamespace(model_type="gpt2", config_name=None, model_name_or_path=None, cache_dir=None,
-                                 n_head=2, n_layer=4, n_embed=512, eta=0.8, gamma=0.4, beta=0.0, timestamp="12",
-                                 dataset="UCI_13", device="cpu", node_feat_file=None)
+                                 n_head=cfg["n_head"], n_layer=cfg["n_layer"], n_embed=cfg["n_embed"], eta=0.8,
+                                 gamma=0.4, beta=0.0, timestamp=T, dataset=ds, device="cpu",
+                                 node_feat_file=os.path.join("resources", "hepth", "node_features.npy"))
     torch.manual_seed(42)
     model, tokenizer, _, args = get_model_tokenizer(args, {"gpt2": (GPT2Config, GPT2LMHeadModel, GPT2Tokenizer)})
     model.eval()
@@ -86,7 +100,7 @@ def main():
 
     def embed(lines):
         # dataloader/retriever.py:23 (batch_encode_plus was removed in transformers 5: tokenizer(...) gives the same ids)
-        ids = tokenizer(lines, add_special_tokens=True, max_length=512, truncation="longest_first")["input_ids"]
+        ids = tokenizer(lines, add_special_tokens=True, max_length=cfg["block"], truncation="longest_first")["input_ids"]
         out = []
         for b0 in range(0, len(ids), 32):                      # per_gpu_eval_batch_size default 32, SequentialSampler
             batch = [torch.tensor(x, dtype=torch.long) for x in ids[b0:b0 + 32]]
@@ -96,9 +110,11 @@ def main():
                 out.append(torch.mean(h, dim=1))               # :420 mean over the PADDED length
         return torch.cat(out, dim=0)
 
-    base = os.path.join("resources", "UCI_13", "12")
+    base = os.path.join("resources", ds, T)
     train_lines = [ln.split("<|pre|>")[0].strip() for ln in read(os.path.join(base, "train.link_prediction"))]  # :51
     test_lines = read(os.path.join(base, "test.link_prediction"))
+    if cfg["pool_rows"]:      # larger datasets: a prefix keeps the fixture small; scoring parity is per pair
+        train_lines, test_lines = train_lines[:cfg["pool_rows"]], test_lines[:cfg["query_rows"]]
     train_embeddings = embed(train_lines)
     test_embeddings = embed(test_lines)
 
@@ -120,29 +136,33 @@ def main():
     np.argsort = orig_argsort
     ref_scores = np.concatenate(rows, axis=0)
 
-    # pool query times: unmodified get_train_query_time.py UCI_13 12
-    argv = sys.argv
-    sys.argv = ["get_train_query_time.py", "UCI_13", "12"]
-    runpy.run_path(os.path.join(REF, "get_train_query_time.py"), run_name="__main__")
-    sys.argv = argv
-    pool_time = torch.load(os.path.join("resources", "UCI_13_train_query_time.pt")).numpy()
+    pool_time = np.zeros(0, dtype=np.float32)
+    if ds == "UCI_13":
+        # pool query times: unmodified get_train_query_time.py UCI_13 12
+        argv = sys.argv
+        sys.argv = ["get_train_query_time.py", "UCI_13", "12"]
+        runpy.run_path(os.path.join(REF, "get_train_query_time.py"), run_name="__main__")
+        sys.argv = argv
+        pool_time = torch.load(os.path.join("resources", "UCI_13_train_query_time.pt")).numpy()
 
     def sha(p):
         return hashlib.sha256(open(p, "rb").read()).hexdigest()
-    np.savez_compressed(os.path.join(GOLD, "dense_UCI13.npz"), pool_emb=train_embeddings.numpy(),
+    tag = {"UCI_13": "UCI13"}.get(ds, ds)
+    np.savez_compressed(os.path.join(GOLD, f"dense_{tag}.npz"), pool_emb=train_embeddings.numpy(),
                         query_emb=test_embeddings.numpy(), ref_scores=ref_scores, pool_time=pool_time)
     man_path = os.path.join(GOLD, "manifest.json")
     man = json.load(open(man_path))
-    man["dense_UCI13"] = {"model": "reference models.modeling_rag.GPT2LMHeadModel, 4 layers/2 heads/512-d, seed 42, random init",
+    man[f"dense_{tag}"] = {"model": f"reference models.modeling_rag.GPT2LMHeadModel, {cfg['n_layer']} layers/{cfg['n_head']} heads/"
+                                    f"{cfg['n_embed']}-d, seed 42, random init; pool rows {len(train_lines)}, queries {len(test_lines)}",
                           "pool": list(train_embeddings.shape), "queries": list(test_embeddings.shape),
                           "test_index.gen": {"sha256": sha("out/test_index.gen"), "bytes": os.path.getsize("out/test_index.gen")},
                           "test_score.gen": {"sha256": sha("out/test_score.gen"), "bytes": os.path.getsize("out/test_score.gen")},
                           "score_range": [float(ref_scores.min()), float(ref_scores.max())],
-                          "pool_time_range": [float(pool_time.min()), float(pool_time.max())],
+                          "pool_time_range": [float(pool_time.min()), float(pool_time.max())] if pool_time.size else None,
                           "torch": torch.__version__, "transformers": transformers.__version__}
     json.dump(man, open(man_path, "w"), indent=1, sort_keys=True)
     print("dense golden written:", train_embeddings.shape, test_embeddings.shape, ref_scores.min(), ref_scores.max())
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1] if len(sys.argv) > 1 else "UCI_13")
