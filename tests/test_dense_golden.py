@@ -91,3 +91,37 @@ def test_decay_with_real_pool_times(gold):
     assert np.abs(got - ref).max() <= 1e-5
     ts, ti = index.topk(q, 10, mode=dr.DENSE_COS_DECAY, q_time=qt.cuda(), lam=lam)
     assert not do.topk_tolerance_ok(ref, ti.cpu().numpy(), ts.cpu().numpy(), 10, 1e-5)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# hepth (12 layers, 256-d, node-feature embeddings) and dialog (2 layers, 256-d): a 1,500-row pool prefix x 128 test
+# queries, embeddings + score rows from the reference's own model / scoring lines (oracle/make_dense_golden.py <ds>)
+@pytest.fixture(scope="module", params=["hepth", "dialog"])
+def gold_ds(request):
+    z = np.load(os.path.join(GOLD, f"dense_{request.param}.npz"))
+    return request.param, {k: z[k] for k in z.files}
+
+
+def test_oracle_matches_reference_scores_hepth_dialog(gold_ds):
+    ds, g = gold_ds
+    got = do.score_block(torch.from_numpy(g["query_emb"]), torch.from_numpy(g["pool_emb"])).numpy()
+    assert got.shape == g["ref_scores"].shape == (128, 1500)
+    assert np.abs(got - g["ref_scores"]).max() <= 2e-6, ds
+
+
+@pytest.mark.gpu
+def test_kernel_on_reference_embeddings_hepth_dialog(gold_ds):
+    from rag4dyg_b200 import dense_retrieval as dr
+    ds, g = gold_ds
+    q, p = torch.from_numpy(g["query_emb"]).cuda(), torch.from_numpy(g["pool_emb"]).cuda()
+    ref = g["ref_scores"]
+    for prec, tol in ((dr.PREC_BF16X3, 1e-5), (dr.PREC_BF16, 3e-3)):
+        index = dr.DenseIndex(p, prec=prec)
+        err = np.abs(index.scores(q).cpu().numpy() - ref).max()
+        assert err <= tol, f"{ds} prec {prec}: max |score err| {err:.3g} > {tol}"
+        ts, ti = index.topk(q, 10)
+        bad = do.topk_tolerance_ok(ref, ti.cpu().numpy(), ts.cpu().numpy(), 10, tol)
+        assert not bad, (ds, bad[:3])
+    full_rank = dr.engine.rank_rows(dr.DenseIndex(p).scores(q)).cpu().numpy()
+    ranked = np.take_along_axis(ref.astype(np.float64), full_rank, axis=1)
+    assert np.all(np.diff(ranked, axis=1) <= 2e-5), "reference scores non-increasing along our full ranking"
