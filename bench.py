@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--queries-per-step", type=int, default=Q_STEP)
     ap.add_argument("--mean-set", type=float, default=1.0 / 0.45, help="mean set size (y-like 2.2; x-like 20)")
     ap.add_argument("--dense-d", type=int, default=DENSE_D, help="embedding width (experiments; the metric uses 768)")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: fused NVLink peer-store exchange (symmetric memory) or NCCL all-gathers")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -290,12 +292,21 @@ def main():
         n_batches = QUERY_N // qs
         ws = torch.empty(_lib.load().r4d_jaccard_topk_workspace_bytes(qs, hi - lo, TOPK), dtype=torch.uint8, device=dev)
         result = {}
+        jex, exchange_used = None, "none (single GPU)"
+        if world > 1:
+            exchange_used = "nccl all-gather"
+            if args.exchange == "p2p":
+                try:
+                    jex = sharded.P2PExchange(qs, TOPK, 3)
+                    exchange_used = "fused NVLink peer stores from the merge kernel + 1 symmetric-memory barrier"
+                except Exception as e:          # symmetric memory not available: the NCCL collective is used instead
+                    exchange_used = f"nccl all-gather (p2p unavailable: {type(e).__name__})"
 
         def step_resident(i):
             b = i % n_batches
             bq = bq_all.rows(b * qs, (b + 1) * qs)
-            # local fused top-K on the shard, then ONE exchange: all-gather of [Q, K] candidates + merge
-            result["last"] = sharded.jaccard_topk_sharded(bq, bp, TOPK, pool_base=lo, workspace=ws)
+            # local fused top-K on the shard, then ONE exchange of [Q, K] candidates + merge
+            result["last"] = sharded.jaccard_topk_sharded(bq, bp, TOPK, pool_base=lo, workspace=ws, exchange=jex)
 
         sampler = ClockSampler(local_rank) if rank == 0 else None
         ms, launches, clocks = timed(step_resident, sampler)
@@ -342,7 +353,7 @@ def main():
             xi, xo = csr_rows(xp_ids, xp_off, lo, hi)
             bxp = set_encoder.encode_csr(xi, xo, V_BITS, dev)
             bxq = set_encoder.encode_csr(xq_ids, xq_off, V_BITS, dev)
-            x_ms, _, _ = timed(lambda i: sharded.jaccard_topk_sharded(bxq, bxp, TOPK, pool_base=lo, workspace=ws))
+            x_ms, _, _ = timed(lambda i: sharded.jaccard_topk_sharded(bxq, bxp, TOPK, pool_base=lo, workspace=ws, exchange=jex))
             x_like = {"value": pairs_per_step * K / (x_ms * 1e-3), "unit": "pairs/s", "ms_per_step": x_ms / K,
                       "mean_set_size": 20.0}
             del bxp, bxq
@@ -359,7 +370,7 @@ def main():
                 qi, qo = q_pins[i % n_batches]
                 bq = set_encoder.encode_csr(qi, qo, V_BITS, dev)                     # H2D + encode (queries)
                 bpool = set_encoder.encode_csr(sh_ids_pin, sh_off_pin, V_BITS, dev)   # H2D + encode (pool shard)
-                r = sharded.jaccard_topk_sharded(bq, bpool, TOPK, pool_base=lo, workspace=ws)
+                r = sharded.jaccard_topk_sharded(bq, bpool, TOPK, pool_base=lo, workspace=ws, exchange=jex)
                 host_out["r"] = [t.cpu() for t in r]                                  # D2H of the step's result
             e_ms, _, _ = timed(step_e2e)
             h2d = (q_pins[0][0].numel() * 4 + q_pins[0][1].numel() * 8 + sh_ids.numel() * 4 + sh_off.numel() * 8)
@@ -381,7 +392,7 @@ def main():
         out = {"metric": "query-pool pairs scored+top-K/sec (Jaccard)", "value": value, "unit": "pairs/s",
                "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
                "scaling": "strong", "vs_baseline": None, "dtype": "u32 (bitset AND+POPC, exact integer counts)",
-               "data": "synthetic", "config": workload_config(args, world), "roofline": roofline,
+               "data": "synthetic", "config": dict(workload_config(args, world), exchange=exchange_used), "roofline": roofline,
                "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches * world, "clocks": clocks,
                "x_like": x_like}
         del bp, bq_all, ws
@@ -410,11 +421,17 @@ def main():
         q_times = [t.to(dev) for t in qt_host]
         ws = torch.empty(_lib.load().r4d_dense_topk_workspace_bytes(qs, hi - lo, TOPK), dtype=torch.uint8, device=dev)
         mode = engine.DENSE_COS_DECAY
+        dex = None
+        if world > 1 and args.exchange == "p2p":
+            try:
+                dex = sharded.P2PExchange(qs, TOPK, 2)
+            except Exception:
+                dex = None
 
         def dstep(i):
             b = i % n_batches
             sharded.dense_topk_sharded(q_planes[b], pool, TOPK, pool_base=lo, mode=mode, q_time=q_times[b], p_time=p_time,
-                                       lam=DENSE_LAMBDA, workspace=ws)
+                                       lam=DENSE_LAMBDA, workspace=ws, exchange=dex)
         sampler = ClockSampler(local_rank) if rank == 0 else None
         d_ms, d_launch, d_clocks = timed(dstep, sampler)
         pairs = qs * n_pool
@@ -442,7 +459,7 @@ def main():
                 qd = q_host[b].to(dev, non_blocking=True)                     # H2D fp32 query embeddings + times
                 qt = qt_host[b].to(dev, non_blocking=True)
                 r = sharded.dense_topk_sharded(engine.dense_prepare(qd, engine.PREC_BF16), pool, TOPK, pool_base=lo, mode=mode,
-                                               q_time=qt, p_time=p_time, lam=DENSE_LAMBDA, workspace=ws)
+                                               q_time=qt, p_time=p_time, lam=DENSE_LAMBDA, workspace=ws, exchange=dex)
                 host["r"] = [t.cpu() for t in r]
             de_ms, _, _ = timed(dstep_e2e)
             d_e2e = {"value": pairs * K / (de_ms * 1e-3), "unit": "pairs/s",
@@ -470,7 +487,9 @@ def main():
                  "scaling": "strong", "dtype": "bf16 operands, fp32 accumulate (tcgen05 kind::f16)", "data": "synthetic",
                  "config": {"workload": f"synthetic dense top-K: {n_pool:,} x {DENSE_D} pool x {QUERY_N:,} queries, K={TOPK}, "
                                         f"cos*exp(-{DENSE_LAMBDA}|dt|) epilogue; step = {qs:,}-query batch vs the whole pool",
-                            "parallelism": f"pool-sharded x{world}", "l2": "inputs larger than L2 (pool 15.4 GB / n_gpus)"},
+                            "parallelism": f"pool-sharded x{world}", "l2": "inputs larger than L2 (pool 15.4 GB / n_gpus)",
+                            "exchange": ("fused NVLink peer stores" if dex is not None else
+                                         ("nccl all-gather" if world > 1 else "none (single GPU)"))},
                  "roofline": d_roof, "cpu_baseline": d_cpu, "e2e": d_e2e, "gpu_launches": d_launch * world,
                  "clocks": d_clocks}
         if out:

@@ -33,6 +33,7 @@ typedef void* r4d_stream_t; /* cudaStream_t */
 #define R4D_E_WORKSPACE (-3) /* workspace too small */
 #define R4D_IDX_NONE 0x7fffffff
 #define R4D_TOPK_MAX 32    /* fused top-K width limit (one list entry per lane) */
+#define R4D_MAX_PEERS 16   /* GPUs of one NVLink domain addressed by the fused exchange */
 
 /* dense scorer epilogue modes (r4d_dense_*) */
 #define R4D_DENSE_HALF_COS 0       /* (cos+1)/2                  train/train_retriever.py:437-438 */
@@ -101,6 +102,16 @@ int r4d_jaccard_topk_merge(const uint32_t* inter, const uint32_t* uni, const int
                            int64_t nq, int32_t k_in, int32_t k_out, uint32_t* out_inter, uint32_t* out_union,
                            int32_t* out_idx, r4d_stream_t stream);
 
+/* Fused exchange (multi-GPU): like r4d_jaccard_topk on this rank's pool shard, but the final per-rank
+ * lists are not written locally: the merge kernel stores them straight into slot `rank` of every peer's gather
+ * buffer over NVLink.  peer_base [host] holds `world` device pointers (this rank's own buffer included) to buffers of
+ * layout uint32 [3][world][nq][k] (planes: inter, union, idx) obtained from a symmetric-memory rendezvous.  After a
+ * cross-GPU barrier each rank runs r4d_jaccard_topk_merge over its own buffer's planes (n_lists = world). */
+int r4d_jaccard_topk_scatter(const uint32_t* qbits, const uint32_t* qcard, int64_t nq, const uint32_t* pbits,
+                             const uint32_t* pcard, int64_t np, int32_t words, int32_t pitch_words, int32_t k,
+                             int32_t zero_diag, int64_t query_base, int64_t pool_base, void* const* peer_base,
+                             int32_t world, int32_t rank, void* workspace, size_t workspace_bytes, r4d_stream_t stream);
+
 /* ---------------------------------------------------------------- ranking of score matrices
  * Full descending STABLE ranking of every row: order[q][:] = np.argsort(-scores[q], kind='stable').
  * Replaces np.argsort(-M, axis=1) in save_index_score (retrieval_data_annotation.py:89,
@@ -154,6 +165,12 @@ int r4d_dense_topk(const void* q_hi, const void* q_lo, int64_t nq, const void* p
                    int32_t d_pad, int32_t prec, const float* q_time, const float* p_time, float lambda,
                    int32_t mode, int32_t k, int64_t pool_base, float* top_score, int32_t* top_idx,
                    void* workspace, size_t workspace_bytes, r4d_stream_t stream);
+
+/* Fused exchange for the dense scorer: peer buffers of layout [2][world][nq][k] (planes: float32 score, int32 idx). */
+int r4d_dense_topk_scatter(const void* q_hi, const void* q_lo, int64_t nq, const void* p_hi, const void* p_lo, int64_t np,
+                           int32_t d_pad, int32_t prec, const float* q_time, const float* p_time, float lambda,
+                           int32_t mode, int32_t k, int64_t pool_base, void* const* peer_base, int32_t world,
+                           int32_t rank, void* workspace, size_t workspace_bytes, r4d_stream_t stream);
 
 /* Same contraction + epilogue, full score rows scores[nq][ld] (the `.gen` score files need them,
  * train/train_retriever.py:357-368). */

@@ -40,6 +40,8 @@ PROTOTYPES = {
     "r4d_jaccard_topk_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "r4d_jaccard_topk": (_c.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i64, _i64, _vp, _vp, _vp,
                                     _vp, _sz, _vp]),
+    "r4d_jaccard_topk_scatter": (_c.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i64, _i64, _vp, _i32, _i32,
+                                            _vp, _sz, _vp]),
     "r4d_jaccard_topk_merge": (_c.c_int, [_vp, _vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp, _vp]),
     "r4d_rank_rows_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "r4d_rank_rows_f64": (_c.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _sz, _vp]),
@@ -52,6 +54,8 @@ PROTOTYPES = {
     "r4d_dense_topk_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "r4d_dense_topk": (_c.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _f32, _i32, _i32, _i64, _vp,
                                   _vp, _vp, _sz, _vp]),
+    "r4d_dense_topk_scatter": (_c.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _f32, _i32, _i32, _i64, _vp,
+                                          _i32, _i32, _vp, _sz, _vp]),
     "r4d_dense_full": (_c.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _f32, _i32, _vp, _i64, _vp]),
     "r4d_dense_topk_merge": (_c.c_int, [_vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp]),
     "r4d_meanpool_workspace_bytes": (_sz, [_i64, _i32]),

@@ -302,7 +302,8 @@ dense_prepare_kernel(const float* __restrict__ x, int64_t n, int32_t d, int64_t 
 
 __global__ void __launch_bounds__(256)
 dense_merge_kernel(const float* __restrict__ score, const int32_t* __restrict__ idx, int32_t n_lists, int64_t nq,
-                   int32_t k_in, int32_t k_out, float* __restrict__ out_score, int32_t* __restrict__ out_idx) {
+                   int32_t k_in, int32_t k_out, float* __restrict__ out_score, int32_t* __restrict__ out_idx,
+                   const PeerOut peers) {
     const int lane = threadIdx.x & 31;
     const int64_t wpg = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); q < nq; q += wpg) {
@@ -324,8 +325,19 @@ dense_merge_kernel(const float* __restrict__ score, const int32_t* __restrict__ 
             }
         }
         if (lane < k_out) {
-            out_score[q * k_out + lane] = tk.mine.s;
-            out_idx[q * k_out + lane] = tk.mine.idx;
+            if (peers.world == 0) {
+                out_score[q * k_out + lane] = tk.mine.s;
+                out_idx[q * k_out + lane] = tk.mine.idx;
+            } else {
+                // fused exchange: slot `rank` of every peer's gather buffer [2][world][nq][k] over NVLink P2P
+                const int64_t plane = (int64_t)peers.world * nq * k_out;
+                const int64_t at = ((int64_t)peers.rank * nq + q) * k_out + lane;
+                for (int r = 0; r < peers.world; ++r) {
+                    float* dst = reinterpret_cast<float*>(peers.base[r]);
+                    dst[at] = tk.mine.s;
+                    reinterpret_cast<int32_t*>(dst)[plane + at] = tk.mine.idx;
+                }
+            }
         }
     }
 }
@@ -460,17 +472,30 @@ size_t r4d_dense_topk_workspace_bytes(int64_t nq, int64_t np, int32_t k) {
     return need;
 }
 
-int r4d_dense_topk(const void* q_hi, const void* q_lo, int64_t nq, const void* p_hi, const void* p_lo, int64_t np,
-                   int32_t d_pad, int32_t prec, const float* q_time, const float* p_time, float lambda, int32_t mode,
-                   int32_t k, int64_t pool_base, float* top_score, int32_t* top_idx, void* workspace,
-                   size_t workspace_bytes, r4d_stream_t stream) {
+static int dense_merge_launch(const float* score, const int32_t* idx, int32_t n_lists, int64_t nq, int32_t k_in,
+                              int32_t k_out, float* out_score, int32_t* out_idx, const r4d::PeerOut& peers,
+                              r4d_stream_t stream) {
+    using namespace r4d;
+    int64_t blocks = (nq + 7) / 8;
+    const int64_t cap = (int64_t)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    dense_merge_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(score, idx, n_lists, nq, k_in, k_out, out_score,
+                                                                       out_idx, peers);
+    R4D_CUDA(cudaGetLastError());
+    return R4D_OK;
+}
+
+static int dense_topk_impl(const void* q_hi, const void* q_lo, int64_t nq, const void* p_hi, const void* p_lo, int64_t np,
+                           int32_t d_pad, int32_t prec, const float* q_time, const float* p_time, float lambda,
+                           int32_t mode, int32_t k, int64_t pool_base, float* top_score, int32_t* top_idx,
+                           const r4d::PeerOut& peers, void* workspace, size_t workspace_bytes, r4d_stream_t stream) {
     using namespace r4d;
     int rc = dense_check(q_hi, q_lo, nq, p_hi, p_lo, np, d_pad, prec, q_time, p_time, mode);
     if (rc) return rc;
     R4D_REQUIRE(k >= 1 && k <= R4D_TOPK_MAX, "dense_topk: k=%d out of range [1, %d]", k, R4D_TOPK_MAX);
     R4D_REQUIRE(pool_base >= 0 && pool_base + np < (int64_t)R4D_IDX_NONE, "dense_topk: pool_base+np exceeds int32");
     if (nq == 0) return R4D_OK;
-    R4D_REQUIRE(top_score && top_idx, "dense_topk: null output");
+    R4D_REQUIRE(peers.world > 0 || (top_score && top_idx), "dense_topk: null output");
     if (np > 0 && dense2_supported(nq, np, d_pad, prec, k)) {
         // throughput path: CTA pairs (cta_group::2), resident query tile, register top-K (dense2.cu)
         const size_t need2 = dense2_workspace_bytes(nq, np, d_pad, k);
@@ -484,7 +509,7 @@ int r4d_dense_topk(const void* q_hi, const void* q_lo, int64_t nq, const void* p
         rc = dense2_topk(q_hi, nq, p_hi, np, d_pad, q_time, p_time, lambda, mode, k, pool_base, ps, pi, &n_lists,
                          as_stream(stream));
         if (rc) return rc;
-        return r4d_dense_topk_merge(ps, pi, n_lists, nq, k, k, top_score, top_idx, stream);
+        return dense_merge_launch(ps, pi, n_lists, nq, k, k, top_score, top_idx, peers, stream);
     }
     const DensePlan pl = dense_plan(nq, np, true);
     const size_t per = (size_t)pl.n_stripes * 2 * (size_t)nq * (size_t)k;
@@ -492,8 +517,7 @@ int r4d_dense_topk(const void* q_hi, const void* q_lo, int64_t nq, const void* p
         set_error("dense_topk: workspace %zu B < required %zu B", workspace_bytes, per * 8);
         return R4D_E_WORKSPACE;
     }
-    if (np == 0)
-        return r4d_dense_topk_merge(nullptr, nullptr, 0, nq, k, k, top_score, top_idx, stream);
+    if (np == 0) return dense_merge_launch(nullptr, nullptr, 0, nq, k, k, top_score, top_idx, peers, stream);
     DenseParams prm{};
     prm.nq = nq;
     prm.np = np;
@@ -511,7 +535,34 @@ int r4d_dense_topk(const void* q_hi, const void* q_lo, int64_t nq, const void* p
     prm.part_idx = reinterpret_cast<int32_t*>(prm.part_score + per);
     rc = dense_launch(DMODE_TOPK, q_hi, q_lo, nq, p_hi, p_lo, np, d_pad, prec, prm, as_stream(stream));
     if (rc) return rc;
-    return r4d_dense_topk_merge(prm.part_score, prm.part_idx, pl.n_stripes * 2, nq, k, k, top_score, top_idx, stream);
+    return dense_merge_launch(prm.part_score, prm.part_idx, pl.n_stripes * 2, nq, k, k, top_score, top_idx, peers, stream);
+}
+
+int r4d_dense_topk(const void* q_hi, const void* q_lo, int64_t nq, const void* p_hi, const void* p_lo, int64_t np,
+                   int32_t d_pad, int32_t prec, const float* q_time, const float* p_time, float lambda, int32_t mode,
+                   int32_t k, int64_t pool_base, float* top_score, int32_t* top_idx, void* workspace,
+                   size_t workspace_bytes, r4d_stream_t stream) {
+    r4d::PeerOut none{};
+    return dense_topk_impl(q_hi, q_lo, nq, p_hi, p_lo, np, d_pad, prec, q_time, p_time, lambda, mode, k, pool_base,
+                           top_score, top_idx, none, workspace, workspace_bytes, stream);
+}
+
+int r4d_dense_topk_scatter(const void* q_hi, const void* q_lo, int64_t nq, const void* p_hi, const void* p_lo, int64_t np,
+                           int32_t d_pad, int32_t prec, const float* q_time, const float* p_time, float lambda,
+                           int32_t mode, int32_t k, int64_t pool_base, void* const* peer_base, int32_t world,
+                           int32_t rank, void* workspace, size_t workspace_bytes, r4d_stream_t stream) {
+    using namespace r4d;
+    R4D_REQUIRE(peer_base && world >= 1 && world <= R4D_MAX_PEERS && rank >= 0 && rank < world,
+                "fused exchange: world=%d rank=%d (max %d peers)", world, rank, R4D_MAX_PEERS);
+    PeerOut po{};
+    po.world = world;
+    po.rank = rank;
+    for (int r = 0; r < world; ++r) {
+        R4D_REQUIRE(peer_base[r] != nullptr, "fused exchange: null peer pointer %d", r);
+        po.base[r] = peer_base[r];
+    }
+    return dense_topk_impl(q_hi, q_lo, nq, p_hi, p_lo, np, d_pad, prec, q_time, p_time, lambda, mode, k, pool_base,
+                           nullptr, nullptr, po, workspace, workspace_bytes, stream);
 }
 
 int r4d_dense_full(const void* q_hi, const void* q_lo, int64_t nq, const void* p_hi, const void* p_lo, int64_t np,
@@ -549,13 +600,8 @@ int r4d_dense_topk_merge(const float* score, const int32_t* idx, int32_t n_lists
     if (nq == 0) return R4D_OK;
     R4D_REQUIRE(out_score && out_idx, "dense_topk_merge: null output");
     R4D_REQUIRE(n_lists == 0 || (score && idx), "dense_topk_merge: null input");
-    int64_t blocks = (nq + 7) / 8;
-    const int64_t cap = (int64_t)num_sms() * 16;
-    if (blocks > cap) blocks = cap;
-    dense_merge_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(score, idx, n_lists, nq, k_in, k_out, out_score,
-                                                                       out_idx);
-    R4D_CUDA(cudaGetLastError());
-    return R4D_OK;
+    r4d::PeerOut none{};
+    return dense_merge_launch(score, idx, n_lists, nq, k_in, k_out, out_score, out_idx, none, stream);
 }
 
 }  // extern "C"

@@ -364,7 +364,8 @@ jaccard_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 __global__ void __launch_bounds__(256)
 jaccard_merge_kernel(const uint32_t* __restrict__ inter, const uint32_t* __restrict__ uni,
                      const int32_t* __restrict__ idx, int32_t n_lists, int64_t nq, int32_t k_in, int32_t k_out,
-                     uint32_t* __restrict__ out_inter, uint32_t* __restrict__ out_union, int32_t* __restrict__ out_idx) {
+                     uint32_t* __restrict__ out_inter, uint32_t* __restrict__ out_union, int32_t* __restrict__ out_idx,
+                     const PeerOut peers) {
     const int lane = threadIdx.x & 31;
     const int64_t wpg = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); q < nq; q += wpg) {
@@ -385,9 +386,21 @@ jaccard_merge_kernel(const uint32_t* __restrict__ inter, const uint32_t* __restr
             }
         }
         if (lane < k_out) {
-            out_inter[q * k_out + lane] = tk.mine.inter;
-            out_union[q * k_out + lane] = tk.mine.uni;
-            out_idx[q * k_out + lane] = tk.mine.idx;
+            if (peers.world == 0) {
+                out_inter[q * k_out + lane] = tk.mine.inter;
+                out_union[q * k_out + lane] = tk.mine.uni;
+                out_idx[q * k_out + lane] = tk.mine.idx;
+            } else {
+                // fused exchange: store into slot `rank` of every peer's gather buffer [3][world][nq][k] (NVLink P2P)
+                const int64_t plane = (int64_t)peers.world * nq * k_out;
+                const int64_t at = ((int64_t)peers.rank * nq + q) * k_out + lane;
+                for (int r = 0; r < peers.world; ++r) {
+                    uint32_t* dst = reinterpret_cast<uint32_t*>(peers.base[r]);
+                    dst[at] = tk.mine.inter;
+                    dst[plane + at] = tk.mine.uni;
+                    dst[2 * plane + at] = (uint32_t)tk.mine.idx;
+                }
+            }
         }
     }
 }
@@ -504,21 +517,47 @@ size_t r4d_jaccard_topk_workspace_bytes(int64_t nq, int64_t np, int32_t k) {
     return (size_t)pl.n_stripes * (size_t)nq * (size_t)k * 12 + 256;
 }
 
-int r4d_jaccard_topk(const uint32_t* qbits, const uint32_t* qcard, int64_t nq, const uint32_t* pbits,
-                     const uint32_t* pcard, int64_t np, int32_t words, int32_t pitch_words, int32_t k,
-                     int32_t zero_diag, int64_t query_base, int64_t pool_base, uint32_t* top_inter,
-                     uint32_t* top_union, int32_t* top_idx, void* workspace, size_t workspace_bytes,
-                     r4d_stream_t stream) {
+static int merge_launch(const uint32_t* inter, const uint32_t* uni, const int32_t* idx, int32_t n_lists, int64_t nq,
+                        int32_t k_in, int32_t k_out, uint32_t* out_inter, uint32_t* out_union, int32_t* out_idx,
+                        const r4d::PeerOut& peers, r4d_stream_t stream) {
+    using namespace r4d;
+    int64_t blocks = (nq + 7) / 8;
+    const int64_t cap = (int64_t)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    jaccard_merge_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(inter, uni, idx, n_lists, nq, k_in, k_out,
+                                                                         out_inter, out_union, out_idx, peers);
+    R4D_CUDA(cudaGetLastError());
+    return R4D_OK;
+}
+
+static int make_peers(r4d::PeerOut& po, void* const* peer_base, int32_t world, int32_t rank) {
+    using namespace r4d;
+    R4D_REQUIRE(peer_base && world >= 1 && world <= R4D_MAX_PEERS && rank >= 0 && rank < world,
+                "fused exchange: world=%d rank=%d (max %d peers)", world, rank, R4D_MAX_PEERS);
+    po.world = world;
+    po.rank = rank;
+    for (int r = 0; r < world; ++r) {
+        R4D_REQUIRE(peer_base[r] != nullptr, "fused exchange: null peer pointer %d", r);
+        po.base[r] = peer_base[r];
+    }
+    return R4D_OK;
+}
+
+static int jaccard_topk_impl(const uint32_t* qbits, const uint32_t* qcard, int64_t nq, const uint32_t* pbits,
+                             const uint32_t* pcard, int64_t np, int32_t words, int32_t pitch_words, int32_t k,
+                             int32_t zero_diag, int64_t query_base, int64_t pool_base, uint32_t* top_inter,
+                             uint32_t* top_union, int32_t* top_idx, const r4d::PeerOut& peers, void* workspace,
+                             size_t workspace_bytes, r4d_stream_t stream) {
     using namespace r4d;
     int rc = check_common(qbits, qcard, nq, pbits, pcard, np, words, pitch_words);
     if (rc) return rc;
     R4D_REQUIRE(k >= 1 && k <= R4D_TOPK_MAX, "jaccard_topk: k=%d out of range [1, %d]", k, R4D_TOPK_MAX);
     R4D_REQUIRE(pool_base >= 0 && pool_base + np < (int64_t)R4D_IDX_NONE, "jaccard_topk: pool_base+np exceeds int32");
     if (nq == 0) return R4D_OK;
-    R4D_REQUIRE(top_inter && top_union && top_idx, "jaccard_topk: null output");
+    R4D_REQUIRE(peers.world > 0 || (top_inter && top_union && top_idx), "jaccard_topk: null output");
     cudaStream_t st = as_stream(stream);
     if (np == 0)  // no pool rows: every list is padding; the merge of zero lists writes it, no workspace needed
-        return r4d_jaccard_topk_merge(nullptr, nullptr, nullptr, 0, nq, k, k, top_inter, top_union, top_idx, stream);
+        return merge_launch(nullptr, nullptr, nullptr, 0, nq, k, k, top_inter, top_union, top_idx, peers, stream);
     const JaccardPlan pl = plan_topk(nq, np);
     const size_t per = (size_t)pl.n_stripes * (size_t)nq * (size_t)k;
     if (workspace_bytes < per * 12 || (!workspace && per)) {
@@ -543,8 +582,29 @@ int r4d_jaccard_topk(const uint32_t* qbits, const uint32_t* qcard, int64_t nq, c
     prm.part_idx = reinterpret_cast<int32_t*>(prm.part_union + per);
     rc = launch<MODE_TOPK>(qbits, nq, pbits, np, words, pitch_words, prm, st);
     if (rc) return rc;
-    return r4d_jaccard_topk_merge(prm.part_inter, prm.part_union, prm.part_idx, pl.n_stripes, nq, k, k, top_inter,
-                                  top_union, top_idx, stream);
+    return merge_launch(prm.part_inter, prm.part_union, prm.part_idx, pl.n_stripes, nq, k, k, top_inter, top_union,
+                        top_idx, peers, stream);
+}
+
+int r4d_jaccard_topk(const uint32_t* qbits, const uint32_t* qcard, int64_t nq, const uint32_t* pbits,
+                     const uint32_t* pcard, int64_t np, int32_t words, int32_t pitch_words, int32_t k,
+                     int32_t zero_diag, int64_t query_base, int64_t pool_base, uint32_t* top_inter,
+                     uint32_t* top_union, int32_t* top_idx, void* workspace, size_t workspace_bytes,
+                     r4d_stream_t stream) {
+    r4d::PeerOut none{};
+    return jaccard_topk_impl(qbits, qcard, nq, pbits, pcard, np, words, pitch_words, k, zero_diag, query_base, pool_base,
+                             top_inter, top_union, top_idx, none, workspace, workspace_bytes, stream);
+}
+
+int r4d_jaccard_topk_scatter(const uint32_t* qbits, const uint32_t* qcard, int64_t nq, const uint32_t* pbits,
+                             const uint32_t* pcard, int64_t np, int32_t words, int32_t pitch_words, int32_t k,
+                             int32_t zero_diag, int64_t query_base, int64_t pool_base, void* const* peer_base,
+                             int32_t world, int32_t rank, void* workspace, size_t workspace_bytes, r4d_stream_t stream) {
+    r4d::PeerOut po{};
+    int rc = make_peers(po, peer_base, world, rank);
+    if (rc) return rc;
+    return jaccard_topk_impl(qbits, qcard, nq, pbits, pcard, np, words, pitch_words, k, zero_diag, query_base, pool_base,
+                             nullptr, nullptr, nullptr, po, workspace, workspace_bytes, stream);
 }
 
 int r4d_jaccard_topk_merge(const uint32_t* inter, const uint32_t* uni, const int32_t* idx, int32_t n_lists,
@@ -556,13 +616,8 @@ int r4d_jaccard_topk_merge(const uint32_t* inter, const uint32_t* uni, const int
     if (nq == 0) return R4D_OK;
     R4D_REQUIRE(out_inter && out_union && out_idx, "jaccard_topk_merge: null output");
     R4D_REQUIRE(n_lists == 0 || (inter && uni && idx), "jaccard_topk_merge: null input");
-    int64_t blocks = (nq + 7) / 8;
-    const int64_t cap = (int64_t)num_sms() * 16;
-    if (blocks > cap) blocks = cap;
-    jaccard_merge_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(inter, uni, idx, n_lists, nq, k_in, k_out,
-                                                                         out_inter, out_union, out_idx);
-    R4D_CUDA(cudaGetLastError());
-    return R4D_OK;
+    r4d::PeerOut none{};
+    return merge_launch(inter, uni, idx, n_lists, nq, k_in, k_out, out_inter, out_union, out_idx, none, stream);
 }
 
 }  // extern "C"

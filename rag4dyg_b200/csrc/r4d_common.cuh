@@ -41,6 +41,14 @@ Options& options();  // process-wide knobs (r4d_set_option); environment variabl
 int make_tmap_2d(CUtensorMap* map, CUtensorMapDataType dtype, int elem_bytes, const void* base, uint64_t dim0,
                  uint64_t dim1, uint64_t row_stride_bytes, uint32_t box0, uint32_t box1, CUtensorMapSwizzle swz);
 
+// Peer scatter target of the fused exchange: every rank's merge kernel stores its [nq][k] result planes into slot
+// `rank` of EVERY peer's gather buffer (layout [n_planes][world][nq][k], 4-byte elements) through NVLink peer pointers.
+struct PeerOut {
+    void* base[R4D_MAX_PEERS];
+    int32_t world;  // 0: no scatter (plain local output)
+    int32_t rank;
+};
+
 static inline cudaStream_t as_stream(r4d_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // ---------------------------------------------------------------- device side

@@ -12,7 +12,7 @@ from ._lib import (DENSE_COS_DECAY, DENSE_HALF_COS, DENSE_HALF_COS_DECAY, PREC_B
                    R4D_TOPK_MAX, R4DError, check)
 
 __all__ = [
-    "BitsetMatrix", "encode_bitsets", "jaccard_full", "jaccard_topk", "jaccard_topk_merge", "rank_rows", "topk_rows",
+    "BitsetMatrix", "encode_bitsets", "jaccard_full", "jaccard_topk", "jaccard_topk_merge", "jaccard_topk_scatter", "dense_topk_scatter", "rank_rows", "topk_rows",
     "triplet_mine", "triplet_sample", "DensePlanes", "dense_prepare", "dense_topk", "dense_full", "dense_topk_merge", "meanpool_prepare", "R4D_IDX_NONE",
     "R4D_TOPK_MAX", "DENSE_HALF_COS", "DENSE_COS_DECAY", "DENSE_HALF_COS_DECAY", "PREC_BF16", "PREC_BF16X3",
     "launch_count", "reset_launch_count",
@@ -127,6 +127,22 @@ def jaccard_topk(q, p, k, zero_diag=False, query_base=0, pool_base=0, workspace=
                                _ptr(top_idx), _ptr(workspace), workspace.numel(), _stream()), "r4d_jaccard_topk")
     _count(2 if nq and np_ else (1 if nq else 0))
     return top_inter, top_union, top_idx
+
+
+def jaccard_topk_scatter(q, p, k, peer_ptrs, world, rank, zero_diag=False, query_base=0, pool_base=0, workspace=None):
+    """Fused exchange: local fused top-K whose final lists are stored straight into slot `rank` of every peer's
+    gather buffer [3][world][nq][k] over NVLink.  peer_ptrs: ctypes array of `world` device pointers.
+    r4d_jaccard_topk_scatter."""
+    lib = _lib.load()
+    _check_pair(q, p)
+    nq, np_ = q.n_rows, p.n_rows
+    need = lib.r4d_jaccard_topk_workspace_bytes(nq, np_, k)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty((need,), dtype=torch.uint8, device=q.bits.device)
+    check(lib.r4d_jaccard_topk_scatter(_ptr(q.bits), _ptr(q.card), nq, _ptr(p.bits), _ptr(p.card), np_, q.words,
+                                       q.pitch_words, k, int(bool(zero_diag)), query_base, pool_base, peer_ptrs, world,
+                                       rank, _ptr(workspace), workspace.numel(), _stream()), "r4d_jaccard_topk_scatter")
+    _count(2 if nq and np_ else (1 if nq else 0))
 
 
 def jaccard_topk_merge(inter, uni, idx, k_out):
@@ -290,6 +306,22 @@ def dense_topk(q, p, k, mode=DENSE_HALF_COS, q_time=None, p_time=None, lam=0.0, 
                              workspace.numel(), _stream()), "r4d_dense_topk")
     _count(2 if nq and np_ else (1 if nq else 0))
     return ts, ti
+
+
+def dense_topk_scatter(q, p, k, peer_ptrs, world, rank, mode=DENSE_HALF_COS, q_time=None, p_time=None, lam=0.0,
+                       pool_base=0, workspace=None):
+    """Fused exchange for the dense scorer: peers' buffers are [2][world][nq][k] (float32 scores, int32 indices).
+    r4d_dense_topk_scatter."""
+    lib = _lib.load()
+    _check_dense(q, p, q_time, p_time, mode)
+    nq, np_ = q.n_rows, p.n_rows
+    need = lib.r4d_dense_topk_workspace_bytes(nq, np_, k)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty((need,), dtype=torch.uint8, device=q.hi.device)
+    check(lib.r4d_dense_topk_scatter(_ptr(q.hi), _ptr(q.lo), nq, _ptr(p.hi), _ptr(p.lo), np_, q.d_pad, q.prec,
+                                     _ptr(q_time), _ptr(p_time), float(lam), mode, k, pool_base, peer_ptrs, world, rank,
+                                     _ptr(workspace), workspace.numel(), _stream()), "r4d_dense_topk_scatter")
+    _count(2 if nq and np_ else (1 if nq else 0))
 
 
 def dense_full(q, p, mode=DENSE_HALF_COS, q_time=None, p_time=None, lam=0.0):

@@ -6,6 +6,8 @@ all-gather of the per-shard [Q, K] candidate lists (NCCL over NVLink/NVSwitch, g
 with the same exact comparator and (score desc, global index asc) tie rule, so the result does not depend on `world`.
 The reference has no multi-GPU code on this path (its DDP/DataParallel paths only wrap model training).
 """
+import ctypes
+
 import torch
 import torch.distributed as dist
 
@@ -39,8 +41,51 @@ def gather_candidates(parts, group=None):
     return tuple(out)
 
 
-def jaccard_topk_sharded(q, p_shard, k, pool_base, zero_diag=False, query_base=0, group=None, workspace=None):
-    """q: replicated query bitsets; p_shard: this rank's pool rows.  Returns the GLOBAL (inter, union, idx) [Q, K]."""
+class P2PExchange:
+    """Fused exchange over NVLink peer memory (second step): symmetric-memory gather buffers
+    [n_planes][world][nq][k] (4-byte elements), double buffered.  Each rank's final merge kernel stores its lists into
+    slot `rank` of EVERY peer's buffer (r4d_*_topk_scatter), one cross-GPU barrier follows, then every rank merges its
+    own buffer locally.  Replaces the three (two) NCCL all-gathers of the plain path.
+
+    Double buffering makes one barrier per step sufficient: a peer can only overwrite buffer b again two steps later,
+    which is behind the next step's barrier, which this rank reaches only after its merge of buffer b was enqueued."""
+
+    def __init__(self, nq, k, n_planes, group=None, device=None):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if hasattr(symm, "enable_symm_mem_for_group"):
+            try:
+                symm.enable_symm_mem_for_group(self.group.group_name)
+            except Exception:
+                pass
+        self.bufs, self.hdls, self.ptrs = [], [], []
+        for _ in range(2):
+            t = symm.empty((n_planes, self.world, nq, k), dtype=torch.int32, device=device)
+            h = symm.rendezvous(t, self.group.group_name)
+            off = int(getattr(h, "offset", 0) or 0)
+            self.bufs.append(t)
+            self.hdls.append(h)
+            self.ptrs.append((ctypes.c_void_p * self.world)(*[int(p) + off for p in h.buffer_ptrs]))
+        self.step = 0
+
+    def next(self):
+        b = self.step & 1
+        self.step += 1
+        return self.bufs[b], self.hdls[b], self.ptrs[b]
+
+
+def jaccard_topk_sharded(q, p_shard, k, pool_base, zero_diag=False, query_base=0, group=None, workspace=None,
+                         exchange=None):
+    """q: replicated query bitsets; p_shard: this rank's pool rows.  Returns the GLOBAL (inter, union, idx) [Q, K].
+    exchange: a P2PExchange(nq, k, 3) selects the fused NVLink path instead of NCCL all-gathers."""
+    if exchange is not None:
+        buf, hdl, ptrs = exchange.next()
+        engine.jaccard_topk_scatter(q, p_shard, k, ptrs, exchange.world, exchange.rank, zero_diag=zero_diag,
+                                    query_base=query_base, pool_base=pool_base, workspace=workspace)
+        hdl.barrier()
+        return engine.jaccard_topk_merge(buf[0], buf[1], buf[2], k)
     parts = engine.jaccard_topk(q, p_shard, k, zero_diag=zero_diag, query_base=query_base, pool_base=pool_base,
                                 workspace=workspace)
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
@@ -50,8 +95,14 @@ def jaccard_topk_sharded(q, p_shard, k, pool_base, zero_diag=False, query_base=0
 
 
 def dense_topk_sharded(q, p_shard, k, pool_base, mode=engine.DENSE_HALF_COS, q_time=None, p_time=None, lam=0.0,
-                       group=None, workspace=None):
-    """Dense analogue: local tcgen05 top-K on the shard, all-gather, merge.  Returns (score, idx) [Q, K]."""
+                       group=None, workspace=None, exchange=None):
+    """Dense analogue: local tcgen05 top-K on the shard, all-gather (or fused P2PExchange(nq, k, 2)), merge."""
+    if exchange is not None:
+        buf, hdl, ptrs = exchange.next()
+        engine.dense_topk_scatter(q, p_shard, k, ptrs, exchange.world, exchange.rank, mode, q_time, p_time, lam,
+                                  pool_base=pool_base, workspace=workspace)
+        hdl.barrier()
+        return engine.dense_topk_merge(buf[0].view(torch.float32), buf[1], k)
     parts = engine.dense_topk(q, p_shard, k, mode, q_time, p_time, lam, pool_base=pool_base, workspace=workspace)
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return parts

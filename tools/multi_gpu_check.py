@@ -41,6 +41,17 @@ def main():
         oi, ou, ox = jo.c_topk(*to_csr(q[:200]), *to_csr(p), k)
         ok &= np.array_equal(got[2][:200].cpu().numpy(), ox) and np.array_equal(got[0][:200].cpu().numpy(), oi)
         print(f"[multi_gpu_check] world={world} jaccard sharded == single-GPU == oracle: {ok}", flush=True)
+    # fused exchange: final lists stored into every peer's buffer over NVLink, one barrier, local merge
+    p2p_ok = True
+    try:
+        ex = sharded.P2PExchange(nq, k, 3)
+        for _ in range(3):          # several steps: exercises the double buffering
+            got2 = sharded.jaccard_topk_sharded(bq, bp_shard, k, pool_base=lo, exchange=ex)
+            p2p_ok &= all(torch.equal(a, b) for a, b in zip(got, got2))
+        print(f"[multi_gpu_check] world={world} rank={rank} jaccard fused P2P exchange == NCCL path: {p2p_ok}", flush=True)
+    except Exception as e:  # symmetric memory unavailable on this box: report, do not fail the NCCL verdict
+        print(f"[multi_gpu_check] world={world} rank={rank} fused P2P exchange unavailable: {type(e).__name__}: {e}", flush=True)
+        ex = None
 
     g = torch.Generator().manual_seed(7)
     pe, qe = torch.randn(50000, 256, generator=g), torch.randn(300, 256, generator=g)
@@ -51,12 +62,20 @@ def main():
         pp = engine.dense_prepare(pe[lo:hi].to(dev), prec)
         gs, gi = sharded.dense_topk_sharded(qp, pp, k, pool_base=lo, mode=engine.DENSE_COS_DECAY, q_time=tq.to(dev),
                                             p_time=tp[lo:hi].to(dev), lam=0.01)
+        if ex is not None:
+            dex = sharded.P2PExchange(300, k, 2)
+            for _ in range(2):
+                fs, fi = sharded.dense_topk_sharded(qp, pp, k, pool_base=lo, mode=engine.DENSE_COS_DECAY,
+                                                    q_time=tq.to(dev), p_time=tp[lo:hi].to(dev), lam=0.01, exchange=dex)
+                p2p_ok &= torch.equal(fi, gi) and torch.equal(fs, gs)
+            print(f"[multi_gpu_check] world={world} rank={rank} dense prec={prec} fused P2P == NCCL path: {p2p_ok}", flush=True)
         if rank == 0:
             pa = engine.dense_prepare(pe.to(dev), prec)
             rs, ri = engine.dense_topk(qp, pa, k, engine.DENSE_COS_DECAY, tq.to(dev), tp.to(dev), 0.01)
             same = torch.equal(gi, ri) and torch.equal(gs, rs)
             ok &= same
             print(f"[multi_gpu_check] world={world} dense prec={prec} sharded == single-GPU: {same}", flush=True)
+    ok &= p2p_ok
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
     dist.barrier()
