@@ -55,11 +55,14 @@ class P2PExchange:
         self.group = group if group is not None else dist.group.WORLD
         self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
         device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
-        if hasattr(symm, "enable_symm_mem_for_group"):
-            try:
-                symm.enable_symm_mem_for_group(self.group.group_name)
-            except Exception:
-                pass
+        if hasattr(symm, "enable_symm_mem_for_group"):  # needed by older torch, a deprecated no-op in newer ones
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                try:
+                    symm.enable_symm_mem_for_group(self.group.group_name)
+                except Exception:
+                    pass
         self.bufs, self.hdls, self.ptrs = [], [], []
         for _ in range(2):
             t = symm.empty((n_planes, self.world, nq, k), dtype=torch.int32, device=device)
