@@ -182,11 +182,28 @@ def _read_lines(path):
         return [line for line in f.read().splitlines() if (len(line) > 0 and not line.isspace())]
 
 
-def annotate(dataset_name, timestamp, threshold, neg_num=5, topk=10):
+class _StageTimer:
+    """Wall time per stage (device work is synchronised at stage boundaries only when timing is requested)."""
+
+    def __init__(self, enabled):
+        import time
+        self.enabled, self.t, self.clock, self.stages = enabled, time.perf_counter(), time.perf_counter, {}
+
+    def mark(self, name):
+        if self.enabled:
+            torch.cuda.synchronize()
+            now = self.clock()
+            self.stages[name] = self.stages.get(name, 0.0) + now - self.t
+            self.t = now
+
+
+def annotate(dataset_name, timestamp, threshold, neg_num=5, topk=10, timing=None):
     """The whole stage on the device (reference __main__, :109-200): bitsets stay in HBM, the train top-k comes
-    from the fused scorer+top-K kernel (no [N, N] ranking), only what is written to disk crosses to the host."""
+    from the fused scorer+top-K kernel (no [N, N] ranking), only what is written to disk crosses to the host.
+    timing: optional dict that receives wall seconds per stage (parse / encode / score / mine+triplets / rank / write)."""
     global dataset
     dataset = dataset_name
+    tm = _StageTimer(timing is not None)
     save_path = os.path.join("./resources/", dataset, str(timestamp), "train_retrieval")
     os.makedirs(save_path, exist_ok=True)
     save_path_gen = os.path.join("./resources/train_generator", dataset, str(timestamp), "train_gt_topk")
@@ -202,6 +219,7 @@ def annotate(dataset_name, timestamp, threshold, neg_num=5, topk=10):
     train_in, train_out = get_inout_list(train_data, train_data)
     _, test_out = get_inout_list(test_data, test_gt)
     _, val_out = get_inout_list(val_data, val_gt)
+    tm.mark("read+parse")
 
     # subsystem 1: set encoder.  One universe for label sets (train/test/val), one for history sets.
     uni_out = set_encoder.Universe().add(train_out).add(test_out).add(val_out)
@@ -210,19 +228,26 @@ def annotate(dataset_name, timestamp, threshold, neg_num=5, topk=10):
     b_test_out = set_encoder.encode_sequences(test_out, uni_out, _DEVICE)
     b_val_out = set_encoder.encode_sequences(val_out, uni_out, _DEVICE)
     b_train_in = set_encoder.encode_sequences(train_in, uni_in, _DEVICE)
+    tm.mark("universe+csr+encode")
 
     # subsystem 2: Jaccard matrices (diagonals zeroed as :172-173)
     _, s_train_out = engine.jaccard_full(b_train_out, b_train_out, zero_diag=True)
     _, s_train_in = engine.jaccard_full(b_train_in, b_train_in, zero_diag=True)
+    tm.mark("jaccard train matrices (GPU)")
     _mine_and_write(s_train_out, s_train_in, os.path.join(save_path, "train_index.retrieval"),
                     os.path.join(save_path, "train_score.retrieval"), threshold, neg_num)
     del s_train_in
+    tm.mark("triplet mining (GPU) + numpy RNG replay + write")
 
     for name, b in (("test", b_test_out), ("val", b_val_out)):
         _, s = engine.jaccard_full(b, b_train_out, zero_diag=False)
         order = engine.rank_rows(s)
-        writers.write_int_rows(os.path.join(save_path, f"{name}_index.retrieval"), order.cpu().numpy())
-        writers.write_float_rows(os.path.join(save_path, f"{name}_score.retrieval"), s.cpu().numpy(), writers.fmt_str)
+        tm.mark("jaccard + full ranking val/test (GPU)")
+        order_h, s_h = order.cpu().numpy(), s.cpu().numpy()
+        tm.mark("D2H val/test")
+        writers.write_int_rows(os.path.join(save_path, f"{name}_index.retrieval"), order_h)
+        writers.write_float_rows(os.path.join(save_path, f"{name}_score.retrieval"), s_h, writers.fmt_str)
+        tm.mark("format+write val/test files")
 
     # subsystem 4: fused scorer + top-K for the generator's train_gt_topk (never ranks the [N, N] matrix)
     k = min(topk, b_train_out.n_rows)
@@ -230,6 +255,9 @@ def annotate(dataset_name, timestamp, threshold, neg_num=5, topk=10):
     writers.write_int_rows(os.path.join(save_path_gen, "train_index.gen"), t_idx.cpu().numpy())
     writers.write_float_rows(os.path.join(save_path_gen, "train_score.gen"),
                              writers.jaccard_scores_f64(t_inter.cpu().numpy(), t_union.cpu().numpy()), writers.fmt_str)
+    tm.mark("fused top-K train_gt_topk (GPU) + write")
+    if timing is not None:
+        timing.update(tm.stages)
     print("Done!")
 
 

@@ -8,6 +8,7 @@ reference's own formatter and rows are assembled by table lookup.
 import ctypes
 
 import numpy as np
+import pandas as pd
 
 from . import _lib
 
@@ -44,8 +45,9 @@ def _float_codes(mat, fmt):
         raw = mat.view(np.uint32)
     else:
         raise TypeError(f"unsupported score dtype {mat.dtype}")
-    uniq, inv = np.unique(raw.ravel(), return_inverse=True)
-    vals = uniq.view(mat.dtype)
+    # hash-based factorisation (O(n)); np.unique would sort 10^7 values to find ~10^3 distinct ones
+    inv, uniq = pd.factorize(raw.ravel())
+    vals = np.asarray(uniq).view(mat.dtype)
     strings = np.array([fmt(v) for v in vals], dtype=object)
     return inv.reshape(mat.shape), strings
 
