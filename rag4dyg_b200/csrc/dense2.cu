@@ -406,6 +406,7 @@ static Dense2Plan dense2_plan(int64_t nq, int64_t np, int32_t d_pad, int32_t k) 
             best = st;
         }
     }
+    if (options().dense_stripes > 0) best = options().dense_stripes < pl.n_ptiles ? options().dense_stripes : pl.n_ptiles;
     pl.ptiles_per_stripe = (int32_t)((pl.n_ptiles + best - 1) / best);
     pl.n_stripes = (pl.n_ptiles + pl.ptiles_per_stripe - 1) / pl.ptiles_per_stripe;
     pl.ok = true;

@@ -18,6 +18,8 @@ struct Options {
     int jaccard_warps = 16;
     int dense_pair_kernel = 1;
     int dense_pair_qres = -1;
+    int jaccard_stripes = 0;    // 0: automatic; > 0: force the number of pool stripes (experiments)
+    int dense_stripes = 0;
     int stripe_interleave = 0;  // dense pair kernel: 1 = stripe s owns pool tiles s, s+S, ...; 0 = contiguous stripes
 };
 Options& options();  // process-wide knobs (r4d_set_option); environment variables R4D_* give the initial values

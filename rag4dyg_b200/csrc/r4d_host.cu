@@ -42,6 +42,8 @@ Options& options() {
         if (const char* e = getenv("R4D_JACCARD_WARPS")) v.jaccard_warps = atoi(e) == 8 ? 8 : 16;
         if (const char* e = getenv("R4D_DENSE_V1")) v.dense_pair_kernel = atoi(e) ? 0 : 1;
         if (const char* e = getenv("R4D_DENSE2_QRES")) v.dense_pair_qres = atoi(e);
+        if (const char* e = getenv("R4D_JACCARD_STRIPES")) v.jaccard_stripes = atoi(e);
+        if (const char* e = getenv("R4D_DENSE_STRIPES")) v.dense_stripes = atoi(e);
         return v;
     }();
     return o;
@@ -108,6 +110,8 @@ int r4d_set_option(const char* key, int value) {
     else if (!strcmp(key, "dense_pair_kernel")) slot = &o.dense_pair_kernel;
     else if (!strcmp(key, "dense_pair_qres")) slot = &o.dense_pair_qres;
     else if (!strcmp(key, "stripe_interleave")) slot = &o.stripe_interleave;
+    else if (!strcmp(key, "jaccard_stripes")) slot = &o.jaccard_stripes;
+    else if (!strcmp(key, "dense_stripes")) slot = &o.dense_stripes;
     if (!slot || (slot == &o.jaccard_warps && value != 8 && value != 16)) {
         r4d::set_error("r4d_set_option: unknown key or bad value (%s = %d)", key, value);
         return R4D_E_ARG;
