@@ -53,6 +53,8 @@ int r4d_device_ok(void);
  *   "jaccard_warps"     [16] consumer warps per CTA (8 or 16)
  *   "dense_pair_kernel" [1]  use the CTA-pair (cta_group::2) kernel for bf16 top-K when it applies
  *   "dense_pair_qres"   [-1] query tile resident in smem: -1 auto (when >= 4 pool stages fit), 0 never
+ *   "jaccard_stripes"   [0]  0 = automatic; > 0 forces the number of pool stripes of the fused top-K (experiments)
+ *   "dense_stripes"     [0]  same for the dense CTA-pair kernel
  *   "stripe_interleave" [0]  dense pair kernel: 1 = stripe s owns pool tiles s, s+S, s+2S, ... (measured: same
  *                            time, 1.7x the DRAM reads), 0 = contiguous stripes */
 int r4d_set_option(const char* key, int value);
