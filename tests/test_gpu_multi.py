@@ -19,3 +19,6 @@ def test_sharded_equals_single_gpu_over_nccl():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "sharded == single-GPU == oracle: True" in r.stdout
+    assert "sharded == single-GPU: True" in r.stdout and "sharded == single-GPU: False" not in r.stdout
+    # fused NVLink exchange (symmetric memory): must agree with the NCCL path wherever it is available
+    assert "fused P2P exchange == NCCL path: False" not in r.stdout and "fused P2P == NCCL path: False" not in r.stdout
