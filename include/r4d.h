@@ -50,6 +50,7 @@ int r4d_device_ok(void);
 
 /* Tuning / measurement knobs (process-wide; defaults in brackets).  Returns the previous value, or R4D_E_ARG.
  *   "jaccard_skip_zero" [1]  skip 8-word spans that are all-zero across a warp (exact; 0 = execute every word-op)
+ *   "jaccard_sparse_q"  [1]  fused top-K: query tiles with few non-zero spans use the sparse-query kernel (exact)
  *   "jaccard_warps"     [16] consumer warps per CTA (8 or 16)
  *   "dense_pair_kernel" [1]  use the CTA-pair (cta_group::2) kernel for bf16 top-K when it applies
  *   "dense_pair_qres"   [-1] query tile resident in smem: -1 auto (when >= 4 pool stages fit), 0 never

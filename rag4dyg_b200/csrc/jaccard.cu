@@ -19,7 +19,7 @@
 //    sorted list (WarpTopK).  Per-stripe lists are merged by jaccard_merge_kernel.
 #include <cstdlib>
 
-#include "r4d_common.cuh"
+#include "jaccard_common.cuh"
 
 namespace r4d {
 
@@ -44,6 +44,7 @@ struct JaccardParams {
     int32_t last_groups;  // 16-byte groups holding real words in the last chunk (1..8)
     int32_t k;
     int32_t zero_diag;
+    const uint32_t* tile_filter;  // non-null: only query tiles with tile_filter[qtile] != 0 (the rest ran sparse)
     int64_t query_base, pool_base;
     int32_t n_qtiles, n_ptiles, n_stripes, ptiles_per_stripe;
     // top-K partial lists [n_stripes][nq][k]
@@ -138,7 +139,9 @@ jaccard_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     const bool is_producer = threadIdx.x == 0;
     int p_item = blockIdx.x, p_qtile = 0, p_pt = 0, p_pt_end = 0, p_c = 0, p_stage = 0;
     uint32_t p_phase = 0;
+    auto item_mine = [&](int it) { return prm.tile_filter == nullptr || prm.tile_filter[it % prm.n_qtiles] != 0u; };
     auto p_open_item = [&]() {
+        while (p_item < n_items && !item_mine(p_item)) p_item += gridDim.x;
         if (p_item < n_items) {
             const int stripe = p_item / prm.n_qtiles;
             p_qtile = p_item - stripe * prm.n_qtiles;
@@ -189,6 +192,7 @@ jaccard_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     uint32_t phase = 0;
 
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        if (!item_mine(item)) continue;  // block-uniform: this query tile was handled by the sparse-query kernel
         const int stripe = item / prm.n_qtiles;
         const int qtile = item - stripe * prm.n_qtiles;
         const int pt_beg = stripe * prm.ptiles_per_stripe;
@@ -517,7 +521,7 @@ size_t r4d_jaccard_topk_workspace_bytes(int64_t nq, int64_t np, int32_t k) {
     using namespace r4d;
     if (nq <= 0 || np <= 0 || k <= 0) return 256;
     const JaccardPlan pl = plan_topk(nq, np);
-    return (size_t)pl.n_stripes * (size_t)nq * (size_t)k * 12 + 256;
+    return (size_t)pl.n_stripes * (size_t)nq * (size_t)k * 12 + 256 + sparseq_workspace_bytes(nq);
 }
 
 static int merge_launch(const uint32_t* inter, const uint32_t* uni, const int32_t* idx, int32_t n_lists, int64_t nq,
@@ -583,6 +587,17 @@ static int jaccard_topk_impl(const uint32_t* qbits, const uint32_t* qcard, int64
     prm.part_inter = reinterpret_cast<uint32_t*>(workspace);
     prm.part_union = prm.part_inter + per;
     prm.part_idx = reinterpret_cast<int32_t*>(prm.part_union + per);
+    if (sparseq_supported(words, k) && workspace_bytes >= per * 12 + 256 + sparseq_workspace_bytes(nq)) {
+        // sparse query tiles -> jaccard_sparse_kernel; tiles flagged dense -> the kernel below (same partial slots)
+        const SparseQ sq = sparseq_carve(reinterpret_cast<uint8_t*>(workspace) + per * 12, nq);
+        rc = sparseq_build(qbits, nq, words, pitch_words, sq, st);
+        if (rc) return rc;
+        rc = sparseq_topk_launch(pbits, qcard, pcard, nq, np, words, pitch_words, k, zero_diag, query_base, pool_base,
+                                 pl.n_qtiles, pl.n_ptiles, pl.n_stripes, pl.ptiles_per_stripe, prm.part_inter,
+                                 prm.part_union, prm.part_idx, sq, st);
+        if (rc) return rc;
+        prm.tile_filter = sq.tile_dense;
+    }
     rc = launch<MODE_TOPK>(qbits, nq, pbits, np, words, pitch_words, prm, st);
     if (rc) return rc;
     return merge_launch(prm.part_inter, prm.part_union, prm.part_idx, pl.n_stripes, nq, k, k, top_inter, top_union,

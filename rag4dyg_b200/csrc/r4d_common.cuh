@@ -15,6 +15,7 @@ int num_sms();  // SM count of the current device (cached)
 
 struct Options {
     int jaccard_skip_zero = 1;
+    int jaccard_sparse_q = 1;   // fused top-K: sparse query-side span lists for sparse query tiles (jaccard_sparse.cu)
     int jaccard_warps = 16;
     int dense_pair_kernel = 1;
     int dense_pair_qres = -1;
@@ -168,6 +169,10 @@ struct JEntry {
     __device__ __forceinline__ JEntry shfl_up1() const {
         return JEntry{__shfl_up_sync(0xffffffffu, inter, 1), __shfl_up_sync(0xffffffffu, uni, 1),
                       __shfl_up_sync(0xffffffffu, idx, 1)};
+    }
+    __device__ __forceinline__ JEntry shfl_down1() const {
+        return JEntry{__shfl_down_sync(0xffffffffu, inter, 1), __shfl_down_sync(0xffffffffu, uni, 1),
+                      __shfl_down_sync(0xffffffffu, idx, 1)};
     }
 };
 

@@ -39,6 +39,7 @@ Options& options() {
     static Options o = [] {
         Options v;
         if (const char* e = getenv("R4D_JACCARD_NOSKIP")) v.jaccard_skip_zero = atoi(e) ? 0 : 1;
+        if (const char* e = getenv("R4D_JACCARD_NOSPARSE")) v.jaccard_sparse_q = atoi(e) ? 0 : 1;
         if (const char* e = getenv("R4D_JACCARD_WARPS")) v.jaccard_warps = atoi(e) == 8 ? 8 : 16;
         if (const char* e = getenv("R4D_DENSE_V1")) v.dense_pair_kernel = atoi(e) ? 0 : 1;
         if (const char* e = getenv("R4D_DENSE2_QRES")) v.dense_pair_qres = atoi(e);
@@ -106,6 +107,7 @@ int r4d_set_option(const char* key, int value) {
     r4d::Options& o = r4d::options();
     int* slot = nullptr;
     if (!strcmp(key, "jaccard_skip_zero")) slot = &o.jaccard_skip_zero;
+    else if (!strcmp(key, "jaccard_sparse_q")) slot = &o.jaccard_sparse_q;
     else if (!strcmp(key, "jaccard_warps")) slot = &o.jaccard_warps;
     else if (!strcmp(key, "dense_pair_kernel")) slot = &o.dense_pair_kernel;
     else if (!strcmp(key, "dense_pair_qres")) slot = &o.dense_pair_qres;

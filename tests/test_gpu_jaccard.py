@@ -164,15 +164,18 @@ def test_zero_span_skipping_and_warp_variants_are_exact(warps):
     prev_w = _lib.set_option("jaccard_warps", warps)
     try:
         outs = []
-        for skip in (1, 0):
+        for skip, sparse in ((1, 1), (1, 0), (0, 0)):      # sparse-query path, dense kernel with skipping, plain dense
             _lib.set_option("jaccard_skip_zero", skip)
+            _lib.set_option("jaccard_sparse_q", sparse)
             top = engine.jaccard_topk(bq, bp, 10)
             inter, score = engine.jaccard_full(bq, bp)
             outs.append([t.clone() for t in top] + [inter, score])
-        for a, b in zip(*outs):
-            assert torch.equal(a, b)
+        for other in outs[1:]:
+            for a, b in zip(outs[0], other):
+                assert torch.equal(a, b)
         oi, ou, ox = jo.c_topk(*to_csr(q), *to_csr(p), 10)
         assert np.array_equal(outs[0][2].cpu().numpy(), ox) and np.array_equal(outs[0][0].cpu().numpy(), oi)
     finally:
         _lib.set_option("jaccard_skip_zero", 1)
+        _lib.set_option("jaccard_sparse_q", 1)
         _lib.set_option("jaccard_warps", prev_w)
