@@ -365,28 +365,70 @@ jaccard_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 }
 
 // Merge n_lists lists of k_in candidates per query into the best k_out.  One warp per query.
+// Optional (query-index path): `cnt[l * nq + q]` = number of valid, UNSORTED entries of list l (lists of query tiles
+// flagged in `tile_dense` are full sorted lists written by the dense kernel); `n_fill` > 0 appends the zero-score
+// fillers the query-index kernel never produces: pool rows 0 .. n_fill-1 of this shard unless already listed.
+struct MergeExtra {
+    const uint8_t* cnt;
+    const uint32_t* tile_dense;
+    const uint32_t* qcard;
+    const uint32_t* pcard;
+    int64_t pool_base;
+    int32_t n_fill;
+    int64_t q_off, nq_total;  // fused exchange with query batches: row offset / rows of the whole call
+};
+
 __global__ void __launch_bounds__(256)
 jaccard_merge_kernel(const uint32_t* __restrict__ inter, const uint32_t* __restrict__ uni,
                      const int32_t* __restrict__ idx, int32_t n_lists, int64_t nq, int32_t k_in, int32_t k_out,
                      uint32_t* __restrict__ out_inter, uint32_t* __restrict__ out_union, int32_t* __restrict__ out_idx,
-                     const PeerOut peers) {
+                     const PeerOut peers, const MergeExtra ex) {
     const int lane = threadIdx.x & 31;
     const int64_t wpg = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); q < nq; q += wpg) {
         WarpTopK<JEntry> tk;
         tk.init(k_out);
-        for (int l = 0; l < n_lists; ++l) {
-            const int64_t base = ((int64_t)l * nq + q) * k_in;
-            for (int e0 = 0; e0 < k_in; e0 += 32) {
-                const int e = e0 + lane;
-                JEntry c = JEntry::worst();
-                if (e < k_in) c = JEntry{inter[base + e], uni[base + e], idx[base + e]};
-                uint32_t m = __ballot_sync(0xffffffffu, e < k_in && c.idx != R4D_IDX_NONE && JEntry::better(c, tk.kth));
-                while (m) {
-                    const int src = __ffs(m) - 1;
-                    m &= m - 1;
-                    tk.insert(c.shfl(src));
+        if (ex.cnt != nullptr && !(ex.tile_dense && ex.tile_dense[q >> 7])) {
+            // short unsorted lists: lane L walks list l0 + L, all lanes in parallel
+            for (int l0 = 0; l0 < n_lists; l0 += 32) {
+                const int l = l0 + lane;
+                const int n = l < n_lists ? (int)ex.cnt[(int64_t)l * nq + q] : 0;
+                const int n_max = __reduce_max_sync(0xffffffffu, n);
+                const int64_t base = ((int64_t)l * nq + q) * k_in;
+                for (int e = 0; e < n_max; ++e) {
+                    JEntry c = JEntry::worst();
+                    if (e < n) c = JEntry{inter[base + e], uni[base + e], idx[base + e]};
+                    uint32_t m = __ballot_sync(0xffffffffu, e < n && JEntry::better(c, tk.kth));
+                    while (m) {
+                        const int src = __ffs(m) - 1;
+                        m &= m - 1;
+                        tk.insert(c.shfl(src));
+                    }
                 }
+            }
+        } else {
+            for (int l = 0; l < n_lists; ++l) {
+                const int64_t base = ((int64_t)l * nq + q) * k_in;
+                for (int e0 = 0; e0 < k_in; e0 += 32) {
+                    const int e = e0 + lane;
+                    JEntry c = JEntry::worst();
+                    if (e < k_in) c = JEntry{inter[base + e], uni[base + e], idx[base + e]};
+                    uint32_t m = __ballot_sync(0xffffffffu, e < k_in && c.idx != R4D_IDX_NONE && JEntry::better(c, tk.kth));
+                    while (m) {
+                        const int src = __ffs(m) - 1;
+                        m &= m - 1;
+                        tk.insert(c.shfl(src));
+                    }
+                }
+            }
+        }
+        if (ex.n_fill > 0) {
+            const uint32_t cq = ex.qcard[q];
+            const uint32_t cp = lane < ex.n_fill ? ex.pcard[lane] : 0u;
+            for (int i = 0; i < ex.n_fill; ++i) {
+                const JEntry c{0u, max(cq + __shfl_sync(0xffffffffu, cp, i), 1u), (int32_t)(ex.pool_base + i)};
+                if (__ballot_sync(0xffffffffu, lane < k_out && tk.mine.idx == c.idx)) continue;  // listed already
+                tk.insert(c);
             }
         }
         if (lane < k_out) {
@@ -396,8 +438,9 @@ jaccard_merge_kernel(const uint32_t* __restrict__ inter, const uint32_t* __restr
                 out_idx[q * k_out + lane] = tk.mine.idx;
             } else {
                 // fused exchange: store into slot `rank` of every peer's gather buffer [3][world][nq][k] (NVLink P2P)
-                const int64_t plane = (int64_t)peers.world * nq * k_out;
-                const int64_t at = ((int64_t)peers.rank * nq + q) * k_out + lane;
+                const int64_t nq_all = ex.nq_total > 0 ? ex.nq_total : nq;
+                const int64_t plane = (int64_t)peers.world * nq_all * k_out;
+                const int64_t at = ((int64_t)peers.rank * nq_all + ex.q_off + q) * k_out + lane;
                 for (int r = 0; r < peers.world; ++r) {
                     uint32_t* dst = reinterpret_cast<uint32_t*>(peers.base[r]);
                     dst[at] = tk.mine.inter;
@@ -521,18 +564,28 @@ size_t r4d_jaccard_topk_workspace_bytes(int64_t nq, int64_t np, int32_t k) {
     using namespace r4d;
     if (nq <= 0 || np <= 0 || k <= 0) return 256;
     const JaccardPlan pl = plan_topk(nq, np);
-    return (size_t)pl.n_stripes * (size_t)nq * (size_t)k * 12 + 256 + sparseq_workspace_bytes(nq);
+    size_t need = (size_t)pl.n_stripes * (size_t)nq * (size_t)k * 12 + 256;
+    // query-index path: the call is served in batches of <= SQ_QB query rows that reuse one workspace
+    size_t batch = 0;
+    const int64_t sizes[2] = {nq < SQ_QB ? nq : (int64_t)SQ_QB, nq % SQ_QB};
+    for (int64_t nb : sizes) {
+        if (nb <= 0) continue;
+        const JaccardPlan pb = plan_topk(nb, np);
+        const size_t b = (size_t)pb.n_stripes * (size_t)nb * (size_t)k * 12 + 256 + sparseq_workspace_bytes(nb, pb.n_stripes);
+        if (b > batch) batch = b;
+    }
+    return need > batch ? need : batch;
 }
 
 static int merge_launch(const uint32_t* inter, const uint32_t* uni, const int32_t* idx, int32_t n_lists, int64_t nq,
                         int32_t k_in, int32_t k_out, uint32_t* out_inter, uint32_t* out_union, int32_t* out_idx,
-                        const r4d::PeerOut& peers, r4d_stream_t stream) {
+                        const r4d::PeerOut& peers, const r4d::MergeExtra& ex, r4d_stream_t stream) {
     using namespace r4d;
     int64_t blocks = (nq + 7) / 8;
     const int64_t cap = (int64_t)num_sms() * 16;
     if (blocks > cap) blocks = cap;
     jaccard_merge_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(inter, uni, idx, n_lists, nq, k_in, k_out,
-                                                                         out_inter, out_union, out_idx, peers);
+                                                                         out_inter, out_union, out_idx, peers, ex);
     R4D_CUDA(cudaGetLastError());
     return R4D_OK;
 }
@@ -563,45 +616,66 @@ static int jaccard_topk_impl(const uint32_t* qbits, const uint32_t* qcard, int64
     if (nq == 0) return R4D_OK;
     R4D_REQUIRE(peers.world > 0 || (top_inter && top_union && top_idx), "jaccard_topk: null output");
     cudaStream_t st = as_stream(stream);
+    const MergeExtra no_extra{};
     if (np == 0)  // no pool rows: every list is padding; the merge of zero lists writes it, no workspace needed
-        return merge_launch(nullptr, nullptr, nullptr, 0, nq, k, k, top_inter, top_union, top_idx, peers, stream);
-    const JaccardPlan pl = plan_topk(nq, np);
-    const size_t per = (size_t)pl.n_stripes * (size_t)nq * (size_t)k;
-    if (workspace_bytes < per * 12 || (!workspace && per)) {
-        set_error("jaccard_topk: workspace %zu B < required %zu B", workspace_bytes, per * 12);
-        return R4D_E_WORKSPACE;
-    }
-    JaccardParams prm{};
-    prm.qcard = qcard;
-    prm.pcard = pcard;
-    prm.nq = nq;
-    prm.np = np;
-    prm.k = k;
-    prm.zero_diag = zero_diag;
-    prm.query_base = query_base;
-    prm.pool_base = pool_base;
-    prm.n_qtiles = pl.n_qtiles;
-    prm.n_ptiles = pl.n_ptiles;
-    prm.n_stripes = pl.n_stripes;
-    prm.ptiles_per_stripe = pl.ptiles_per_stripe;
-    prm.part_inter = reinterpret_cast<uint32_t*>(workspace);
-    prm.part_union = prm.part_inter + per;
-    prm.part_idx = reinterpret_cast<int32_t*>(prm.part_union + per);
-    if (sparseq_supported(words, k) && workspace_bytes >= per * 12 + 256 + sparseq_workspace_bytes(nq)) {
-        // sparse query tiles -> jaccard_sparse_kernel; tiles flagged dense -> the kernel below (same partial slots)
-        const SparseQ sq = sparseq_carve(reinterpret_cast<uint8_t*>(workspace) + per * 12, nq);
-        rc = sparseq_build(qbits, nq, words, pitch_words, sq, st);
+        return merge_launch(nullptr, nullptr, nullptr, 0, nq, k, k, top_inter, top_union, top_idx, peers, no_extra, stream);
+    const bool use_index = sparseq_supported(words, k);
+    // query-index path: batches of <= SQ_QB query rows, each a full launch sequence on the same workspace
+    const int64_t q_batch = use_index ? (int64_t)SQ_QB : nq;
+    for (int64_t q0 = 0; q0 < nq; q0 += q_batch) {
+        const int64_t nb = nq - q0 < q_batch ? nq - q0 : q_batch;
+        const JaccardPlan pl = plan_topk(nb, np);
+        const size_t per = (size_t)pl.n_stripes * (size_t)nb * (size_t)k;
+        const size_t need = per * 12 + (use_index ? 256 + sparseq_workspace_bytes(nb, pl.n_stripes) : 0);
+        if (workspace_bytes < need || !workspace) {
+            set_error("jaccard_topk: workspace %zu B < required %zu B", workspace_bytes, need);
+            return R4D_E_WORKSPACE;
+        }
+        const uint32_t* qb = qbits + q0 * pitch_words;
+        JaccardParams prm{};
+        prm.qcard = qcard + q0;
+        prm.pcard = pcard;
+        prm.nq = nb;
+        prm.np = np;
+        prm.k = k;
+        prm.zero_diag = zero_diag;
+        prm.query_base = query_base + q0;
+        prm.pool_base = pool_base;
+        prm.n_qtiles = pl.n_qtiles;
+        prm.n_ptiles = pl.n_ptiles;
+        prm.n_stripes = pl.n_stripes;
+        prm.ptiles_per_stripe = pl.ptiles_per_stripe;
+        prm.part_inter = reinterpret_cast<uint32_t*>(workspace);
+        prm.part_union = prm.part_inter + per;
+        prm.part_idx = reinterpret_cast<int32_t*>(prm.part_union + per);
+        MergeExtra ex{};
+        ex.q_off = q0;
+        ex.nq_total = nq;
+        if (use_index) {
+            // sparse query tiles -> jaccard_qindex_kernel; tiles flagged dense -> the kernel below (same partial slots)
+            const QIndex qi = sparseq_carve(reinterpret_cast<uint8_t*>(workspace) + per * 12, nb, pl.n_stripes);
+            rc = sparseq_build(qb, nb, words, pitch_words, pl.n_stripes, qi, st);
+            if (rc) return rc;
+            rc = sparseq_topk_launch(pbits, prm.qcard, pcard, nb, np, words, pitch_words, k, zero_diag, prm.query_base,
+                                     pool_base, pl.n_qtiles, pl.n_ptiles, pl.n_stripes, pl.ptiles_per_stripe,
+                                     prm.part_inter, prm.part_union, prm.part_idx, qi, st);
+            if (rc) return rc;
+            prm.tile_filter = qi.tile_dense;
+            ex.cnt = qi.cnt;
+            ex.tile_dense = qi.tile_dense;
+            ex.qcard = prm.qcard;
+            ex.pcard = pcard;
+            ex.pool_base = pool_base;
+            ex.n_fill = (int32_t)(np < k ? np : k);
+        }
+        rc = launch<MODE_TOPK>(qb, nb, pbits, np, words, pitch_words, prm, st);
         if (rc) return rc;
-        rc = sparseq_topk_launch(pbits, qcard, pcard, nq, np, words, pitch_words, k, zero_diag, query_base, pool_base,
-                                 pl.n_qtiles, pl.n_ptiles, pl.n_stripes, pl.ptiles_per_stripe, prm.part_inter,
-                                 prm.part_union, prm.part_idx, sq, st);
+        rc = merge_launch(prm.part_inter, prm.part_union, prm.part_idx, pl.n_stripes, nb, k, k,
+                          top_inter ? top_inter + q0 * k : nullptr, top_union ? top_union + q0 * k : nullptr,
+                          top_idx ? top_idx + q0 * k : nullptr, peers, ex, stream);
         if (rc) return rc;
-        prm.tile_filter = sq.tile_dense;
     }
-    rc = launch<MODE_TOPK>(qbits, nq, pbits, np, words, pitch_words, prm, st);
-    if (rc) return rc;
-    return merge_launch(prm.part_inter, prm.part_union, prm.part_idx, pl.n_stripes, nq, k, k, top_inter, top_union,
-                        top_idx, peers, stream);
+    return R4D_OK;
 }
 
 int r4d_jaccard_topk(const uint32_t* qbits, const uint32_t* qcard, int64_t nq, const uint32_t* pbits,
@@ -635,7 +709,7 @@ int r4d_jaccard_topk_merge(const uint32_t* inter, const uint32_t* uni, const int
     R4D_REQUIRE(out_inter && out_union && out_idx, "jaccard_topk_merge: null output");
     R4D_REQUIRE(n_lists == 0 || (inter && uni && idx), "jaccard_topk_merge: null input");
     r4d::PeerOut none{};
-    return merge_launch(inter, uni, idx, n_lists, nq, k_in, k_out, out_inter, out_union, out_idx, none, stream);
+    return merge_launch(inter, uni, idx, n_lists, nq, k_in, k_out, out_inter, out_union, out_idx, none, MergeExtra{}, stream);
 }
 
 }  // extern "C"

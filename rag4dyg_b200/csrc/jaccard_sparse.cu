@@ -1,161 +1,216 @@
-// jaccard_sparse.cu — fused Jaccard top-K with a SPARSE QUERY SIDE (pool side unchanged: bitset tiles streamed by TMA,
-// AND + POPC on 8-word spans, exact rational ranking, warp-level top-K lists).
+// jaccard_sparse.cu — fused Jaccard top-K with a QUERY-SIDE WORD INDEX (pool side unchanged: bitset tiles streamed by
+// TMA, AND + POPC, exact rational ranking).
 //
-// Why: node-id sets are tiny next to the vocabulary (2.2 of 20 000 bits), so a query row has ~2 non-zero 8-word spans
-// out of 80.  The dense kernel (jaccard.cu) still walks all 80 spans of every (query slab, pool slab) to find that out
-// and re-streams the query tile for every pool tile.  Here the query tile is turned ONCE per launch into a list of its
-// non-zero spans, bucketed by 32-word chunk; per pool chunk the entries are dealt round-robin to the 16 warps and each
-// is tested against the 128 pool rows of the tile.  Non-zero intersections are rare, so they are accumulated with smem
-// atomics in a count tile and remembered in the "touched" list of the warp that owns the query row; the per-tile
-// epilogue visits only those cells.
-// Zero-score candidates matter only as the lowest-index filler of a short list: every list starts with the first k pool
-// rows of its stripe as (score 0) placeholders, which real candidates for the same row replace.
+// Why: node-id sets are tiny next to the vocabulary (2.2 of 20 000 bits), so a query row has ~2 non-zero words out of
+// 625 and only ~2.4e-4 of all (query, pool) pairs intersect at all.  The dense kernel (jaccard.cu) re-streams the pool
+// for every 128-query tile and walks every 8-word span of every pair to find that out.  Here
+//   1. qindex_kernel turns a query batch (<= 8 192 rows) ONCE into the list of its non-zero words, by row;
+//   2. jaccard_qindex_kernel: every CTA owns a pool stripe.  It loads the index of a whole group of query tiles into
+//      shared memory re-sorted BY WORD (counting sort), then streams its pool bitsets through a TMA ring exactly once
+//      per group.  Each warp owns 8 rows of the 128-row pool tile: two conflict-free LDS.128 per lane per 32-word
+//      chunk bring the warp's slice into registers (the ring stage is released right away), a ballot finds the
+//      non-zero pool words, and each of them looks up the query entries with the same word id: AND + POPC.
+//   3. A hit (query r, pool row p, word w) is completed on the spot: the warp re-reads row r's entries (by-row
+//      index, L2) against pool row p, sums the POPCs (full intersection) and keeps the hit only if w is the FIRST
+//      intersecting word of the pair, so every intersecting pair is emitted exactly once without any accumulator tile.
+//   4. Emitted candidates go to the (stripe, query) partial list in global memory (append while short, replace-the-
+//      worst when full) under a per-query lock bit in shared memory.
+// Zero-score candidates are never produced here: they only matter as the lowest-index filler of a short list, which
+// the merge kernel adds (jaccard.cu, jaccard_merge_kernel `n_fill`).
 //
-// Query tiles with more than SQ_E_MAX non-zero spans (dense data, e.g. history sets) are flagged by the span-list
-// kernel and handled by the dense kernel in the same launch sequence; both write the same per-stripe partial lists.
+// Query tiles with more than SQ_T1 non-zero words (dense data, e.g. history sets) are flagged by qindex_kernel and
+// handled by the dense kernel in the same launch sequence; both write the same per-stripe partial lists.
 // Results are bit-identical to the dense kernel (tests/test_gpu_jaccard.py).
 #include "jaccard_common.cuh"
 
 namespace r4d {
 
-// ---------------------------------------------------------------------------- span lists of a query tile
-// grid = n_qtiles CTAs.  Entries are bucketed by 32-word chunk; inside a chunk their order is arbitrary.
+// ---------------------------------------------------------------------------- by-row index of a query tile
+// grid = n_qtiles CTAs of 256 threads (8 warps, 16 rows each).
 __global__ void __launch_bounds__(256)
-qspans_kernel(const uint32_t* __restrict__ qbits, int64_t nq, int32_t pitch_words, int32_t n_chunks, SparseQ sq) {
-    __shared__ uint32_t cnt[SQ_MAX_CHUNKS];
-    __shared__ uint32_t cur[SQ_MAX_CHUNKS];
-    __shared__ uint32_t lane_tot[32];
-    __shared__ uint32_t total_s;
-    const int t = blockIdx.x, tid = threadIdx.x;
-    const int nb = n_chunks, n_spans = n_chunks * 4;
-    for (int i = tid; i < nb; i += 256) cnt[i] = 0u;
-    __syncthreads();
-
-    auto span_words = [&](int r, int s, uint4& a, uint4& b) -> bool {
-        a = make_uint4(0, 0, 0, 0);
-        b = make_uint4(0, 0, 0, 0);
-        const int64_t gq = (int64_t)t * SQ_TQ + r;
-        if (gq >= nq || s * 8 >= pitch_words) return false;
-        const uint4* row = reinterpret_cast<const uint4*>(qbits + gq * pitch_words + s * 8);
-        a = row[0];
-        if (s * 8 + 4 < pitch_words) b = row[1];
-        return ((a.x | a.y | a.z | a.w) | (b.x | b.y | b.z | b.w)) != 0u;
-    };
-
-    for (int u = tid; u < SQ_TQ * n_spans; u += 256) {
-        const int r = u / n_spans, s = u - r * n_spans;
-        uint4 a, b;
-        if (span_words(r, s, a, b)) atomicAdd(&cnt[s >> 2], 1u);
+qindex_kernel(const uint32_t* __restrict__ qbits, int64_t nq, int32_t words, int32_t pitch_words, QIndex qi) {
+    __shared__ uint32_t rowcnt[SQ_TQ];
+    __shared__ uint32_t rowstart[SQ_TQ + 1];
+    const int t = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = warp; i < SQ_TQ; i += 8) {
+        const int64_t gq = (int64_t)t * SQ_TQ + i;
+        uint32_t c = 0;
+        if (gq < nq) {
+            const uint32_t* row = qbits + gq * pitch_words;
+            for (int w0 = 0; w0 < words; w0 += 32) {
+                const int w = w0 + lane;
+                const uint32_t v = w < words ? row[w] : 0u;
+                c += __popc(__ballot_sync(0xffffffffu, v != 0u));
+            }
+        }
+        if (lane == 0) rowcnt[i] = c;
     }
     __syncthreads();
-    if (tid < 32) {  // exclusive scan of the bucket counts by one warp
-        const int per = (nb + 31) / 32;
-        uint32_t sum = 0;
-        for (int i = tid * per; i < min(nb, (tid + 1) * per); ++i) sum += cnt[i];
+    if (warp == 0) {  // exclusive scan of 128 row counts, 4 per lane
+        uint32_t v[4], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            v[j] = rowcnt[lane * 4 + j];
+            sum += v[j];
+        }
         uint32_t incl = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (tid >= o) incl += v;
+            const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += x;
         }
         uint32_t run = incl - sum;
-        for (int i = tid * per; i < min(nb, (tid + 1) * per); ++i) {
-            cur[i] = run;
-            run += cnt[i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            rowstart[lane * 4 + j] = run;
+            run += v[j];
         }
-        if (tid == 31) total_s = incl;
-        (void)lane_tot;
+        if (lane == 31) rowstart[SQ_TQ] = incl;
     }
     __syncthreads();
-    const uint32_t total = total_s;
-    if (total > (uint32_t)SQ_E_MAX) {  // too dense for the sparse path: the dense kernel takes this tile
-        if (tid == 0) sq.tile_dense[t] = 1u;
+    const uint32_t total = rowstart[SQ_TQ];
+    if (total > (uint32_t)SQ_T1) {  // too dense for the index path: the dense kernel takes this tile
+        if (threadIdx.x == 0) {
+            qi.tile_dense[t] = 1u;
+            qi.tile_cnt[t] = 0u;
+        }
         return;
     }
-    uint16_t* off = sq.off + (size_t)t * SQ_OFF_LD;
-    for (int i = tid; i < nb; i += 256) off[i] = (uint16_t)cur[i];
-    if (tid == 0) {
-        off[nb] = (uint16_t)total;
-        sq.tile_dense[t] = 0u;
+    if (threadIdx.x == 0) {
+        qi.tile_dense[t] = 0u;
+        qi.tile_cnt[t] = total;
     }
-    __syncthreads();
-    uint32_t* hdr = sq.hdr + (size_t)t * SQ_E_MAX;
-    uint4* words = reinterpret_cast<uint4*>(sq.words + (size_t)t * SQ_E_MAX * 8);
-    for (int u = tid; u < SQ_TQ * n_spans; u += 256) {
-        const int r = u / n_spans, s = u - r * n_spans;
-        uint4 a, b;
-        if (span_words(r, s, a, b)) {
-            const uint32_t pos = atomicAdd(&cur[s >> 2], 1u);
-            hdr[pos] = (uint32_t)r | ((uint32_t)(s & 3) << 8);
-            words[pos * 2] = a;
-            words[pos * 2 + 1] = b;
+    uint16_t* rowoff = qi.rowoff + (size_t)t * SQ_ROWOFF_LD;
+    for (int i = threadIdx.x; i <= SQ_TQ; i += 256) rowoff[i] = (uint16_t)rowstart[i];
+    uint16_t* ew = qi.ent_word + (size_t)t * SQ_T1;
+    uint32_t* ev = qi.ent_val + (size_t)t * SQ_T1;
+    for (int i = warp; i < SQ_TQ; i += 8) {
+        const int64_t gq = (int64_t)t * SQ_TQ + i;
+        if (gq >= nq) continue;
+        const uint32_t* row = qbits + gq * pitch_words;
+        uint32_t base = rowstart[i];
+        for (int w0 = 0; w0 < words; w0 += 32) {
+            const int w = w0 + lane;
+            const uint32_t v = w < words ? row[w] : 0u;
+            const uint32_t b = __ballot_sync(0xffffffffu, v != 0u);
+            if (v != 0u) {
+                const uint32_t pos = base + __popc(b & ((1u << lane) - 1u));
+                ew[pos] = (uint16_t)w;
+                ev[pos] = v;
+            }
+            base += __popc(b);
         }
     }
 }
 
 // ---------------------------------------------------------------------------- main kernel
 struct SparseParams {
+    const uint32_t* pbits;
     const uint32_t* qcard;
     const uint32_t* pcard;
     int64_t nq, np;
-    int32_t n_chunks, k, zero_diag, n_stages;
+    int32_t pitch_words, n_words, n_chunks, k, zero_diag;
     int64_t query_base, pool_base;
     int32_t n_qtiles, n_ptiles, n_stripes, ptiles_per_stripe;
     uint32_t* part_inter;
     uint32_t* part_union;
     int32_t* part_idx;
-    SparseQ sq;
+    QIndex qi;
+    int32_t debug;  // experiments: 1 = scan only (no lookups), 2 = lookups but no hit completion, 3 = no list update
 };
 
+__device__ __forceinline__ uint32_t atoms_or(uint32_t addr, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ uint32_t atoms_add(uint32_t addr, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ void atoms_and(uint32_t addr, uint32_t v) {
+    asm volatile("red.shared.and.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) {
+    asm volatile("st.volatile.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ void lds128s(uint4& v, uint32_t addr) {
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
 }
 
+// shared-memory layout (offsets from the 1024-aligned base)
+constexpr int SQ_OFF_WORDS = SQ_MAX_WORDS + 5;  // off[0 .. n_words], padded
+constexpr size_t SQ_SM_STAGES = 0;
+constexpr size_t SQ_SM_BARS = SQ_SM_STAGES + (size_t)SQ_STAGES * SQ_STAGE_BYTES;
+constexpr size_t SQ_SM_OFF = SQ_SM_BARS + 128;
+constexpr size_t SQ_SM_VAL = SQ_SM_OFF + (size_t)SQ_OFF_WORDS * 4;
+constexpr size_t SQ_SM_ROW = SQ_SM_VAL + (size_t)SQ_E_CAP * 4;
+constexpr size_t SQ_SM_COUNT = SQ_SM_ROW + (size_t)SQ_E_CAP * 2;
+constexpr size_t SQ_SM_LOCK = SQ_SM_COUNT + SQ_QB;
+constexpr size_t SQ_SM_GROUPS = SQ_SM_LOCK + SQ_QB / 8;
+constexpr size_t SQ_SM_SCAN = SQ_SM_GROUPS + (size_t)(SQ_MAX_TILES + 2) * 8;
+constexpr size_t SQ_SM_TOTAL = SQ_SM_SCAN + 32 * 4 + 1024;  // + alignment slack
+static_assert(SQ_SM_TOTAL <= 227 * 1024, "query-index kernel: shared memory budget");
+
 __global__ void __launch_bounds__(SQ_THREADS + 32, 1)
-jaccard_sparse_kernel(const __grid_constant__ CUtensorMap tm_p, const SparseParams prm) {
+jaccard_qindex_kernel(const __grid_constant__ CUtensorMap tm_p, const SparseParams prm) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int NST = prm.n_stages;
-    uint8_t* stages = smem;                                                      // [NST][128 rows x 128 B]
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)NST * SQ_STAGE_BYTES);
+    uint8_t* stages = smem + SQ_SM_STAGES;                                   // [STAGES][128 rows x 128 B], swizzled
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SQ_SM_BARS);
     uint64_t* empty_bar = full_bar + 8;
-    uint32_t* acc = reinterpret_cast<uint32_t*>(empty_bar + 8);                  // [128][128] intersection counts
-    uint4* ent_words = reinterpret_cast<uint4*>(acc + SQ_TQ * SQ_TP);            // [E_MAX][2]
-    uint32_t* ent_hdr = reinterpret_cast<uint32_t*>(ent_words + SQ_E_MAX * 2);   // [E_MAX]
-    uint16_t* off_s = reinterpret_cast<uint16_t*>(ent_hdr + SQ_E_MAX);           // [SQ_OFF_LD]
-    uint16_t* touched = off_s + SQ_OFF_LD;                                       // [16 owners][SQ_TOUCH_CAP]
-    uint32_t* t_cnt = reinterpret_cast<uint32_t*>(touched + SQ_WARPS * SQ_TOUCH_CAP);    // [16] cells per owner
-    uint32_t* l_inter = t_cnt + SQ_WARPS;                                        // [128][k] x 3
-    const int K = prm.k;
-    uint32_t* l_union = l_inter + SQ_TQ * K;
-    int32_t* l_idx = reinterpret_cast<int32_t*>(l_union + SQ_TQ * K);
+    uint32_t* off = reinterpret_cast<uint32_t*>(smem + SQ_SM_OFF);           // entries of word w: [off[w], off[w+1])
+    uint32_t* val_s = reinterpret_cast<uint32_t*>(smem + SQ_SM_VAL);         // [E] word value, sorted by word id
+    uint16_t* row_s = reinterpret_cast<uint16_t*>(smem + SQ_SM_ROW);         // [E] group-relative query row
+    volatile uint8_t* count = reinterpret_cast<volatile uint8_t*>(smem + SQ_SM_COUNT);  // [rows] candidates stored
+    uint32_t* lock = reinterpret_cast<uint32_t*>(smem + SQ_SM_LOCK);         // one bit per group row
+    int32_t* g_first = reinterpret_cast<int32_t*>(smem + SQ_SM_GROUPS);      // [n_groups + 1] first tile of a group
+    int32_t* g_ent = g_first + SQ_MAX_TILES + 2;                             // [n_groups] entries of the group
+    uint32_t* scan_s = reinterpret_cast<uint32_t*>(smem + SQ_SM_SCAN);       // [17] warp totals, [31] = n_groups
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tm_p);
-        for (int s = 0; s < NST; ++s) {
+        for (int s = 0; s < SQ_STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], SQ_WARPS);
         }
         fence_barrier_init();
+        // greedy packing of consecutive query tiles into groups of <= SQ_E_CAP entries (every CTA computes the same)
+        int g = 0, sum = 0;
+        g_first[0] = 0;
+        for (int t = 0; t < prm.n_qtiles; ++t) {
+            const int c = (int)prm.qi.tile_cnt[t];
+            if (sum + c > SQ_E_CAP) {
+                g_ent[g] = sum;
+                g_first[++g] = t;
+                sum = 0;
+            }
+            sum += c;
+        }
+        g_ent[g] = sum;
+        g_first[g + 1] = prm.n_qtiles;
+        scan_s[31] = (uint32_t)(g + 1);
     }
-    for (int i = threadIdx.x; i < SQ_TQ * SQ_TP; i += SQ_THREADS + 32) acc[i] = 0u;  // cells are reset after every use
-    if (threadIdx.x < SQ_WARPS) t_cnt[threadIdx.x] = 0u;
     __syncthreads();
+    const int n_groups = (int)scan_s[31];
+    const int n_items = n_groups * prm.n_stripes;
 
-    const int n_items = prm.n_qtiles * prm.n_stripes;
-    auto item_mine = [&](int item) { return prm.sq.tile_dense[item % prm.n_qtiles] == 0u; };
-
-    // ---- dedicated TMA producer: warp 16 (this kernel needs < 96 registers per thread, so a 17th warp is affordable;
-    // an inline producer lane would have to wait for the slowest warp of the previous chunk before its own chunk).
+    // ---- dedicated TMA producer (warp 16)
     if (warp == SQ_WARPS) {
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                if (!item_mine(item)) continue;
-                const int stripe = item / prm.n_qtiles;
+                const int g = item / prm.n_stripes, stripe = item - g * prm.n_stripes;
+                if (g_ent[g] == 0) continue;
                 const int pt_beg = stripe * prm.ptiles_per_stripe;
                 const int pt_end = min(pt_beg + prm.ptiles_per_stripe, prm.n_ptiles);
                 for (int pt = pt_beg; pt < pt_end; ++pt)
@@ -164,7 +219,7 @@ jaccard_sparse_kernel(const __grid_constant__ CUtensorMap tm_p, const SparsePara
                         mbar_arrive_expect_tx(&full_bar[stage], SQ_STAGE_BYTES);
                         tma_load_2d(stages + (size_t)stage * SQ_STAGE_BYTES, &tm_p, &full_bar[stage], c * SQ_CHUNK_WORDS,
                                     pt * SQ_TP);
-                        if (++stage == NST) {
+                        if (++stage == SQ_STAGES) {
                             stage = 0;
                             phase ^= 1;
                         }
@@ -175,191 +230,263 @@ jaccard_sparse_kernel(const __grid_constant__ CUtensorMap tm_p, const SparsePara
     }
 
     const uint32_t stages_u32 = smem_u32(stages);
-    const uint32_t sw = (uint32_t)(lane & 7);  // (pool row & 7) of every row this lane tests: rows lane + 32 j
+    const uint32_t lock_u32 = smem_u32(lock), count_u32 = smem_u32(smem + SQ_SM_COUNT), off_u32 = smem_u32(off);
+    const int K = prm.k;
     int stage = 0;
     uint32_t phase = 0;
-    uint16_t* my_touched = touched + warp * SQ_TOUCH_CAP;  // cells of the rows this warp owns (r & 15 == warp)
+    int cur_g = -1;
 
-    // insert a non-zero candidate into the list of query row r (all 32 lanes call with warp-uniform arguments)
-    auto take = [&](int r, int64_t gq, int64_t gp, uint32_t inter) {
-        if (gq >= prm.nq || gp >= prm.np || inter == 0u) return;
-        if (prm.zero_diag && prm.query_base + gq == prm.pool_base + gp) return;  // score forced to 0: stays a filler
-        const uint32_t uni = prm.qcard[gq] + prm.pcard[gp] - inter;
-        const JEntry c{inter, uni, (int32_t)(prm.pool_base + gp)};
-        JEntry mine = lane < K ? JEntry{l_inter[r * K + lane], l_union[r * K + lane], l_idx[r * K + lane]} : JEntry::worst();
-        // a zero-score placeholder of the same pool row is replaced, not duplicated
-        const uint32_t same = __ballot_sync(0xffffffffu, lane < K && mine.idx == c.idx);
-        if (same) {
-            const int pos = __ffs(same) - 1;
-            const JEntry dn = mine.shfl_down1();
-            if (lane >= pos && lane < K) mine = (lane == K - 1) ? JEntry::worst() : dn;
-        }
-        WarpTopK<JEntry> tk;
-        tk.k = K;
-        tk.mine = mine;
-        tk.refresh_kth();
-        tk.insert(c);
-        if (lane < K) {
-            l_inter[r * K + lane] = tk.mine.inter;
-            l_union[r * K + lane] = tk.mine.uni;
-            l_idx[r * K + lane] = tk.mine.idx;
-        }
-        __syncwarp();
-    };
+    // this lane's two 16-byte units of every chunk: rows warp*8 + (lane>>3) + {0, 4}, unit lane&7 (128B swizzle)
+    const int prow0 = warp * 8 + (lane >> 3);
+    const uint32_t unit = (uint32_t)(lane & 7);
+    const uint32_t a0 = (uint32_t)prow0 * 128u + ((unit ^ (uint32_t)(prow0 & 7)) << 4);
+    const uint32_t a1 = (uint32_t)(prow0 + 4) * 128u + ((unit ^ (uint32_t)((prow0 + 4) & 7)) << 4);
 
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        if (!item_mine(item)) continue;  // block-uniform
-        const int stripe = item / prm.n_qtiles;
-        const int qtile = item - stripe * prm.n_qtiles;
+        const int g = item / prm.n_stripes, stripe = item - g * prm.n_stripes;
+        if (g_ent[g] == 0) continue;  // block-uniform: nothing but empty / dense-flagged tiles
+        const int t0 = g_first[g], t1 = g_first[g + 1];
+        const int64_t row0 = (int64_t)t0 * SQ_TQ;                                  // first query row of the group
+        const int g_rows = (int)(min((int64_t)t1 * SQ_TQ, prm.nq) - row0);
         const int pt_beg = stripe * prm.ptiles_per_stripe;
         const int pt_end = min(pt_beg + prm.ptiles_per_stripe, prm.n_ptiles);
-        const int nb = prm.n_chunks;
 
-        named_bar_sync(1, SQ_THREADS);  // previous item's lists / entries are no longer in use (consumer warps only)
-        {
-            const uint32_t* g_off = reinterpret_cast<const uint32_t*>(prm.sq.off + (size_t)qtile * SQ_OFF_LD);
-            uint32_t* s_off = reinterpret_cast<uint32_t*>(off_s);
-            for (int i = threadIdx.x; i < SQ_OFF_LD / 2; i += SQ_THREADS) s_off[i] = g_off[i];
-        }
-        named_bar_sync(1, SQ_THREADS);
-        const int total = off_s[nb];
-        {
-            const uint32_t* g_hdr = prm.sq.hdr + (size_t)qtile * SQ_E_MAX;
-            const uint4* g_words = reinterpret_cast<const uint4*>(prm.sq.words + (size_t)qtile * SQ_E_MAX * 8);
-            for (int i = threadIdx.x; i < total; i += SQ_THREADS) ent_hdr[i] = g_hdr[i];
-            for (int i = threadIdx.x; i < total * 2; i += SQ_THREADS) ent_words[i] = g_words[i];
-        }
-        // lists of the 8 rows this warp owns (r & 15 == warp) start with the stripe's first k pool rows at score 0
-        for (int i = 0; i < 8; ++i) {
-            const int r = warp + 16 * i;
-            const int64_t gq = (int64_t)qtile * SQ_TQ + r;
-            if (lane < K) {
-                const int64_t gp = (int64_t)pt_beg * SQ_TP + lane;
-                const bool ok = gq < prm.nq && gp < prm.np && gp < (int64_t)pt_end * SQ_TP;
-                const uint32_t u = ok ? max(prm.qcard[gq] + prm.pcard[gp], 1u) : 1u;
-                l_inter[r * K + lane] = 0u;
-                l_union[r * K + lane] = u;
-                l_idx[r * K + lane] = ok ? (int32_t)(prm.pool_base + gp) : R4D_IDX_NONE;
+        named_bar_sync(1, SQ_THREADS);  // previous item: all hits handled, counts flushed
+        if (g != cur_g) {               // ---- load the group's entries re-sorted by word id (counting sort)
+            cur_g = g;
+            const int nw = prm.n_words;
+            for (int i = threadIdx.x; i <= nw; i += SQ_THREADS) off[i] = 0u;
+            named_bar_sync(1, SQ_THREADS);
+            for (int t = t0; t < t1; ++t) {
+                const int n = (int)prm.qi.tile_cnt[t];
+                const uint16_t* ew = prm.qi.ent_word + (size_t)t * SQ_T1;
+                for (int e = threadIdx.x; e < n; e += SQ_THREADS) atoms_add(off_u32 + ((uint32_t)ew[e] + 1u) * 4u, 1u);
+            }
+            named_bar_sync(1, SQ_THREADS);
+            {   // exclusive scan of off[1 .. nw] in place: off[w + 1] = first entry of word w
+                const int per = (nw + SQ_THREADS - 1) / SQ_THREADS;  // <= 4
+                const int b = 1 + threadIdx.x * per;
+                uint32_t v[4], sum = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    v[j] = (j < per && b + j <= nw) ? off[b + j] : 0u;
+                    sum += v[j];
+                }
+                uint32_t incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += x;
+                }
+                if (lane == 31) scan_s[warp] = incl;
+                named_bar_sync(1, SQ_THREADS);
+                uint32_t wbase = 0;
+                for (int w = 0; w < warp; ++w) wbase += scan_s[w];
+                uint32_t run = wbase + incl - sum;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (j < per && b + j <= nw) {
+                        off[b + j] = run;
+                        run += v[j];
+                    }
+            }
+            named_bar_sync(1, SQ_THREADS);
+            for (int t = t0; t < t1; ++t) {
+                if (prm.qi.tile_cnt[t] == 0u) continue;  // empty or dense-flagged tile (its row offsets are not written)
+                const uint16_t* ro = prm.qi.rowoff + (size_t)t * SQ_ROWOFF_LD;
+                const uint16_t* ew = prm.qi.ent_word + (size_t)t * SQ_T1;
+                const uint32_t* ev = prm.qi.ent_val + (size_t)t * SQ_T1;
+                // one thread per (row, entry-of-row): rows are short, so walk rows and let lanes take entries
+                for (int i = warp; i < SQ_TQ; i += SQ_WARPS) {
+                    const int rb = ro[i], re = ro[i + 1];
+                    for (int e = rb + lane; e < re; e += 32) {
+                        const uint32_t pos = atoms_add(off_u32 + ((uint32_t)ew[e] + 1u) * 4u, 1u);  // afterwards off[w + 1] = end of w
+                        val_s[pos] = ev[e];
+                        row_s[pos] = (uint16_t)((t - t0) * SQ_TQ + i);
+                    }
+                }
             }
         }
+        for (int i = threadIdx.x; i < (g_rows + 3) / 4; i += SQ_THREADS)
+            reinterpret_cast<volatile uint32_t*>(smem + SQ_SM_COUNT)[i] = 0u;
+        for (int i = threadIdx.x; i < (g_rows + 31) / 32; i += SQ_THREADS) lock[i] = 0u;
         named_bar_sync(1, SQ_THREADS);
+
+        // a hit: query row rr (group-relative) x pool row gp at word w.  All 32 lanes call with uniform arguments.
+        auto hit = [&](int rr, int64_t gp, int w) {
+            if (prm.debug == 2) return;
+            const int t = t0 + (rr >> 7), i = rr & (SQ_TQ - 1);
+            const int64_t gq = (int64_t)t * SQ_TQ + i;
+            if (prm.zero_diag && prm.query_base + gq == prm.pool_base + gp) return;  // score forced to 0: a filler
+            const uint16_t* ro = prm.qi.rowoff + (size_t)t * SQ_ROWOFF_LD + i;
+            const int rb = ro[0], re = ro[1];
+            const uint32_t cq = prm.qcard[gq], cp = prm.pcard[gp];
+            const uint16_t* ew = prm.qi.ent_word + (size_t)t * SQ_T1;
+            const uint32_t* ev = prm.qi.ent_val + (size_t)t * SQ_T1;
+            const uint32_t* prow = prm.pbits + gp * prm.pitch_words;
+            uint32_t inter = 0, first = 0xffffffffu;
+            for (int e = rb + lane; e < re; e += 32) {
+                const uint32_t ww = ew[e];
+                const uint32_t c = __popc(ev[e] & __ldg(prow + ww));
+                inter += c;
+                if (c) first = min(first, ww);
+            }
+            inter = __reduce_add_sync(0xffffffffu, inter);
+            first = __reduce_min_sync(0xffffffffu, first);
+            if (first != (uint32_t)w) return;  // emitted at the pair's first intersecting word only
+            if (prm.debug == 3) return;
+            const JEntry cand{inter, cq + cp - inter, (int32_t)(prm.pool_base + gp)};
+            const int64_t base = ((int64_t)stripe * prm.nq + gq) * K;
+            const uint32_t bit = 1u << (rr & 31);
+            const uint32_t lock_a = lock_u32 + (uint32_t)(rr >> 5) * 4u, count_a = count_u32 + (uint32_t)rr;
+            if (lane == 0) {
+                uint32_t polls = 0;
+                while (atoms_or(lock_a, bit) & bit)
+                    if (++polls > (1u << 28)) __trap();  // a lost unlock must surface as a launch failure, not a hang
+            }
+            __syncwarp();
+            __threadfence_block();
+            // read by lane 0 only: after __syncwarp the lanes may still run as separate groups, and lane 0's own update
+            // below must not be seen by lanes that read later (n has to be warp-uniform)
+            int n = 0;
+            if (lane == 0) n = (int)lds_u8(count_a);
+            n = __shfl_sync(0xffffffffu, n, 0);
+            if (prm.debug == 4) {
+            } else if (n < K) {
+                if (lane == 0) {
+                    prm.part_inter[base + n] = cand.inter;
+                    prm.part_union[base + n] = cand.uni;
+                    prm.part_idx[base + n] = cand.idx;
+                    sts_u8(count_a, (uint32_t)(n + 1));
+                }
+            } else if (prm.debug == 5) {
+            } else {  // full: the candidate replaces the worst entry if it ranks before it
+                JEntry wv = lane < K ? JEntry{__ldcg(prm.part_inter + base + lane), __ldcg(prm.part_union + base + lane),
+                                              __ldcg(prm.part_idx + base + lane)}
+                                     : JEntry{0xffffffffu, 1u, -1};  // ranks before every real entry
+                int wl = lane;
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1) {
+                    const JEntry ov{__shfl_xor_sync(0xffffffffu, wv.inter, o), __shfl_xor_sync(0xffffffffu, wv.uni, o),
+                                    __shfl_xor_sync(0xffffffffu, wv.idx, o)};
+                    const int ol = __shfl_xor_sync(0xffffffffu, wl, o);
+                    if (JEntry::better(wv, ov)) {
+                        wv = ov;
+                        wl = ol;
+                    }
+                }
+                if (lane == 0 && JEntry::better(cand, wv)) {
+                    prm.part_inter[base + wl] = cand.inter;
+                    prm.part_union[base + wl] = cand.uni;
+                    prm.part_idx[base + wl] = cand.idx;
+                }
+            }
+            __threadfence();  // the entry must be in L2 before another warp can find the list full and read it back
+            __syncwarp();
+            if (lane == 0) atoms_and(lock_a, ~bit);
+        };
+
+        // one non-zero pool word pv (word id w) of pool row gp: look up the queries holding word w
+        auto pool_word = [&](uint32_t pv, int w, int64_t gp) {
+            const int beg = (int)off[w], end = (int)off[w + 1];
+            for (int e0 = beg; e0 < end; e0 += 32) {
+                const int e = e0 + lane;
+                const bool m = e < end && (val_s[e] & pv) != 0u;
+                const int r = e < end ? (int)row_s[e] : 0;
+                uint32_t mb = __ballot_sync(0xffffffffu, m);
+                while (mb) {
+                    const int src = __ffs(mb) - 1;
+                    mb &= mb - 1;
+                    hit(__shfl_sync(0xffffffffu, r, src), gp, w);
+                }
+            }
+        };
 
         for (int pt = pt_beg; pt < pt_end; ++pt) {
             for (int c = 0; c < prm.n_chunks; ++c) {
                 mbar_wait(&full_bar[stage], phase);
                 const uint32_t sbase = stages_u32 + (uint32_t)stage * SQ_STAGE_BYTES;
-                // the chunk's entries are dealt round-robin to the 16 warps: balanced whatever rows they belong to
-                const int e_end = off_s[c + 1];
-                for (int e = off_s[c] + warp; e < e_end; e += SQ_WARPS) {
-                    const uint32_t h = ent_hdr[e];
-                    const int r = (int)(h & 0xffu);
-                    const uint32_t sub2 = ((h >> 8) & 3u) * 2u;  // first 16-byte unit of the span inside the chunk
-                    const uint4 qa = ent_words[e * 2], qb = ent_words[e * 2 + 1];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int p = lane + 32 * j;
-                        const uint32_t row_addr = sbase + (uint32_t)p * 128u;
-                        uint4 pa, pb;
-                        lds128s(pa, row_addr + ((sub2 ^ sw) << 4));
-                        lds128s(pb, row_addr + (((sub2 + 1u) ^ sw) << 4));
-                        if (((pa.x | pa.y | pa.z | pa.w) | (pb.x | pb.y | pb.z | pb.w)) != 0u) {
-                            const uint32_t v = __popc(qa.x & pa.x) + __popc(qa.y & pa.y) + __popc(qa.z & pa.z) +
-                                               __popc(qa.w & pa.w) + __popc(qb.x & pb.x) + __popc(qb.y & pb.y) +
-                                               __popc(qb.z & pb.z) + __popc(qb.w & pb.w);
-                            // another warp may hold a different span of the same query row: atomic (and rare)
-                            if (v && atomicAdd(&acc[r * SQ_TP + p], v) == 0u) {
-                                const uint32_t pos = atomicAdd(&t_cnt[r & 15], 1u);  // first hit: remember the cell
-                                if (pos < (uint32_t)SQ_TOUCH_CAP) touched[(r & 15) * SQ_TOUCH_CAP + pos] = (uint16_t)((r << 7) | p);
-                            }
-                        }
-                    }
-                }
-                __syncwarp();
+                uint4 v0, v1;
+                lds128s(v0, sbase + a0);
+                lds128s(v1, sbase + a1);
+                const uint32_t b0 = __ballot_sync(0xffffffffu, (v0.x | v0.y | v0.z | v0.w) != 0u);
+                const uint32_t b1 = __ballot_sync(0xffffffffu, (v1.x | v1.y | v1.z | v1.w) != 0u);
+                // the warp's slice of the chunk is in registers: hand the stage back before any hit is processed
+                asm volatile("" ::"r"(b0), "r"(b1) : "memory");  // both ballots (hence every lane's loads) are complete
                 if (lane == 0) mbar_arrive(&empty_bar[stage]);
-                if (++stage == NST) {
+                if (++stage == SQ_STAGES) {
                     stage = 0;
                     phase ^= 1;
                 }
-            }
-            // ---- per-tile epilogue: every warp serves the rows it owns (r & 15 == warp), only non-zero cells
-            named_bar_sync(1, SQ_THREADS);  // all counts of this pool tile are final
-            const uint32_t tcount = t_cnt[warp];
-            if (tcount > (uint32_t)SQ_TOUCH_CAP) {
-                // list overflowed (many matches): scan the 8 x 128 cells this warp owns
-                for (int i = 0; i < 8; ++i) {
-                    const int r = warp + 16 * i;
-                    const int64_t gq = (int64_t)qtile * SQ_TQ + r;
-#pragma unroll 1
-                    for (int j = 0; j < 4; ++j) {
-                        const int p = lane + 32 * j;
-                        const uint32_t v = acc[r * SQ_TP + p];
-                        acc[r * SQ_TP + p] = 0u;
-                        uint32_t m = __ballot_sync(0xffffffffu, v != 0u);
-                        while (m) {
-                            const int src = __ffs(m) - 1;
-                            m &= m - 1;
-                            take(r, gq, (int64_t)pt * SQ_TP + src + 32 * j, __shfl_sync(0xffffffffu, v, src));
-                        }
+                if ((b0 | b1) == 0u || prm.debug == 1) continue;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t b = half ? b1 : b0;
+                    const uint4 v = half ? v1 : v0;
+                    while (b) {
+                        const int src = __ffs(b) - 1;
+                        b &= b - 1;
+                        const uint32_t x0 = __shfl_sync(0xffffffffu, v.x, src), x1 = __shfl_sync(0xffffffffu, v.y, src);
+                        const uint32_t x2 = __shfl_sync(0xffffffffu, v.z, src), x3 = __shfl_sync(0xffffffffu, v.w, src);
+                        const int64_t gp = (int64_t)pt * SQ_TP + warp * 8 + (src >> 3) + 4 * half;
+                        const int wb = c * SQ_CHUNK_WORDS + (src & 7) * 4;
+                        if (gp >= prm.np) continue;  // TMA zero-fills rows past the pool: never non-zero, kept for safety
+                        if (x0) pool_word(x0, wb, gp);
+                        if (x1) pool_word(x1, wb + 1, gp);
+                        if (x2) pool_word(x2, wb + 2, gp);
+                        if (x3) pool_word(x3, wb + 3, gp);
                     }
                 }
-            } else {
-                for (uint32_t t = 0; t < tcount; ++t) {
-                    const uint32_t cell = my_touched[t];
-                    const int r = (int)(cell >> 7), p = (int)(cell & 127u);
-                    const uint32_t v = acc[r * SQ_TP + p];
-                    __syncwarp();
-                    if (lane == 0) acc[r * SQ_TP + p] = 0u;
-                    take(r, (int64_t)qtile * SQ_TQ + r, (int64_t)pt * SQ_TP + p, v);
-                }
             }
-            __syncwarp();
-            if (lane == 0) t_cnt[warp] = 0u;
-            named_bar_sync(1, SQ_THREADS);  // cells and counters are clean before the next pool tile accumulates
         }
 
-        // flush the lists of the rows this warp owns
-        for (int i = 0; i < 8; ++i) {
-            const int r = warp + 16 * i;
-            const int64_t gq = (int64_t)qtile * SQ_TQ + r;
-            if (gq < prm.nq && lane < K) {
-                const int64_t o = ((int64_t)stripe * prm.nq + gq) * K + lane;
-                prm.part_inter[o] = l_inter[r * K + lane];
-                prm.part_union[o] = l_union[r * K + lane];
-                prm.part_idx[o] = l_idx[r * K + lane];
-            }
+        named_bar_sync(1, SQ_THREADS);  // every hit of this item is stored
+        {
+            uint8_t* dst = prm.qi.cnt + (size_t)stripe * prm.nq + row0;
+            for (int i = threadIdx.x; i < g_rows; i += SQ_THREADS) dst[i] = count[i];
         }
     }
 }
 
 // ---------------------------------------------------------------------------- host side
-size_t sparseq_workspace_bytes(int64_t nq) {
-    const size_t n_qtiles = (size_t)((nq + SQ_TQ - 1) / SQ_TQ);
-    return 256 + n_qtiles * (sizeof(uint32_t) + SQ_OFF_LD * sizeof(uint16_t) + SQ_E_MAX * 4 + (size_t)SQ_E_MAX * 32) + 256;
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+size_t sparseq_workspace_bytes(int64_t nq_batch, int32_t n_stripes) {
+    const size_t n_qtiles = (size_t)((nq_batch + SQ_TQ - 1) / SQ_TQ);
+    return 256 + align256(n_qtiles * 4) * 2 + align256(n_qtiles * SQ_ROWOFF_LD * 2) + align256(n_qtiles * SQ_T1 * 2) +
+           align256(n_qtiles * SQ_T1 * 4) + align256((size_t)n_stripes * (size_t)nq_batch);
 }
 
 bool sparseq_supported(int32_t words, int32_t k) {
-    const int n_chunks = (words + SQ_CHUNK_WORDS - 1) / SQ_CHUNK_WORDS;
-    return options().jaccard_sparse_q != 0 && options().jaccard_skip_zero != 0 && n_chunks <= SQ_MAX_CHUNKS && k <= R4D_TOPK_MAX;
+    return options().jaccard_sparse_q != 0 && options().jaccard_skip_zero != 0 && words <= SQ_MAX_WORDS && k <= R4D_TOPK_MAX &&
+           k <= 32;
 }
 
-SparseQ sparseq_carve(void* base, int64_t nq) {
-    const size_t n_qtiles = (size_t)((nq + SQ_TQ - 1) / SQ_TQ);
+QIndex sparseq_carve(void* base, int64_t nq_batch, int32_t n_stripes) {
+    const size_t n_qtiles = (size_t)((nq_batch + SQ_TQ - 1) / SQ_TQ);
     uint8_t* p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(base) + 255) & ~uintptr_t(255));
-    SparseQ sq;
-    sq.words = reinterpret_cast<uint32_t*>(p);
-    p += n_qtiles * (size_t)SQ_E_MAX * 32;
-    sq.hdr = reinterpret_cast<uint32_t*>(p);
-    p += n_qtiles * (size_t)SQ_E_MAX * 4;
-    sq.off = reinterpret_cast<uint16_t*>(p);
-    p += n_qtiles * (size_t)SQ_OFF_LD * 2;
-    sq.tile_dense = reinterpret_cast<uint32_t*>(p);
-    return sq;
+    QIndex qi;
+    qi.ent_val = reinterpret_cast<uint32_t*>(p);
+    p += align256(n_qtiles * SQ_T1 * 4);
+    qi.ent_word = reinterpret_cast<uint16_t*>(p);
+    p += align256(n_qtiles * SQ_T1 * 2);
+    qi.rowoff = reinterpret_cast<uint16_t*>(p);
+    p += align256(n_qtiles * SQ_ROWOFF_LD * 2);
+    qi.tile_cnt = reinterpret_cast<uint32_t*>(p);
+    p += align256(n_qtiles * 4);
+    qi.tile_dense = reinterpret_cast<uint32_t*>(p);
+    p += align256(n_qtiles * 4);
+    qi.cnt = p;
+    (void)n_stripes;
+    return qi;
 }
 
-int sparseq_build(const uint32_t* qbits, int64_t nq, int32_t words, int32_t pitch_words, const SparseQ& sq, cudaStream_t st) {
+int sparseq_build(const uint32_t* qbits, int64_t nq, int32_t words, int32_t pitch_words, int32_t n_stripes,
+                  const QIndex& qi, cudaStream_t st) {
     const int n_qtiles = (int)((nq + SQ_TQ - 1) / SQ_TQ);
-    const int n_chunks = (words + SQ_CHUNK_WORDS - 1) / SQ_CHUNK_WORDS;
-    qspans_kernel<<<n_qtiles, 256, 0, st>>>(qbits, nq, pitch_words, n_chunks, sq);
+    R4D_REQUIRE(nq <= SQ_QB, "jaccard query-index path: batch of %lld rows > %d", (long long)nq, SQ_QB);
+    R4D_CUDA(cudaMemsetAsync(qi.cnt, 0, (size_t)n_stripes * (size_t)nq, st));
+    qindex_kernel<<<n_qtiles, 256, 0, st>>>(qbits, nq, words, pitch_words, qi);
     R4D_CUDA(cudaGetLastError());
     return R4D_OK;
 }
@@ -367,16 +494,19 @@ int sparseq_build(const uint32_t* qbits, int64_t nq, int32_t words, int32_t pitc
 int sparseq_topk_launch(const uint32_t* pbits, const uint32_t* qcard, const uint32_t* pcard, int64_t nq, int64_t np,
                         int32_t words, int32_t pitch_words, int32_t k, int32_t zero_diag, int64_t query_base,
                         int64_t pool_base, int32_t n_qtiles, int32_t n_ptiles, int32_t n_stripes, int32_t ptiles_per_stripe,
-                        uint32_t* part_inter, uint32_t* part_union, int32_t* part_idx, const SparseQ& sq, cudaStream_t st) {
+                        uint32_t* part_inter, uint32_t* part_union, int32_t* part_idx, const QIndex& qi, cudaStream_t st) {
     CUtensorMap tm_p;
     int rc = make_tmap_2d(&tm_p, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, pbits, (uint64_t)pitch_words, (uint64_t)np,
                           (uint64_t)pitch_words * 4, SQ_CHUNK_WORDS, SQ_TP, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     SparseParams prm{};
+    prm.pbits = pbits;
     prm.qcard = qcard;
     prm.pcard = pcard;
     prm.nq = nq;
     prm.np = np;
+    prm.pitch_words = pitch_words;
+    prm.n_words = words;
     prm.n_chunks = (words + SQ_CHUNK_WORDS - 1) / SQ_CHUNK_WORDS;
     prm.k = k;
     prm.zero_diag = zero_diag;
@@ -389,26 +519,16 @@ int sparseq_topk_launch(const uint32_t* pbits, const uint32_t* qcard, const uint
     prm.part_inter = part_inter;
     prm.part_union = part_union;
     prm.part_idx = part_idx;
-    prm.sq = sq;
-    const size_t fixed = 1024 + 16 * sizeof(uint64_t) + (size_t)SQ_TQ * SQ_TP * 4 + (size_t)SQ_E_MAX * 32 + (size_t)SQ_E_MAX * 4 +
-                         (size_t)SQ_OFF_LD * 2 + (size_t)SQ_WARPS * SQ_TOUCH_CAP * 2 + SQ_WARPS * 4 + 3 * (size_t)SQ_TQ * (size_t)k * 4;
-    int n_stages = (int)((227 * 1024 - fixed) / SQ_STAGE_BYTES);
-    if (n_stages > 8) n_stages = 8;
-    if (n_stages < 2) {
-        set_error("jaccard sparse path: not enough shared memory (k=%d)", k);
-        return R4D_E_ARG;
+    prm.qi = qi;
+    prm.debug = options().jaccard_debug;
+    static bool attr_done = false;
+    if (!attr_done) {
+        R4D_CUDA(cudaFuncSetAttribute(jaccard_qindex_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SQ_SM_TOTAL));
+        attr_done = true;
     }
-    prm.n_stages = n_stages;
-    const size_t smem = fixed + (size_t)n_stages * SQ_STAGE_BYTES;
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-        R4D_CUDA(cudaFuncSetAttribute(jaccard_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem = smem;
-    }
-    const int64_t n_items = (int64_t)n_qtiles * n_stripes;
     int grid = num_sms();
-    if (n_items < grid) grid = (int)n_items;
-    jaccard_sparse_kernel<<<grid, SQ_THREADS + 32, smem, st>>>(tm_p, prm);
+    if (n_stripes < grid) grid = n_stripes;
+    jaccard_qindex_kernel<<<grid, SQ_THREADS + 32, SQ_SM_TOTAL, st>>>(tm_p, prm);
     R4D_CUDA(cudaGetLastError());
     return R4D_OK;
 }

@@ -16,6 +16,7 @@ int num_sms();  // SM count of the current device (cached)
 struct Options {
     int jaccard_skip_zero = 1;
     int jaccard_sparse_q = 1;   // fused top-K: sparse query-side span lists for sparse query tiles (jaccard_sparse.cu)
+    int jaccard_debug = 0;      // query-index kernel experiments (stage bypass); results are wrong unless 0
     int jaccard_warps = 16;
     int dense_pair_kernel = 1;
     int dense_pair_qres = -1;

@@ -108,6 +108,7 @@ int r4d_set_option(const char* key, int value) {
     int* slot = nullptr;
     if (!strcmp(key, "jaccard_skip_zero")) slot = &o.jaccard_skip_zero;
     else if (!strcmp(key, "jaccard_sparse_q")) slot = &o.jaccard_sparse_q;
+    else if (!strcmp(key, "jaccard_debug")) slot = &o.jaccard_debug;
     else if (!strcmp(key, "jaccard_warps")) slot = &o.jaccard_warps;
     else if (!strcmp(key, "dense_pair_kernel")) slot = &o.dense_pair_kernel;
     else if (!strcmp(key, "dense_pair_qres")) slot = &o.dense_pair_qres;

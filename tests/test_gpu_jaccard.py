@@ -179,3 +179,66 @@ def test_zero_span_skipping_and_warp_variants_are_exact(warps):
         _lib.set_option("jaccard_skip_zero", 1)
         _lib.set_option("jaccard_sparse_q", 1)
         _lib.set_option("jaccard_warps", prev_w)
+
+
+def _index_case(case):
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(case.encode()) % 1000)
+    if case == "hot_small_universe":       # ~18 % of all pairs intersect: (stripe, query) lists overflow k all the time
+        n_bits, k, zd = 50, 10, False
+        q = random_sets(rng, 300, n_bits, mean=3, max_len=8, p_empty=0.05)
+        p = random_sets(rng, 4000, n_bits, mean=3, max_len=8, p_empty=0.05)
+    elif case == "duplicates":             # pool drawn from 40 distinct sets: long runs of equal scores, ties by index
+        n_bits, k, zd = 2000, 10, False
+        base = random_sets(rng, 40, n_bits, mean=3, max_len=8)
+        p = [base[int(i)] for i in rng.integers(0, 40, 6000)]
+        q = [base[int(i)] for i in rng.integers(0, 40, 200)] + random_sets(rng, 100, n_bits, mean=3)
+    elif case == "multiword":              # several intersecting words per pair: each pair must be emitted once
+        n_bits, k, zd = 400, 10, False
+        q = random_sets(rng, 260, n_bits, mean=6, max_len=7)
+        p = random_sets(rng, 3000, n_bits, mean=6, max_len=12)
+    elif case == "batches":                # more than one 8 192-row query batch
+        n_bits, k, zd = 5000, 10, False
+        q = random_sets(rng, 8192 + 300, n_bits, mean=2.2, max_len=16, p_empty=0.02)
+        p = random_sets(rng, 2000, n_bits, mean=2.2, max_len=16)
+    elif case == "mixed_dense_tiles":      # tiles above the per-tile entry limit go to the dense kernel
+        n_bits, k, zd = 20000, 10, False
+        q = (random_sets(rng, 128, n_bits, mean=40, max_len=64) + random_sets(rng, 200, n_bits, mean=2.2) +
+             random_sets(rng, 100, n_bits, mean=40, max_len=64))
+        p = random_sets(rng, 3000, n_bits, mean=2.2) + random_sets(rng, 300, n_bits, mean=40, max_len=64)
+    elif case == "tiny_pool":
+        n_bits, k, zd = 300, 10, False
+        q = random_sets(rng, 140, n_bits, mean=3, p_empty=0.2)
+        p = random_sets(rng, 3, n_bits, mean=3)
+    elif case == "zero_diag_self":         # train x train: the diagonal is a forced zero, hence only ever a filler
+        n_bits, k, zd = 700, 10, True
+        p = random_sets(rng, 1500, n_bits, mean=2.2, p_empty=0.05)
+        q = p[:700]
+    elif case == "all_empty_queries":
+        n_bits, k, zd = 300, 5, False
+        q = [[] for _ in range(130)]
+        p = random_sets(rng, 500, n_bits, mean=3, p_empty=0.3)
+    else:
+        raise AssertionError(case)
+    return n_bits, k, zd, q, p
+
+
+@pytest.mark.parametrize("case", ["hot_small_universe", "duplicates", "multiword", "batches", "mixed_dense_tiles",
+                                  "tiny_pool", "zero_diag_self", "all_empty_queries"])
+def test_query_index_path_hard_cases(case):
+    """The query-index kernel (jaccard_sparse.cu) against the oracle and against the dense-bitset kernel."""
+    from rag4dyg_b200 import _lib
+    n_bits, k, zd, q, p = _index_case(case)
+    bq, bp = encode(q, n_bits), encode(p, n_bits)
+    got = engine.jaccard_topk(bq, bp, k, zero_diag=zd)
+    _lib.set_option("jaccard_sparse_q", 0)
+    try:
+        dense = engine.jaccard_topk(bq, bp, k, zero_diag=zd)
+    finally:
+        _lib.set_option("jaccard_sparse_q", 1)
+    for a, b in zip(got, dense):
+        assert torch.equal(a, b)
+    oi, ou, ox = jo.c_topk(*to_csr(q), *to_csr(p), k, zero_diag=zd)
+    assert np.array_equal(got[2].cpu().numpy(), ox)
+    assert np.array_equal(got[0].cpu().numpy().astype(np.int64), oi)
+    assert np.array_equal(got[1].cpu().numpy().astype(np.int64), ou)
