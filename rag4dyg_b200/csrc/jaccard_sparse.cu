@@ -26,13 +26,14 @@
 namespace r4d {
 
 // ---------------------------------------------------------------------------- by-row index of a query tile
-// grid = n_qtiles CTAs of 256 threads (8 warps, 16 rows each).
-__global__ void __launch_bounds__(256)
+// grid = n_qtiles CTAs of 1024 threads (32 warps, 4 rows each).
+constexpr int QI_THREADS = 1024;
+__global__ void __launch_bounds__(QI_THREADS)
 qindex_kernel(const uint32_t* __restrict__ qbits, int64_t nq, int32_t words, int32_t pitch_words, QIndex qi) {
     __shared__ uint32_t rowcnt[SQ_TQ];
     __shared__ uint32_t rowstart[SQ_TQ + 1];
     const int t = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = warp; i < SQ_TQ; i += 8) {
+    for (int i = warp; i < SQ_TQ; i += QI_THREADS / 32) {
         const int64_t gq = (int64_t)t * SQ_TQ + i;
         uint32_t c = 0;
         if (gq < nq) {
@@ -81,10 +82,10 @@ qindex_kernel(const uint32_t* __restrict__ qbits, int64_t nq, int32_t words, int
         qi.tile_cnt[t] = total;
     }
     uint16_t* rowoff = qi.rowoff + (size_t)t * SQ_ROWOFF_LD;
-    for (int i = threadIdx.x; i <= SQ_TQ; i += 256) rowoff[i] = (uint16_t)rowstart[i];
+    for (int i = threadIdx.x; i <= SQ_TQ; i += QI_THREADS) rowoff[i] = (uint16_t)rowstart[i];
     uint16_t* ew = qi.ent_word + (size_t)t * SQ_T1;
     uint32_t* ev = qi.ent_val + (size_t)t * SQ_T1;
-    for (int i = warp; i < SQ_TQ; i += 8) {
+    for (int i = warp; i < SQ_TQ; i += QI_THREADS / 32) {
         const int64_t gq = (int64_t)t * SQ_TQ + i;
         if (gq >= nq) continue;
         const uint32_t* row = qbits + gq * pitch_words;
@@ -140,8 +141,182 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
 __device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) {
     asm volatile("st.volatile.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint32_t v;
+    asm volatile("{\n\t.reg .u16 t;\n\tld.shared.u16 t, [%1];\n\tcvt.u32.u16 %0, t;\n\t}" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ void lds128s(uint4& v, uint32_t addr) {
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+}
+
+// Append the candidates of the lanes with `keep` set, one by one, to their (stripe, query) partial list in global
+// memory: unsorted while the list is short, replace-the-worst once it holds k entries; a per-query lock bit in shared
+// memory serialises the warps of the CTA that hit the same query.
+__device__ __noinline__ void append_candidates(const SparseParams& prm, bool keep, uint32_t rr, uint32_t inter, uint32_t uni,
+                                               int32_t idx, int t0, int stripe, uint32_t lock_u32, uint32_t count_u32) {
+    const int lane = threadIdx.x & 31;
+    const int K = prm.k;
+    uint32_t pb = __ballot_sync(0xffffffffu, keep);
+    while (pb) {
+        const int src = __ffs(pb) - 1;
+        pb &= pb - 1;
+        const uint32_t r = __shfl_sync(0xffffffffu, rr, src);
+        const JEntry cand{__shfl_sync(0xffffffffu, inter, src), __shfl_sync(0xffffffffu, uni, src),
+                          __shfl_sync(0xffffffffu, idx, src)};
+        const int64_t gq = (int64_t)t0 * SQ_TQ + r;
+        const int64_t base = ((int64_t)stripe * prm.nq + gq) * K;
+        const uint32_t bit = 1u << (r & 31);
+        const uint32_t lock_a = lock_u32 + (r >> 5) * 4u, count_a = count_u32 + r;
+        if (lane == 0) {
+            uint32_t polls = 0;
+            while (atoms_or(lock_a, bit) & bit)
+                if (++polls > (1u << 28)) __trap();  // a lost unlock must surface as a launch failure, not a hang
+        }
+        __syncwarp();
+        __threadfence_block();
+        // read by lane 0 only: after __syncwarp the lanes may still run as separate groups, and lane 0's own update
+        // below must not be seen by lanes that read later (n has to be warp-uniform)
+        int n = 0;
+        if (lane == 0) n = (int)lds_u8(count_a);
+        n = __shfl_sync(0xffffffffu, n, 0);
+        if (prm.debug == 4) {
+        } else if (n < K) {
+            if (lane == 0) {
+                prm.part_inter[base + n] = cand.inter;
+                prm.part_union[base + n] = cand.uni;
+                prm.part_idx[base + n] = cand.idx;
+                sts_u8(count_a, (uint32_t)(n + 1));
+            }
+        } else if (prm.debug == 5) {
+        } else {  // full: the candidate replaces the worst entry if it ranks before it
+            JEntry wv = lane < K ? JEntry{__ldcg(prm.part_inter + base + lane), __ldcg(prm.part_union + base + lane),
+                                          __ldcg(prm.part_idx + base + lane)}
+                                 : JEntry{0xffffffffu, 1u, -1};  // ranks before every real entry
+            int wl = lane;
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) {
+                const JEntry ov{__shfl_xor_sync(0xffffffffu, wv.inter, o), __shfl_xor_sync(0xffffffffu, wv.uni, o),
+                                __shfl_xor_sync(0xffffffffu, wv.idx, o)};
+                const int ol = __shfl_xor_sync(0xffffffffu, wl, o);
+                if (JEntry::better(wv, ov)) {
+                    wv = ov;
+                    wl = ol;
+                }
+            }
+            if (lane == 0 && JEntry::better(cand, wv)) {
+                prm.part_inter[base + wl] = cand.inter;
+                prm.part_union[base + wl] = cand.uni;
+                prm.part_idx[base + wl] = cand.idx;
+            }
+        }
+        // entries must be in L2 before another warp can find the list full and read them back (ld.cg)
+        if (n + 1 >= K) __threadfence();
+        else __threadfence_block();
+        __syncwarp();
+        if (lane == 0) atoms_and(lock_a, ~bit);
+    }
+}
+
+// Fallback completion (pool rows too dense for the per-tile lists): up to 32 queued hits, lane i holds hit i
+// (a = query row | word << 13, b = pool row relative to the stripe).  Per lane: the row's entries (by-row index, L2)
+// against the pool row give the full intersection and the pair's first intersecting word; only the hit AT that word
+// is kept, so a pair is emitted exactly once whatever the order the hits arrive in.
+__device__ __noinline__ void flush_hits(const SparseParams& prm, uint32_t hit_a, uint32_t hit_b, int qn, int t0, int stripe,
+                                        int pt_beg, uint32_t lock_u32, uint32_t count_u32) {
+    const int lane = threadIdx.x & 31;
+    bool primary = false;
+    uint32_t rr = 0, inter = 0, uni = 0;
+    int32_t idx = 0;
+    if (lane < qn && prm.debug != 2) {
+        rr = hit_a & 0x1fffu;
+        const uint32_t w = hit_a >> 13;
+        const int64_t gp = (int64_t)pt_beg * SQ_TP + hit_b;
+        const int t = t0 + (int)(rr >> 7), i = (int)(rr & (SQ_TQ - 1));
+        const int64_t gq = (int64_t)t0 * SQ_TQ + rr;
+        if (!(prm.zero_diag && prm.query_base + gq == prm.pool_base + gp)) {  // the diagonal is a forced zero: a filler
+            const uint16_t* ro = prm.qi.rowoff + (size_t)t * SQ_ROWOFF_LD + i;
+            const int rb = ro[0], re = ro[1];
+            const uint32_t cq = prm.qcard[gq], cp = prm.pcard[gp];
+            const uint16_t* ew = prm.qi.ent_word + (size_t)t * SQ_T1;
+            const uint32_t* ev = prm.qi.ent_val + (size_t)t * SQ_T1;
+            const uint32_t* prow = prm.pbits + gp * prm.pitch_words;
+            uint32_t first = 0xffffffffu;
+            for (int e = rb; e < re; ++e) {
+                const uint32_t ww = ew[e];
+                const uint32_t c = __popc(ev[e] & __ldg(prow + ww));
+                inter += c;
+                if (c) first = min(first, ww);
+            }
+            primary = first == w && prm.debug != 3;
+            uni = cq + cp - inter;
+            idx = (int32_t)(prm.pool_base + gp);
+        }
+    }
+    append_candidates(prm, primary, rr, inter, uni, idx, t0, stripe, lock_u32, count_u32);
+}
+
+// The warp's share of one pool tile (8 rows), after all its chunks were scanned: `pw_n` non-zero pool words
+// (value, word id | row-in-warp << 11) wait in shared memory.  Each looks up the query entries with its word id
+// (AND + POPC); hits (query row, pool row, count) go to the warp's hit buffer; hits of the same pair are summed --
+// every word of both rows has been seen, so the sum IS the intersection -- and the pair is emitted once.
+// Returns 1 (nothing emitted) when the hit buffer overflows: the caller replays the tile through flush_hits.
+constexpr int SQ_PW_CAP = 64;   // non-zero pool words per warp per tile kept for the lookup phase
+constexpr int SQ_HB_CAP = 64;   // hits per warp per tile
+__device__ __noinline__ int tile_hits(const SparseParams& prm, uint32_t pw_a, int pw_n, uint32_t hb_a, uint32_t off_a,
+                                      uint32_t val_a, uint32_t row_a, int t0, int stripe, int64_t gp0, uint32_t lock_u32,
+                                      uint32_t count_u32) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    int hn = 0;
+    for (int i = 0; i < pw_n; ++i) {
+        const uint32_t pv = lds_u32(pw_a + i * 8), meta = lds_u32(pw_a + i * 8 + 4);
+        const uint32_t w = meta & 0x7ffu, pl = meta >> 11;
+        const int beg = (int)lds_u32(off_a + w * 4), end = (int)lds_u32(off_a + w * 4 + 4);
+        for (int e0 = beg; e0 < end; e0 += 32) {
+            const int e = e0 + lane;
+            uint32_t x = 0;
+            if (e < end) x = lds_u32(val_a + e * 4) & pv;
+            const uint32_t mb = __ballot_sync(0xffffffffu, x != 0u);
+            if (!mb) continue;
+            const int add = __popc(mb);
+            if (hn + add > SQ_HB_CAP) return 1;
+            if (x) sts_u32(hb_a + (hn + __popc(mb & lt)) * 4, lds_u16(row_a + e * 2) | ((uint32_t)__popc(x) << 13) | (pl << 19));
+            hn += add;
+        }
+    }
+    if (hn == 0 || prm.debug == 2) return 0;
+    __syncwarp();
+    constexpr uint32_t KEY = 0x1fffu | (7u << 19);
+    for (int b = 0; b < hn; b += 32) {
+        const int i = b + lane;
+        const uint32_t mine = i < hn ? lds_u32(hb_a + i * 4) : 0u;
+        uint32_t sum = 0;
+        bool leader = i < hn;
+        for (int j = 0; j < hn; ++j) {
+            const uint32_t hj = lds_u32(hb_a + j * 4);
+            if (((hj ^ mine) & KEY) == 0u) {
+                sum += (hj >> 13) & 63u;
+                if (j < i) leader = false;
+            }
+        }
+        const uint32_t rr = mine & 0x1fffu;
+        const int64_t gq = (int64_t)t0 * SQ_TQ + rr, gp = gp0 + (mine >> 19);
+        if (prm.zero_diag && prm.query_base + gq == prm.pool_base + gp) leader = false;  // forced zero: a filler
+        if (prm.debug == 3) leader = false;
+        uint32_t uni = 0;
+        if (leader) uni = prm.qcard[gq] + prm.pcard[gp] - sum;
+        append_candidates(prm, leader, rr, sum, uni, (int32_t)(prm.pool_base + gp), t0, stripe, lock_u32, count_u32);
+    }
+    return 0;
 }
 
 // shared-memory layout (offsets from the 1024-aligned base)
@@ -155,11 +330,13 @@ constexpr size_t SQ_SM_COUNT = SQ_SM_ROW + (size_t)SQ_E_CAP * 2;
 constexpr size_t SQ_SM_LOCK = SQ_SM_COUNT + SQ_QB;
 constexpr size_t SQ_SM_GROUPS = SQ_SM_LOCK + SQ_QB / 8;
 constexpr size_t SQ_SM_SCAN = SQ_SM_GROUPS + (size_t)(SQ_MAX_TILES + 2) * 8;
-constexpr size_t SQ_SM_TOTAL = SQ_SM_SCAN + 32 * 4 + 1024;  // + alignment slack
+constexpr size_t SQ_SM_PW = SQ_SM_SCAN + 32 * 4;                                  // [16 warps][SQ_PW_CAP] x 8 B
+constexpr size_t SQ_SM_HB = SQ_SM_PW + (size_t)SQ_WARPS * SQ_PW_CAP * 8;          // [16 warps][SQ_HB_CAP] x 4 B
+constexpr size_t SQ_SM_TOTAL = SQ_SM_HB + (size_t)SQ_WARPS * SQ_HB_CAP * 4 + 1024;  // + alignment slack
 static_assert(SQ_SM_TOTAL <= 227 * 1024, "query-index kernel: shared memory budget");
 
 __global__ void __launch_bounds__(SQ_THREADS + 32, 1)
-jaccard_qindex_kernel(const __grid_constant__ CUtensorMap tm_p, const SparseParams prm) {
+jaccard_qindex_kernel(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ SparseParams prm) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* stages = smem + SQ_SM_STAGES;                                   // [STAGES][128 rows x 128 B], swizzled
@@ -231,10 +408,14 @@ jaccard_qindex_kernel(const __grid_constant__ CUtensorMap tm_p, const SparsePara
 
     const uint32_t stages_u32 = smem_u32(stages);
     const uint32_t lock_u32 = smem_u32(lock), count_u32 = smem_u32(smem + SQ_SM_COUNT), off_u32 = smem_u32(off);
-    const int K = prm.k;
     int stage = 0;
     uint32_t phase = 0;
     int cur_g = -1;
+    uint32_t hit_a = 0, hit_b = 0;  // fallback path: register-resident hit queue, lane i holds hit i
+    int qn = 0;
+    const uint32_t pw_a = smem_u32(smem + SQ_SM_PW) + (uint32_t)warp * SQ_PW_CAP * 8u;  // this warp's pool-word list
+    const uint32_t hb_a = smem_u32(smem + SQ_SM_HB) + (uint32_t)warp * SQ_HB_CAP * 4u;  // this warp's hit buffer
+    int pw_n = 0;
 
     // this lane's two 16-byte units of every chunk: rows warp*8 + (lane>>3) + {0, 4}, unit lane&7 (128B swizzle)
     const int prow0 = warp * 8 + (lane >> 3);
@@ -312,97 +493,42 @@ jaccard_qindex_kernel(const __grid_constant__ CUtensorMap tm_p, const SparsePara
         for (int i = threadIdx.x; i < (g_rows + 31) / 32; i += SQ_THREADS) lock[i] = 0u;
         named_bar_sync(1, SQ_THREADS);
 
-        // a hit: query row rr (group-relative) x pool row gp at word w.  All 32 lanes call with uniform arguments.
-        auto hit = [&](int rr, int64_t gp, int w) {
-            if (prm.debug == 2) return;
-            const int t = t0 + (rr >> 7), i = rr & (SQ_TQ - 1);
-            const int64_t gq = (int64_t)t * SQ_TQ + i;
-            if (prm.zero_diag && prm.query_base + gq == prm.pool_base + gp) return;  // score forced to 0: a filler
-            const uint16_t* ro = prm.qi.rowoff + (size_t)t * SQ_ROWOFF_LD + i;
-            const int rb = ro[0], re = ro[1];
-            const uint32_t cq = prm.qcard[gq], cp = prm.pcard[gp];
-            const uint16_t* ew = prm.qi.ent_word + (size_t)t * SQ_T1;
-            const uint32_t* ev = prm.qi.ent_val + (size_t)t * SQ_T1;
-            const uint32_t* prow = prm.pbits + gp * prm.pitch_words;
-            uint32_t inter = 0, first = 0xffffffffu;
-            for (int e = rb + lane; e < re; e += 32) {
-                const uint32_t ww = ew[e];
-                const uint32_t c = __popc(ev[e] & __ldg(prow + ww));
-                inter += c;
-                if (c) first = min(first, ww);
-            }
-            inter = __reduce_add_sync(0xffffffffu, inter);
-            first = __reduce_min_sync(0xffffffffu, first);
-            if (first != (uint32_t)w) return;  // emitted at the pair's first intersecting word only
-            if (prm.debug == 3) return;
-            const JEntry cand{inter, cq + cp - inter, (int32_t)(prm.pool_base + gp)};
-            const int64_t base = ((int64_t)stripe * prm.nq + gq) * K;
-            const uint32_t bit = 1u << (rr & 31);
-            const uint32_t lock_a = lock_u32 + (uint32_t)(rr >> 5) * 4u, count_a = count_u32 + (uint32_t)rr;
-            if (lane == 0) {
-                uint32_t polls = 0;
-                while (atoms_or(lock_a, bit) & bit)
-                    if (++polls > (1u << 28)) __trap();  // a lost unlock must surface as a launch failure, not a hang
-            }
-            __syncwarp();
-            __threadfence_block();
-            // read by lane 0 only: after __syncwarp the lanes may still run as separate groups, and lane 0's own update
-            // below must not be seen by lanes that read later (n has to be warp-uniform)
-            int n = 0;
-            if (lane == 0) n = (int)lds_u8(count_a);
-            n = __shfl_sync(0xffffffffu, n, 0);
-            if (prm.debug == 4) {
-            } else if (n < K) {
-                if (lane == 0) {
-                    prm.part_inter[base + n] = cand.inter;
-                    prm.part_union[base + n] = cand.uni;
-                    prm.part_idx[base + n] = cand.idx;
-                    sts_u8(count_a, (uint32_t)(n + 1));
-                }
-            } else if (prm.debug == 5) {
-            } else {  // full: the candidate replaces the worst entry if it ranks before it
-                JEntry wv = lane < K ? JEntry{__ldcg(prm.part_inter + base + lane), __ldcg(prm.part_union + base + lane),
-                                              __ldcg(prm.part_idx + base + lane)}
-                                     : JEntry{0xffffffffu, 1u, -1};  // ranks before every real entry
-                int wl = lane;
-#pragma unroll
-                for (int o = 16; o >= 1; o >>= 1) {
-                    const JEntry ov{__shfl_xor_sync(0xffffffffu, wv.inter, o), __shfl_xor_sync(0xffffffffu, wv.uni, o),
-                                    __shfl_xor_sync(0xffffffffu, wv.idx, o)};
-                    const int ol = __shfl_xor_sync(0xffffffffu, wl, o);
-                    if (JEntry::better(wv, ov)) {
-                        wv = ov;
-                        wl = ol;
-                    }
-                }
-                if (lane == 0 && JEntry::better(cand, wv)) {
-                    prm.part_inter[base + wl] = cand.inter;
-                    prm.part_union[base + wl] = cand.uni;
-                    prm.part_idx[base + wl] = cand.idx;
-                }
-            }
-            __threadfence();  // the entry must be in L2 before another warp can find the list full and read it back
-            __syncwarp();
-            if (lane == 0) atoms_and(lock_a, ~bit);
-        };
-
-        // one non-zero pool word pv (word id w) of pool row gp: look up the queries holding word w
-        auto pool_word = [&](uint32_t pv, int w, int64_t gp) {
+        // fallback path for one non-zero pool word pv (word id w) of pool row p_rel (relative to the stripe): every
+        // intersecting query entry is a hit, queued one per lane and completed 32 at a time by flush_hits
+        auto pool_word_slow = [&](uint32_t pv, int w, uint32_t p_rel) {
             const int beg = (int)off[w], end = (int)off[w + 1];
             for (int e0 = beg; e0 < end; e0 += 32) {
                 const int e = e0 + lane;
                 const bool m = e < end && (val_s[e] & pv) != 0u;
-                const int r = e < end ? (int)row_s[e] : 0;
+                const uint32_t r = e < end ? (uint32_t)row_s[e] : 0u;
                 uint32_t mb = __ballot_sync(0xffffffffu, m);
                 while (mb) {
                     const int src = __ffs(mb) - 1;
                     mb &= mb - 1;
-                    hit(__shfl_sync(0xffffffffu, r, src), gp, w);
+                    const uint32_t rr = __shfl_sync(0xffffffffu, r, src);
+                    if (lane == qn) {
+                        hit_a = rr | ((uint32_t)w << 13);
+                        hit_b = p_rel;
+                    }
+                    if (++qn == 32) {
+                        flush_hits(prm, hit_a, hit_b, qn, t0, stripe, pt_beg, lock_u32, count_u32);
+                        qn = 0;
+                    }
                 }
             }
         };
+        // replay the words collected so far through the fallback path (the tile turned out too dense for the lists)
+        auto replay_slow = [&](int pt) {
+#pragma unroll 1
+            for (int i = 0; i < pw_n; ++i) {
+                const uint32_t pv = lds_u32(pw_a + i * 8), meta = lds_u32(pw_a + i * 8 + 4);
+                pool_word_slow(pv, (int)(meta & 0x7ffu), (uint32_t)((pt - pt_beg) * SQ_TP + warp * 8) + (meta >> 11));
+            }
+            pw_n = 0;
+        };
 
         for (int pt = pt_beg; pt < pt_end; ++pt) {
+            bool slow = false;  // this warp's rows of this tile go through the fallback path
             for (int c = 0; c < prm.n_chunks; ++c) {
                 mbar_wait(&full_bar[stage], phase);
                 const uint32_t sbase = stages_u32 + (uint32_t)stage * SQ_STAGE_BYTES;
@@ -411,7 +537,7 @@ jaccard_qindex_kernel(const __grid_constant__ CUtensorMap tm_p, const SparsePara
                 lds128s(v1, sbase + a1);
                 const uint32_t b0 = __ballot_sync(0xffffffffu, (v0.x | v0.y | v0.z | v0.w) != 0u);
                 const uint32_t b1 = __ballot_sync(0xffffffffu, (v1.x | v1.y | v1.z | v1.w) != 0u);
-                // the warp's slice of the chunk is in registers: hand the stage back before any hit is processed
+                // the warp's slice of the chunk is in registers: hand the stage back right away
                 asm volatile("" ::"r"(b0), "r"(b1) : "memory");  // both ballots (hence every lane's loads) are complete
                 if (lane == 0) mbar_arrive(&empty_bar[stage]);
                 if (++stage == SQ_STAGES) {
@@ -419,7 +545,7 @@ jaccard_qindex_kernel(const __grid_constant__ CUtensorMap tm_p, const SparsePara
                     phase ^= 1;
                 }
                 if ((b0 | b1) == 0u || prm.debug == 1) continue;
-#pragma unroll
+#pragma unroll 1
                 for (int half = 0; half < 2; ++half) {
                     uint32_t b = half ? b1 : b0;
                     const uint4 v = half ? v1 : v0;
@@ -428,16 +554,45 @@ jaccard_qindex_kernel(const __grid_constant__ CUtensorMap tm_p, const SparsePara
                         b &= b - 1;
                         const uint32_t x0 = __shfl_sync(0xffffffffu, v.x, src), x1 = __shfl_sync(0xffffffffu, v.y, src);
                         const uint32_t x2 = __shfl_sync(0xffffffffu, v.z, src), x3 = __shfl_sync(0xffffffffu, v.w, src);
-                        const int64_t gp = (int64_t)pt * SQ_TP + warp * 8 + (src >> 3) + 4 * half;
+                        const uint32_t pl = (uint32_t)((src >> 3) + 4 * half);  // pool row inside the warp's 8 rows
                         const int wb = c * SQ_CHUNK_WORDS + (src & 7) * 4;
-                        if (gp >= prm.np) continue;  // TMA zero-fills rows past the pool: never non-zero, kept for safety
-                        if (x0) pool_word(x0, wb, gp);
-                        if (x1) pool_word(x1, wb + 1, gp);
-                        if (x2) pool_word(x2, wb + 2, gp);
-                        if (x3) pool_word(x3, wb + 3, gp);
+                        if (!slow && pw_n + 4 > SQ_PW_CAP) {  // word list full: the rest of the tile takes the fallback
+                            slow = true;
+                            replay_slow(pt);
+                        }
+                        if (!slow) {  // lanes 0..3 store the unit's non-zero words
+                            const uint32_t pv = lane == 0 ? x0 : (lane == 1 ? x1 : (lane == 2 ? x2 : x3));
+                            const bool nzw = lane < 4 && pv != 0u;
+                            const uint32_t nz = __ballot_sync(0xffffffffu, nzw);
+                            if (nzw) {
+                                const uint32_t at = pw_a + (uint32_t)(pw_n + __popc(nz & ((1u << lane) - 1u))) * 8u;
+                                sts_u32(at, pv);
+                                sts_u32(at + 4, (uint32_t)(wb + lane) | (pl << 11));
+                            }
+                            pw_n += __popc(nz);
+                        } else {
+                            const uint32_t p_rel = (uint32_t)((pt - pt_beg) * SQ_TP + warp * 8) + pl;
+#pragma unroll 1
+                            for (int j = 0; j < 4; ++j) {
+                                const uint32_t pv = j == 0 ? x0 : (j == 1 ? x1 : (j == 2 ? x2 : x3));
+                                if (pv) pool_word_slow(pv, wb + j, p_rel);
+                            }
+                        }
                     }
                 }
             }
+            // ---- the tile's lookup phase: every word of the warp's 8 pool rows has been seen
+            if (pw_n) {
+                __syncwarp();
+                if (tile_hits(prm, pw_a, pw_n, hb_a, off_u32, smem_u32(val_s), smem_u32(row_s), t0, stripe,
+                              (int64_t)pt * SQ_TP + warp * 8, lock_u32, count_u32))
+                    replay_slow(pt);
+                pw_n = 0;
+            }
+        }
+        if (qn) {
+            flush_hits(prm, hit_a, hit_b, qn, t0, stripe, pt_beg, lock_u32, count_u32);
+            qn = 0;
         }
 
         named_bar_sync(1, SQ_THREADS);  // every hit of this item is stored
@@ -486,7 +641,7 @@ int sparseq_build(const uint32_t* qbits, int64_t nq, int32_t words, int32_t pitc
     const int n_qtiles = (int)((nq + SQ_TQ - 1) / SQ_TQ);
     R4D_REQUIRE(nq <= SQ_QB, "jaccard query-index path: batch of %lld rows > %d", (long long)nq, SQ_QB);
     R4D_CUDA(cudaMemsetAsync(qi.cnt, 0, (size_t)n_stripes * (size_t)nq, st));
-    qindex_kernel<<<n_qtiles, 256, 0, st>>>(qbits, nq, words, pitch_words, qi);
+    qindex_kernel<<<n_qtiles, QI_THREADS, 0, st>>>(qbits, nq, words, pitch_words, qi);
     R4D_CUDA(cudaGetLastError());
     return R4D_OK;
 }
