@@ -7,11 +7,13 @@ namespace r4d {
 
 constexpr int SQ_TQ = 128;            // query rows per tile (same tiling as jaccard.cu)
 constexpr int SQ_TP = 128;            // pool rows per tile
-constexpr int SQ_CHUNK_WORDS = 32;    // words of every pool row per TMA stage
-constexpr int SQ_STAGE_BYTES = SQ_TP * SQ_CHUNK_WORDS * 4;  // 16 KB
-constexpr int SQ_STAGES = 4;
 constexpr int SQ_T1 = 1024;           // non-zero words per query tile served by the query-index path (8 per row)
-constexpr int SQ_E_CAP = 20480;       // index entries resident in shared memory at once (one "group" of query tiles)
+constexpr int SQ_TBITS = 2560;        // set bits per query tile served by the query-index path (20 per row)
+constexpr int SQ_E_CAP = 20480;       // index entries (one per set bit) resident in shared memory at once: one "group"
+                                      // of consecutive query tiles
+constexpr int SQ_BATCH_ROWS = 8;      // pool rows a warp scans before it looks its non-zero words up
+constexpr int SQ_RING_BYTES = 8192;   // per-warp ring of bulk-copy slots (whole pool rows, contiguous in HBM)
+constexpr int SQ_MAX_SLOTS = 4;
 constexpr int SQ_QB = 8192;           // query rows per batch (one launch sequence)
 constexpr int SQ_MAX_TILES = SQ_QB / SQ_TQ;
 constexpr int SQ_MAX_WORDS = 2047;    // counts stay below 2^16 words * 32 and word ids fit uint16
@@ -23,10 +25,12 @@ constexpr int SQ_THREADS = SQ_WARPS * 32;
 // the caller's workspace).
 struct QIndex {
     uint32_t* tile_cnt;    // [n_qtiles]  non-zero words of the tile (0 when the tile is flagged dense)
-    uint32_t* tile_dense;  // [n_qtiles]  1: more than SQ_T1 non-zero words -> the dense kernel handles the tile
+    uint32_t* tile_bits;   // [n_qtiles]  set bits of the tile (0 when the tile is flagged dense)
+    uint32_t* tile_dense;  // [n_qtiles]  1: more than SQ_T1 words / SQ_TBITS bits -> the dense kernel handles the tile
     uint16_t* rowoff;      // [n_qtiles][SQ_ROWOFF_LD]  exclusive offsets of every row's entries inside the tile
     uint16_t* ent_word;    // [n_qtiles][SQ_T1]  word id
     uint32_t* ent_val;     // [n_qtiles][SQ_T1]  word value
+    uint8_t* ent_row;      // [n_qtiles][SQ_T1]  row of the entry inside its tile
     uint8_t* cnt;          // [n_stripes][nq]    candidates stored in the (stripe, query) partial list (unsorted)
 };
 
