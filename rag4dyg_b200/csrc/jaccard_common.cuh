@@ -12,11 +12,12 @@ constexpr int SQ_TBITS = 2560;        // set bits per query tile served by the q
 constexpr int SQ_E_CAP = 20480;       // index entries (one per set bit) resident in shared memory at once: one "group"
                                       // of consecutive query tiles
 constexpr int SQ_BATCH_ROWS = 8;      // pool rows a warp scans before it looks its non-zero words up
-constexpr int SQ_RING_BYTES = 8192;   // per-warp ring of bulk-copy slots (whole pool rows, contiguous in HBM)
+constexpr int SQ_RING_BYTES = 7680;   // per-warp ring of bulk-copy slots (whole pool rows, contiguous in HBM)
+constexpr int SQ_NBK = 20480;         // buckets of the bit index in shared memory (bit id >> shift; shift 0 up to 20 480 bits)
 constexpr int SQ_MAX_SLOTS = 4;
 constexpr int SQ_QB = 8192;           // query rows per batch (one launch sequence)
 constexpr int SQ_MAX_TILES = SQ_QB / SQ_TQ;
-constexpr int SQ_MAX_WORDS = 2047;    // counts stay below 2^16 words * 32 and word ids fit uint16
+constexpr int SQ_MAX_WORDS = 1900;    // one row (+16 zero bytes) fits a warp's ring; bit ids fit 16 bits
 constexpr int SQ_ROWOFF_LD = 132;     // 129 row offsets per tile, padded
 constexpr int SQ_WARPS = 16;
 constexpr int SQ_THREADS = SQ_WARPS * 32;

@@ -134,6 +134,9 @@ struct SparseParams {
     int32_t slot_bytes;    // bytes of a full slot (slot_rows whole pitches, or the live words of one row), 16 B multiple
     int32_t row_units;     // 16-byte units per row inside a slot
     int32_t n_slots;       // slots of a warp's ring (1..SQ_MAX_SLOTS)
+    int32_t slot_rows_log2;
+    int32_t bucket_shift;  // index bucket of a bit id = id >> bucket_shift (0 while the vocabulary fits SQ_NBK buckets)
+    int32_t n_buckets;
     uint32_t* part_inter;
     uint32_t* part_union;
     int32_t* part_idx;
@@ -234,10 +237,12 @@ __device__ __noinline__ void append_candidates(const SparseParams& prm, bool kee
         }
         if (n < (uint32_t)K) {
             const int64_t at = ((int64_t)stripe * prm.nq + (int64_t)t0 * SQ_TQ + rr) * K + n;
-            prm.part_inter[at] = inter;
-            prm.part_union[at] = uni;
-            prm.part_idx[at] = idx;
-            __threadfence_block();  // the entry is visible to the CTA before it counts as published
+            if (prm.debug != 7) {
+                prm.part_inter[at] = inter;
+                prm.part_union[at] = uni;
+                prm.part_idx[at] = idx;
+            }
+            if (prm.debug != 6) __threadfence_block();  // the entry is visible to the CTA before it counts as published
             reds_add(ls.pub + wa, 1u << sh);
         } else {
             over = true;
@@ -291,9 +296,9 @@ __device__ __noinline__ void append_candidates(const SparseParams& prm, bool kee
 }
 
 // Fallback completion (pool batches too dense for the per-warp lists): up to 32 queued hits, lane i holds hit i
-// (a = query row | word << 13 | bit << 24, b = pool row relative to the stripe).  Per lane: the row's entries (by-row
-// index, L2) against the pool row give the full intersection and the pair's first intersecting bit; only the hit AT
-// that bit is kept, so a pair is emitted exactly once whatever the order the hits arrive in.
+// (a = query row | bit id << 13, b = pool row relative to the stripe).  Per lane: the row's entries (by-row index, L2)
+// against the pool row give the full intersection and the pair's first common bit; only the hit AT that bit is kept,
+// so a pair is emitted exactly once whatever the order the hits arrive in.
 __device__ __noinline__ void flush_hits(const SparseParams& prm, uint32_t hit_a, uint32_t hit_b, int qn, int t0, int stripe,
                                         int64_t row_beg, const ListState ls) {
     const int lane = threadIdx.x & 31;
@@ -302,7 +307,7 @@ __device__ __noinline__ void flush_hits(const SparseParams& prm, uint32_t hit_a,
     int32_t idx = 0;
     if (lane < qn && prm.debug != 2) {
         rr = hit_a & 0x1fffu;
-        const uint32_t w = (hit_a >> 13) & 0x7ffu, hb = hit_a >> 24;
+        const uint32_t hbit = hit_a >> 13;
         const int64_t gp = row_beg + hit_b;
         const int t = t0 + (int)(rr >> 7), i = (int)(rr & (SQ_TQ - 1));
         const int64_t gq = (int64_t)t0 * SQ_TQ + rr;
@@ -313,14 +318,14 @@ __device__ __noinline__ void flush_hits(const SparseParams& prm, uint32_t hit_a,
             const uint16_t* ew = prm.qi.ent_word + (size_t)t * SQ_T1;
             const uint32_t* ev = prm.qi.ent_val + (size_t)t * SQ_T1;
             const uint32_t* prow = prm.pbits + gp * prm.pitch_words;
-            uint32_t first = 0xffffffffu;  // word << 5 | bit of the first common element
+            uint32_t first = 0xffffffffu;  // bit id of the first common element
             for (int e = rb; e < re; ++e) {
                 const uint32_t ww = ew[e];
                 const uint32_t x = ev[e] & __ldg(prow + ww);
                 inter += __popc(x);
                 if (x) first = min(first, (ww << 5) | (uint32_t)(__ffs(x) - 1));
             }
-            primary = first == ((w << 5) | hb) && prm.debug != 3;
+            primary = first == hbit && prm.debug != 3;
             uni = cq + cp - inter;
             idx = (int32_t)(prm.pool_base + gp);
         }
@@ -328,32 +333,58 @@ __device__ __noinline__ void flush_hits(const SparseParams& prm, uint32_t hit_a,
     append_candidates(prm, primary, rr, inter, uni, idx, t0, stripe, ls);
 }
 
-// The lookup phase of one batch (8 pool rows of one warp): `pw_n` non-zero pool words (value, word id | row-in-batch
-// << 11) wait in shared memory.  Each looks up the index entries with its word id; an entry whose bit is set in the
-// pool word is a hit (query row | pool row << 13) and goes to the warp's hit buffer.  Every word of the 8 rows has
-// been seen, so the number of hits of a pair IS its intersection; the pair's first hit emits it.
+// The lookup phase of one batch (8 pool rows of one warp): `nb` set pool bits (bit id | row-in-batch << 16) wait in
+// shared memory.  Lane i looks bit i up: the entries of its bucket whose low bits match are hits
+// (query row | pool row << 13) and go to the warp's hit buffer.  Every bit of the 8 rows has been seen, so the
+// number of hits of a pair IS its intersection; the pair's first hit emits it.
 // Returns 1 (nothing emitted) when the hit buffer overflows: the caller replays the batch through flush_hits.
-constexpr int SQ_PW_CAP = 64;    // non-zero pool words per warp per batch kept for the lookup phase
+constexpr int SQ_BL_CAP = 64;    // set pool bits per warp per batch kept for the lookup phase
 constexpr int SQ_HB_CAP = 128;   // hits per warp per batch
-__device__ __noinline__ int batch_hits(const SparseParams& prm, uint32_t pw_a, int pw_n, uint32_t hb_a, uint32_t off_a,
-                                       uint32_t row_a, uint32_t bit_a, int t0, int stripe, int64_t gp0, uint32_t pc_lane,
+constexpr int SQ_LANE_ENT = 8;   // bucket entries a lane walks on its own; longer buckets are walked by the whole warp
+__device__ __noinline__ int batch_hits(const SparseParams& prm, uint32_t bl_a, int nb, uint32_t hb_a, uint32_t off_a,
+                                       uint32_t row_a, int t0, int stripe, int64_t gp0, uint32_t pc_lane,
                                        const ListState ls) {
     const int lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t sh = (uint32_t)prm.bucket_shift, lomask = (1u << sh) - 1u;
     int hn = 0;
-    for (int i = 0; i < pw_n; ++i) {
-        const uint32_t pv = lds_u32(pw_a + i * 8), meta = lds_u32(pw_a + i * 8 + 4);
-        const uint32_t w = meta & 0x7ffu, pl = meta >> 11;
-        const int beg = (int)lds_u32(off_a + w * 4), end = (int)lds_u32(off_a + w * 4 + 4);
-        for (int e0 = beg; e0 < end; e0 += 32) {
-            const int e = e0 + lane;
-            const bool hit = e < end && ((pv >> lds_u8(bit_a + e)) & 1u) != 0u;
+    for (int i0 = 0; i0 < nb; i0 += 32) {
+        const int i = i0 + lane;
+        const bool have = i < nb;
+        const uint32_t ent = have ? lds_u32(bl_a + i * 4) : 0u;
+        const uint32_t bitid = ent & 0xffffu, pl = ent >> 16;
+        const uint32_t bucket = bitid >> sh, lo = bitid & lomask;
+        const int beg = have ? (int)lds_u16(off_a + bucket * 2) : 0;
+        const int end = have ? (int)lds_u16(off_a + bucket * 2 + 2) : 0;
+        const int n_it = min(__reduce_max_sync(0xffffffffu, end - beg), SQ_LANE_ENT);
+        for (int kk = 0; kk < n_it; ++kk) {
+            const int e = beg + kk;
+            const uint32_t x = e < end ? lds_u16(row_a + e * 2) : 0u;
+            const bool hit = e < end && (x & 7u) == lo;
             const uint32_t mb = __ballot_sync(0xffffffffu, hit);
             if (!mb) continue;
             const int add = __popc(mb);
             if (hn + add > SQ_HB_CAP) return 1;
-            if (hit) sts_u16(hb_a + (hn + __popc(mb & lt)) * 2, lds_u16(row_a + e * 2) | (pl << 13));
+            if (hit) sts_u16(hb_a + (hn + __popc(mb & lt)) * 2, (x >> 3) | (pl << 13));
             hn += add;
+        }
+        uint32_t big = __ballot_sync(0xffffffffu, end - beg > SQ_LANE_ENT);   // long buckets: 32 entries at a time
+        while (big) {
+            const int src = __ffs(big) - 1;
+            big &= big - 1;
+            const int b2 = __shfl_sync(0xffffffffu, beg, src) + SQ_LANE_ENT, e2 = __shfl_sync(0xffffffffu, end, src);
+            const uint32_t lo2 = __shfl_sync(0xffffffffu, lo, src), pl2 = __shfl_sync(0xffffffffu, pl, src);
+            for (int e0 = b2; e0 < e2; e0 += 32) {
+                const int e = e0 + lane;
+                const uint32_t x = e < e2 ? lds_u16(row_a + e * 2) : 0u;
+                const bool hit = e < e2 && (x & 7u) == lo2;
+                const uint32_t mb = __ballot_sync(0xffffffffu, hit);
+                if (!mb) continue;
+                const int add = __popc(mb);
+                if (hn + add > SQ_HB_CAP) return 1;
+                if (hit) sts_u16(hb_a + (hn + __popc(mb & lt)) * 2, (x >> 3) | (pl2 << 13));
+                hn += add;
+            }
         }
     }
     if (hn == 0 || prm.debug == 2) return 0;
@@ -363,7 +394,7 @@ __device__ __noinline__ int batch_hits(const SparseParams& prm, uint32_t pw_a, i
         const uint32_t mine = i < hn ? lds_u16(hb_a + i * 2) : 0xffffffffu;
         uint32_t sum = 0;
         bool leader = i < hn;
-        for (int j = 0; j < hn; j += 2) {  // two hits per load (the buffer is padded to an even count)
+        for (int j = 0; j < hn; j += 2) {  // two hits per load (entries past hn are ignored)
             const uint32_t h2 = lds_u32(hb_a + j * 2);
             const uint32_t ha = h2 & 0xffffu, hc = h2 >> 16;
             if (ha == mine) {
@@ -388,39 +419,42 @@ __device__ __noinline__ int batch_hits(const SparseParams& prm, uint32_t pw_a, i
 }
 
 // shared-memory layout (offsets from the 128-aligned base)
-constexpr int SQ_OFF_WORDS = SQ_MAX_WORDS + 5;  // off[0 .. n_words], padded
 constexpr size_t SQ_SM_RINGS = 0;                                                  // [16 warps][SQ_RING_BYTES]
 constexpr size_t SQ_SM_BARS = SQ_SM_RINGS + (size_t)SQ_WARPS * SQ_RING_BYTES;     // [16 warps][SQ_MAX_SLOTS] mbarriers
-constexpr size_t SQ_SM_OFF = SQ_SM_BARS + (size_t)SQ_WARPS * SQ_MAX_SLOTS * 8;
-constexpr size_t SQ_SM_ROW = SQ_SM_OFF + (size_t)SQ_OFF_WORDS * 4;
-constexpr size_t SQ_SM_BIT = SQ_SM_ROW + (size_t)SQ_E_CAP * 2;
-constexpr size_t SQ_SM_ALLOC = SQ_SM_BIT + (size_t)SQ_E_CAP;
+constexpr size_t SQ_SM_OFF = SQ_SM_BARS + (size_t)SQ_WARPS * SQ_MAX_SLOTS * 8;    // u16 off[SQ_NBK + 2], padded
+constexpr size_t SQ_SM_ROW = SQ_SM_OFF + (((size_t)SQ_NBK + 2) * 2 + 15) / 16 * 16;
+constexpr size_t SQ_SM_ALLOC = SQ_SM_ROW + (size_t)SQ_E_CAP * 2;
 constexpr size_t SQ_SM_PUB = SQ_SM_ALLOC + SQ_QB;
 constexpr size_t SQ_SM_LOCK = SQ_SM_PUB + SQ_QB;
 constexpr size_t SQ_SM_GROUPS = SQ_SM_LOCK + SQ_QB / 8;
 constexpr size_t SQ_SM_SCAN = SQ_SM_GROUPS + (size_t)(SQ_MAX_TILES + 2) * 8;
-constexpr size_t SQ_SM_PW = SQ_SM_SCAN + 32 * 4;                                   // [16 warps][SQ_PW_CAP] x 8 B
-constexpr size_t SQ_SM_HB = SQ_SM_PW + (size_t)SQ_WARPS * SQ_PW_CAP * 8;          // [16 warps][SQ_HB_CAP] x 2 B
-constexpr size_t SQ_SM_TOTAL = SQ_SM_HB + (size_t)SQ_WARPS * SQ_HB_CAP * 2 + 128;  // + alignment slack
+// per-warp scratch of 512 B: while a batch is scanned it holds the batch's non-zero words (values [80] u32, then tags
+// [80] u16 = row in batch << 11 | word id); the lookup phase takes them into registers and reuses the space for the
+// bit list ([SQ_BL_CAP] x 4 B) and the hit buffer ([SQ_HB_CAP] x 2 B)
+constexpr int SQ_UL_CAP = 80;
+constexpr int SQ_SCRATCH = 512;
+constexpr size_t SQ_SM_SCR = (SQ_SM_SCAN + 32 * 4 + 15) / 16 * 16;
+constexpr size_t SQ_SM_CNT = SQ_SM_SCR + (size_t)SQ_WARPS * SQ_SCRATCH;             // [16 warps] {units, bits} counters
+constexpr size_t SQ_SM_TOTAL = SQ_SM_CNT + (size_t)SQ_WARPS * 8 + 128;              // + alignment slack
+static_assert(SQ_UL_CAP * 6 <= SQ_SCRATCH && SQ_UL_CAP <= 96 && SQ_BL_CAP * 4 + SQ_HB_CAP * 2 <= SQ_SCRATCH, "per-warp scratch");
 static_assert(SQ_SM_TOTAL <= 227 * 1024, "query-index kernel: shared memory budget");
-static_assert(SQ_SM_OFF % 16 == 0 && SQ_SM_ROW % 4 == 0 && SQ_SM_ALLOC % 4 == 0 && SQ_SM_PW % 8 == 0 && SQ_SM_HB % 4 == 0,
+static_assert(SQ_SM_OFF % 16 == 0 && SQ_SM_ROW % 4 == 0 && SQ_SM_ALLOC % 4 == 0 && SQ_SM_SCR % 16 == 0 && SQ_SM_CNT % 8 == 0,
               "query-index kernel: shared memory alignment");
+static_assert(SQ_E_CAP < 65536, "bucket offsets are 16-bit");
 
 __global__ void __launch_bounds__(SQ_THREADS, 1)
 jaccard_qindex_kernel(const __grid_constant__ SparseParams prm) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SQ_SM_BARS);
-    uint32_t* off = reinterpret_cast<uint32_t*>(smem + SQ_SM_OFF);           // entries of word w: [off[w], off[w+1])
-    uint16_t* row_s = reinterpret_cast<uint16_t*>(smem + SQ_SM_ROW);         // [E] group-relative query row
-    uint8_t* bit_s = smem + SQ_SM_BIT;                                       // [E] bit inside the word
+    uint16_t* off = reinterpret_cast<uint16_t*>(smem + SQ_SM_OFF);           // entries of bucket b: [off[b], off[b+1])
+    uint16_t* row_s = reinterpret_cast<uint16_t*>(smem + SQ_SM_ROW);         // [E] group-relative query row << 3 | low bits
     uint32_t* lock = reinterpret_cast<uint32_t*>(smem + SQ_SM_LOCK);         // one bit per group row
     int32_t* g_first = reinterpret_cast<int32_t*>(smem + SQ_SM_GROUPS);      // [n_groups + 1] first tile of a group
     int32_t* g_ent = g_first + SQ_MAX_TILES + 2;                             // [n_groups] entries of the group
     uint32_t* scan_s = reinterpret_cast<uint32_t*>(smem + SQ_SM_SCAN);       // [16] warp totals, [31] = n_groups
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t lt = (1u << lane) - 1u;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < SQ_WARPS * SQ_MAX_SLOTS; ++s) mbar_init(&bars[s], 1);
@@ -445,22 +479,44 @@ jaccard_qindex_kernel(const __grid_constant__ SparseParams prm) {
     const int n_groups = (int)scan_s[31];
     const int n_items = n_groups * prm.n_stripes;
 
-    const uint32_t off_u32 = smem_u32(off), row_u32 = smem_u32(row_s), bit_u32 = smem_u32(bit_s);
+    const uint32_t off_u32 = smem_u32(off), row_u32 = smem_u32(row_s);
     const ListState ls{smem_u32(lock), smem_u32(smem + SQ_SM_ALLOC), smem_u32(smem + SQ_SM_PUB)};
     const uint32_t ring_u32 = smem_u32(smem + SQ_SM_RINGS) + (uint32_t)warp * SQ_RING_BYTES;   // this warp's ring
     uint64_t* my_bars = bars + warp * SQ_MAX_SLOTS;
-    const uint32_t pw_a = smem_u32(smem + SQ_SM_PW) + (uint32_t)warp * SQ_PW_CAP * 8u;  // this warp's pool-word list
-    const uint32_t hb_a = smem_u32(smem + SQ_SM_HB) + (uint32_t)warp * SQ_HB_CAP * 2u;  // this warp's hit buffer
-    const int R = prm.slot_rows, NS = prm.n_slots;
+    const uint32_t ul_a = smem_u32(smem + SQ_SM_SCR) + (uint32_t)warp * SQ_SCRATCH;     // this warp's word list ...
+    const uint32_t ut_a = ul_a + SQ_UL_CAP * 4u;                                        // ... and its tags
+    const uint32_t bl_a = ul_a;                                                          // pool-bit list (lookup phase)
+    const uint32_t hb_a = ul_a + SQ_BL_CAP * 4u;                                        // hit buffer (lookup phase)
+    const uint32_t uln_a = smem_u32(smem + SQ_SM_CNT) + (uint32_t)warp * 8u;            // units in the list
+    const uint32_t bln_a = uln_a + 4u;                                                  // bits in the list
+    const int R = prm.slot_rows, lgR = prm.slot_rows_log2, NS = prm.n_slots;
     const uint32_t upr = (uint32_t)prm.row_units;                        // 16-byte units per row inside a slot
     const uint32_t row_bytes = R == 1 ? (uint32_t)prm.slot_bytes : (uint32_t)prm.pitch_words * 4u;
+    const uint32_t bsh = (uint32_t)prm.bucket_shift, blo = (1u << bsh) - 1u;
 
     int slot = 0;          // ring position of the next slot to consume; slots are issued and consumed cyclically
     uint32_t phase = 0;
     int cur_g = -1;
     uint32_t hit_a = 0, hit_b = 0;  // fallback path: register-resident hit queue, lane i holds hit i
     int qn = 0;
-    int pw_n = 0;
+    if (lane == 0) {
+        sts_u32(uln_a, 0u);
+        sts_u32(bln_a, 0u);
+    }
+    // every slot is followed by 16 zero bytes: lanes past the end of a slot read those instead of branching
+    const uint32_t slot_stride = (uint32_t)prm.slot_bytes + 16u;
+    if (lane < NS) {
+        const uint32_t za = ring_u32 + (uint32_t)lane * slot_stride + (uint32_t)prm.slot_bytes;
+        sts_u32(za, 0u);
+        sts_u32(za + 4, 0u);
+        sts_u32(za + 8, 0u);
+        sts_u32(za + 12, 0u);
+    }
+    __syncwarp();
+    const uint32_t full_units = (uint32_t)R * upr;   // units of a full slot
+    uint32_t loff[6];                                 // this lane's byte offsets inside a full slot (first 192 units)
+#pragma unroll
+    for (int j = 0; j < 6; ++j) loff[j] = (uint32_t)(j * 32 + lane) < full_units ? (uint32_t)(j * 32 + lane) * 16u : (uint32_t)prm.slot_bytes;
 
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int g = item / prm.n_stripes, stripe = item - g * prm.n_stripes;
@@ -474,28 +530,39 @@ jaccard_qindex_kernel(const __grid_constant__ SparseParams prm) {
         const int n_batches = (n_rows + SQ_BATCH_ROWS - 1) / SQ_BATCH_ROWS;
 
         __syncthreads();  // previous item: all hits handled, counts flushed
-        if (g != cur_g) {               // ---- expand the group's entries to one per set bit, sorted by word id
+        if (g != cur_g) {  // ---- expand the group's entries to one per set bit, sorted by bucket (counting sort)
             cur_g = g;
-            const int nw = prm.n_words;
-            for (int i = threadIdx.x; i <= nw; i += SQ_THREADS) off[i] = 0u;
+            const int nbk = prm.n_buckets;                      // off[0 .. nbk] are used
+            for (int i = threadIdx.x; i < (nbk + 2) / 2 + 1; i += SQ_THREADS) reinterpret_cast<uint32_t*>(off)[i] = 0u;
             __syncthreads();
-            for (int t = t0; t < t1; ++t) {
+            // warps take the group's tiles round-robin; four entries per lane are loaded before they are used
+            for (int t = t0 + warp; t < t1; t += SQ_WARPS) {
                 const int n = (int)prm.qi.tile_cnt[t];
                 const uint16_t* ew = prm.qi.ent_word + (size_t)t * SQ_T1;
                 const uint32_t* ev = prm.qi.ent_val + (size_t)t * SQ_T1;
-                for (int e = threadIdx.x; e < n; e += SQ_THREADS)
-                    atoms_add(off_u32 + ((uint32_t)ew[e] + 1u) * 4u, (uint32_t)__popc(ev[e]));
+                for (int e0 = lane; e0 < n; e0 += 128) {
+                    uint32_t v[4], wb[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int e = e0 + j * 32;
+                        v[j] = e < n ? ev[e] : 0u;
+                        wb[j] = e < n ? (uint32_t)ew[e] << 5 : 0u;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        while (v[j]) {   // count into off[bucket + 1] (16-bit halves of 32-bit words; sums stay < 2^16)
+                            const uint32_t at = (((wb[j] | (uint32_t)(__ffs(v[j]) - 1)) >> bsh) + 1u);
+                            v[j] &= v[j] - 1;
+                            atoms_add(off_u32 + (at >> 1) * 4u, 1u << ((at & 1u) * 16u));
+                        }
+                }
             }
             __syncthreads();
-            {   // exclusive scan of off[1 .. nw] in place: off[w + 1] = first entry of word w
-                const int per = (nw + SQ_THREADS - 1) / SQ_THREADS;  // <= 4
-                const int b = 1 + threadIdx.x * per;
-                uint32_t v[4], sum = 0;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    v[j] = (j < per && b + j <= nw) ? off[b + j] : 0u;
-                    sum += v[j];
-                }
+            {   // exclusive scan of off[1 .. nbk] in place: off[b + 1] = first entry of bucket b
+                const int per = (nbk + SQ_THREADS - 1) / SQ_THREADS;
+                const int b0 = 1 + threadIdx.x * per, b1 = min(b0 + per, nbk + 1);
+                uint32_t sum = 0;
+                for (int i = b0; i < b1; ++i) sum += off[i];
                 uint32_t incl = sum;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -504,33 +571,38 @@ jaccard_qindex_kernel(const __grid_constant__ SparseParams prm) {
                 }
                 if (lane == 31) scan_s[warp] = incl;
                 __syncthreads();
-                uint32_t wbase = 0;
-                for (int w = 0; w < warp; ++w) wbase += scan_s[w];
-                uint32_t run = wbase + incl - sum;
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (j < per && b + j <= nw) {
-                        off[b + j] = run;
-                        run += v[j];
-                    }
+                uint32_t run = incl - sum;
+                for (int w = 0; w < warp; ++w) run += scan_s[w];
+                for (int i = b0; i < b1; ++i) {
+                    const uint32_t c = off[i];
+                    off[i] = (uint16_t)run;
+                    run += c;
+                }
             }
             __syncthreads();
-            for (int t = t0; t < t1; ++t) {
+            for (int t = t0 + warp; t < t1; t += SQ_WARPS) {
                 const int n = (int)prm.qi.tile_cnt[t];  // 0: empty or dense-flagged tile
                 const uint16_t* ew = prm.qi.ent_word + (size_t)t * SQ_T1;
                 const uint32_t* ev = prm.qi.ent_val + (size_t)t * SQ_T1;
                 const uint8_t* er = prm.qi.ent_row + (size_t)t * SQ_T1;
-                for (int e = threadIdx.x; e < n; e += SQ_THREADS) {
-                    uint32_t v = ev[e];
-                    const uint16_t r = (uint16_t)((t - t0) * SQ_TQ + er[e]);
-                    // afterwards off[w + 1] = end of word w = start of word w + 1
-                    uint32_t pos = atoms_add(off_u32 + ((uint32_t)ew[e] + 1u) * 4u, (uint32_t)__popc(v));
-                    while (v) {
-                        row_s[pos] = r;
-                        bit_s[pos] = (uint8_t)(__ffs(v) - 1);
-                        v &= v - 1;
-                        ++pos;
+                for (int e0 = lane; e0 < n; e0 += 128) {
+                    uint32_t v[4], wb[4], r8[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int e = e0 + j * 32;
+                        v[j] = e < n ? ev[e] : 0u;
+                        wb[j] = e < n ? (uint32_t)ew[e] << 5 : 0u;
+                        r8[j] = e < n ? (uint32_t)((t - t0) * SQ_TQ + er[e]) << 3 : 0u;
                     }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        while (v[j]) {   // afterwards off[b + 1] = end of bucket b = start of bucket b + 1
+                            const uint32_t bitid = wb[j] | (uint32_t)(__ffs(v[j]) - 1);
+                            v[j] &= v[j] - 1;
+                            const uint32_t at = (bitid >> bsh) + 1u, hs = (at & 1u) * 16u;
+                            const uint32_t pos = (atoms_add(off_u32 + (at >> 1) * 4u, 1u << hs) >> hs) & 0xffffu;
+                            row_s[pos] = (uint16_t)(r8[j] | (bitid & blo));
+                        }
                 }
             }
         }
@@ -543,45 +615,47 @@ jaccard_qindex_kernel(const __grid_constant__ SparseParams prm) {
 
         // ---- this warp's pipeline over the batches warp, warp + 16, ... of the stripe
         // slots of batch b: ceil(rows of b / R); the issue cursor (ib, is) runs n_slots ahead of the consume cursor
-        auto batch_slots = [&](int b) { return (min(SQ_BATCH_ROWS, n_rows - b * SQ_BATCH_ROWS) + R - 1) / R; };
-        auto issue = [&](int b, int s, int at) {  // lane 0: slot s of batch b into ring position `at`
-            const int64_t first = r_beg + (int64_t)b * SQ_BATCH_ROWS + s * R;
-            const int nr = (int)min((int64_t)R, r_end - first);
-            const uint32_t bytes = R == 1 ? row_bytes : (uint32_t)nr * row_bytes;
-            mbar_arrive_expect_tx(&my_bars[at], bytes);
-            bulk_load(ring_u32 + (uint32_t)at * (uint32_t)prm.slot_bytes, prm.pbits + first * prm.pitch_words, bytes,
-                      smem_u32(&my_bars[at]));
+        auto batch_slots = [&](int b) { return (min(SQ_BATCH_ROWS, n_rows - b * SQ_BATCH_ROWS) + R - 1) >> lgR; };
+        int ib = warp, is = 0, ib_slots = ib < n_batches ? batch_slots(ib) : 0;
+        const uint32_t* isrc = prm.pbits + (r_beg + (int64_t)ib * SQ_BATCH_ROWS) * prm.pitch_words;   // next slot's rows
+        auto issue_next = [&](int at) {   // the next slot of this warp's sequence into ring position `at`
+            if (lane == 0) {
+                uint32_t bytes = row_bytes;
+                if (R != 1) bytes = (uint32_t)min(R, n_rows - ib * SQ_BATCH_ROWS - (is << lgR)) * row_bytes;
+                mbar_arrive_expect_tx(&my_bars[at], bytes);
+                bulk_load(ring_u32 + (uint32_t)at * slot_stride, isrc, bytes, smem_u32(&my_bars[at]));
+            }
+            isrc += (size_t)R * prm.pitch_words;
+            if (++is >= ib_slots) {
+                is = 0;
+                ib += SQ_WARPS;
+                ib_slots = ib < n_batches ? batch_slots(ib) : 0;
+                isrc = prm.pbits + (r_beg + (int64_t)ib * SQ_BATCH_ROWS) * prm.pitch_words;
+            }
         };
-        int ib = warp, is = 0;
         {
             int at = slot;
             for (int j = 0; j < NS && ib < n_batches; ++j) {
-                if (lane == 0) issue(ib, is, at);
+                issue_next(at);
                 if (++at == NS) at = 0;
-                if (++is >= batch_slots(ib)) {
-                    is = 0;
-                    ib += SQ_WARPS;
-                }
             }
         }
 
-        // fallback path for one non-zero pool word pv (word id w) of pool row p_rel (relative to the stripe): every
-        // entry whose bit is set is a hit, queued one per lane and completed 32 at a time by flush_hits
-        auto pool_word_slow = [&](uint32_t pv, int w, uint32_t p_rel) {
-            const int beg = (int)off[w], end = (int)off[w + 1];
+        // fallback path for one set pool bit `bitid` of pool row p_rel (relative to the stripe): every matching entry
+        // of its bucket is a hit, queued one per lane and completed 32 at a time by flush_hits
+        auto pool_bit_slow = [&](uint32_t bitid, uint32_t p_rel) {
+            const uint32_t bucket = bitid >> bsh, lo = bitid & blo;
+            const int beg = (int)off[bucket], end = (int)off[bucket + 1];
             for (int e0 = beg; e0 < end; e0 += 32) {
                 const int e = e0 + lane;
-                const uint32_t eb = e < end ? (uint32_t)bit_s[e] : 0u;
-                const bool m = e < end && ((pv >> eb) & 1u) != 0u;
-                const uint32_t r = e < end ? (uint32_t)row_s[e] : 0u;
-                uint32_t mb = __ballot_sync(0xffffffffu, m);
+                const uint32_t x = e < end ? (uint32_t)row_s[e] : 0u;
+                uint32_t mb = __ballot_sync(0xffffffffu, e < end && (x & 7u) == lo);
                 while (mb) {
                     const int src = __ffs(mb) - 1;
                     mb &= mb - 1;
-                    const uint32_t rr = __shfl_sync(0xffffffffu, r, src);
-                    const uint32_t bb = __shfl_sync(0xffffffffu, eb, src);
+                    const uint32_t rr = __shfl_sync(0xffffffffu, x, src) >> 3;
                     if (lane == qn) {
-                        hit_a = rr | ((uint32_t)w << 13) | (bb << 24);
+                        hit_a = rr | (bitid << 13);
                         hit_b = p_rel;
                     }
                     if (++qn == 32) {
@@ -591,96 +665,83 @@ jaccard_qindex_kernel(const __grid_constant__ SparseParams prm) {
                 }
             }
         };
-        // replay the words collected so far through the fallback path (the batch turned out too dense for the lists)
-        auto replay_slow = [&](int b) {
+        // a batch too dense for the per-warp lists: its rows are read again (global memory, L2) and every set bit
+        // takes the fallback path
+        auto slow_batch = [&](int b) {
+            const int nr = min(SQ_BATCH_ROWS, n_rows - b * SQ_BATCH_ROWS);
 #pragma unroll 1
-            for (int i = 0; i < pw_n; ++i) {
-                const uint32_t pv = lds_u32(pw_a + i * 8), meta = lds_u32(pw_a + i * 8 + 4);
-                pool_word_slow(pv, (int)(meta & 0x7ffu), (uint32_t)(b * SQ_BATCH_ROWS) + (meta >> 11));
+            for (int r = 0; r < nr; ++r) {
+                const uint32_t p_rel = (uint32_t)(b * SQ_BATCH_ROWS + r);
+                const uint32_t* prow = prm.pbits + (r_beg + p_rel) * prm.pitch_words;
+#pragma unroll 1
+                for (int w0 = 0; w0 < prm.n_words; w0 += 32) {
+                    const uint32_t v = w0 + lane < prm.n_words ? __ldg(prow + w0 + lane) : 0u;
+                    uint32_t bm = __ballot_sync(0xffffffffu, v != 0u);
+#pragma unroll 1
+                    while (bm) {
+                        const int src = __ffs(bm) - 1;
+                        bm &= bm - 1;
+                        uint32_t pv = __shfl_sync(0xffffffffu, v, src);
+#pragma unroll 1
+                        while (pv) {
+                            pool_bit_slow(((uint32_t)(w0 + src) << 5) | (uint32_t)(__ffs(pv) - 1), p_rel);
+                            pv &= pv - 1;
+                        }
+                    }
+                }
             }
-            pw_n = 0;
         };
 
         for (int b = warp; b < n_batches; b += SQ_WARPS) {
-            bool slow = false;  // this batch goes through the fallback path
             const int nvs = batch_slots(b);
             const int64_t gp0 = r_beg + (int64_t)b * SQ_BATCH_ROWS;
             // cardinalities of the batch's rows: lane i holds row i (one load, ready long before the lookups)
             const uint32_t pc_lane = (lane < SQ_BATCH_ROWS && gp0 + lane < r_end) ? __ldg(prm.pcard + gp0 + lane) : 0u;
             for (int s = 0; s < nvs; ++s) {
-                const int nr = min(R, n_rows - b * SQ_BATCH_ROWS - s * R);   // rows of this slot
+                const int nr = min(R, n_rows - b * SQ_BATCH_ROWS - (s << lgR));   // rows of this slot
                 const uint32_t n_units = (uint32_t)nr * upr;
-                const uint32_t sbase = ring_u32 + (uint32_t)slot * (uint32_t)prm.slot_bytes;
+                const uint32_t sbase = ring_u32 + (uint32_t)slot * slot_stride;
+                const bool fast = nr == R && full_units <= 6 * 32;   // a full slot of at most 192 units: offsets are precomputed
                 mbar_wait(&my_bars[slot], phase);
 #pragma unroll 1
                 for (uint32_t u0 = 0; u0 < n_units; u0 += 6 * 32) {
                     uint4 v[6];
-                    uint32_t any[6];
+                    uint32_t nzu[6];
 #pragma unroll
                     for (int j = 0; j < 6; ++j) {
-                        const uint32_t u = u0 + j * 32 + lane;
-                        v[j] = make_uint4(0u, 0u, 0u, 0u);
-                        if (u < n_units) lds128s(v[j], sbase + u * 16u);
+                        uint32_t a = loff[j];
+                        if (!fast) {
+                            const uint32_t u = u0 + j * 32 + lane;
+                            a = u < n_units ? u * 16u : (uint32_t)prm.slot_bytes;
+                        }
+                        lds128s(v[j], sbase + a);
                     }
 #pragma unroll
-                    for (int j = 0; j < 6; ++j) any[j] = __ballot_sync(0xffffffffu, (v[j].x | v[j].y | v[j].z | v[j].w) != 0u);
-                    if (u0 + 6 * 32 >= n_units) {
-                        // the whole slot is in registers (the ballots above needed every lane's loads): refill it
-                        asm volatile("" ::"r"(any[0]), "r"(any[1]), "r"(any[2]), "r"(any[3]), "r"(any[4]), "r"(any[5]) : "memory");
-                        if (ib < n_batches) {
-                            if (lane == 0) issue(ib, is, slot);
-                            if (++is >= batch_slots(ib)) {
-                                is = 0;
-                                ib += SQ_WARPS;
+                    for (int j = 0; j < 6; ++j) nzu[j] = v[j].x | v[j].y | v[j].z | v[j].w;
+                    const uint32_t m = nzu[0] | nzu[1] | nzu[2] | nzu[3] | nzu[4] | nzu[5];
+                    // the ballot needs every lane's loads: after it the slot's words are in registers
+                    const uint32_t anyb = __ballot_sync(0xffffffffu, m != 0u);
+                    if (u0 + 6 * 32 >= n_units && ib < n_batches) issue_next(slot);   // refill the slot at once
+                    if (anyb == 0u || prm.debug == 1) continue;
+                    if (m != 0u) {   // divergent: the few lanes holding non-zero words push them to the warp's word list
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) {
+                            if (nzu[j] == 0u) continue;
+                            const uint32_t u = u0 + j * 32 + lane;
+                            uint32_t rs = 0, uw = u;   // row inside the slot, unit inside the row
+                            if (R != 1) {
+                                rs = u / upr;
+                                uw = u - rs * upr;
                             }
-                        }
-                    }
-                    if (prm.debug == 1) continue;
+                            const uint32_t tag = ((((uint32_t)(s << lgR) + rs)) << 11) | (uw * 4u);   // row in batch | word id
 #pragma unroll
-                    for (int j = 0; j < 6; ++j) {
-                        if (any[j] == 0u) continue;
-                        const uint32_t u = u0 + j * 32 + lane;
-                        uint32_t rs = 0, uw = u;   // row inside the slot, unit inside the row
-                        if (R != 1) {
-                            rs = u / upr;
-                            uw = u - rs * upr;
-                        }
-                        const uint32_t pl = (uint32_t)(s * R) + rs;   // row inside the batch
-                        const uint32_t meta = (uw * 4u) | (pl << 11);
-                        if (uw * 4u + 4u > (uint32_t)prm.n_words) {   // words past the vocabulary are padding, whatever they hold
-                            const uint32_t live = uw * 4u < (uint32_t)prm.n_words ? (uint32_t)prm.n_words - uw * 4u : 0u;
-                            if (live < 1u) v[j].x = 0u;
-                            if (live < 2u) v[j].y = 0u;
-                            if (live < 3u) v[j].z = 0u;
-                            v[j].w = 0u;
-                        }
-                        const uint32_t n0 = __ballot_sync(0xffffffffu, v[j].x != 0u), n1 = __ballot_sync(0xffffffffu, v[j].y != 0u);
-                        const uint32_t n2 = __ballot_sync(0xffffffffu, v[j].z != 0u), n3 = __ballot_sync(0xffffffffu, v[j].w != 0u);
-                        const int c0 = __popc(n0), c1 = c0 + __popc(n1), c2 = c1 + __popc(n2), c3 = c2 + __popc(n3);
-                        if (!slow && pw_n + c3 > SQ_PW_CAP) {  // word list full: the rest of the batch takes the fallback
-                            slow = true;
-                            replay_slow(b);
-                        }
-                        if (!slow) {
-                            if (v[j].x) sts_v2(pw_a + (uint32_t)(pw_n + __popc(n0 & lt)) * 8u, v[j].x, meta);
-                            if (v[j].y) sts_v2(pw_a + (uint32_t)(pw_n + c0 + __popc(n1 & lt)) * 8u, v[j].y, meta + 1u);
-                            if (v[j].z) sts_v2(pw_a + (uint32_t)(pw_n + c1 + __popc(n2 & lt)) * 8u, v[j].z, meta + 2u);
-                            if (v[j].w) sts_v2(pw_a + (uint32_t)(pw_n + c2 + __popc(n3 & lt)) * 8u, v[j].w, meta + 3u);
-                            pw_n += c3;
-                        } else {
-                            uint32_t bm = any[j];
-#pragma unroll 1
-                            while (bm) {
-                                const int src = __ffs(bm) - 1;
-                                bm &= bm - 1;
-                                const uint32_t x0 = __shfl_sync(0xffffffffu, v[j].x, src), x1 = __shfl_sync(0xffffffffu, v[j].y, src);
-                                const uint32_t x2 = __shfl_sync(0xffffffffu, v[j].z, src), x3 = __shfl_sync(0xffffffffu, v[j].w, src);
-                                const uint32_t ms = __shfl_sync(0xffffffffu, meta, src);
-                                const uint32_t p_rel = (uint32_t)(b * SQ_BATCH_ROWS) + (ms >> 11);
-#pragma unroll 1
-                                for (int q = 0; q < 4; ++q) {
-                                    const uint32_t pv = q == 0 ? x0 : (q == 1 ? x1 : (q == 2 ? x2 : x3));
-                                    if (pv) pool_word_slow(pv, (int)(ms & 0x7ffu) + q, p_rel);
+                            for (int q = 0; q < 4; ++q) {
+                                const uint32_t x = q == 0 ? v[j].x : (q == 1 ? v[j].y : (q == 2 ? v[j].z : v[j].w));
+                                if (x == 0u) continue;
+                                const uint32_t pos = atoms_add(uln_a, 1u);
+                                if (pos < (uint32_t)SQ_UL_CAP) {
+                                    sts_u32(ul_a + pos * 4u, x);
+                                    sts_u16(ut_a + pos * 2u, tag + q);
                                 }
                             }
                         }
@@ -691,11 +752,47 @@ jaccard_qindex_kernel(const __grid_constant__ SparseParams prm) {
                     phase ^= 1;
                 }
             }
-            // ---- the batch's lookup phase: every word of the warp's 8 pool rows has been seen
-            if (pw_n) {
+            // ---- the batch's lookup phase: every unit of the warp's 8 pool rows has been seen
+            __syncwarp();
+            const int nu = (int)lds_volatile_u32(uln_a);
+            if (nu) {
+                int nb = SQ_BL_CAP + 1;
+                if (nu <= SQ_UL_CAP) {
+                    // lanes take the words into registers, then the scratch is reused: set bits -> bit list
+                    uint32_t xv[3], xt[3];
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        const int i = q * 32 + lane;
+                        xv[q] = 0u;
+                        xt[q] = 0u;
+                        if (i < nu) {
+                            xt[q] = lds_u16(ut_a + (uint32_t)i * 2u);
+                            xv[q] = (xt[q] & 0x7ffu) < (uint32_t)prm.n_words ? lds_u32(ul_a + (uint32_t)i * 4u) : 0u;   // past the vocabulary: padding
+                        }
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        uint32_t x = xv[q];
+                        const uint32_t wb = (xt[q] & 0x7ffu) << 5, ptag = (xt[q] >> 11) << 16;
+                        while (x) {
+                            const uint32_t bitid = wb | (uint32_t)(__ffs(x) - 1);
+                            x &= x - 1;
+                            const uint32_t pos = atoms_add(bln_a, 1u);
+                            if (pos < (uint32_t)SQ_BL_CAP) sts_u32(bl_a + pos * 4u, bitid | ptag);
+                        }
+                    }
+                    __syncwarp();
+                    nb = (int)lds_volatile_u32(bln_a);
+                }
+                if (nb > SQ_BL_CAP || (nb > 0 && batch_hits(prm, bl_a, nb, hb_a, off_u32, row_u32, t0, stripe, gp0, pc_lane, ls)))
+                    slow_batch(b);
                 __syncwarp();
-                if (batch_hits(prm, pw_a, pw_n, hb_a, off_u32, row_u32, bit_u32, t0, stripe, gp0, pc_lane, ls)) replay_slow(b);
-                pw_n = 0;
+                if (lane == 0) {
+                    sts_u32(uln_a, 0u);
+                    sts_u32(bln_a, 0u);
+                }
+                __syncwarp();
             }
         }
         if (qn) {
@@ -786,7 +883,7 @@ int sparseq_topk_launch(const uint32_t* pbits, const uint32_t* qcard, const uint
     // one row (the zero padding of the pitch is not read)
     const int64_t pitch_bytes = (int64_t)pitch_words * 4;
     int R = SQ_BATCH_ROWS;
-    while (R > 1 && R * pitch_bytes > SQ_RING_BYTES / 3) R >>= 1;
+    while (R > 1 && R * pitch_bytes + 16 > SQ_RING_BYTES / 3) R >>= 1;
     if (R > 1) {
         prm.slot_rows = R;
         prm.slot_bytes = (int32_t)(R * pitch_bytes);
@@ -796,7 +893,12 @@ int sparseq_topk_launch(const uint32_t* pbits, const uint32_t* qcard, const uint
         prm.slot_bytes = ((words + 3) / 4) * 16;
         prm.row_units = prm.slot_bytes / 16;
     }
-    prm.n_slots = SQ_RING_BYTES / prm.slot_bytes;
+    prm.slot_rows_log2 = 0;
+    while ((1 << prm.slot_rows_log2) < prm.slot_rows) ++prm.slot_rows_log2;
+    prm.bucket_shift = 0;
+    while ((((int64_t)words * 32 + (1 << prm.bucket_shift) - 1) >> prm.bucket_shift) > SQ_NBK) ++prm.bucket_shift;
+    prm.n_buckets = (int32_t)(((int64_t)words * 32 + (1 << prm.bucket_shift) - 1) >> prm.bucket_shift);
+    prm.n_slots = SQ_RING_BYTES / (prm.slot_bytes + 16);   // every slot is followed by 16 zero bytes
     if (prm.n_slots > SQ_MAX_SLOTS) prm.n_slots = SQ_MAX_SLOTS;
     R4D_REQUIRE(prm.n_slots >= 1, "jaccard query-index path: a row of %d words does not fit the ring", words);
     prm.part_inter = part_inter;
