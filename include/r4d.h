@@ -56,9 +56,15 @@ int r4d_device_ok(void);
  *   "dense_pair_qres"   [-1] query tile resident in smem: -1 auto (when >= 4 pool stages fit), 0 never
  *   "jaccard_stripes"   [0]  0 = automatic; > 0 forces the number of pool stripes of the fused top-K (experiments)
  *   "dense_stripes"     [0]  same for the dense CTA-pair kernel
+ *   "kernel_timing"     [0]  record CUDA events around the dominant kernels (see r4d_profile_read)
  *   "stripe_interleave" [0]  dense pair kernel: 1 = stripe s owns pool tiles s, s+S, s+2S, ... (measured: same
  *                            time, 1.7x the DRAM reads), 0 = contiguous stripes */
 int r4d_set_option(const char* key, int value);
+
+/* Measurement aid for the roofline figures (bench.py): after r4d_set_option("kernel_timing", 1) the library brackets
+ * every launch of its dominant kernels with CUDA events on the launch stream; this call waits for the recorded
+ * events, returns their summed duration and count, and clears them.  kernel: "jaccard_qindex" | "dense_pair". */
+int r4d_profile_read(const char* kernel, double* total_ms, int64_t* launches);
 
 /* ---------------------------------------------------------------- set encoder (subsystem 1)
  * Replaces the per-pair `set(seq_i)`, `set(seq_j)` construction of co_occurrence_ratio

@@ -58,6 +58,7 @@ PROTOTYPES = {
                                           _i32, _i32, _vp, _sz, _vp]),
     "r4d_dense_full": (_c.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _f32, _i32, _vp, _i64, _vp]),
     "r4d_dense_topk_merge": (_c.c_int, [_vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp]),
+    "r4d_profile_read": (_c.c_int, [_c.c_char_p, _vp, _vp]),
     "r4d_meanpool_workspace_bytes": (_sz, [_i64, _i32]),
     "r4d_meanpool_prepare": (_c.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "r4d_format_int_rows_bound": (_sz, [_i64, _i64]),
@@ -108,6 +109,13 @@ def set_option(key, value):
     if prev == R4D_E_ARG and key not in ("dense_pair_qres",):
         raise R4DError(last_error())
     return prev
+
+
+def profile_read(kernel):
+    """r4d_profile_read: (summed ms, launches) of the events recorded since the last read (option "kernel_timing")."""
+    ms, n = ctypes.c_double(0.0), ctypes.c_int64(0)
+    check(load().r4d_profile_read(kernel.encode(), ctypes.byref(ms), ctypes.byref(n)), "r4d_profile_read")
+    return ms.value, n.value
 
 
 def require_device():

@@ -45,6 +45,7 @@ struct JaccardParams {
     int32_t k;
     int32_t zero_diag;
     const uint32_t* tile_filter;  // non-null: only query tiles with tile_filter[qtile] != 0 (the rest ran sparse)
+    const uint32_t* any_filtered; // non-null: *any_filtered == 0 means no tile passes the filter (the launch is a no-op)
     int64_t query_base, pool_base;
     int32_t n_qtiles, n_ptiles, n_stripes, ptiles_per_stripe;
     // top-K partial lists [n_stripes][nq][k]
@@ -119,6 +120,7 @@ jaccard_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     constexpr int SCAN_ROWS = TQ / NCW;   // query rows each warp scans in the top-K epilogue: 16 or 8
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    if (prm.any_filtered != nullptr && *prm.any_filtered == 0u) return;  // every tile was served by the query-index kernel
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tm_q);
@@ -661,6 +663,7 @@ static int jaccard_topk_impl(const uint32_t* qbits, const uint32_t* qcard, int64
                                      prm.part_inter, prm.part_union, prm.part_idx, qi, st);
             if (rc) return rc;
             prm.tile_filter = qi.tile_dense;
+            prm.any_filtered = qi.any_dense;
             ex.cnt = qi.cnt;
             ex.tile_dense = qi.tile_dense;
             ex.qcard = prm.qcard;

@@ -32,6 +32,7 @@ struct QIndex {
     uint16_t* ent_word;    // [n_qtiles][SQ_T1]  word id
     uint32_t* ent_val;     // [n_qtiles][SQ_T1]  word value
     uint8_t* ent_row;      // [n_qtiles][SQ_T1]  row of the entry inside its tile
+    uint32_t* any_dense;   // [1] != 0 when some tile is flagged dense (64 words before `cnt`, cleared with it)
     uint8_t* cnt;          // [n_stripes][nq]    candidates stored in the (stripe, query) partial list (unsorted)
 };
 

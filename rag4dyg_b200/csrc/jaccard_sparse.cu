@@ -87,6 +87,7 @@ qindex_kernel(const uint32_t* __restrict__ qbits, int64_t nq, int32_t words, int
             qi.tile_dense[t] = 1u;
             qi.tile_cnt[t] = 0u;
             qi.tile_bits[t] = 0u;
+            atomicOr(qi.any_dense, 1u);
         }
         return;
     }
@@ -189,7 +190,8 @@ __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 __device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
-    asm volatile("{\n\t.reg .u16 t;\n\tcvt.u16.u32 t, %1;\n\tst.shared.u16 [%0], t;\n\t}" ::"r"(addr), "r"(v) : "memory");
+    const uint16_t h = (uint16_t)v;
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(h) : "memory");
 }
 __device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t a, uint32_t b) {
     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
@@ -442,6 +444,9 @@ static_assert(SQ_SM_OFF % 16 == 0 && SQ_SM_ROW % 4 == 0 && SQ_SM_ALLOC % 4 == 0 
               "query-index kernel: shared memory alignment");
 static_assert(SQ_E_CAP < 65536, "bucket offsets are 16-bit");
 
+// ROW1: one pool row per slot and at most 192 units per row (vocabularies from 1 K to 24 K bits at 128 B pitch): the
+// slot geometry is a compile-time shape, every lane's shared-memory offsets are loop invariant.
+template <bool ROW1>
 __global__ void __launch_bounds__(SQ_THREADS, 1)
 jaccard_qindex_kernel(const __grid_constant__ SparseParams prm) {
     extern __shared__ uint8_t smem_raw[];
@@ -489,7 +494,7 @@ jaccard_qindex_kernel(const __grid_constant__ SparseParams prm) {
     const uint32_t hb_a = ul_a + SQ_BL_CAP * 4u;                                        // hit buffer (lookup phase)
     const uint32_t uln_a = smem_u32(smem + SQ_SM_CNT) + (uint32_t)warp * 8u;            // units in the list
     const uint32_t bln_a = uln_a + 4u;                                                  // bits in the list
-    const int R = prm.slot_rows, lgR = prm.slot_rows_log2, NS = prm.n_slots;
+    const int R = ROW1 ? 1 : prm.slot_rows, lgR = ROW1 ? 0 : prm.slot_rows_log2, NS = prm.n_slots;
     const uint32_t upr = (uint32_t)prm.row_units;                        // 16-byte units per row inside a slot
     const uint32_t row_bytes = R == 1 ? (uint32_t)prm.slot_bytes : (uint32_t)prm.pitch_words * 4u;
     const uint32_t bsh = (uint32_t)prm.bucket_shift, blo = (1u << bsh) - 1u;
@@ -698,13 +703,13 @@ jaccard_qindex_kernel(const __grid_constant__ SparseParams prm) {
             // cardinalities of the batch's rows: lane i holds row i (one load, ready long before the lookups)
             const uint32_t pc_lane = (lane < SQ_BATCH_ROWS && gp0 + lane < r_end) ? __ldg(prm.pcard + gp0 + lane) : 0u;
             for (int s = 0; s < nvs; ++s) {
-                const int nr = min(R, n_rows - b * SQ_BATCH_ROWS - (s << lgR));   // rows of this slot
+                const int nr = ROW1 ? 1 : min(R, n_rows - b * SQ_BATCH_ROWS - (s << lgR));   // rows of this slot
                 const uint32_t n_units = (uint32_t)nr * upr;
                 const uint32_t sbase = ring_u32 + (uint32_t)slot * slot_stride;
-                const bool fast = nr == R && full_units <= 6 * 32;   // a full slot of at most 192 units: offsets are precomputed
+                const bool fast = ROW1 || (nr == R && full_units <= 6 * 32);   // a full slot of <= 192 units: precomputed offsets
                 mbar_wait(&my_bars[slot], phase);
-#pragma unroll 1
-                for (uint32_t u0 = 0; u0 < n_units; u0 += 6 * 32) {
+                uint32_t u0 = 0;
+                do {   // 192 units at a time (ROW1: exactly one pass)
                     uint4 v[6];
                     uint32_t nzu[6];
 #pragma unroll
@@ -721,7 +726,7 @@ jaccard_qindex_kernel(const __grid_constant__ SparseParams prm) {
                     const uint32_t m = nzu[0] | nzu[1] | nzu[2] | nzu[3] | nzu[4] | nzu[5];
                     // the ballot needs every lane's loads: after it the slot's words are in registers
                     const uint32_t anyb = __ballot_sync(0xffffffffu, m != 0u);
-                    if (u0 + 6 * 32 >= n_units && ib < n_batches) issue_next(slot);   // refill the slot at once
+                    if ((ROW1 || u0 + 6 * 32 >= n_units) && ib < n_batches) issue_next(slot);   // refill the slot at once
                     if (anyb == 0u || prm.debug == 1) continue;
                     if (m != 0u) {   // divergent: the few lanes holding non-zero words push them to the warp's word list
 #pragma unroll
@@ -746,7 +751,7 @@ jaccard_qindex_kernel(const __grid_constant__ SparseParams prm) {
                             }
                         }
                     }
-                }
+                } while (!ROW1 && (u0 += 6 * 32) < n_units);
                 if (++slot == NS) {
                     slot = 0;
                     phase ^= 1;
@@ -815,7 +820,7 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 size_t sparseq_workspace_bytes(int64_t nq_batch, int32_t n_stripes) {
     const size_t n_qtiles = (size_t)((nq_batch + SQ_TQ - 1) / SQ_TQ);
     return 256 + align256(n_qtiles * 4) * 3 + align256(n_qtiles * SQ_ROWOFF_LD * 2) + align256(n_qtiles * SQ_T1 * 2) +
-           align256(n_qtiles * SQ_T1 * 4) + align256(n_qtiles * SQ_T1) + align256((size_t)n_stripes * (size_t)nq_batch);
+           align256(n_qtiles * SQ_T1 * 4) + align256(n_qtiles * SQ_T1) + 256 + align256((size_t)n_stripes * (size_t)nq_batch);
 }
 
 bool sparseq_supported(int32_t words, int32_t k) {
@@ -841,6 +846,8 @@ QIndex sparseq_carve(void* base, int64_t nq_batch, int32_t n_stripes) {
     p += align256(n_qtiles * 4);
     qi.tile_dense = reinterpret_cast<uint32_t*>(p);
     p += align256(n_qtiles * 4);
+    qi.any_dense = reinterpret_cast<uint32_t*>(p);
+    p += 256;
     qi.cnt = p;
     (void)n_stripes;
     return qi;
@@ -850,7 +857,7 @@ int sparseq_build(const uint32_t* qbits, int64_t nq, int32_t words, int32_t pitc
                   const QIndex& qi, cudaStream_t st) {
     const int n_qtiles = (int)((nq + SQ_TQ - 1) / SQ_TQ);
     R4D_REQUIRE(nq <= SQ_QB, "jaccard query-index path: batch of %lld rows > %d", (long long)nq, SQ_QB);
-    R4D_CUDA(cudaMemsetAsync(qi.cnt, 0, (size_t)n_stripes * (size_t)nq, st));
+    R4D_CUDA(cudaMemsetAsync(qi.any_dense, 0, 256 + (size_t)n_stripes * (size_t)nq, st));   // flag + counts
     qindex_kernel<<<n_qtiles, QI_THREADS, 0, st>>>(qbits, nq, words, pitch_words, qi);
     R4D_CUDA(cudaGetLastError());
     return R4D_OK;
@@ -908,12 +915,18 @@ int sparseq_topk_launch(const uint32_t* pbits, const uint32_t* qcard, const uint
     prm.debug = options().jaccard_debug;
     static bool attr_done = false;
     if (!attr_done) {
-        R4D_CUDA(cudaFuncSetAttribute(jaccard_qindex_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SQ_SM_TOTAL));
+        R4D_CUDA(cudaFuncSetAttribute(jaccard_qindex_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SQ_SM_TOTAL));
+        R4D_CUDA(cudaFuncSetAttribute(jaccard_qindex_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SQ_SM_TOTAL));
         attr_done = true;
     }
     int grid = num_sms();
     if (n_stripes < grid) grid = n_stripes;
-    jaccard_qindex_kernel<<<grid, SQ_THREADS, SQ_SM_TOTAL, st>>>(prm);
+    prof_begin(PROF_JACCARD_QINDEX, st);
+    if (prm.slot_rows == 1 && prm.row_units <= 6 * 32)
+        jaccard_qindex_kernel<true><<<grid, SQ_THREADS, SQ_SM_TOTAL, st>>>(prm);
+    else
+        jaccard_qindex_kernel<false><<<grid, SQ_THREADS, SQ_SM_TOTAL, st>>>(prm);
+    prof_end(PROF_JACCARD_QINDEX, st);
     R4D_CUDA(cudaGetLastError());
     return R4D_OK;
 }

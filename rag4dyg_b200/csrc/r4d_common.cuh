@@ -23,6 +23,7 @@ struct Options {
     int jaccard_stripes = 0;    // 0: automatic; > 0: force the number of pool stripes (experiments)
     int dense_stripes = 0;
     int stripe_interleave = 0;  // dense pair kernel: 1 = stripe s owns pool tiles s, s+S, ...; 0 = contiguous stripes
+    int kernel_timing = 0;      // bracket the dominant kernels with CUDA events (r4d_profile_read)
 };
 Options& options();  // process-wide knobs (r4d_set_option); environment variables R4D_* give the initial values
 
@@ -54,6 +55,12 @@ struct PeerOut {
 };
 
 static inline cudaStream_t as_stream(r4d_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Measurement aid: with the option "kernel_timing" set, a dominant kernel's launch is bracketed by CUDA events on its
+// own stream (prof_begin / prof_end around the <<<>>>); r4d_profile_read sums the elapsed times.
+enum ProfKernel { PROF_JACCARD_QINDEX = 0, PROF_DENSE_PAIR = 1, PROF_KERNELS = 2 };
+void prof_begin(ProfKernel k, cudaStream_t st);
+void prof_end(ProfKernel k, cudaStream_t st);
 
 // ---------------------------------------------------------------- device side
 #ifdef __CUDACC__

@@ -94,11 +94,64 @@ int make_tmap_2d(CUtensorMap* map, CUtensorMapDataType dtype, int elem_bytes, co
     return R4D_OK;
 }
 
+// ---------------------------------------------------------------- kernel timing (measurement aid)
+struct ProfState {
+    static constexpr int CAP = 4096;
+    cudaEvent_t beg[CAP], end[CAP];
+    int created = 0, used = 0;
+    bool open = false;
+};
+static ProfState g_prof[PROF_KERNELS];
+static std::mutex g_prof_mu;
+
+void prof_begin(ProfKernel k, cudaStream_t st) {
+    if (!options().kernel_timing) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ProfState& p = g_prof[k];
+    if (p.used >= ProfState::CAP) return;
+    if (p.used >= p.created) {
+        if (cudaEventCreate(&p.beg[p.created]) != cudaSuccess || cudaEventCreate(&p.end[p.created]) != cudaSuccess) return;
+        ++p.created;
+    }
+    p.open = cudaEventRecord(p.beg[p.used], st) == cudaSuccess;
+}
+
+void prof_end(ProfKernel k, cudaStream_t st) {
+    if (!options().kernel_timing) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ProfState& p = g_prof[k];
+    if (!p.open) return;
+    p.open = false;
+    if (cudaEventRecord(p.end[p.used], st) == cudaSuccess) ++p.used;
+}
+
 }  // namespace r4d
 
 extern "C" {
 
 int r4d_version(void) { return 100; }
+
+int r4d_profile_read(const char* kernel, double* total_ms, int64_t* launches) {
+    using namespace r4d;
+    R4D_REQUIRE(kernel && total_ms && launches, "r4d_profile_read: null argument");
+    int k = -1;
+    if (!strcmp(kernel, "jaccard_qindex")) k = PROF_JACCARD_QINDEX;
+    else if (!strcmp(kernel, "dense_pair")) k = PROF_DENSE_PAIR;
+    R4D_REQUIRE(k >= 0, "r4d_profile_read: unknown kernel '%s'", kernel);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ProfState& p = g_prof[k];
+    double sum = 0.0;
+    for (int i = 0; i < p.used; ++i) {
+        R4D_CUDA(cudaEventSynchronize(p.end[i]));
+        float ms = 0.f;
+        R4D_CUDA(cudaEventElapsedTime(&ms, p.beg[i], p.end[i]));
+        sum += ms;
+    }
+    *total_ms = sum;
+    *launches = p.used;
+    p.used = 0;
+    return R4D_OK;
+}
 
 const char* r4d_last_error(void) { return r4d::g_err; }
 
@@ -115,6 +168,7 @@ int r4d_set_option(const char* key, int value) {
     else if (!strcmp(key, "stripe_interleave")) slot = &o.stripe_interleave;
     else if (!strcmp(key, "jaccard_stripes")) slot = &o.jaccard_stripes;
     else if (!strcmp(key, "dense_stripes")) slot = &o.dense_stripes;
+    else if (!strcmp(key, "kernel_timing")) slot = &o.kernel_timing;
     if (!slot || (slot == &o.jaccard_warps && value != 8 && value != 16)) {
         r4d::set_error("r4d_set_option: unknown key or bad value (%s = %d)", key, value);
         return R4D_E_ARG;
