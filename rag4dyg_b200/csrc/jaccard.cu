@@ -49,9 +49,7 @@ struct JaccardParams {
     int64_t query_base, pool_base;
     int32_t n_qtiles, n_ptiles, n_stripes, ptiles_per_stripe;
     // top-K partial lists [n_stripes][nq][k]
-    uint32_t* part_inter;
-    uint32_t* part_union;
-    int32_t* part_idx;
+    uint4* part;   // {inter, union, idx, 0}
     // full-matrix outputs
     uint32_t* inter;
     int64_t ld_inter;
@@ -356,9 +354,8 @@ jaccard_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                 if (gq >= prm.nq) break;
                 if (lane < prm.k) {
                     const int64_t o = ((int64_t)stripe * prm.nq + gq) * prm.k + lane;
-                    prm.part_inter[o] = l_inter[q * LIST_LD + lane];
-                    prm.part_union[o] = l_union[q * LIST_LD + lane];
-                    prm.part_idx[o] = l_idx[q * LIST_LD + lane];
+                    prm.part[o] = make_uint4(l_inter[q * LIST_LD + lane], l_union[q * LIST_LD + lane],
+                                             (uint32_t)l_idx[q * LIST_LD + lane], 0u);
                 }
             }
             __syncwarp();
@@ -381,12 +378,20 @@ struct MergeExtra {
 };
 
 __global__ void __launch_bounds__(256)
-jaccard_merge_kernel(const uint32_t* __restrict__ inter, const uint32_t* __restrict__ uni,
+jaccard_merge_kernel(const uint4* __restrict__ part, const uint32_t* __restrict__ inter, const uint32_t* __restrict__ uni,
                      const int32_t* __restrict__ idx, int32_t n_lists, int64_t nq, int32_t k_in, int32_t k_out,
                      uint32_t* __restrict__ out_inter, uint32_t* __restrict__ out_union, int32_t* __restrict__ out_idx,
                      const PeerOut peers, const MergeExtra ex) {
     const int lane = threadIdx.x & 31;
     const int64_t wpg = (int64_t)gridDim.x * (blockDim.x >> 5);
+    // candidates come either from the kernels' own partial lists (16-byte entries) or from three caller planes
+    auto load = [&](int64_t i) {
+        if (part != nullptr) {
+            const uint4 e = part[i];
+            return JEntry{e.x, e.y, (int32_t)e.z};
+        }
+        return JEntry{inter[i], uni[i], idx[i]};
+    };
     for (int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); q < nq; q += wpg) {
         WarpTopK<JEntry> tk;
         tk.init(k_out);
@@ -399,7 +404,7 @@ jaccard_merge_kernel(const uint32_t* __restrict__ inter, const uint32_t* __restr
                 const int64_t base = ((int64_t)l * nq + q) * k_in;
                 for (int e = 0; e < n_max; ++e) {
                     JEntry c = JEntry::worst();
-                    if (e < n) c = JEntry{inter[base + e], uni[base + e], idx[base + e]};
+                    if (e < n) c = load(base + e);
                     uint32_t m = __ballot_sync(0xffffffffu, e < n && JEntry::better(c, tk.kth));
                     while (m) {
                         const int src = __ffs(m) - 1;
@@ -414,7 +419,7 @@ jaccard_merge_kernel(const uint32_t* __restrict__ inter, const uint32_t* __restr
                 for (int e0 = 0; e0 < k_in; e0 += 32) {
                     const int e = e0 + lane;
                     JEntry c = JEntry::worst();
-                    if (e < k_in) c = JEntry{inter[base + e], uni[base + e], idx[base + e]};
+                    if (e < k_in) c = load(base + e);
                     uint32_t m = __ballot_sync(0xffffffffu, e < k_in && c.idx != R4D_IDX_NONE && JEntry::better(c, tk.kth));
                     while (m) {
                         const int src = __ffs(m) - 1;
@@ -566,27 +571,27 @@ size_t r4d_jaccard_topk_workspace_bytes(int64_t nq, int64_t np, int32_t k) {
     using namespace r4d;
     if (nq <= 0 || np <= 0 || k <= 0) return 256;
     const JaccardPlan pl = plan_topk(nq, np);
-    size_t need = (size_t)pl.n_stripes * (size_t)nq * (size_t)k * 12 + 256;
+    size_t need = (size_t)pl.n_stripes * (size_t)nq * (size_t)k * SQ_PART_BYTES + 256;
     // query-index path: the call is served in batches of <= SQ_QB query rows that reuse one workspace
     size_t batch = 0;
     const int64_t sizes[2] = {nq < SQ_QB ? nq : (int64_t)SQ_QB, nq % SQ_QB};
     for (int64_t nb : sizes) {
         if (nb <= 0) continue;
         const JaccardPlan pb = plan_topk(nb, np);
-        const size_t b = (size_t)pb.n_stripes * (size_t)nb * (size_t)k * 12 + 256 + sparseq_workspace_bytes(nb, pb.n_stripes);
+        const size_t b = (size_t)pb.n_stripes * (size_t)nb * (size_t)k * SQ_PART_BYTES + 256 + sparseq_workspace_bytes(nb, pb.n_stripes);
         if (b > batch) batch = b;
     }
     return need > batch ? need : batch;
 }
 
-static int merge_launch(const uint32_t* inter, const uint32_t* uni, const int32_t* idx, int32_t n_lists, int64_t nq,
+static int merge_launch(const uint4* part, const uint32_t* inter, const uint32_t* uni, const int32_t* idx, int32_t n_lists, int64_t nq,
                         int32_t k_in, int32_t k_out, uint32_t* out_inter, uint32_t* out_union, int32_t* out_idx,
                         const r4d::PeerOut& peers, const r4d::MergeExtra& ex, r4d_stream_t stream) {
     using namespace r4d;
     int64_t blocks = (nq + 7) / 8;
     const int64_t cap = (int64_t)num_sms() * 16;
     if (blocks > cap) blocks = cap;
-    jaccard_merge_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(inter, uni, idx, n_lists, nq, k_in, k_out,
+    jaccard_merge_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(part, inter, uni, idx, n_lists, nq, k_in, k_out,
                                                                          out_inter, out_union, out_idx, peers, ex);
     R4D_CUDA(cudaGetLastError());
     return R4D_OK;
@@ -620,7 +625,7 @@ static int jaccard_topk_impl(const uint32_t* qbits, const uint32_t* qcard, int64
     cudaStream_t st = as_stream(stream);
     const MergeExtra no_extra{};
     if (np == 0)  // no pool rows: every list is padding; the merge of zero lists writes it, no workspace needed
-        return merge_launch(nullptr, nullptr, nullptr, 0, nq, k, k, top_inter, top_union, top_idx, peers, no_extra, stream);
+        return merge_launch(nullptr, nullptr, nullptr, nullptr, 0, nq, k, k, top_inter, top_union, top_idx, peers, no_extra, stream);
     const bool use_index = sparseq_supported(words, k);
     // query-index path: batches of <= SQ_QB query rows, each a full launch sequence on the same workspace
     const int64_t q_batch = use_index ? (int64_t)SQ_QB : nq;
@@ -628,11 +633,12 @@ static int jaccard_topk_impl(const uint32_t* qbits, const uint32_t* qcard, int64
         const int64_t nb = nq - q0 < q_batch ? nq - q0 : q_batch;
         const JaccardPlan pl = plan_topk(nb, np);
         const size_t per = (size_t)pl.n_stripes * (size_t)nb * (size_t)k;
-        const size_t need = per * 12 + (use_index ? 256 + sparseq_workspace_bytes(nb, pl.n_stripes) : 0);
+        const size_t need = per * SQ_PART_BYTES + (use_index ? 256 + sparseq_workspace_bytes(nb, pl.n_stripes) : 0);
         if (workspace_bytes < need || !workspace) {
             set_error("jaccard_topk: workspace %zu B < required %zu B", workspace_bytes, need);
             return R4D_E_WORKSPACE;
         }
+        R4D_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "jaccard_topk: workspace must be 16-byte aligned");
         const uint32_t* qb = qbits + q0 * pitch_words;
         JaccardParams prm{};
         prm.qcard = qcard + q0;
@@ -647,20 +653,18 @@ static int jaccard_topk_impl(const uint32_t* qbits, const uint32_t* qcard, int64
         prm.n_ptiles = pl.n_ptiles;
         prm.n_stripes = pl.n_stripes;
         prm.ptiles_per_stripe = pl.ptiles_per_stripe;
-        prm.part_inter = reinterpret_cast<uint32_t*>(workspace);
-        prm.part_union = prm.part_inter + per;
-        prm.part_idx = reinterpret_cast<int32_t*>(prm.part_union + per);
+        prm.part = reinterpret_cast<uint4*>(workspace);
         MergeExtra ex{};
         ex.q_off = q0;
         ex.nq_total = nq;
         if (use_index) {
             // sparse query tiles -> jaccard_qindex_kernel; tiles flagged dense -> the kernel below (same partial slots)
-            const QIndex qi = sparseq_carve(reinterpret_cast<uint8_t*>(workspace) + per * 12, nb, pl.n_stripes);
+            const QIndex qi = sparseq_carve(reinterpret_cast<uint8_t*>(workspace) + per * SQ_PART_BYTES, nb, pl.n_stripes);
             rc = sparseq_build(qb, nb, words, pitch_words, pl.n_stripes, qi, st);
             if (rc) return rc;
             rc = sparseq_topk_launch(pbits, prm.qcard, pcard, nb, np, words, pitch_words, k, zero_diag, prm.query_base,
                                      pool_base, pl.n_qtiles, pl.n_ptiles, pl.n_stripes, pl.ptiles_per_stripe,
-                                     prm.part_inter, prm.part_union, prm.part_idx, qi, st);
+                                     prm.part, qi, st);
             if (rc) return rc;
             prm.tile_filter = qi.tile_dense;
             prm.any_filtered = qi.any_dense;
@@ -673,7 +677,7 @@ static int jaccard_topk_impl(const uint32_t* qbits, const uint32_t* qcard, int64
         }
         rc = launch<MODE_TOPK>(qb, nb, pbits, np, words, pitch_words, prm, st);
         if (rc) return rc;
-        rc = merge_launch(prm.part_inter, prm.part_union, prm.part_idx, pl.n_stripes, nb, k, k,
+        rc = merge_launch(prm.part, nullptr, nullptr, nullptr, pl.n_stripes, nb, k, k,
                           top_inter ? top_inter + q0 * k : nullptr, top_union ? top_union + q0 * k : nullptr,
                           top_idx ? top_idx + q0 * k : nullptr, peers, ex, stream);
         if (rc) return rc;
@@ -712,7 +716,7 @@ int r4d_jaccard_topk_merge(const uint32_t* inter, const uint32_t* uni, const int
     R4D_REQUIRE(out_inter && out_union && out_idx, "jaccard_topk_merge: null output");
     R4D_REQUIRE(n_lists == 0 || (inter && uni && idx), "jaccard_topk_merge: null input");
     r4d::PeerOut none{};
-    return merge_launch(inter, uni, idx, n_lists, nq, k_in, k_out, out_inter, out_union, out_idx, none, MergeExtra{}, stream);
+    return merge_launch(nullptr, inter, uni, idx, n_lists, nq, k_in, k_out, out_inter, out_union, out_idx, none, MergeExtra{}, stream);
 }
 
 }  // extern "C"

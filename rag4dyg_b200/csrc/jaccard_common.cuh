@@ -22,6 +22,10 @@ constexpr int SQ_ROWOFF_LD = 132;     // 129 row offsets per tile, padded
 constexpr int SQ_WARPS = 16;
 constexpr int SQ_THREADS = SQ_WARPS * 32;
 
+// Per-stripe partial candidate lists [n_stripes][nq][k]: one 16-byte entry {inter, union, pool index, 0} per
+// candidate, so a candidate costs one memory sector to store and one to merge.
+constexpr int SQ_PART_BYTES = 16;
+
 // By-row index of the non-zero words of one query batch + per-(stripe, query) candidate counts (device memory inside
 // the caller's workspace).
 struct QIndex {
@@ -46,6 +50,6 @@ int sparseq_build(const uint32_t* qbits, int64_t nq, int32_t words, int32_t pitc
 int sparseq_topk_launch(const uint32_t* pbits, const uint32_t* qcard, const uint32_t* pcard, int64_t nq, int64_t np,
                         int32_t words, int32_t pitch_words, int32_t k, int32_t zero_diag, int64_t query_base,
                         int64_t pool_base, int32_t n_qtiles, int32_t n_ptiles, int32_t n_stripes, int32_t ptiles_per_stripe,
-                        uint32_t* part_inter, uint32_t* part_union, int32_t* part_idx, const QIndex& qi, cudaStream_t st);
+                        uint4* part, const QIndex& qi, cudaStream_t st);
 
 }  // namespace r4d

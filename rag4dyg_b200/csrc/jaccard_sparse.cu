@@ -45,11 +45,18 @@ qindex_kernel(const uint32_t* __restrict__ qbits, int64_t nq, int32_t words, int
         uint32_t c = 0, bits = 0;
         if (gq < nq) {
             const uint32_t* row = qbits + gq * pitch_words;
-            for (int w0 = 0; w0 < words; w0 += 32) {
-                const int w = w0 + lane;
-                const uint32_t v = w < words ? row[w] : 0u;
-                c += __popc(__ballot_sync(0xffffffffu, v != 0u));
-                bits += __popc(v);
+            for (int w0 = 0; w0 < words; w0 += 8 * 32) {   // eight independent loads in flight per lane
+                uint32_t v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int w = w0 + j * 32 + lane;
+                    v[j] = w < words ? __ldg(row + w) : 0u;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    c += __popc(__ballot_sync(0xffffffffu, v[j] != 0u));
+                    bits += __popc(v[j]);
+                }
             }
         }
         bits = __reduce_add_sync(0xffffffffu, bits);
@@ -106,17 +113,25 @@ qindex_kernel(const uint32_t* __restrict__ qbits, int64_t nq, int32_t words, int
         if (gq >= nq) continue;
         const uint32_t* row = qbits + gq * pitch_words;
         uint32_t base = rowstart[i];
-        for (int w0 = 0; w0 < words; w0 += 32) {
-            const int w = w0 + lane;
-            const uint32_t v = w < words ? row[w] : 0u;
-            const uint32_t b = __ballot_sync(0xffffffffu, v != 0u);
-            if (v != 0u) {
-                const uint32_t pos = base + __popc(b & ((1u << lane) - 1u));
-                ew[pos] = (uint16_t)w;
-                ev[pos] = v;
-                er[pos] = (uint8_t)i;
+        if (rowcnt[i] == 0u) continue;
+        for (int w0 = 0; w0 < words; w0 += 8 * 32) {
+            uint32_t v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int w = w0 + j * 32 + lane;
+                v[j] = w < words ? __ldg(row + w) : 0u;
             }
-            base += __popc(b);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t b = __ballot_sync(0xffffffffu, v[j] != 0u);
+                if (v[j] != 0u) {
+                    const uint32_t pos = base + __popc(b & ((1u << lane) - 1u));
+                    ew[pos] = (uint16_t)(w0 + j * 32 + lane);
+                    ev[pos] = v[j];
+                    er[pos] = (uint8_t)i;
+                }
+                base += __popc(b);
+            }
         }
     }
 }
@@ -138,9 +153,7 @@ struct SparseParams {
     int32_t slot_rows_log2;
     int32_t bucket_shift;  // index bucket of a bit id = id >> bucket_shift (0 while the vocabulary fits SQ_NBK buckets)
     int32_t n_buckets;
-    uint32_t* part_inter;
-    uint32_t* part_union;
-    int32_t* part_idx;
+    uint4* part;           // [n_stripes][nq][k] {inter, union, idx, 0}
     QIndex qi;
     int32_t debug;  // experiments: 1 = scan only (no lookups), 2 = lookups but no hit completion, 3 = no list update
 };
@@ -199,9 +212,9 @@ __device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t a, uint32_t b) {
 __device__ __forceinline__ void lds128s(uint4& v, uint32_t addr) {
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
 }
-__device__ __forceinline__ uint32_t ldg_volatile_u32(const void* p) {
-    uint32_t v;
-    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ uint4 ldg_volatile_v4(const void* p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
 // TMA bulk copy of `bytes` contiguous bytes (16 B multiple) global -> shared, completion on an mbarrier (SASS: UBLKCP).
@@ -240,9 +253,7 @@ __device__ __noinline__ void append_candidates(const SparseParams& prm, bool kee
         if (n < (uint32_t)K) {
             const int64_t at = ((int64_t)stripe * prm.nq + (int64_t)t0 * SQ_TQ + rr) * K + n;
             if (prm.debug != 7) {
-                prm.part_inter[at] = inter;
-                prm.part_union[at] = uni;
-                prm.part_idx[at] = idx;
+                prm.part[at] = make_uint4(inter, uni, (uint32_t)idx, 0u);
             }
             if (prm.debug != 6) __threadfence_block();  // the entry is visible to the CTA before it counts as published
             reds_add(ls.pub + wa, 1u << sh);
@@ -271,9 +282,11 @@ __device__ __noinline__ void append_candidates(const SparseParams& prm, bool kee
         __syncwarp();
         __threadfence_block();
         if (prm.debug != 5) {  // full list: the candidate replaces the worst entry if it ranks before it
-            JEntry wv = lane < K ? JEntry{ldg_volatile_u32(prm.part_inter + base + lane), ldg_volatile_u32(prm.part_union + base + lane),
-                                          (int32_t)ldg_volatile_u32(prm.part_idx + base + lane)}
-                                 : JEntry{0xffffffffu, 1u, -1};  // ranks before every real entry
+            JEntry wv{0xffffffffu, 1u, -1};  // ranks before every real entry
+            if (lane < K) {
+                const uint4 e = ldg_volatile_v4(prm.part + base + lane);
+                wv = JEntry{e.x, e.y, (int32_t)e.z};
+            }
             int wl = lane;
 #pragma unroll
             for (int o = 16; o >= 1; o >>= 1) {
@@ -286,9 +299,7 @@ __device__ __noinline__ void append_candidates(const SparseParams& prm, bool kee
                 }
             }
             if (lane == 0 && JEntry::better(cand, wv)) {
-                prm.part_inter[base + wl] = cand.inter;
-                prm.part_union[base + wl] = cand.uni;
-                prm.part_idx[base + wl] = cand.idx;
+                prm.part[base + wl] = make_uint4(cand.inter, cand.uni, (uint32_t)cand.idx, 0u);
             }
         }
         __threadfence_block();  // the replacement is visible to the CTA before the lock is released
@@ -444,9 +455,9 @@ static_assert(SQ_SM_OFF % 16 == 0 && SQ_SM_ROW % 4 == 0 && SQ_SM_ALLOC % 4 == 0 
               "query-index kernel: shared memory alignment");
 static_assert(SQ_E_CAP < 65536, "bucket offsets are 16-bit");
 
-// ROW1: one pool row per slot and at most 192 units per row (vocabularies from 1 K to 24 K bits at 128 B pitch): the
-// slot geometry is a compile-time shape, every lane's shared-memory offsets are loop invariant.
-template <bool ROW1>
+// NU > 0 ("ROW1"): one pool row per slot and at most NU * 32 16-byte units per row (vocabularies up to 24 K bits): the
+// slot geometry is a compile-time shape and every lane's shared-memory offsets are immediates.  NU == 0: any geometry.
+template <int NU>
 __global__ void __launch_bounds__(SQ_THREADS, 1)
 jaccard_qindex_kernel(const __grid_constant__ SparseParams prm) {
     extern __shared__ uint8_t smem_raw[];
@@ -460,6 +471,8 @@ jaccard_qindex_kernel(const __grid_constant__ SparseParams prm) {
     uint32_t* scan_s = reinterpret_cast<uint32_t*>(smem + SQ_SM_SCAN);       // [16] warp totals, [31] = n_groups
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr bool ROW1 = NU > 0;
+    constexpr int NJ = ROW1 ? NU : 6;   // 16-byte units a lane loads per pass over a slot
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < SQ_WARPS * SQ_MAX_SLOTS; ++s) mbar_init(&bars[s], 1);
@@ -519,9 +532,9 @@ jaccard_qindex_kernel(const __grid_constant__ SparseParams prm) {
     }
     __syncwarp();
     const uint32_t full_units = (uint32_t)R * upr;   // units of a full slot
-    uint32_t loff[6];                                 // this lane's byte offsets inside a full slot (first 192 units)
+    uint32_t loff[NJ];                                // this lane's byte offsets inside a full slot (first 192 units)
 #pragma unroll
-    for (int j = 0; j < 6; ++j) loff[j] = (uint32_t)(j * 32 + lane) < full_units ? (uint32_t)(j * 32 + lane) * 16u : (uint32_t)prm.slot_bytes;
+    for (int j = 0; j < NJ; ++j) loff[j] = (uint32_t)(j * 32 + lane) < full_units ? (uint32_t)(j * 32 + lane) * 16u : (uint32_t)prm.slot_bytes;
 
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int g = item / prm.n_stripes, stripe = item - g * prm.n_stripes;
@@ -710,27 +723,37 @@ jaccard_qindex_kernel(const __grid_constant__ SparseParams prm) {
                 mbar_wait(&my_bars[slot], phase);
                 uint32_t u0 = 0;
                 do {   // 192 units at a time (ROW1: exactly one pass)
-                    uint4 v[6];
-                    uint32_t nzu[6];
+                    uint4 v[NJ];
+                    uint32_t nzu[NJ];
+                    if (ROW1) {   // units lane, lane + 32, ...: immediates off one base; only the last may be past the row
+                        const uint32_t a0 = sbase + (uint32_t)lane * 16u;
 #pragma unroll
-                    for (int j = 0; j < 6; ++j) {
-                        uint32_t a = loff[j];
-                        if (!fast) {
-                            const uint32_t u = u0 + j * 32 + lane;
-                            a = u < n_units ? u * 16u : (uint32_t)prm.slot_bytes;
+                        for (int j = 0; j < NJ - 1; ++j) lds128s(v[j], a0 + (uint32_t)j * 512u);
+                        lds128s(v[NJ - 1], sbase + loff[NJ - 1]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j) {
+                            uint32_t a = loff[j];
+                            if (!fast) {
+                                const uint32_t u = u0 + j * 32 + lane;
+                                a = u < n_units ? u * 16u : (uint32_t)prm.slot_bytes;
+                            }
+                            lds128s(v[j], sbase + a);
                         }
-                        lds128s(v[j], sbase + a);
                     }
+                    uint32_t m = 0;
 #pragma unroll
-                    for (int j = 0; j < 6; ++j) nzu[j] = v[j].x | v[j].y | v[j].z | v[j].w;
-                    const uint32_t m = nzu[0] | nzu[1] | nzu[2] | nzu[3] | nzu[4] | nzu[5];
+                    for (int j = 0; j < NJ; ++j) {
+                        nzu[j] = v[j].x | v[j].y | v[j].z | v[j].w;
+                        m |= nzu[j];
+                    }
                     // the ballot needs every lane's loads: after it the slot's words are in registers
                     const uint32_t anyb = __ballot_sync(0xffffffffu, m != 0u);
                     if ((ROW1 || u0 + 6 * 32 >= n_units) && ib < n_batches) issue_next(slot);   // refill the slot at once
                     if (anyb == 0u || prm.debug == 1) continue;
                     if (m != 0u) {   // divergent: the few lanes holding non-zero words push them to the warp's word list
 #pragma unroll
-                        for (int j = 0; j < 6; ++j) {
+                        for (int j = 0; j < NJ; ++j) {
                             if (nzu[j] == 0u) continue;
                             const uint32_t u = u0 + j * 32 + lane;
                             uint32_t rs = 0, uw = u;   // row inside the slot, unit inside the row
@@ -866,7 +889,7 @@ int sparseq_build(const uint32_t* qbits, int64_t nq, int32_t words, int32_t pitc
 int sparseq_topk_launch(const uint32_t* pbits, const uint32_t* qcard, const uint32_t* pcard, int64_t nq, int64_t np,
                         int32_t words, int32_t pitch_words, int32_t k, int32_t zero_diag, int64_t query_base,
                         int64_t pool_base, int32_t n_qtiles, int32_t n_ptiles, int32_t n_stripes, int32_t ptiles_per_stripe,
-                        uint32_t* part_inter, uint32_t* part_union, int32_t* part_idx, const QIndex& qi, cudaStream_t st) {
+                        uint4* part, const QIndex& qi, cudaStream_t st) {
     R4D_REQUIRE((reinterpret_cast<uintptr_t>(pbits) & 15) == 0 && pitch_words % 4 == 0,
                 "jaccard query-index path: pool bitsets must be 16-byte aligned (base %p, pitch %d words)", (const void*)pbits,
                 pitch_words);
@@ -908,24 +931,30 @@ int sparseq_topk_launch(const uint32_t* pbits, const uint32_t* qcard, const uint
     prm.n_slots = SQ_RING_BYTES / (prm.slot_bytes + 16);   // every slot is followed by 16 zero bytes
     if (prm.n_slots > SQ_MAX_SLOTS) prm.n_slots = SQ_MAX_SLOTS;
     R4D_REQUIRE(prm.n_slots >= 1, "jaccard query-index path: a row of %d words does not fit the ring", words);
-    prm.part_inter = part_inter;
-    prm.part_union = part_union;
-    prm.part_idx = part_idx;
+    prm.part = part;
     prm.qi = qi;
     prm.debug = options().jaccard_debug;
-    static bool attr_done = false;
-    if (!attr_done) {
-        R4D_CUDA(cudaFuncSetAttribute(jaccard_qindex_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SQ_SM_TOTAL));
-        R4D_CUDA(cudaFuncSetAttribute(jaccard_qindex_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SQ_SM_TOTAL));
-        attr_done = true;
+    // NU = units per lane of a one-row slot (0: generic geometry)
+    const int nu = (prm.slot_rows == 1 && prm.row_units <= 6 * 32) ? (prm.row_units + 31) / 32 : 0;
+    void (*kern)(const SparseParams) = jaccard_qindex_kernel<0>;
+    switch (nu) {
+        case 1: kern = jaccard_qindex_kernel<1>; break;
+        case 2: kern = jaccard_qindex_kernel<2>; break;
+        case 3: kern = jaccard_qindex_kernel<3>; break;
+        case 4: kern = jaccard_qindex_kernel<4>; break;
+        case 5: kern = jaccard_qindex_kernel<5>; break;
+        case 6: kern = jaccard_qindex_kernel<6>; break;
+        default: break;
+    }
+    static bool attr_done[7] = {false, false, false, false, false, false, false};
+    if (!attr_done[nu]) {
+        R4D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SQ_SM_TOTAL));
+        attr_done[nu] = true;
     }
     int grid = num_sms();
     if (n_stripes < grid) grid = n_stripes;
     prof_begin(PROF_JACCARD_QINDEX, st);
-    if (prm.slot_rows == 1 && prm.row_units <= 6 * 32)
-        jaccard_qindex_kernel<true><<<grid, SQ_THREADS, SQ_SM_TOTAL, st>>>(prm);
-    else
-        jaccard_qindex_kernel<false><<<grid, SQ_THREADS, SQ_SM_TOTAL, st>>>(prm);
+    kern<<<grid, SQ_THREADS, SQ_SM_TOTAL, st>>>(prm);
     prof_end(PROF_JACCARD_QINDEX, st);
     R4D_CUDA(cudaGetLastError());
     return R4D_OK;
