@@ -65,6 +65,8 @@ int r4d_set_option(const char* key, int value);
  * every launch of its dominant kernels with CUDA events on the launch stream; this call waits for the recorded
  * events, returns their summed duration and count, and clears them.  kernel: "jaccard_qindex" | "dense_pair". */
 int r4d_profile_read(const char* kernel, double* total_ms, int64_t* launches);
+/* Kernels this library has enqueued since it was loaded (every <<<>>> of its own; memsets and copies not counted). */
+int64_t r4d_kernel_launches(void);
 
 /* ---------------------------------------------------------------- set encoder (subsystem 1)
  * Replaces the per-pair `set(seq_i)`, `set(seq_j)` construction of co_occurrence_ratio

@@ -59,6 +59,7 @@ PROTOTYPES = {
     "r4d_dense_full": (_c.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _f32, _i32, _vp, _i64, _vp]),
     "r4d_dense_topk_merge": (_c.c_int, [_vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp]),
     "r4d_profile_read": (_c.c_int, [_c.c_char_p, _vp, _vp]),
+    "r4d_kernel_launches": (_i64, []),
     "r4d_meanpool_workspace_bytes": (_sz, [_i64, _i32]),
     "r4d_meanpool_prepare": (_c.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "r4d_format_int_rows_bound": (_sz, [_i64, _i64]),

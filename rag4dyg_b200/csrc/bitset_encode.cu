@@ -61,7 +61,7 @@ int r4d_bitset_encode(const int32_t* bit_pos, const int64_t* row_off, int64_t n_
     const int64_t cap = (int64_t)num_sms() * 32;
     if (blocks > cap) blocks = cap;
     bitset_scatter_kernel<<<(unsigned)blocks, warps_per_block * 32, 0, st>>>(bit_pos, row_off, n_rows, n_bits,
-                                                                           pitch_words, bits, card);
+                                                                           pitch_words, bits, card); note_launch();
     R4D_CUDA(cudaGetLastError());
     return R4D_OK;
 }

@@ -410,10 +410,10 @@ static int dense_launch(int dmode, const void* q_hi, const void* q_lo, int64_t n
     if (n_items < grid) grid = (int)n_items;
     if (dmode == DMODE_TOPK) {
         R4D_CUDA(cudaFuncSetAttribute(dense_kernel<DMODE_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dense_kernel<DMODE_TOPK><<<grid, D_THREADS, smem, st>>>(tm_qh, tm_ql, tm_ph, tm_pl, prm);
+        dense_kernel<DMODE_TOPK><<<grid, D_THREADS, smem, st>>>(tm_qh, tm_ql, tm_ph, tm_pl, prm); note_launch();
     } else {
         R4D_CUDA(cudaFuncSetAttribute(dense_kernel<DMODE_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dense_kernel<DMODE_FULL><<<grid, D_THREADS, smem, st>>>(tm_qh, tm_ql, tm_ph, tm_pl, prm);
+        dense_kernel<DMODE_FULL><<<grid, D_THREADS, smem, st>>>(tm_qh, tm_ql, tm_ph, tm_pl, prm); note_launch();
     }
     R4D_CUDA(cudaGetLastError());
     return R4D_OK;
@@ -451,7 +451,7 @@ int r4d_dense_prepare(const float* x, int64_t n, int32_t d, int64_t ld, int32_t 
     if (blocks > cap) blocks = cap;
     dense_prepare_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
         x, n, d, ld, r4d_dense_dpad(d), prec == R4D_PREC_BF16X3 ? 1 : 0, reinterpret_cast<__nv_bfloat16*>(hi),
-        reinterpret_cast<__nv_bfloat16*>(lo));
+        reinterpret_cast<__nv_bfloat16*>(lo)); note_launch();
     R4D_CUDA(cudaGetLastError());
     return R4D_OK;
 }
@@ -480,7 +480,7 @@ static int dense_merge_launch(const float* score, const int32_t* idx, int32_t n_
     const int64_t cap = (int64_t)num_sms() * 16;
     if (blocks > cap) blocks = cap;
     dense_merge_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(score, idx, n_lists, nq, k_in, k_out, out_score,
-                                                                       out_idx, peers);
+                                                                       out_idx, peers); note_launch();
     R4D_CUDA(cudaGetLastError());
     return R4D_OK;
 }

@@ -466,11 +466,11 @@ int dense2_topk(const void* q_hi, int64_t nq, const void* p_hi, int64_t np, int3
     if (pl.qres) {
         R4D_CUDA(cudaFuncSetAttribute(dense2_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         prof_begin(PROF_DENSE_PAIR, st);
-        dense2_kernel<256, true><<<2 * n_clusters, D2_THREADS, smem, st>>>(tm_q, tm_p, prm);
+        dense2_kernel<256, true><<<2 * n_clusters, D2_THREADS, smem, st>>>(tm_q, tm_p, prm); note_launch();
     } else {
         R4D_CUDA(cudaFuncSetAttribute(dense2_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         prof_begin(PROF_DENSE_PAIR, st);
-        dense2_kernel<256, false><<<2 * n_clusters, D2_THREADS, smem, st>>>(tm_q, tm_p, prm);
+        dense2_kernel<256, false><<<2 * n_clusters, D2_THREADS, smem, st>>>(tm_q, tm_p, prm); note_launch();
     }
     prof_end(PROF_DENSE_PAIR, st);
     R4D_CUDA(cudaGetLastError());

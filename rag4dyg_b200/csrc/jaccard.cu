@@ -377,7 +377,7 @@ struct MergeExtra {
     int64_t q_off, nq_total;  // fused exchange with query batches: row offset / rows of the whole call
 };
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 jaccard_merge_kernel(const uint4* __restrict__ part, const uint32_t* __restrict__ inter, const uint32_t* __restrict__ uni,
                      const int32_t* __restrict__ idx, int32_t n_lists, int64_t nq, int32_t k_in, int32_t k_out,
                      uint32_t* __restrict__ out_inter, uint32_t* __restrict__ out_union, int32_t* __restrict__ out_idx,
@@ -396,20 +396,40 @@ jaccard_merge_kernel(const uint4* __restrict__ part, const uint32_t* __restrict_
         WarpTopK<JEntry> tk;
         tk.init(k_out);
         if (ex.cnt != nullptr && !(ex.tile_dense && ex.tile_dense[q >> 7])) {
-            // short unsorted lists: lane L walks list l0 + L, all lanes in parallel
-            for (int l0 = 0; l0 < n_lists; l0 += 32) {
-                const int l = l0 + lane;
-                const int n = l < n_lists ? (int)ex.cnt[(int64_t)l * nq + q] : 0;
-                const int n_max = __reduce_max_sync(0xffffffffu, n);
-                const int64_t base = ((int64_t)l * nq + q) * k_in;
+            // short unsorted lists of the query-index kernel, entries {inter, |pool set|, idx}: union = |q| + |p| - inter.
+            // Lane L walks lists L, L + 32, ...; the counts and then the e-th entries of up to six lists per lane are
+            // loaded back to back (independent loads in flight) before any of them is ranked.
+            const uint32_t cq = ex.qcard[q];
+            for (int l0 = 0; l0 < n_lists; l0 += 6 * 32) {
+                const int nj = min(6, (n_lists - l0 + 31) / 32);
+                int n[6], n_max = 0;
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    const int l = l0 + j * 32 + lane;
+                    n[j] = (j < nj && l < n_lists) ? (int)ex.cnt[(int64_t)l * nq + q] : 0;
+                }
+#pragma unroll
+                for (int j = 0; j < 6; ++j) n_max = max(n_max, n[j]);
+                n_max = __reduce_max_sync(0xffffffffu, n_max);
                 for (int e = 0; e < n_max; ++e) {
-                    JEntry c = JEntry::worst();
-                    if (e < n) c = load(base + e);
-                    uint32_t m = __ballot_sync(0xffffffffu, e < n && JEntry::better(c, tk.kth));
-                    while (m) {
-                        const int src = __ffs(m) - 1;
-                        m &= m - 1;
-                        tk.insert(c.shfl(src));
+                    JEntry c[6];
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) {
+                        c[j] = JEntry::worst();
+                        if (e < n[j]) {
+                            const uint4 x = part[((int64_t)(l0 + j * 32 + lane) * nq + q) * k_in + e];
+                            c[j] = JEntry{x.x, cq + x.y - x.x, (int32_t)x.z};
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) {
+                        if (j >= nj) break;
+                        uint32_t m = __ballot_sync(0xffffffffu, e < n[j] && JEntry::better(c[j], tk.kth));
+                        while (m) {
+                            const int src = __ffs(m) - 1;
+                            m &= m - 1;
+                            tk.insert(c[j].shfl(src));
+                        }
                     }
                 }
             }
@@ -508,7 +528,7 @@ static int launch_ncw(const CUtensorMap& tm_q, const CUtensorMap& tm_p, const Ja
     const int64_t n_items = (int64_t)prm.n_qtiles * prm.n_stripes;
     int grid = num_sms();
     if (n_items < grid) grid = (int)n_items;
-    jaccard_kernel<MODE, NCW, SKIP><<<grid, 32 * NCW, smem, st>>>(tm_q, tm_p, prm);
+    jaccard_kernel<MODE, NCW, SKIP><<<grid, 32 * NCW, smem, st>>>(tm_q, tm_p, prm); note_launch();
     R4D_CUDA(cudaGetLastError());
     return R4D_OK;
 }
@@ -592,7 +612,7 @@ static int merge_launch(const uint4* part, const uint32_t* inter, const uint32_t
     const int64_t cap = (int64_t)num_sms() * 16;
     if (blocks > cap) blocks = cap;
     jaccard_merge_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(part, inter, uni, idx, n_lists, nq, k_in, k_out,
-                                                                         out_inter, out_union, out_idx, peers, ex);
+                                                                         out_inter, out_union, out_idx, peers, ex); note_launch();
     R4D_CUDA(cudaGetLastError());
     return R4D_OK;
 }

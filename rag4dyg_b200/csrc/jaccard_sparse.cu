@@ -153,7 +153,7 @@ struct SparseParams {
     int32_t slot_rows_log2;
     int32_t bucket_shift;  // index bucket of a bit id = id >> bucket_shift (0 while the vocabulary fits SQ_NBK buckets)
     int32_t n_buckets;
-    uint4* part;           // [n_stripes][nq][k] {inter, union, idx, 0}
+    uint4* part;           // [n_stripes][nq][k] {inter, |pool set|, idx, 0}: the merge kernel forms union = |q| + |p| - inter
     QIndex qi;
     int32_t debug;  // experiments: 1 = scan only (no lookups), 2 = lookups but no hit completion, 3 = no list update
 };
@@ -218,10 +218,17 @@ __device__ __forceinline__ uint4 ldg_volatile_v4(const void* p) {
     return v;
 }
 // TMA bulk copy of `bytes` contiguous bytes (16 B multiple) global -> shared, completion on an mbarrier (SASS: UBLKCP).
-__device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
-                 "l"(src), "r"(bytes), "r"(bar)
+// `policy`: an L2 cache policy (createpolicy); the pool is read once per launch, so its lines are marked evict-first
+// and the candidate lists written meanwhile stay in L2 for the merge kernel.
+__device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+                 "l"(src), "r"(bytes), "r"(bar), "l"(policy)
                  : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
 }
 
 // shared-memory addresses (u32) of the candidate bookkeeping of the current item
@@ -235,7 +242,7 @@ struct ListState {
 // Fast path, all lanes in parallel: a CAS on the row's slot counter hands out an empty slot; the entry is stored and
 // then published (counter `pub`).  A candidate that finds all k slots taken goes through the per-row lock: wait until
 // the k entries are published, replace the worst one if the candidate ranks before it.
-__device__ __noinline__ void append_candidates(const SparseParams& prm, bool keep, uint32_t rr, uint32_t inter, uint32_t uni,
+__device__ __noinline__ void append_candidates(const SparseParams& prm, bool keep, uint32_t rr, uint32_t inter, uint32_t pcard,
                                                int32_t idx, int t0, int stripe, const ListState ls) {
     const int lane = threadIdx.x & 31;
     const int K = prm.k;
@@ -253,7 +260,7 @@ __device__ __noinline__ void append_candidates(const SparseParams& prm, bool kee
         if (n < (uint32_t)K) {
             const int64_t at = ((int64_t)stripe * prm.nq + (int64_t)t0 * SQ_TQ + rr) * K + n;
             if (prm.debug != 7) {
-                prm.part[at] = make_uint4(inter, uni, (uint32_t)idx, 0u);
+                prm.part[at] = make_uint4(inter, pcard, (uint32_t)idx, 0u);
             }
             if (prm.debug != 6) __threadfence_block();  // the entry is visible to the CTA before it counts as published
             reds_add(ls.pub + wa, 1u << sh);
@@ -266,8 +273,9 @@ __device__ __noinline__ void append_candidates(const SparseParams& prm, bool kee
         const int src = __ffs(pb) - 1;
         pb &= pb - 1;
         const uint32_t r = __shfl_sync(0xffffffffu, rr, src);
-        const JEntry cand{__shfl_sync(0xffffffffu, inter, src), __shfl_sync(0xffffffffu, uni, src),
-                          __shfl_sync(0xffffffffu, idx, src)};
+        const uint32_t cq = prm.qcard[(int64_t)t0 * SQ_TQ + r];   // entries hold |pool set|: union = |q| + |p| - inter
+        const uint32_t c_inter = __shfl_sync(0xffffffffu, inter, src), c_pcard = __shfl_sync(0xffffffffu, pcard, src);
+        const JEntry cand{c_inter, cq + c_pcard - c_inter, __shfl_sync(0xffffffffu, idx, src)};
         const int64_t base = ((int64_t)stripe * prm.nq + (int64_t)t0 * SQ_TQ + r) * K;
         const uint32_t bit = 1u << (r & 31);
         const uint32_t lock_a = ls.lock + (r >> 5) * 4u;
@@ -285,7 +293,7 @@ __device__ __noinline__ void append_candidates(const SparseParams& prm, bool kee
             JEntry wv{0xffffffffu, 1u, -1};  // ranks before every real entry
             if (lane < K) {
                 const uint4 e = ldg_volatile_v4(prm.part + base + lane);
-                wv = JEntry{e.x, e.y, (int32_t)e.z};
+                wv = JEntry{e.x, cq + e.y - e.x, (int32_t)e.z};
             }
             int wl = lane;
 #pragma unroll
@@ -299,7 +307,7 @@ __device__ __noinline__ void append_candidates(const SparseParams& prm, bool kee
                 }
             }
             if (lane == 0 && JEntry::better(cand, wv)) {
-                prm.part[base + wl] = make_uint4(cand.inter, cand.uni, (uint32_t)cand.idx, 0u);
+                prm.part[base + wl] = make_uint4(c_inter, c_pcard, (uint32_t)cand.idx, 0u);
             }
         }
         __threadfence_block();  // the replacement is visible to the CTA before the lock is released
@@ -327,7 +335,7 @@ __device__ __noinline__ void flush_hits(const SparseParams& prm, uint32_t hit_a,
         if (!(prm.zero_diag && prm.query_base + gq == prm.pool_base + gp)) {  // the diagonal is a forced zero: a filler
             const uint16_t* ro = prm.qi.rowoff + (size_t)t * SQ_ROWOFF_LD + i;
             const int rb = ro[0], re = ro[1];
-            const uint32_t cq = prm.qcard[gq], cp = prm.pcard[gp];
+            const uint32_t cp = prm.pcard[gp];
             const uint16_t* ew = prm.qi.ent_word + (size_t)t * SQ_T1;
             const uint32_t* ev = prm.qi.ent_val + (size_t)t * SQ_T1;
             const uint32_t* prow = prm.pbits + gp * prm.pitch_words;
@@ -339,7 +347,7 @@ __device__ __noinline__ void flush_hits(const SparseParams& prm, uint32_t hit_a,
                 if (x) first = min(first, (ww << 5) | (uint32_t)(__ffs(x) - 1));
             }
             primary = first == hbit && prm.debug != 3;
-            uni = cq + cp - inter;
+            uni = cp;   // the list entry holds |pool set|
             idx = (int32_t)(prm.pool_base + gp);
         }
     }
@@ -423,10 +431,8 @@ __device__ __noinline__ int batch_hits(const SparseParams& prm, uint32_t bl_a, i
         const int64_t gq = (int64_t)t0 * SQ_TQ + rr, gp = gp0 + pl;
         if (prm.zero_diag && prm.query_base + gq == prm.pool_base + gp) leader = false;  // forced zero: a filler
         if (prm.debug == 3) leader = false;
-        const uint32_t cp = __shfl_sync(0xffffffffu, pc_lane, (int)pl);
-        uint32_t uni = 0;
-        if (leader) uni = prm.qcard[gq] + cp - sum;
-        append_candidates(prm, leader, rr, sum, uni, (int32_t)(prm.pool_base + gp), t0, stripe, ls);
+        const uint32_t cp = __shfl_sync(0xffffffffu, pc_lane, (int)pl);   // |pool set|; the union is formed at the merge
+        append_candidates(prm, leader, rr, sum, cp, (int32_t)(prm.pool_base + gp), t0, stripe, ls);
     }
     return 0;
 }
@@ -512,6 +518,7 @@ jaccard_qindex_kernel(const __grid_constant__ SparseParams prm) {
     const uint32_t row_bytes = R == 1 ? (uint32_t)prm.slot_bytes : (uint32_t)prm.pitch_words * 4u;
     const uint32_t bsh = (uint32_t)prm.bucket_shift, blo = (1u << bsh) - 1u;
 
+    const uint64_t l2_stream = l2_policy_evict_first();
     int slot = 0;          // ring position of the next slot to consume; slots are issued and consumed cyclically
     uint32_t phase = 0;
     int cur_g = -1;
@@ -641,7 +648,7 @@ jaccard_qindex_kernel(const __grid_constant__ SparseParams prm) {
                 uint32_t bytes = row_bytes;
                 if (R != 1) bytes = (uint32_t)min(R, n_rows - ib * SQ_BATCH_ROWS - (is << lgR)) * row_bytes;
                 mbar_arrive_expect_tx(&my_bars[at], bytes);
-                bulk_load(ring_u32 + (uint32_t)at * slot_stride, isrc, bytes, smem_u32(&my_bars[at]));
+                bulk_load(ring_u32 + (uint32_t)at * slot_stride, isrc, bytes, smem_u32(&my_bars[at]), l2_stream);
             }
             isrc += (size_t)R * prm.pitch_words;
             if (++is >= ib_slots) {
@@ -881,7 +888,7 @@ int sparseq_build(const uint32_t* qbits, int64_t nq, int32_t words, int32_t pitc
     const int n_qtiles = (int)((nq + SQ_TQ - 1) / SQ_TQ);
     R4D_REQUIRE(nq <= SQ_QB, "jaccard query-index path: batch of %lld rows > %d", (long long)nq, SQ_QB);
     R4D_CUDA(cudaMemsetAsync(qi.any_dense, 0, 256 + (size_t)n_stripes * (size_t)nq, st));   // flag + counts
-    qindex_kernel<<<n_qtiles, QI_THREADS, 0, st>>>(qbits, nq, words, pitch_words, qi);
+    qindex_kernel<<<n_qtiles, QI_THREADS, 0, st>>>(qbits, nq, words, pitch_words, qi); note_launch();
     R4D_CUDA(cudaGetLastError());
     return R4D_OK;
 }
@@ -954,7 +961,7 @@ int sparseq_topk_launch(const uint32_t* pbits, const uint32_t* qcard, const uint
     int grid = num_sms();
     if (n_stripes < grid) grid = n_stripes;
     prof_begin(PROF_JACCARD_QINDEX, st);
-    kern<<<grid, SQ_THREADS, SQ_SM_TOTAL, st>>>(prm);
+    kern<<<grid, SQ_THREADS, SQ_SM_TOTAL, st>>>(prm); note_launch();
     prof_end(PROF_JACCARD_QINDEX, st);
     R4D_CUDA(cudaGetLastError());
     return R4D_OK;

@@ -100,7 +100,7 @@ int r4d_meanpool_prepare(const float* hidden, int64_t batch, int32_t len, int32_
     for (int64_t b0 = 0; b0 < batch; b0 += 2147483647ll) {  // gridDim.x limit (never hit in practice)
         const int64_t nb = batch - b0 < 2147483647ll ? batch - b0 : 2147483647ll;
         meanpool_partial_kernel<<<dim3((unsigned)nb, MP_LSPLIT), 256, 0, st>>>(hidden + b0 * len * (int64_t)d, nb, len, d,
-                                                                              partial + b0 * MP_LSPLIT * (int64_t)d);
+                                                                              partial + b0 * MP_LSPLIT * (int64_t)d); note_launch();
     }
     R4D_CUDA(cudaGetLastError());
     int64_t blocks = (batch + 7) / 8;
@@ -109,7 +109,7 @@ int r4d_meanpool_prepare(const float* hidden, int64_t batch, int32_t len, int32_
     meanpool_finish_kernel<<<(unsigned)blocks, 256, 0, st>>>(partial, batch, len, d, r4d_dense_dpad(d),
                                                              prec == R4D_PREC_BF16X3 ? 1 : 0, mean_out,
                                                              reinterpret_cast<__nv_bfloat16*>(hi),
-                                                             reinterpret_cast<__nv_bfloat16*>(lo));
+                                                             reinterpret_cast<__nv_bfloat16*>(lo)); note_launch();
     R4D_CUDA(cudaGetLastError());
     return R4D_OK;
 }

@@ -12,6 +12,7 @@ namespace r4d {
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 int num_sms();  // SM count of the current device (cached)
+void note_launch();  // counts the kernels this library has enqueued (r4d_kernel_launches)
 
 struct Options {
     int jaccard_skip_zero = 1;

@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 
 #include "r4d_common.cuh"
@@ -34,6 +35,10 @@ int num_sms() {
     }
     return cached[dev];
 }
+
+static std::atomic<long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launches_so_far() { return g_launches.load(std::memory_order_relaxed); }
 
 Options& options() {
     static Options o = [] {
@@ -130,6 +135,8 @@ void prof_end(ProfKernel k, cudaStream_t st) {
 extern "C" {
 
 int r4d_version(void) { return 100; }
+
+int64_t r4d_kernel_launches(void) { return (int64_t)r4d::launches_so_far(); }
 
 int r4d_profile_read(const char* kernel, double* total_ms, int64_t* launches) {
     using namespace r4d;

@@ -272,7 +272,7 @@ static int rank_rows_impl(const T* scores, int64_t nq, int64_t n, int64_t ld, in
         return R4D_E_WORKSPACE;
     }
     rank_rows_kernel<T><<<(unsigned)grid, RK_THREADS, 0, st>>>(scores, nq, n, ld, order,
-                                                              reinterpret_cast<uint8_t*>(workspace), per);
+                                                              reinterpret_cast<uint8_t*>(workspace), per); note_launch();
     R4D_CUDA(cudaGetLastError());
     return R4D_OK;
 }
@@ -309,7 +309,7 @@ int r4d_topk_rows_f64(const double* scores, int64_t nq, int64_t n, int64_t ld, i
     int64_t blocks = (nq + 7) / 8;
     const int64_t cap = (int64_t)num_sms() * 16;
     if (blocks > cap) blocks = cap;
-    topk_rows_f64_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(scores, nq, n, ld, k, top_score, top_idx);
+    topk_rows_f64_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(scores, nq, n, ld, k, top_score, top_idx); note_launch();
     R4D_CUDA(cudaGetLastError());
     return R4D_OK;
 }
@@ -324,7 +324,7 @@ int r4d_triplet_sample(const int64_t* pos_row, const int64_t* row_start, int64_t
     const int64_t cap = (int64_t)num_sms() * 8;
     if (blocks > cap) blocks = cap;
     triplet_sample_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(pos_row, row_start, n_pairs, neg, n_neg, neg_num,
-                                                                         seed, choice);
+                                                                         seed, choice); note_launch();
     R4D_CUDA(cudaGetLastError());
     return R4D_OK;
 }
@@ -340,7 +340,7 @@ int r4d_triplet_mine_f64(const double* out, const double* in, int64_t n, int64_t
     const int64_t cap = (int64_t)num_sms() * 16;
     if (blocks > cap) blocks = cap;
     triplet_mine_f64_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(out, in, n, ld, thr, neg_num, n_pos, neg,
-                                                                          n_neg);
+                                                                          n_neg); note_launch();
     R4D_CUDA(cudaGetLastError());
     return R4D_OK;
 }

@@ -18,21 +18,21 @@ __all__ = [
     "launch_count", "reset_launch_count",
 ]
 
-_launches = 0  # kernels of OURS enqueued through this module (bench.py reports it as gpu_launches)
+_launch_base = 0  # library launch counter at the last reset (bench.py reports the difference as gpu_launches)
 
 
 def launch_count():
-    return _launches
+    """Kernels of OURS the library has enqueued since reset_launch_count() (counted inside libr4d.so at every <<<>>>)."""
+    return int(_lib.load().r4d_kernel_launches()) - _launch_base
 
 
 def reset_launch_count():
-    global _launches
-    _launches = 0
+    global _launch_base
+    _launch_base = int(_lib.load().r4d_kernel_launches())
 
 
 def _count(n):
-    global _launches
-    _launches += n
+    """Kept for call-site symmetry; the library counts its own launches."""
 
 
 def _stream():
