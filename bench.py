@@ -33,6 +33,8 @@ POOL_N = 1_000_000
 QUERY_N = 100_000
 TOPK = 10
 Q_STEP = 8192
+JQ_STEP = 32768          # Jaccard step: four 8,192-query launch sequences inside ONE C-ABI call
+JQ_LAUNCH = 8192         # query rows the library serves per pool stream (SQ_QB in csrc/jaccard_common.cuh)
 DENSE_POOL_N = 10_000_000
 DENSE_D = 768
 DENSE_LAMBDA = 1e-4
@@ -49,7 +51,9 @@ def parse_args():
     ap.add_argument("--scorers", default="jaccard,dense")
     ap.add_argument("--pool", type=int, default=POOL_N)
     ap.add_argument("--dense-pool", type=int, default=DENSE_POOL_N)
-    ap.add_argument("--queries-per-step", type=int, default=Q_STEP)
+    ap.add_argument("--queries-per-step", type=int, default=Q_STEP, help="dense scorer: queries per step")
+    ap.add_argument("--jaccard-queries-per-step", type=int, default=JQ_STEP,
+                    help="Jaccard scorer: queries per step (one r4d_jaccard_topk call = ceil(q / 8192) launch sequences)")
     ap.add_argument("--mean-set", type=float, default=1.0 / 0.45, help="mean set size (y-like 2.2; x-like 20)")
     ap.add_argument("--dense-d", type=int, default=DENSE_D, help="embedding width (experiments; the metric uses 768)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
@@ -179,7 +183,7 @@ def run_reference(args, rank, world):
     procs = os.cpu_count() or 1
     n_p_sample, q_per_worker = 100_000, 4
     pool_ids, pool_off = synth_sets(n_p_sample, SEED_POOL, args.mean_set)
-    q_ids, q_off = synth_sets(args.queries_per_step, SEED_QUERY, args.mean_set)
+    q_ids, q_off = synth_sets(JQ_LAUNCH, SEED_QUERY, args.mean_set)
     times = []
     for step in range(args.warmup + args.steps):
         rate, dt, nq = cpu_port_sample(pool_ids, pool_off, q_ids, q_off, q_per_worker * procs, n_p_sample, procs)
@@ -190,7 +194,7 @@ def run_reference(args, rank, world):
     value = pairs * args.steps / total
     sample = (f"{q_per_worker * procs} queries x {n_p_sample} pool sets per step (same distribution/seeds as the GPU "
               f"workload), Python-set Jaccard + stable argsort top-{TOPK}, {procs} processes on disjoint query slices")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "query-pool pairs scored+top-K/sec (Jaccard)", "value": value,
         "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -198,20 +202,35 @@ def run_reference(args, rank, world):
         "config": workload_config(args, 1),
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": procs, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
 
 
 def workload_config(args, world):
     return {"workload": f"synthetic Jaccard top-K: {args.pool:,}-set pool x {QUERY_N:,} queries, vocab {V_BITS:,} "
-                        f"(W=625 uint32 words), K={TOPK}; step = {args.queries_per_step:,}-query batch vs the whole pool",
-            "pool": args.pool, "queries_total": QUERY_N, "queries_per_step": args.queries_per_step, "vocab": V_BITS,
+                        f"(W=625 uint32 words), K={TOPK}; step = one r4d_jaccard_topk call: {args.jaccard_queries_per_step:,} queries "
+                        f"vs the whole pool (the library serves it as {JQ_LAUNCH:,}-query launch sequences)",
+            "pool": args.pool, "queries_total": QUERY_N, "queries_per_step": args.jaccard_queries_per_step, "vocab": V_BITS,
             "k": TOPK, "mean_set_size": round(args.mean_set, 3), "parallelism": f"pool-sharded x{world}",
             "l2": "inputs larger than L2 (pool bitsets 2.56 GB / n_gpus; a different query batch every step)"}
 
 
 # ------------------------------------------------------------------------------------------ our arm
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """The ONE JSON line of the contract, written to the process' original stdout."""
+    line = (json.dumps(obj) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, line)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    # everything else that reaches fd 1 (library banners such as "NCCL version ...", stray prints) goes to stderr
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -303,7 +322,9 @@ def main():
     out = {}
     # =============================================================== Jaccard
     if "jaccard" in scorers:
-        n_pool, qs = args.pool, args.queries_per_step
+        n_pool, qs = args.pool, args.jaccard_queries_per_step
+        ql = min(qs, JQ_LAUNCH)                                 # query rows per launch sequence
+        n_launch = (qs + JQ_LAUNCH - 1) // JQ_LAUNCH            # pool streams per step
         lo, hi = rank * n_pool // world, (rank + 1) * n_pool // world
         pool_ids, pool_off = synth_sets(n_pool, SEED_POOL, args.mean_set)
         q_ids, q_off = synth_sets(QUERY_N, SEED_QUERY, args.mean_set)
@@ -311,7 +332,7 @@ def main():
         sh_ids_pin, sh_off_pin = sh_ids.pin_memory(), sh_off.pin_memory()
         bp = set_encoder.encode_csr(sh_ids_pin, sh_off_pin, V_BITS, dev)      # pool shard resident in HBM
         bq_all = set_encoder.encode_csr(q_ids, q_off, V_BITS, dev)            # all 100k queries resident (250 MB)
-        n_batches = QUERY_N // qs
+        n_batches = max(1, QUERY_N // qs)
         ws = torch.empty(_lib.load().r4d_jaccard_topk_workspace_bytes(qs, hi - lo, TOPK), dtype=torch.uint8, device=dev)
         result = {}
         jex, exchange_used = None, "none (single GPU)"
@@ -349,28 +370,31 @@ def main():
         _lib.set_option("kernel_timing", 0)
         main_s = max_over_ranks(main_ms / max(main_n, 1)) * 1e-3
         # dense case: the bitset-streaming kernel with zero-span skipping disabled executes every algorithmic word-op
+        # (one 8,192-query launch per step: it is ~1000x slower than the index path)
+        def kernel_dense_case(i):
+            engine.jaccard_topk(bq_all.rows((i % 4) * ql, (i % 4 + 1) * ql), bp, TOPK, pool_base=lo, workspace=ws)
         _lib.set_option("jaccard_skip_zero", 0)
-        kd_ms, _, _ = timed(kernel_only, steps=K_AUX)
+        kd_ms, _, _ = timed(kernel_dense_case, steps=K_AUX)
         _lib.set_option("jaccard_skip_zero", 1)
         kd_s = kd_ms * 1e-3 / K_AUX
         words = 625
-        word_ops = qs * (hi - lo) * words                      # algorithmic AND+POPC word-ops per launch (W per pair)
+        word_ops = ql * (hi - lo) * words                      # algorithmic AND+POPC word-ops per launch (W per pair)
         sm_max = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz", 1965.0)
         popc_peak = 148 * 16 * sm_max * 1e6                    # 16 POPC lanes/clk/SM (measured 15.8, tools/microbench.cu)
         two_pipe = 148 * (64 / 2.125) * sm_max * 1e6           # CSA kernel: 17 ALU ops (64 lanes/clk/SM) + 4 POPC per 8 words
         pool_bytes = (hi - lo) * words * 4                     # the main kernel streams every pool row once per launch
-        call_bytes = ((hi - lo) + qs) * words * 4 + qs * TOPK * 12   # compulsory bytes of the whole call
+        call_bytes = (n_launch * (hi - lo) + qs) * words * 4 + qs * TOPK * 12   # whole call: one pool stream per launch
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         roofline = {"bound": "hbm", "achieved": pool_bytes / main_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": pool_bytes / main_s / 1e9 / hbm_peak,
-                    "traffic": dram_traffic("jaccard_topk", queries=qs, pool=hi - lo) if world == 1 else None,
+                    "traffic": dram_traffic("jaccard_topk", queries=ql, pool=hi - lo) if world == 1 else None,
                     "kernel": "r4d::jaccard_qindex_kernel<ROW1> (query-side bit index in smem, pool bitsets streamed once "
                               "per 8,192-query batch by per-warp TMA bulk copies)",
                     "kernel_ms": main_s * 1e3, "launches_timed": int(main_n),
                     "algorithmic_bytes": pool_bytes,
                     "algorithmic_bytes_what": "4*W B per pool row of the shard, each row read once per launch (W = 625 words)",
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy bandwidth)" if peaks else "fallback 6650 GB/s",
-                    "call": {"what": "whole r4d_jaccard_topk call: qindex_kernel + memset + main kernel + merge kernel",
+                    "call": {"what": f"whole r4d_jaccard_topk call = {n_launch} x (qindex_kernel + memset + main kernel + merge kernel)",
                              "ms": k_ms / K, "algorithmic_bytes": call_bytes, "achieved_GBps": call_bytes / (k_ms * 1e-3 / K) / 1e9,
                              "frac": call_bytes / (k_ms * 1e-3 / K) / 1e9 / hbm_peak},
                     "int_pipe_equivalent": {"what": "the same launch expressed in the algorithmic W word-ops per pair of SURVEY "
@@ -379,7 +403,7 @@ def main():
                                             "ratio": word_ops / main_s / popc_peak},
                     "dense_case": {"what": "the bitset-streaming kernel (jaccard_kernel<TOPK,16,noskip>) on the same data: "
                                            "every word-op executed; INT-pipe bound",
-                                   "pairs_per_s": qs * (hi - lo) / kd_s * world, "kernel_ms": kd_ms / K_AUX,
+                                   "pairs_per_s": ql * (hi - lo) / kd_s * world, "kernel_ms": kd_ms / K_AUX,
                                    "achieved_Twordops": word_ops / kd_s / 1e12, "frac_popc_roof": word_ops / kd_s / popc_peak,
                                    "two_pipe_roof": two_pipe / 1e12, "frac_two_pipe_roof": word_ops / kd_s / two_pipe}}
 
@@ -387,14 +411,14 @@ def main():
         x_like = None
         if not args.no_e2e and abs(args.mean_set - 1.0 / 0.45) < 1e-6:
             xp_ids, xp_off = synth_sets(n_pool, SEED_POOL + 1, 20.0)
-            xq_ids, xq_off = synth_sets(qs, SEED_QUERY + 1, 20.0)
+            xq_ids, xq_off = synth_sets(ql, SEED_QUERY + 1, 20.0)
             xi, xo = csr_rows(xp_ids, xp_off, lo, hi)
             bxp = set_encoder.encode_csr(xi, xo, V_BITS, dev)
             bxq = set_encoder.encode_csr(xq_ids, xq_off, V_BITS, dev)
-            x_ms, _, _ = timed(lambda i: sharded.jaccard_topk_sharded(bxq, bxp, TOPK, pool_base=lo, workspace=ws, exchange=jex),
-                               steps=K_AUX)
-            x_like = {"value": pairs_per_step * K_AUX / (x_ms * 1e-3), "unit": "pairs/s", "ms_per_step": x_ms / K_AUX,
-                      "mean_set_size": 20.0}
+            # (NCCL exchange here: the fused-exchange buffers are sized for the headline step)
+            x_ms, _, _ = timed(lambda i: sharded.jaccard_topk_sharded(bxq, bxp, TOPK, pool_base=lo, workspace=ws), steps=K_AUX)
+            x_like = {"value": ql * n_pool * K_AUX / (x_ms * 1e-3), "unit": "pairs/s", "ms_per_step": x_ms / K_AUX,
+                      "mean_set_size": 20.0, "queries_per_step": ql}
             del bxp, bxq
 
         e2e = None
@@ -555,7 +579,7 @@ def main():
             out = dense
 
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

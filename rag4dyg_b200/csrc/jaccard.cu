@@ -353,7 +353,7 @@ jaccard_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                 const int64_t gq = (int64_t)qtile * TQ + q;
                 if (gq >= prm.nq) break;
                 if (lane < prm.k) {
-                    const int64_t o = ((int64_t)stripe * prm.nq + gq) * prm.k + lane;
+                    const int64_t o = ((int64_t)gq * prm.n_stripes + stripe) * prm.k + lane;   // query-major [nq][n_stripes][k]
                     prm.part[o] = make_uint4(l_inter[q * LIST_LD + lane], l_union[q * LIST_LD + lane],
                                              (uint32_t)l_idx[q * LIST_LD + lane], 0u);
                 }
@@ -364,7 +364,9 @@ jaccard_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 }
 
 // Merge n_lists lists of k_in candidates per query into the best k_out.  One warp per query.
-// Optional (query-index path): `cnt[l * nq + q]` = number of valid, UNSORTED entries of list l (lists of query tiles
+// The kernels' own partial lists (`part`) are query-major, [nq][n_lists][k_in], so that one query's lists and counts
+// are contiguous for this kernel; caller planes (all-gather buffers) are list-major, [n_lists][nq][k_in].
+// Optional (query-index path): `cnt[q * n_lists + l]` = number of valid, UNSORTED entries of list l (lists of query tiles
 // flagged in `tile_dense` are full sorted lists written by the dense kernel); `n_fill` > 0 appends the zero-score
 // fillers the query-index kernel never produces: pool rows 0 .. n_fill-1 of this shard unless already listed.
 struct MergeExtra {
@@ -397,16 +399,22 @@ jaccard_merge_kernel(const uint4* __restrict__ part, const uint32_t* __restrict_
         tk.init(k_out);
         if (ex.cnt != nullptr && !(ex.tile_dense && ex.tile_dense[q >> 7])) {
             // short unsorted lists of the query-index kernel, entries {inter, |pool set|, idx}: union = |q| + |p| - inter.
-            // Lane L walks lists L, L + 32, ...; the counts and then the e-th entries of up to six lists per lane are
-            // loaded back to back (independent loads in flight) before any of them is ranked.
+            // Lane L walks lists L, L + 32, ... (six per lane and pass, their loads issued back to back).
+            //   pass 1: every lane finds the best of its own candidates; a bitonic sort ranks the 32 lane-bests, the
+            //           first k_out of them seed the list (the others cannot be in the top k_out);
+            //   pass 2: the remaining candidates (L1/L2 hits now) are inserted only if they beat the current k-th —
+            //           a handful per query instead of k (1 + ln(n / k)) serial insertions.
             const uint32_t cq = ex.qcard[q];
+            const bool two_pass = n_lists <= 6 * 32;   // one chunk: the counts stay in registers between the passes
+            int n[6];
+            JEntry lb = JEntry::worst();
             for (int l0 = 0; l0 < n_lists; l0 += 6 * 32) {
                 const int nj = min(6, (n_lists - l0 + 31) / 32);
-                int n[6], n_max = 0;
+                int n_max = 0;
 #pragma unroll
                 for (int j = 0; j < 6; ++j) {
                     const int l = l0 + j * 32 + lane;
-                    n[j] = (j < nj && l < n_lists) ? (int)ex.cnt[(int64_t)l * nq + q] : 0;
+                    n[j] = (j < nj && l < n_lists) ? (int)ex.cnt[q * n_lists + l] : 0;
                 }
 #pragma unroll
                 for (int j = 0; j < 6; ++j) n_max = max(n_max, n[j]);
@@ -417,14 +425,62 @@ jaccard_merge_kernel(const uint4* __restrict__ part, const uint32_t* __restrict_
                     for (int j = 0; j < 6; ++j) {
                         c[j] = JEntry::worst();
                         if (e < n[j]) {
-                            const uint4 x = part[((int64_t)(l0 + j * 32 + lane) * nq + q) * k_in + e];
+                            const uint4 x = part[(q * n_lists + (l0 + j * 32 + lane)) * k_in + e];
                             c[j] = JEntry{x.x, cq + x.y - x.x, (int32_t)x.z};
                         }
                     }
+                    if (two_pass) {
+#pragma unroll
+                        for (int j = 0; j < 6; ++j)
+                            if (e < n[j] && JEntry::better(c[j], lb)) lb = c[j];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) {
+                            if (j >= nj) break;
+                            uint32_t m = __ballot_sync(0xffffffffu, e < n[j] && JEntry::better(c[j], tk.kth));
+                            while (m) {
+                                const int src = __ffs(m) - 1;
+                                m &= m - 1;
+                                tk.insert(c[j].shfl(src));
+                            }
+                        }
+                    }
+                }
+            }
+            if (two_pass) {
+                JEntry v = lb;   // bitonic sort of the lane-bests, best first
+#pragma unroll
+                for (int k2 = 2; k2 <= 32; k2 <<= 1)
+#pragma unroll
+                    for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+                        const JEntry o{__shfl_xor_sync(0xffffffffu, v.inter, j2), __shfl_xor_sync(0xffffffffu, v.uni, j2),
+                                       __shfl_xor_sync(0xffffffffu, v.idx, j2)};
+                        const bool want_better = ((lane & j2) == 0) == ((lane & k2) == 0);
+                        if (JEntry::better(o, v) == want_better && o.idx != v.idx) v = o;
+                    }
+                if (lane < k_out) tk.mine = v;
+                tk.refresh_kth();
+                int n_max = 0;
+#pragma unroll
+                for (int j = 0; j < 6; ++j) n_max = max(n_max, n[j]);
+                n_max = __reduce_max_sync(0xffffffffu, n_max);
+                for (int e = 0; e < n_max; ++e) {
+                    JEntry c[6];
+                    bool pass = false;
 #pragma unroll
                     for (int j = 0; j < 6; ++j) {
-                        if (j >= nj) break;
-                        uint32_t m = __ballot_sync(0xffffffffu, e < n[j] && JEntry::better(c[j], tk.kth));
+                        c[j] = JEntry::worst();
+                        if (e < n[j]) {
+                            const uint4 x = part[(q * n_lists + (j * 32 + lane)) * k_in + e];
+                            c[j] = JEntry{x.x, cq + x.y - x.x, (int32_t)x.z};
+                            if (c[j].idx == lb.idx) c[j] = JEntry::worst();   // the lane-best was ranked in pass 1
+                            pass |= JEntry::better(c[j], tk.kth);
+                        }
+                    }
+                    if (!__ballot_sync(0xffffffffu, pass)) continue;
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) {
+                        uint32_t m = __ballot_sync(0xffffffffu, JEntry::better(c[j], tk.kth));
                         while (m) {
                             const int src = __ffs(m) - 1;
                             m &= m - 1;
@@ -435,7 +491,7 @@ jaccard_merge_kernel(const uint4* __restrict__ part, const uint32_t* __restrict_
             }
         } else {
             for (int l = 0; l < n_lists; ++l) {
-                const int64_t base = ((int64_t)l * nq + q) * k_in;
+                const int64_t base = part != nullptr ? (q * n_lists + l) * k_in : ((int64_t)l * nq + q) * k_in;
                 for (int e0 = 0; e0 < k_in; e0 += 32) {
                     const int e = e0 + lane;
                     JEntry c = JEntry::worst();

@@ -22,7 +22,7 @@ constexpr int SQ_ROWOFF_LD = 132;     // 129 row offsets per tile, padded
 constexpr int SQ_WARPS = 16;
 constexpr int SQ_THREADS = SQ_WARPS * 32;
 
-// Per-stripe partial candidate lists [n_stripes][nq][k]: one 16-byte entry {inter, union, pool index, 0} per
+// Per-stripe partial candidate lists, query-major [nq][n_stripes][k]: one 16-byte entry {inter, union, pool index, 0} per
 // candidate, so a candidate costs one memory sector to store and one to merge.
 constexpr int SQ_PART_BYTES = 16;
 
@@ -37,7 +37,7 @@ struct QIndex {
     uint32_t* ent_val;     // [n_qtiles][SQ_T1]  word value
     uint8_t* ent_row;      // [n_qtiles][SQ_T1]  row of the entry inside its tile
     uint32_t* any_dense;   // [1] != 0 when some tile is flagged dense (64 words before `cnt`, cleared with it)
-    uint8_t* cnt;          // [n_stripes][nq]    candidates stored in the (stripe, query) partial list (unsorted)
+    uint8_t* cnt;          // [nq][n_stripes]    candidates stored in the (stripe, query) partial list (unsorted)
 };
 
 bool sparseq_supported(int32_t words, int32_t k);

@@ -258,7 +258,7 @@ __device__ __noinline__ void append_candidates(const SparseParams& prm, bool kee
             cur = old;
         }
         if (n < (uint32_t)K) {
-            const int64_t at = ((int64_t)stripe * prm.nq + (int64_t)t0 * SQ_TQ + rr) * K + n;
+            const int64_t at = (((int64_t)t0 * SQ_TQ + rr) * prm.n_stripes + stripe) * K + n;   // query-major lists
             if (prm.debug != 7) {
                 prm.part[at] = make_uint4(inter, pcard, (uint32_t)idx, 0u);
             }
@@ -276,7 +276,7 @@ __device__ __noinline__ void append_candidates(const SparseParams& prm, bool kee
         const uint32_t cq = prm.qcard[(int64_t)t0 * SQ_TQ + r];   // entries hold |pool set|: union = |q| + |p| - inter
         const uint32_t c_inter = __shfl_sync(0xffffffffu, inter, src), c_pcard = __shfl_sync(0xffffffffu, pcard, src);
         const JEntry cand{c_inter, cq + c_pcard - c_inter, __shfl_sync(0xffffffffu, idx, src)};
-        const int64_t base = ((int64_t)stripe * prm.nq + (int64_t)t0 * SQ_TQ + r) * K;
+        const int64_t base = (((int64_t)t0 * SQ_TQ + r) * prm.n_stripes + stripe) * K;
         const uint32_t bit = 1u << (r & 31);
         const uint32_t lock_a = ls.lock + (r >> 5) * 4u;
         if (lane == 0) {
@@ -837,9 +837,9 @@ jaccard_qindex_kernel(const __grid_constant__ SparseParams prm) {
 
         __syncthreads();  // every hit of this item is stored
         {
-            uint8_t* dst = prm.qi.cnt + (size_t)stripe * prm.nq + row0;
+            uint8_t* dst = prm.qi.cnt + (size_t)row0 * prm.n_stripes + stripe;   // query-major [nq][n_stripes]
             const uint8_t* alloc = smem + SQ_SM_ALLOC;
-            for (int i = threadIdx.x; i < g_rows; i += SQ_THREADS) dst[i] = alloc[i];
+            for (int i = threadIdx.x; i < g_rows; i += SQ_THREADS) dst[(size_t)i * prm.n_stripes] = alloc[i];
         }
     }
 }
