@@ -489,6 +489,47 @@ jaccard_merge_kernel(const uint4* __restrict__ part, const uint32_t* __restrict_
                     }
                 }
             }
+        } else if (n_lists * k_in <= 6 * 32) {
+            // few candidates (the exchange merge: `world` lists of k): all of them are loaded at once, six per lane;
+            // the lane-bests, ranked by a bitonic sort, seed the list and only the rest goes through insertions
+            const int total = n_lists * k_in;
+            JEntry c[6];
+            JEntry lb = JEntry::worst();
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                const int ci = lane + 32 * i;
+                c[i] = JEntry::worst();
+                if (ci < total) {
+                    const int l = ci / k_in, e = ci - l * k_in;
+                    c[i] = load((part != nullptr ? (q * n_lists + l) * k_in : ((int64_t)l * nq + q) * k_in) + e);
+                    if (c[i].idx == R4D_IDX_NONE) c[i] = JEntry::worst();
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 6; ++i)
+                if (JEntry::better(c[i], lb)) lb = c[i];
+            JEntry v = lb;
+#pragma unroll
+            for (int k2 = 2; k2 <= 32; k2 <<= 1)
+#pragma unroll
+                for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+                    const JEntry o{__shfl_xor_sync(0xffffffffu, v.inter, j2), __shfl_xor_sync(0xffffffffu, v.uni, j2),
+                                   __shfl_xor_sync(0xffffffffu, v.idx, j2)};
+                    const bool want_better = ((lane & j2) == 0) == ((lane & k2) == 0);
+                    if (JEntry::better(o, v) == want_better && o.idx != v.idx) v = o;
+                }
+            if (lane < k_out) tk.mine = v;
+            tk.refresh_kth();
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                if (32 * i >= total) break;
+                uint32_t m = __ballot_sync(0xffffffffu, c[i].idx != lb.idx && JEntry::better(c[i], tk.kth));
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    tk.insert(c[i].shfl(src));
+                }
+            }
         } else {
             for (int l = 0; l < n_lists; ++l) {
                 const int64_t base = part != nullptr ? (q * n_lists + l) * k_in : ((int64_t)l * nq + q) * k_in;

@@ -446,10 +446,12 @@ constexpr size_t SQ_SM_ALLOC = SQ_SM_ROW + (size_t)SQ_E_CAP * 2;
 constexpr size_t SQ_SM_PUB = SQ_SM_ALLOC + SQ_QB;
 constexpr size_t SQ_SM_LOCK = SQ_SM_PUB + SQ_QB;
 constexpr size_t SQ_SM_GROUPS = SQ_SM_LOCK + SQ_QB / 8;
-constexpr size_t SQ_SM_SCAN = SQ_SM_GROUPS + (size_t)(SQ_MAX_TILES + 2) * 8;
+constexpr size_t SQ_SM_TCNT = SQ_SM_GROUPS + (size_t)(SQ_MAX_TILES + 2) * 8;    // [SQ_MAX_TILES] u16 entries of a tile
+constexpr size_t SQ_SM_SCAN = SQ_SM_TCNT + (size_t)SQ_MAX_TILES * 2;
 // per-warp scratch of 512 B: while a batch is scanned it holds the batch's non-zero words (values [80] u32, then tags
 // [80] u16 = row in batch << 11 | word id); the lookup phase takes them into registers and reuses the space for the
 // bit list ([SQ_BL_CAP] x 4 B) and the hit buffer ([SQ_HB_CAP] x 2 B)
+constexpr int SQ_IB = 9;         // index build: entries a lane loads per round (9 * 32 = 288 covers a typical tile)
 constexpr int SQ_UL_CAP = 80;
 constexpr int SQ_SCRATCH = 512;
 constexpr size_t SQ_SM_SCR = (SQ_SM_SCAN + 32 * 4 + 15) / 16 * 16;
@@ -475,11 +477,13 @@ jaccard_qindex_kernel(const __grid_constant__ SparseParams prm) {
     int32_t* g_first = reinterpret_cast<int32_t*>(smem + SQ_SM_GROUPS);      // [n_groups + 1] first tile of a group
     int32_t* g_ent = g_first + SQ_MAX_TILES + 2;                             // [n_groups] entries of the group
     uint32_t* scan_s = reinterpret_cast<uint32_t*>(smem + SQ_SM_SCAN);       // [16] warp totals, [31] = n_groups
+    uint16_t* t_cnt = reinterpret_cast<uint16_t*>(smem + SQ_SM_TCNT);        // [n_qtiles] word entries of every tile
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr bool ROW1 = NU > 0;
     constexpr int NJ = ROW1 ? NU : 6;   // 16-byte units a lane loads per pass over a slot
 
+    for (int t = threadIdx.x; t < prm.n_qtiles; t += SQ_THREADS) t_cnt[t] = (uint16_t)prm.qi.tile_cnt[t];
     if (threadIdx.x == 0) {
         for (int s = 0; s < SQ_WARPS * SQ_MAX_SLOTS; ++s) mbar_init(&bars[s], 1);
         fence_barrier_init();
@@ -560,21 +564,22 @@ jaccard_qindex_kernel(const __grid_constant__ SparseParams prm) {
             const int nbk = prm.n_buckets;                      // off[0 .. nbk] are used
             for (int i = threadIdx.x; i < (nbk + 2) / 2 + 1; i += SQ_THREADS) reinterpret_cast<uint32_t*>(off)[i] = 0u;
             __syncthreads();
-            // warps take the group's tiles round-robin; four entries per lane are loaded before they are used
+            // warps take the group's tiles round-robin; nine entries per lane (a typical tile in one round) are loaded
+            // before they are used
             for (int t = t0 + warp; t < t1; t += SQ_WARPS) {
-                const int n = (int)prm.qi.tile_cnt[t];
+                const int n = (int)t_cnt[t];
                 const uint16_t* ew = prm.qi.ent_word + (size_t)t * SQ_T1;
                 const uint32_t* ev = prm.qi.ent_val + (size_t)t * SQ_T1;
-                for (int e0 = lane; e0 < n; e0 += 128) {
-                    uint32_t v[4], wb[4];
+                for (int e0 = lane; e0 < n; e0 += SQ_IB * 32) {
+                    uint32_t v[SQ_IB], wb[SQ_IB];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
+                    for (int j = 0; j < SQ_IB; ++j) {
                         const int e = e0 + j * 32;
                         v[j] = e < n ? ev[e] : 0u;
                         wb[j] = e < n ? (uint32_t)ew[e] << 5 : 0u;
                     }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
+                    for (int j = 0; j < SQ_IB; ++j)
                         while (v[j]) {   // count into off[bucket + 1] (16-bit halves of 32-bit words; sums stay < 2^16)
                             const uint32_t at = (((wb[j] | (uint32_t)(__ffs(v[j]) - 1)) >> bsh) + 1u);
                             v[j] &= v[j] - 1;
@@ -606,21 +611,21 @@ jaccard_qindex_kernel(const __grid_constant__ SparseParams prm) {
             }
             __syncthreads();
             for (int t = t0 + warp; t < t1; t += SQ_WARPS) {
-                const int n = (int)prm.qi.tile_cnt[t];  // 0: empty or dense-flagged tile
+                const int n = (int)t_cnt[t];  // 0: empty or dense-flagged tile
                 const uint16_t* ew = prm.qi.ent_word + (size_t)t * SQ_T1;
                 const uint32_t* ev = prm.qi.ent_val + (size_t)t * SQ_T1;
                 const uint8_t* er = prm.qi.ent_row + (size_t)t * SQ_T1;
-                for (int e0 = lane; e0 < n; e0 += 128) {
-                    uint32_t v[4], wb[4], r8[4];
+                for (int e0 = lane; e0 < n; e0 += SQ_IB * 32) {
+                    uint32_t v[SQ_IB], wb[SQ_IB], r8[SQ_IB];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
+                    for (int j = 0; j < SQ_IB; ++j) {
                         const int e = e0 + j * 32;
                         v[j] = e < n ? ev[e] : 0u;
                         wb[j] = e < n ? (uint32_t)ew[e] << 5 : 0u;
                         r8[j] = e < n ? (uint32_t)((t - t0) * SQ_TQ + er[e]) << 3 : 0u;
                     }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
+                    for (int j = 0; j < SQ_IB; ++j)
                         while (v[j]) {   // afterwards off[b + 1] = end of bucket b = start of bucket b + 1
                             const uint32_t bitid = wb[j] | (uint32_t)(__ffs(v[j]) - 1);
                             v[j] &= v[j] - 1;
