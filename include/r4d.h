@@ -50,7 +50,8 @@ int r4d_device_ok(void);
 
 /* Tuning / measurement knobs (process-wide; defaults in brackets).  Returns the previous value, or R4D_E_ARG.
  *   "jaccard_skip_zero" [1]  skip 8-word spans that are all-zero across a warp (exact; 0 = execute every word-op)
- *   "jaccard_sparse_q"  [1]  fused top-K: query tiles with few non-zero spans use the sparse-query kernel (exact)
+ *   "jaccard_sparse_q"  [1]  fused top-K: sparse query tiles are served by the query-index kernel, which streams the
+ *                            pool once per 8 192-query batch (exact; 0 = bitset-streaming kernel for every tile)
  *   "jaccard_warps"     [16] consumer warps per CTA (8 or 16)
  *   "dense_pair_kernel" [1]  use the CTA-pair (cta_group::2) kernel for bf16 top-K when it applies
  *   "dense_pair_qres"   [-1] query tile resident in smem: -1 auto (when >= 4 pool stages fit), 0 never
@@ -98,7 +99,9 @@ int r4d_jaccard_full(const uint32_t* qbits, const uint32_t* qcard, int64_t nq, c
  * Replaces occurrence_matrix + np.argsort(-row)[:k] (retrieval_data_annotation.py:97-103).
  * Outputs [nq][k]: exact integer counts (score = inter/union) and GLOBAL pool index pool_base+p,
  * ordered (score desc, index asc).  1 <= k <= R4D_TOPK_MAX.  Rows short of k are padded with
- * (0, 1, R4D_IDX_NONE). */
+ * (0, 1, R4D_IDX_NONE).  Bitset rows must be zero padded up to pitch_words (r4d_bitset_encode does that); the
+ * workspace must be 16-byte aligned.  Calls with more than 8 192 query rows are served as consecutive 8 192-row
+ * launch sequences on the same workspace (one pass over the pool each). */
 size_t r4d_jaccard_topk_workspace_bytes(int64_t nq, int64_t np, int32_t k);
 int r4d_jaccard_topk(const uint32_t* qbits, const uint32_t* qcard, int64_t nq, const uint32_t* pbits,
                      const uint32_t* pcard, int64_t np, int32_t words, int32_t pitch_words, int32_t k,

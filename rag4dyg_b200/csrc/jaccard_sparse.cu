@@ -30,15 +30,25 @@
 namespace r4d {
 
 // ---------------------------------------------------------------------------- by-row index of a query tile
-// grid = n_qtiles CTAs of 1024 threads (32 warps, 4 rows each).
+// grid = n_qtiles CTAs of 1024 threads (32 warps, 4 rows each).  One pass over the tile's bitsets: the non-zero words
+// are staged in shared memory in arrival order, then written out grouped by row (the order inside a row is arbitrary;
+// every consumer is order independent).
 constexpr int QI_THREADS = 1024;
 __global__ void __launch_bounds__(QI_THREADS)
 qindex_kernel(const uint32_t* __restrict__ qbits, int64_t nq, int32_t words, int32_t pitch_words, QIndex qi) {
     __shared__ uint32_t rowcnt[SQ_TQ];
     __shared__ uint32_t rowstart[SQ_TQ + 1];
-    __shared__ uint32_t tot_bits;
+    __shared__ uint32_t rowfill[SQ_TQ];
+    __shared__ uint32_t st_val[SQ_T1];
+    __shared__ uint16_t st_word[SQ_T1];
+    __shared__ uint8_t st_row[SQ_T1];
+    __shared__ uint32_t tot_bits, n_ent;
     const int t = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) tot_bits = 0u;
+    if (threadIdx.x == 0) {
+        tot_bits = 0u;
+        n_ent = 0u;
+    }
+    if (threadIdx.x < SQ_TQ) rowfill[threadIdx.x] = 0u;
     __syncthreads();
     for (int i = warp; i < SQ_TQ; i += QI_THREADS / 32) {
         const int64_t gq = (int64_t)t * SQ_TQ + i;
@@ -54,7 +64,20 @@ qindex_kernel(const uint32_t* __restrict__ qbits, int64_t nq, int32_t words, int
                 }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    c += __popc(__ballot_sync(0xffffffffu, v[j] != 0u));
+                    const uint32_t b = __ballot_sync(0xffffffffu, v[j] != 0u);
+                    if (b == 0u) continue;
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(&n_ent, (uint32_t)__popc(b));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (v[j] != 0u) {
+                        const uint32_t pos = base + __popc(b & ((1u << lane) - 1u));
+                        if (pos < (uint32_t)SQ_T1) {
+                            st_val[pos] = v[j];
+                            st_word[pos] = (uint16_t)(w0 + j * 32 + lane);
+                            st_row[pos] = (uint8_t)i;
+                        }
+                    }
+                    c += __popc(b);
                     bits += __popc(v[j]);
                 }
             }
@@ -108,31 +131,12 @@ qindex_kernel(const uint32_t* __restrict__ qbits, int64_t nq, int32_t words, int
     uint16_t* ew = qi.ent_word + (size_t)t * SQ_T1;
     uint32_t* ev = qi.ent_val + (size_t)t * SQ_T1;
     uint8_t* er = qi.ent_row + (size_t)t * SQ_T1;
-    for (int i = warp; i < SQ_TQ; i += QI_THREADS / 32) {
-        const int64_t gq = (int64_t)t * SQ_TQ + i;
-        if (gq >= nq) continue;
-        const uint32_t* row = qbits + gq * pitch_words;
-        uint32_t base = rowstart[i];
-        if (rowcnt[i] == 0u) continue;
-        for (int w0 = 0; w0 < words; w0 += 8 * 32) {
-            uint32_t v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int w = w0 + j * 32 + lane;
-                v[j] = w < words ? __ldg(row + w) : 0u;
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const uint32_t b = __ballot_sync(0xffffffffu, v[j] != 0u);
-                if (v[j] != 0u) {
-                    const uint32_t pos = base + __popc(b & ((1u << lane) - 1u));
-                    ew[pos] = (uint16_t)(w0 + j * 32 + lane);
-                    ev[pos] = v[j];
-                    er[pos] = (uint8_t)i;
-                }
-                base += __popc(b);
-            }
-        }
+    for (uint32_t e = threadIdx.x; e < total; e += QI_THREADS) {
+        const uint32_t r = st_row[e];
+        const uint32_t pos = rowstart[r] + atomicAdd(&rowfill[r], 1u);
+        ew[pos] = st_word[e];
+        ev[pos] = st_val[e];
+        er[pos] = (uint8_t)r;
     }
 }
 
@@ -447,7 +451,8 @@ constexpr size_t SQ_SM_PUB = SQ_SM_ALLOC + SQ_QB;
 constexpr size_t SQ_SM_LOCK = SQ_SM_PUB + SQ_QB;
 constexpr size_t SQ_SM_GROUPS = SQ_SM_LOCK + SQ_QB / 8;
 constexpr size_t SQ_SM_TCNT = SQ_SM_GROUPS + (size_t)(SQ_MAX_TILES + 2) * 8;    // [SQ_MAX_TILES] u16 entries of a tile
-constexpr size_t SQ_SM_SCAN = SQ_SM_TCNT + (size_t)SQ_MAX_TILES * 2;
+constexpr size_t SQ_SM_TBITS = SQ_SM_TCNT + (size_t)SQ_MAX_TILES * 2;           // [SQ_MAX_TILES] u16 set bits of a tile
+constexpr size_t SQ_SM_SCAN = SQ_SM_TBITS + (size_t)SQ_MAX_TILES * 2;
 // per-warp scratch of 512 B: while a batch is scanned it holds the batch's non-zero words (values [80] u32, then tags
 // [80] u16 = row in batch << 11 | word id); the lookup phase takes them into registers and reuses the space for the
 // bit list ([SQ_BL_CAP] x 4 B) and the hit buffer ([SQ_HB_CAP] x 2 B)
@@ -483,15 +488,22 @@ jaccard_qindex_kernel(const __grid_constant__ SparseParams prm) {
     constexpr bool ROW1 = NU > 0;
     constexpr int NJ = ROW1 ? NU : 6;   // 16-byte units a lane loads per pass over a slot
 
-    for (int t = threadIdx.x; t < prm.n_qtiles; t += SQ_THREADS) t_cnt[t] = (uint16_t)prm.qi.tile_cnt[t];
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < SQ_WARPS * SQ_MAX_SLOTS; ++s) mbar_init(&bars[s], 1);
+    uint16_t* t_bits = reinterpret_cast<uint16_t*>(smem + SQ_SM_TBITS);
+    for (int t = threadIdx.x; t < prm.n_qtiles; t += SQ_THREADS) {   // one round of parallel loads, not a serial chain
+        t_cnt[t] = (uint16_t)prm.qi.tile_cnt[t];
+        t_bits[t] = (uint16_t)prm.qi.tile_bits[t];
+    }
+    if (threadIdx.x < SQ_WARPS * SQ_MAX_SLOTS) {
+        mbar_init(&bars[threadIdx.x], 1);
         fence_barrier_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
         // greedy packing of consecutive query tiles into groups of <= SQ_E_CAP entries (every CTA computes the same)
         int g = 0, sum = 0;
         g_first[0] = 0;
         for (int t = 0; t < prm.n_qtiles; ++t) {
-            const int c = (int)prm.qi.tile_bits[t];
+            const int c = (int)t_bits[t];
             if (sum + c > SQ_E_CAP) {
                 g_ent[g] = sum;
                 g_first[++g] = t;

@@ -214,6 +214,20 @@ def _index_case(case):
         n_bits, k, zd = 700, 10, True
         p = random_sets(rng, 1500, n_bits, mean=2.2, p_empty=0.05)
         q = p[:700]
+    elif case == "wide_vocab_shared_buckets":   # 50 000 bits: index buckets shared by 4 bit ids, one 6 KB row per ring slot
+        n_bits, k, zd = 50_000, 10, False
+        q = random_sets(rng, 400, n_bits, mean=2.5, max_len=12, p_empty=0.02)
+        p = random_sets(rng, 5000, n_bits, mean=2.5, max_len=12, p_empty=0.02)
+        for i in range(0, 400, 7):             # plant real matches: with 50 000 ids random sets hardly ever intersect
+            q[i] = list(p[(i * 13) % 5000]) + q[i][:1]
+    elif case == "multi_group":                 # > 20 480 set bits in one 8 192-row batch: the pool is streamed per group
+        n_bits, k, zd = 20000, 10, False
+        q = random_sets(rng, 8192, n_bits, mean=5, max_len=7)
+        p = random_sets(rng, 3000, n_bits, mean=5, max_len=7)
+    elif case == "k32_hot":                     # k = 32 (the largest list) with lists that overflow all the time
+        n_bits, k, zd = 64, 32, False
+        q = random_sets(rng, 200, n_bits, mean=3, max_len=8)
+        p = random_sets(rng, 6000, n_bits, mean=3, max_len=8)
     elif case == "all_empty_queries":
         n_bits, k, zd = 300, 5, False
         q = [[] for _ in range(130)]
@@ -224,7 +238,8 @@ def _index_case(case):
 
 
 @pytest.mark.parametrize("case", ["hot_small_universe", "duplicates", "multiword", "batches", "mixed_dense_tiles",
-                                  "tiny_pool", "zero_diag_self", "all_empty_queries"])
+                                  "tiny_pool", "zero_diag_self", "all_empty_queries", "wide_vocab_shared_buckets",
+                                  "multi_group", "k32_hot"])
 def test_query_index_path_hard_cases(case):
     """The query-index kernel (jaccard_sparse.cu) against the oracle and against the dense-bitset kernel."""
     from rag4dyg_b200 import _lib
