@@ -462,7 +462,7 @@ def main():
 
         cpu_baseline = None
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
-            n_p_s, n_q_s = 100_000, 64
+            n_p_s, n_q_s = 100_000, 256            # ~14 s of single-core CPU work
             rate, dt, nq_s = cpu_port_sample(pool_ids, pool_off, q_ids, q_off, n_q_s, n_p_s, 1)
             c_rate, c_dt = cpu_c_port_sample(pool_ids, pool_off, q_ids, q_off, 512, n_p_s)
             cpu_baseline = {"value": rate, "unit": "pairs/s", "cores": 1, "kind": "port",
