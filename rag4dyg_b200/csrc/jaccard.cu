@@ -379,7 +379,9 @@ struct MergeExtra {
     int64_t q_off, nq_total;  // fused exchange with query batches: row offset / rows of the whole call
 };
 
-__global__ void __launch_bounds__(256, 4)
+// IDX: launched behind the query-index kernel (ex.cnt set); that instance keeps 6 blocks per SM resident.
+template <bool IDX>
+__global__ void __launch_bounds__(256, IDX ? 6 : 4)
 jaccard_merge_kernel(const uint4* __restrict__ part, const uint32_t* __restrict__ inter, const uint32_t* __restrict__ uni,
                      const int32_t* __restrict__ idx, int32_t n_lists, int64_t nq, int32_t k_in, int32_t k_out,
                      uint32_t* __restrict__ out_inter, uint32_t* __restrict__ out_union, int32_t* __restrict__ out_idx,
@@ -397,99 +399,78 @@ jaccard_merge_kernel(const uint4* __restrict__ part, const uint32_t* __restrict_
     for (int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); q < nq; q += wpg) {
         WarpTopK<JEntry> tk;
         tk.init(k_out);
-        if (ex.cnt != nullptr && !(ex.tile_dense && ex.tile_dense[q >> 7])) {
+        if (IDX && !(ex.tile_dense && ex.tile_dense[q >> 7])) {
             // short unsorted lists of the query-index kernel, entries {inter, |pool set|, idx}: union = |q| + |p| - inter.
-            // Lane L walks lists L, L + 32, ... (six per lane and pass, their loads issued back to back).
+            // Lane L walks lists L, L + 32, ... (three per lane at a time, their loads issued back to back).
             //   pass 1: every lane finds the best of its own candidates; a bitonic sort ranks the 32 lane-bests, the
             //           first k_out of them seed the list (the others cannot be in the top k_out);
             //   pass 2: the remaining candidates (L1/L2 hits now) are inserted only if they beat the current k-th —
             //           a handful per query instead of k (1 + ln(n / k)) serial insertions.
             const uint32_t cq = ex.qcard[q];
-            const bool two_pass = n_lists <= 6 * 32;   // one chunk: the counts stay in registers between the passes
-            int n[6];
             JEntry lb = JEntry::worst();
-            for (int l0 = 0; l0 < n_lists; l0 += 6 * 32) {
-                const int nj = min(6, (n_lists - l0 + 31) / 32);
-                int n_max = 0;
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll 1
+                for (int l0 = 0; l0 < n_lists; l0 += 3 * 32) {   // three lists per lane at a time (keeps 6 blocks per SM)
+                    int n[3], n_max = 0;
 #pragma unroll
-                for (int j = 0; j < 6; ++j) {
-                    const int l = l0 + j * 32 + lane;
-                    n[j] = (j < nj && l < n_lists) ? (int)ex.cnt[q * n_lists + l] : 0;
-                }
-#pragma unroll
-                for (int j = 0; j < 6; ++j) n_max = max(n_max, n[j]);
-                n_max = __reduce_max_sync(0xffffffffu, n_max);
-                for (int e = 0; e < n_max; ++e) {
-                    JEntry c[6];
-#pragma unroll
-                    for (int j = 0; j < 6; ++j) {
-                        c[j] = JEntry::worst();
-                        if (e < n[j]) {
-                            const uint4 x = part[(q * n_lists + (l0 + j * 32 + lane)) * k_in + e];
-                            c[j] = JEntry{x.x, cq + x.y - x.x, (int32_t)x.z};
-                        }
+                    for (int j = 0; j < 3; ++j) {
+                        const int l = l0 + j * 32 + lane;
+                        n[j] = l < n_lists ? (int)ex.cnt[q * n_lists + l] : 0;
+                        n_max = max(n_max, n[j]);
                     }
-                    if (two_pass) {
+                    n_max = __reduce_max_sync(0xffffffffu, n_max);
+                    const uint4* p0 = part + (q * n_lists + l0 + lane) * k_in;   // list j of this lane: p0 + j * 32 * k_in
+                    for (int e = 0; e < n_max; ++e) {
+                        JEntry c[3];
 #pragma unroll
-                        for (int j = 0; j < 6; ++j)
-                            if (e < n[j] && JEntry::better(c[j], lb)) lb = c[j];
-                    } else {
+                        for (int j = 0; j < 3; ++j) {
+                            c[j] = JEntry::worst();
+                            if (e < n[j]) {
+                                const uint4 x = p0[(int64_t)j * 32 * k_in + e];
+                                c[j] = JEntry{x.x, cq + x.y - x.x, (int32_t)x.z};
+                            }
+                        }
+                        if (pass == 0) {
 #pragma unroll
-                        for (int j = 0; j < 6; ++j) {
-                            if (j >= nj) break;
-                            uint32_t m = __ballot_sync(0xffffffffu, e < n[j] && JEntry::better(c[j], tk.kth));
-                            while (m) {
-                                const int src = __ffs(m) - 1;
-                                m &= m - 1;
-                                tk.insert(c[j].shfl(src));
+                            for (int j = 0; j < 3; ++j)
+                                if (JEntry::better(c[j], lb)) lb = c[j];
+                        } else {
+                            bool any = false;
+#pragma unroll
+                            for (int j = 0; j < 3; ++j) {
+                                if (c[j].idx == lb.idx) c[j] = JEntry::worst();   // the lane-best was ranked in pass 1
+                                any |= JEntry::better(c[j], tk.kth);
+                            }
+                            if (!__ballot_sync(0xffffffffu, any)) continue;
+#pragma unroll
+                            for (int j = 0; j < 3; ++j) {
+                                uint32_t m = __ballot_sync(0xffffffffu, JEntry::better(c[j], tk.kth));
+                                while (m) {
+                                    const int src = __ffs(m) - 1;
+                                    m &= m - 1;
+                                    tk.insert(c[j].shfl(src));
+                                }
                             }
                         }
                     }
                 }
-            }
-            if (two_pass) {
-                JEntry v = lb;   // bitonic sort of the lane-bests, best first
+                if (pass == 0) {
+                    JEntry v = lb;   // bitonic sort of the lane-bests, best first
 #pragma unroll
-                for (int k2 = 2; k2 <= 32; k2 <<= 1)
+                    for (int k2 = 2; k2 <= 32; k2 <<= 1)
 #pragma unroll
-                    for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
-                        const JEntry o{__shfl_xor_sync(0xffffffffu, v.inter, j2), __shfl_xor_sync(0xffffffffu, v.uni, j2),
-                                       __shfl_xor_sync(0xffffffffu, v.idx, j2)};
-                        const bool want_better = ((lane & j2) == 0) == ((lane & k2) == 0);
-                        if (JEntry::better(o, v) == want_better && o.idx != v.idx) v = o;
-                    }
-                if (lane < k_out) tk.mine = v;
-                tk.refresh_kth();
-                int n_max = 0;
-#pragma unroll
-                for (int j = 0; j < 6; ++j) n_max = max(n_max, n[j]);
-                n_max = __reduce_max_sync(0xffffffffu, n_max);
-                for (int e = 0; e < n_max; ++e) {
-                    JEntry c[6];
-                    bool pass = false;
-#pragma unroll
-                    for (int j = 0; j < 6; ++j) {
-                        c[j] = JEntry::worst();
-                        if (e < n[j]) {
-                            const uint4 x = part[(q * n_lists + (j * 32 + lane)) * k_in + e];
-                            c[j] = JEntry{x.x, cq + x.y - x.x, (int32_t)x.z};
-                            if (c[j].idx == lb.idx) c[j] = JEntry::worst();   // the lane-best was ranked in pass 1
-                            pass |= JEntry::better(c[j], tk.kth);
+                        for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+                            const JEntry o{__shfl_xor_sync(0xffffffffu, v.inter, j2), __shfl_xor_sync(0xffffffffu, v.uni, j2),
+                                           __shfl_xor_sync(0xffffffffu, v.idx, j2)};
+                            const bool want_better = ((lane & j2) == 0) == ((lane & k2) == 0);
+                            if (JEntry::better(o, v) == want_better && o.idx != v.idx) v = o;
                         }
-                    }
-                    if (!__ballot_sync(0xffffffffu, pass)) continue;
-#pragma unroll
-                    for (int j = 0; j < 6; ++j) {
-                        uint32_t m = __ballot_sync(0xffffffffu, JEntry::better(c[j], tk.kth));
-                        while (m) {
-                            const int src = __ffs(m) - 1;
-                            m &= m - 1;
-                            tk.insert(c[j].shfl(src));
-                        }
-                    }
+                    if (lane < k_out) tk.mine = v;
+                    tk.refresh_kth();
                 }
             }
-        } else if (n_lists * k_in <= 6 * 32) {
+        } else if (!IDX && n_lists * k_in <= 6 * 32) {
             // few candidates (the exchange merge: `world` lists of k): all of them are loaded at once, six per lane;
             // the lane-bests, ranked by a bitonic sort, seed the list and only the rest goes through insertions
             const int total = n_lists * k_in;
@@ -708,8 +689,13 @@ static int merge_launch(const uint4* part, const uint32_t* inter, const uint32_t
     int64_t blocks = (nq + 7) / 8;
     const int64_t cap = (int64_t)num_sms() * 16;
     if (blocks > cap) blocks = cap;
-    jaccard_merge_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(part, inter, uni, idx, n_lists, nq, k_in, k_out,
-                                                                         out_inter, out_union, out_idx, peers, ex); note_launch();
+    if (ex.cnt != nullptr)
+        jaccard_merge_kernel<true><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(part, inter, uni, idx, n_lists, nq, k_in, k_out,
+                                                                                   out_inter, out_union, out_idx, peers, ex);
+    else
+        jaccard_merge_kernel<false><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(part, inter, uni, idx, n_lists, nq, k_in, k_out,
+                                                                                    out_inter, out_union, out_idx, peers, ex);
+    note_launch();
     R4D_CUDA(cudaGetLastError());
     return R4D_OK;
 }
