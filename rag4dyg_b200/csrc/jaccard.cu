@@ -370,6 +370,8 @@ jaccard_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 // flagged in `tile_dense` are full sorted lists written by the dense kernel); `n_fill` > 0 appends the zero-score
 // fillers the query-index kernel never produces: pool rows 0 .. n_fill-1 of this shard unless already listed.
 struct MergeExtra {
+    const uint32_t* gcount;   // query-index path: candidates offered to the query's contiguous array glist[q][SQ_GC]
+    const uint4* glist;
     const uint8_t* cnt;
     const uint32_t* tile_dense;
     const uint32_t* qcard;
@@ -400,58 +402,83 @@ jaccard_merge_kernel(const uint4* __restrict__ part, const uint32_t* __restrict_
         WarpTopK<JEntry> tk;
         tk.init(k_out);
         if (IDX && !(ex.tile_dense && ex.tile_dense[q >> 7])) {
-            // short unsorted lists of the query-index kernel, entries {inter, |pool set|, idx}: union = |q| + |p| - inter.
-            // Lane L walks lists L, L + 32, ... (three per lane at a time, their loads issued back to back).
+            // candidates of the query-index kernel, entries {inter, |pool set|, idx}: union = |q| + |p| - inter.  The
+            // first SQ_GC of a query sit in its own contiguous array (coalesced loads); only a query that overflowed
+            // it also has entries in the short unsorted per-stripe lists.
             //   pass 1: every lane finds the best of its own candidates; a bitonic sort ranks the 32 lane-bests, the
             //           first k_out of them seed the list (the others cannot be in the top k_out);
             //   pass 2: the remaining candidates (L1/L2 hits now) are inserted only if they beat the current k-th —
             //           a handful per query instead of k (1 + ln(n / k)) serial insertions.
             const uint32_t cq = ex.qcard[q];
+            const uint32_t g_tot = ex.gcount[q];
+            const int ng = (int)min(g_tot, (uint32_t)SQ_GC);
+            const bool overflow = g_tot > (uint32_t)SQ_GC;   // warp-uniform: later candidates sit in the per-stripe lists
+            const uint4* gl = ex.glist + q * SQ_GC;
             JEntry lb = JEntry::worst();
 #pragma unroll 1
             for (int pass = 0; pass < 2; ++pass) {
-#pragma unroll 1
-                for (int l0 = 0; l0 < n_lists; l0 += 3 * 32) {   // three lists per lane at a time (keeps 6 blocks per SM)
-                    int n[3], n_max = 0;
+                auto consume = [&](JEntry(&c)[4]) {
+                    if (pass == 0) {
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) {
-                        const int l = l0 + j * 32 + lane;
-                        n[j] = l < n_lists ? (int)ex.cnt[q * n_lists + l] : 0;
-                        n_max = max(n_max, n[j]);
-                    }
-                    n_max = __reduce_max_sync(0xffffffffu, n_max);
-                    const uint4* p0 = part + (q * n_lists + l0 + lane) * k_in;   // list j of this lane: p0 + j * 32 * k_in
-                    for (int e = 0; e < n_max; ++e) {
-                        JEntry c[3];
+                        for (int j = 0; j < 4; ++j)
+                            if (JEntry::better(c[j], lb)) lb = c[j];
+                    } else {
+                        bool any = false;
 #pragma unroll
-                        for (int j = 0; j < 3; ++j) {
-                            c[j] = JEntry::worst();
-                            if (e < n[j]) {
-                                const uint4 x = p0[(int64_t)j * 32 * k_in + e];
-                                c[j] = JEntry{x.x, cq + x.y - x.x, (int32_t)x.z};
+                        for (int j = 0; j < 4; ++j) {
+                            if (c[j].idx == lb.idx) c[j] = JEntry::worst();   // the lane-best was ranked in pass 1
+                            any |= JEntry::better(c[j], tk.kth);
+                        }
+                        if (!__ballot_sync(0xffffffffu, any)) return;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint32_t m = __ballot_sync(0xffffffffu, JEntry::better(c[j], tk.kth));
+                            while (m) {
+                                const int src = __ffs(m) - 1;
+                                m &= m - 1;
+                                tk.insert(c[j].shfl(src));
                             }
                         }
-                        if (pass == 0) {
+                    }
+                };
+                // the query's own array: contiguous, four coalesced 16-byte loads in flight per lane
+#pragma unroll 1
+                for (int e0 = 0; e0 < ng; e0 += 4 * 32) {
+                    JEntry c[4];
 #pragma unroll
-                            for (int j = 0; j < 3; ++j)
-                                if (JEntry::better(c[j], lb)) lb = c[j];
-                        } else {
-                            bool any = false;
+                    for (int j = 0; j < 4; ++j) {
+                        const int e = e0 + j * 32 + lane;
+                        c[j] = JEntry::worst();
+                        if (e < ng) {
+                            const uint4 x = gl[e];
+                            c[j] = JEntry{x.x, cq + x.y - x.x, (int32_t)x.z};
+                        }
+                    }
+                    consume(c);
+                }
+                if (overflow) {   // lane L walks the stripe lists L, L + 32, ..., four at a time
+#pragma unroll 1
+                    for (int l0 = 0; l0 < n_lists; l0 += 4 * 32) {
+                        int n[4], n_max = 0;
 #pragma unroll
-                            for (int j = 0; j < 3; ++j) {
-                                if (c[j].idx == lb.idx) c[j] = JEntry::worst();   // the lane-best was ranked in pass 1
-                                any |= JEntry::better(c[j], tk.kth);
-                            }
-                            if (!__ballot_sync(0xffffffffu, any)) continue;
+                        for (int j = 0; j < 4; ++j) {
+                            const int l = l0 + j * 32 + lane;
+                            n[j] = l < n_lists ? (int)ex.cnt[q * n_lists + l] : 0;
+                            n_max = max(n_max, n[j]);
+                        }
+                        n_max = __reduce_max_sync(0xffffffffu, n_max);
+                        const uint4* p0 = part + (q * n_lists + l0 + lane) * k_in;   // list j of this lane: p0 + j * 32 * k_in
+                        for (int e = 0; e < n_max; ++e) {
+                            JEntry c[4];
 #pragma unroll
-                            for (int j = 0; j < 3; ++j) {
-                                uint32_t m = __ballot_sync(0xffffffffu, JEntry::better(c[j], tk.kth));
-                                while (m) {
-                                    const int src = __ffs(m) - 1;
-                                    m &= m - 1;
-                                    tk.insert(c[j].shfl(src));
+                            for (int j = 0; j < 4; ++j) {
+                                c[j] = JEntry::worst();
+                                if (e < n[j]) {
+                                    const uint4 x = p0[(int64_t)j * 32 * k_in + e];
+                                    c[j] = JEntry{x.x, cq + x.y - x.x, (int32_t)x.z};
                                 }
                             }
+                            consume(c);
                         }
                     }
                 }
@@ -772,6 +799,8 @@ static int jaccard_topk_impl(const uint32_t* qbits, const uint32_t* qcard, int64
             prm.tile_filter = qi.tile_dense;
             prm.any_filtered = qi.any_dense;
             ex.cnt = qi.cnt;
+            ex.gcount = qi.gcount;
+            ex.glist = qi.glist;
             ex.tile_dense = qi.tile_dense;
             ex.qcard = prm.qcard;
             ex.pcard = pcard;

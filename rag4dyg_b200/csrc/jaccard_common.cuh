@@ -16,6 +16,8 @@ constexpr int SQ_RING_BYTES = 7680;   // per-warp ring of bulk-copy slots (whole
 constexpr int SQ_NBK = 20480;         // buckets of the bit index in shared memory (bit id >> shift; shift 0 up to 20 480 bits)
 constexpr int SQ_MAX_SLOTS = 4;
 constexpr int SQ_QB = 8192;           // query rows per batch (one launch sequence)
+constexpr int SQ_GC = 1024;           // slots of a query's global candidate array (first arrivals; the rest goes to the
+                                      // per-stripe lists)
 constexpr int SQ_MAX_TILES = SQ_QB / SQ_TQ;
 constexpr int SQ_MAX_WORDS = 1900;    // one row (+16 zero bytes) fits a warp's ring; bit ids fit 16 bits
 constexpr int SQ_ROWOFF_LD = 132;     // 129 row offsets per tile, padded
@@ -36,6 +38,8 @@ struct QIndex {
     uint16_t* ent_word;    // [n_qtiles][SQ_T1]  word id
     uint32_t* ent_val;     // [n_qtiles][SQ_T1]  word value
     uint8_t* ent_row;      // [n_qtiles][SQ_T1]  row of the entry inside its tile
+    uint32_t* gcount;      // [nq]  candidates offered to the query's global array (may exceed SQ_GC); cleared with `cnt`
+    uint4* glist;          // [nq][SQ_GC] {inter, |pool set|, idx, 0}: the first SQ_GC candidates of a query, contiguous
     uint32_t* any_dense;   // [1] != 0 when some tile is flagged dense (64 words before `cnt`, cleared with it)
     uint8_t* cnt;          // [nq][n_stripes]    candidates stored in the (stripe, query) partial list (unsorted)
 };

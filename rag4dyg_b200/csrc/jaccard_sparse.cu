@@ -251,7 +251,15 @@ __device__ __noinline__ void append_candidates(const SparseParams& prm, bool kee
     const int lane = threadIdx.x & 31;
     const int K = prm.k;
     bool over = false;
-    if (keep) {
+    if (keep) {   // first choice: the next free slot of the query's own contiguous array (one global atomic)
+        const int64_t gq = (int64_t)t0 * SQ_TQ + rr;
+        const uint32_t slot = atomicAdd(prm.qi.gcount + gq, 1u);
+        if (slot < (uint32_t)SQ_GC) {
+            if (prm.debug != 7) prm.qi.glist[gq * SQ_GC + slot] = make_uint4(inter, pcard, (uint32_t)idx, 0u);
+            keep = false;
+        }
+    }
+    if (keep) {   // the array is full: this stripe's k-entry list of the query
         const uint32_t wa = (rr & ~3u), sh = (rr & 3u) * 8u;
         uint32_t cur = lds_volatile_u32(ls.alloc + wa), n;
         for (;;) {
@@ -867,7 +875,8 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 size_t sparseq_workspace_bytes(int64_t nq_batch, int32_t n_stripes) {
     const size_t n_qtiles = (size_t)((nq_batch + SQ_TQ - 1) / SQ_TQ);
     return 256 + align256(n_qtiles * 4) * 3 + align256(n_qtiles * SQ_ROWOFF_LD * 2) + align256(n_qtiles * SQ_T1 * 2) +
-           align256(n_qtiles * SQ_T1 * 4) + align256(n_qtiles * SQ_T1) + 256 + align256((size_t)n_stripes * (size_t)nq_batch);
+           align256(n_qtiles * SQ_T1 * 4) + align256(n_qtiles * SQ_T1) + align256((size_t)nq_batch * SQ_GC * 16) +
+           align256((size_t)nq_batch * 4) + 256 + align256((size_t)n_stripes * (size_t)nq_batch);
 }
 
 bool sparseq_supported(int32_t words, int32_t k) {
@@ -893,6 +902,10 @@ QIndex sparseq_carve(void* base, int64_t nq_batch, int32_t n_stripes) {
     p += align256(n_qtiles * 4);
     qi.tile_dense = reinterpret_cast<uint32_t*>(p);
     p += align256(n_qtiles * 4);
+    qi.glist = reinterpret_cast<uint4*>(p);
+    p += align256((size_t)nq_batch * SQ_GC * 16);
+    qi.gcount = reinterpret_cast<uint32_t*>(p);   // gcount, any_dense and cnt are adjacent: one memset clears them
+    p += align256((size_t)nq_batch * 4);
     qi.any_dense = reinterpret_cast<uint32_t*>(p);
     p += 256;
     qi.cnt = p;
@@ -904,7 +917,7 @@ int sparseq_build(const uint32_t* qbits, int64_t nq, int32_t words, int32_t pitc
                   const QIndex& qi, cudaStream_t st) {
     const int n_qtiles = (int)((nq + SQ_TQ - 1) / SQ_TQ);
     R4D_REQUIRE(nq <= SQ_QB, "jaccard query-index path: batch of %lld rows > %d", (long long)nq, SQ_QB);
-    R4D_CUDA(cudaMemsetAsync(qi.any_dense, 0, 256 + (size_t)n_stripes * (size_t)nq, st));   // flag + counts
+    R4D_CUDA(cudaMemsetAsync(qi.gcount, 0, align256((size_t)nq * 4) + 256 + (size_t)n_stripes * (size_t)nq, st));   // counts + flag
     qindex_kernel<<<n_qtiles, QI_THREADS, 0, st>>>(qbits, nq, words, pitch_words, qi); note_launch();
     R4D_CUDA(cudaGetLastError());
     return R4D_OK;

@@ -184,7 +184,11 @@ def test_zero_span_skipping_and_warp_variants_are_exact(warps):
 def _index_case(case):
     import zlib
     rng = np.random.default_rng(zlib.crc32(case.encode()) % 1000)
-    if case == "hot_small_universe":       # ~18 % of all pairs intersect: (stripe, query) lists overflow k all the time
+    if case == "hot_small_universe":       # ~18 % of all pairs intersect (~2 700 per query): the queries' 1 024-slot arrays
+        n_bits, k, zd = 50, 10, False      # overflow and the (stripe, query) lists behind them overflow k all the time
+        q = random_sets(rng, 300, n_bits, mean=3, max_len=8, p_empty=0.05)
+        p = random_sets(rng, 15000, n_bits, mean=3, max_len=8, p_empty=0.05)
+    elif case == "hot_no_overflow":        # same data density, but every query's candidates fit its own array
         n_bits, k, zd = 50, 10, False
         q = random_sets(rng, 300, n_bits, mean=3, max_len=8, p_empty=0.05)
         p = random_sets(rng, 4000, n_bits, mean=3, max_len=8, p_empty=0.05)
@@ -227,7 +231,7 @@ def _index_case(case):
     elif case == "k32_hot":                     # k = 32 (the largest list) with lists that overflow all the time
         n_bits, k, zd = 64, 32, False
         q = random_sets(rng, 200, n_bits, mean=3, max_len=8)
-        p = random_sets(rng, 6000, n_bits, mean=3, max_len=8)
+        p = random_sets(rng, 20000, n_bits, mean=3, max_len=8)
     elif case == "all_empty_queries":
         n_bits, k, zd = 300, 5, False
         q = [[] for _ in range(130)]
@@ -239,7 +243,7 @@ def _index_case(case):
 
 @pytest.mark.parametrize("case", ["hot_small_universe", "duplicates", "multiword", "batches", "mixed_dense_tiles",
                                   "tiny_pool", "zero_diag_self", "all_empty_queries", "wide_vocab_shared_buckets",
-                                  "multi_group", "k32_hot"])
+                                  "multi_group", "k32_hot", "hot_no_overflow"])
 def test_query_index_path_hard_cases(case):
     """The query-index kernel (jaccard_sparse.cu) against the oracle and against the dense-bitset kernel."""
     from rag4dyg_b200 import _lib
