@@ -409,6 +409,12 @@ jaccard_merge_kernel(const uint4* __restrict__ part, const uint32_t* __restrict_
             //           first k_out of them seed the list (the others cannot be in the top k_out);
             //   pass 2: the remaining candidates (L1/L2 hits now) are inserted only if they beat the current k-th —
             //           a handful per query instead of k (1 + ln(n / k)) serial insertions.
+            // unions on this path are below 2^16 (vocabularies of at most SQ_MAX_WORDS * 32 bits): the exact
+            // cross-multiplication fits 32 bits
+            auto bet = [](const JEntry& a, const JEntry& b) {
+                const uint32_t l = a.inter * b.uni, r = b.inter * a.uni;
+                return (l > r) || (l == r && a.idx < b.idx);
+            };
             const uint32_t cq = ex.qcard[q];
             const uint32_t g_tot = ex.gcount[q];
             const int ng = (int)min(g_tot, (uint32_t)SQ_GC);
@@ -421,18 +427,18 @@ jaccard_merge_kernel(const uint4* __restrict__ part, const uint32_t* __restrict_
                     if (pass == 0) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
-                            if (JEntry::better(c[j], lb)) lb = c[j];
+                            if (bet(c[j], lb)) lb = c[j];
                     } else {
                         bool any = false;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             if (c[j].idx == lb.idx) c[j] = JEntry::worst();   // the lane-best was ranked in pass 1
-                            any |= JEntry::better(c[j], tk.kth);
+                            any |= bet(c[j], tk.kth);
                         }
                         if (!__ballot_sync(0xffffffffu, any)) return;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            uint32_t m = __ballot_sync(0xffffffffu, JEntry::better(c[j], tk.kth));
+                            uint32_t m = __ballot_sync(0xffffffffu, bet(c[j], tk.kth));
                             while (m) {
                                 const int src = __ffs(m) - 1;
                                 m &= m - 1;
@@ -491,7 +497,7 @@ jaccard_merge_kernel(const uint4* __restrict__ part, const uint32_t* __restrict_
                             const JEntry o{__shfl_xor_sync(0xffffffffu, v.inter, j2), __shfl_xor_sync(0xffffffffu, v.uni, j2),
                                            __shfl_xor_sync(0xffffffffu, v.idx, j2)};
                             const bool want_better = ((lane & j2) == 0) == ((lane & k2) == 0);
-                            if (JEntry::better(o, v) == want_better && o.idx != v.idx) v = o;
+                            if (bet(o, v) == want_better && o.idx != v.idx) v = o;
                         }
                     if (lane < k_out) tk.mine = v;
                     tk.refresh_kth();
@@ -554,7 +560,7 @@ jaccard_merge_kernel(const uint4* __restrict__ part, const uint32_t* __restrict_
                 }
             }
         }
-        if (ex.n_fill > 0) {
+        if (ex.n_fill > 0 && tk.kth.inter == 0u) {   // fillers score 0: they only matter while the k-th entry does too
             const uint32_t cq = ex.qcard[q];
             const uint32_t cp = lane < ex.n_fill ? ex.pcard[lane] : 0u;
             for (int i = 0; i < ex.n_fill; ++i) {
