@@ -52,6 +52,7 @@ int r4d_device_ok(void);
  *   "jaccard_skip_zero" [1]  skip 8-word spans that are all-zero across a warp (exact; 0 = execute every word-op)
  *   "jaccard_sparse_q"  [1]  fused top-K: sparse query tiles are served by the query-index kernel, which streams the
  *                            pool once per 8 192-query batch (exact; 0 = bitset-streaming kernel for every tile)
+ *   "jaccard_debug"     [0]  query-index kernel: stage bypass for measurements (results are WRONG unless 0)
  *   "jaccard_warps"     [16] consumer warps per CTA (8 or 16)
  *   "dense_pair_kernel" [1]  use the CTA-pair (cta_group::2) kernel for bf16 top-K when it applies
  *   "dense_pair_qres"   [-1] query tile resident in smem: -1 auto (when >= 4 pool stages fit), 0 never

@@ -159,7 +159,9 @@ struct SparseParams {
     int32_t n_buckets;
     uint4* part;           // [n_stripes][nq][k] {inter, |pool set|, idx, 0}: the merge kernel forms union = |q| + |p| - inter
     QIndex qi;
-    int32_t debug;  // experiments: 1 = scan only (no lookups), 2 = lookups but no hit completion, 3 = no list update
+    int32_t debug;  // stage bypass for measurements (tools/probe_qindex.py; results are wrong unless 0): 1 = scan only,
+                    // 2 = lookups but no hit completion, 3 = no candidate is emitted, 5 = full lists are never updated,
+                    // 6 = no fence before a per-stripe entry is published, 7 = candidate stores skipped
 };
 
 __device__ __forceinline__ uint32_t atoms_or(uint32_t addr, uint32_t v) {
@@ -198,20 +200,12 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
     asm volatile("{\n\t.reg .u16 t;\n\tld.shared.u16 t, [%1];\n\tcvt.u32.u16 %0, t;\n\t}" : "=r"(v) : "r"(addr) : "memory");
     return v;
 }
-__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    return v;
-}
 __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 __device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
     const uint16_t h = (uint16_t)v;
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(h) : "memory");
-}
-__device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t a, uint32_t b) {
-    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
 __device__ __forceinline__ void lds128s(uint4& v, uint32_t addr) {
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
