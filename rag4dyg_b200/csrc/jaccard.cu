@@ -703,15 +703,16 @@ size_t r4d_jaccard_topk_workspace_bytes(int64_t nq, int64_t np, int32_t k) {
     if (nq <= 0 || np <= 0 || k <= 0) return 256;
     const JaccardPlan pl = plan_topk(nq, np);
     size_t need = (size_t)pl.n_stripes * (size_t)nq * (size_t)k * SQ_PART_BYTES + 256;
-    // query-index path: the call is served in batches of <= SQ_QB query rows that reuse one workspace
+    // query-index path: one index for the whole call + a per-batch region that the <= SQ_QB-row batches reuse
     size_t batch = 0;
     const int64_t sizes[2] = {nq < SQ_QB ? nq : (int64_t)SQ_QB, nq % SQ_QB};
     for (int64_t nb : sizes) {
         if (nb <= 0) continue;
         const JaccardPlan pb = plan_topk(nb, np);
-        const size_t b = (size_t)pb.n_stripes * (size_t)nb * (size_t)k * SQ_PART_BYTES + 256 + sparseq_workspace_bytes(nb, pb.n_stripes);
+        const size_t b = (size_t)pb.n_stripes * (size_t)nb * (size_t)k * SQ_PART_BYTES + 256 + sparseq_batch_bytes(nb, pb.n_stripes);
         if (b > batch) batch = b;
     }
+    batch += sparseq_index_bytes(nq) + 256;
     return need > batch ? need : batch;
 }
 
@@ -763,13 +764,27 @@ static int jaccard_topk_impl(const uint32_t* qbits, const uint32_t* qcard, int64
     if (np == 0)  // no pool rows: every list is padding; the merge of zero lists writes it, no workspace needed
         return merge_launch(nullptr, nullptr, nullptr, nullptr, 0, nq, k, k, top_inter, top_union, top_idx, peers, no_extra, stream);
     const bool use_index = sparseq_supported(words, k);
-    // query-index path: batches of <= SQ_QB query rows, each a full launch sequence on the same workspace
+    // query-index path: batches of <= SQ_QB query rows, each a launch sequence on the same per-batch region; the by-row
+    // index of ALL batches is built up front by one launch
     const int64_t q_batch = use_index ? (int64_t)SQ_QB : nq;
+    const size_t idx_bytes = use_index ? (sparseq_index_bytes(nq) + 255) / 256 * 256 : 0;
+    uint8_t* const batch_base = reinterpret_cast<uint8_t*>(workspace) + idx_bytes;
+    QIndex q_all{};
+    if (use_index) {
+        if (workspace_bytes < idx_bytes || !workspace) {
+            set_error("jaccard_topk: workspace %zu B < required %zu B", workspace_bytes, idx_bytes);
+            return R4D_E_WORKSPACE;
+        }
+        R4D_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "jaccard_topk: workspace must be 16-byte aligned");
+        q_all = sparseq_carve_index(workspace, nq);
+        rc = sparseq_build_all(qbits, nq, words, pitch_words, q_all, st);
+        if (rc) return rc;
+    }
     for (int64_t q0 = 0; q0 < nq; q0 += q_batch) {
         const int64_t nb = nq - q0 < q_batch ? nq - q0 : q_batch;
         const JaccardPlan pl = plan_topk(nb, np);
         const size_t per = (size_t)pl.n_stripes * (size_t)nb * (size_t)k;
-        const size_t need = per * SQ_PART_BYTES + (use_index ? 256 + sparseq_workspace_bytes(nb, pl.n_stripes) : 0);
+        const size_t need = idx_bytes + per * SQ_PART_BYTES + (use_index ? 256 + sparseq_batch_bytes(nb, pl.n_stripes) : 0);
         if (workspace_bytes < need || !workspace) {
             set_error("jaccard_topk: workspace %zu B < required %zu B", workspace_bytes, need);
             return R4D_E_WORKSPACE;
@@ -789,14 +804,14 @@ static int jaccard_topk_impl(const uint32_t* qbits, const uint32_t* qcard, int64
         prm.n_ptiles = pl.n_ptiles;
         prm.n_stripes = pl.n_stripes;
         prm.ptiles_per_stripe = pl.ptiles_per_stripe;
-        prm.part = reinterpret_cast<uint4*>(workspace);
+        prm.part = reinterpret_cast<uint4*>(batch_base);
         MergeExtra ex{};
         ex.q_off = q0;
         ex.nq_total = nq;
         if (use_index) {
             // sparse query tiles -> jaccard_qindex_kernel; tiles flagged dense -> the kernel below (same partial slots)
-            const QIndex qi = sparseq_carve(reinterpret_cast<uint8_t*>(workspace) + per * SQ_PART_BYTES, nb, pl.n_stripes);
-            rc = sparseq_build(qb, nb, words, pitch_words, pl.n_stripes, qi, st);
+            const QIndex qi = sparseq_batch_view(q_all, q0, batch_base + per * SQ_PART_BYTES, nb, pl.n_stripes);
+            rc = sparseq_clear_batch(qi, nb, pl.n_stripes, st);
             if (rc) return rc;
             rc = sparseq_topk_launch(pbits, prm.qcard, pcard, nb, np, words, pitch_words, k, zero_diag, prm.query_base,
                                      pool_base, pl.n_qtiles, pl.n_ptiles, pl.n_stripes, pl.ptiles_per_stripe,

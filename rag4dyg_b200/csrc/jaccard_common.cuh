@@ -40,16 +40,19 @@ struct QIndex {
     uint8_t* ent_row;      // [n_qtiles][SQ_T1]  row of the entry inside its tile
     uint32_t* gcount;      // [nq]  candidates offered to the query's global array (may exceed SQ_GC); cleared with `cnt`
     uint4* glist;          // [nq][SQ_GC] {inter, |pool set|, idx, 0}: the first SQ_GC candidates of a query, contiguous
-    uint32_t* any_dense;   // [1] != 0 when some tile is flagged dense (64 words before `cnt`, cleared with it)
+    uint32_t* any_dense;   // [1] != 0 when some tile of the batch is flagged dense
     uint8_t* cnt;          // [nq][n_stripes]    candidates stored in the (stripe, query) partial list (unsorted)
 };
 
 bool sparseq_supported(int32_t words, int32_t k);
-size_t sparseq_workspace_bytes(int64_t nq_batch, int32_t n_stripes);
-QIndex sparseq_carve(void* base, int64_t nq_batch, int32_t n_stripes);
-// Build the index of a query batch (nq <= SQ_QB rows) and clear the candidate counts.
-int sparseq_build(const uint32_t* qbits, int64_t nq, int32_t words, int32_t pitch_words, int32_t n_stripes,
-                  const QIndex& qi, cudaStream_t st);
+size_t sparseq_index_bytes(int64_t nq_total);
+size_t sparseq_batch_bytes(int64_t nq_batch, int32_t n_stripes);
+QIndex sparseq_carve_index(void* base, int64_t nq_total);
+QIndex sparseq_batch_view(const QIndex& all, int64_t q0, void* batch_base, int64_t nq_batch, int32_t n_stripes);
+// Build the by-row index of every tile of the call with one launch; clear one batch's candidate counts.
+int sparseq_build_all(const uint32_t* qbits, int64_t nq_total, int32_t words, int32_t pitch_words, const QIndex& all,
+                      cudaStream_t st);
+int sparseq_clear_batch(const QIndex& qi, int64_t nq, int32_t n_stripes, cudaStream_t st);
 // Stream the pool once per group of query tiles; every non-zero pool word looks up the queries holding that word.
 int sparseq_topk_launch(const uint32_t* pbits, const uint32_t* qcard, const uint32_t* pcard, int64_t nq, int64_t np,
                         int32_t words, int32_t pitch_words, int32_t k, int32_t zero_diag, int64_t query_base,

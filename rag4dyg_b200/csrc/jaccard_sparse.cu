@@ -117,7 +117,7 @@ qindex_kernel(const uint32_t* __restrict__ qbits, int64_t nq, int32_t words, int
             qi.tile_dense[t] = 1u;
             qi.tile_cnt[t] = 0u;
             qi.tile_bits[t] = 0u;
-            atomicOr(qi.any_dense, 1u);
+            atomicOr(qi.any_dense + t / SQ_MAX_TILES, 1u);   // one flag per 8 192-row batch
         }
         return;
     }
@@ -866,11 +866,18 @@ jaccard_qindex_kernel(const __grid_constant__ SparseParams prm) {
 // ---------------------------------------------------------------------------- host side
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-size_t sparseq_workspace_bytes(int64_t nq_batch, int32_t n_stripes) {
-    const size_t n_qtiles = (size_t)((nq_batch + SQ_TQ - 1) / SQ_TQ);
+// Workspace of the query-index path = [index of the WHOLE call (by-row word lists of every tile, one any-dense flag per
+// 8 192-row batch)] [per-batch region, reused by every batch: candidate arrays, their counts, per-stripe counts].
+size_t sparseq_index_bytes(int64_t nq_total) {
+    const size_t n_qtiles = (size_t)((nq_total + SQ_TQ - 1) / SQ_TQ);
+    const size_t n_batches = (size_t)((nq_total + SQ_QB - 1) / SQ_QB);
     return 256 + align256(n_qtiles * 4) * 3 + align256(n_qtiles * SQ_ROWOFF_LD * 2) + align256(n_qtiles * SQ_T1 * 2) +
-           align256(n_qtiles * SQ_T1 * 4) + align256(n_qtiles * SQ_T1) + align256((size_t)nq_batch * SQ_GC * 16) +
-           align256((size_t)nq_batch * 4) + 256 + align256((size_t)n_stripes * (size_t)nq_batch);
+           align256(n_qtiles * SQ_T1 * 4) + align256(n_qtiles * SQ_T1) + align256(n_batches * 4);
+}
+
+size_t sparseq_batch_bytes(int64_t nq_batch, int32_t n_stripes) {
+    return 256 + align256((size_t)nq_batch * SQ_GC * 16) + align256((size_t)nq_batch * 4) +
+           align256((size_t)n_stripes * (size_t)nq_batch);
 }
 
 bool sparseq_supported(int32_t words, int32_t k) {
@@ -878,10 +885,11 @@ bool sparseq_supported(int32_t words, int32_t k) {
            k <= 32;
 }
 
-QIndex sparseq_carve(void* base, int64_t nq_batch, int32_t n_stripes) {
-    const size_t n_qtiles = (size_t)((nq_batch + SQ_TQ - 1) / SQ_TQ);
+QIndex sparseq_carve_index(void* base, int64_t nq_total) {
+    const size_t n_qtiles = (size_t)((nq_total + SQ_TQ - 1) / SQ_TQ);
+    const size_t n_batches = (size_t)((nq_total + SQ_QB - 1) / SQ_QB);
     uint8_t* p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(base) + 255) & ~uintptr_t(255));
-    QIndex qi;
+    QIndex qi{};
     qi.ent_val = reinterpret_cast<uint32_t*>(p);
     p += align256(n_qtiles * SQ_T1 * 4);
     qi.ent_word = reinterpret_cast<uint16_t*>(p);
@@ -896,24 +904,48 @@ QIndex sparseq_carve(void* base, int64_t nq_batch, int32_t n_stripes) {
     p += align256(n_qtiles * 4);
     qi.tile_dense = reinterpret_cast<uint32_t*>(p);
     p += align256(n_qtiles * 4);
+    qi.any_dense = reinterpret_cast<uint32_t*>(p);   // [n_batches]
+    (void)n_batches;
+    return qi;
+}
+
+// The view of batch `q0 / SQ_QB` (rows q0 .. q0 + nq_batch): its tiles of the call-wide index + the per-batch arrays.
+QIndex sparseq_batch_view(const QIndex& all, int64_t q0, void* batch_base, int64_t nq_batch, int32_t n_stripes) {
+    const size_t t0 = (size_t)(q0 / SQ_TQ);
+    QIndex qi = all;
+    qi.ent_val += t0 * SQ_T1;
+    qi.ent_word += t0 * SQ_T1;
+    qi.ent_row += t0 * SQ_T1;
+    qi.rowoff += t0 * SQ_ROWOFF_LD;
+    qi.tile_cnt += t0;
+    qi.tile_bits += t0;
+    qi.tile_dense += t0;
+    qi.any_dense += (size_t)(q0 / SQ_QB);
+    uint8_t* p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(batch_base) + 255) & ~uintptr_t(255));
     qi.glist = reinterpret_cast<uint4*>(p);
     p += align256((size_t)nq_batch * SQ_GC * 16);
-    qi.gcount = reinterpret_cast<uint32_t*>(p);   // gcount, any_dense and cnt are adjacent: one memset clears them
+    qi.gcount = reinterpret_cast<uint32_t*>(p);   // gcount and cnt are adjacent: one memset clears them
     p += align256((size_t)nq_batch * 4);
-    qi.any_dense = reinterpret_cast<uint32_t*>(p);
-    p += 256;
     qi.cnt = p;
     (void)n_stripes;
     return qi;
 }
 
-int sparseq_build(const uint32_t* qbits, int64_t nq, int32_t words, int32_t pitch_words, int32_t n_stripes,
-                  const QIndex& qi, cudaStream_t st) {
-    const int n_qtiles = (int)((nq + SQ_TQ - 1) / SQ_TQ);
-    R4D_REQUIRE(nq <= SQ_QB, "jaccard query-index path: batch of %lld rows > %d", (long long)nq, SQ_QB);
-    R4D_CUDA(cudaMemsetAsync(qi.gcount, 0, align256((size_t)nq * 4) + 256 + (size_t)n_stripes * (size_t)nq, st));   // counts + flag
-    qindex_kernel<<<n_qtiles, QI_THREADS, 0, st>>>(qbits, nq, words, pitch_words, qi); note_launch();
+// ONE launch builds the by-row index of every tile of the call (all batches).
+int sparseq_build_all(const uint32_t* qbits, int64_t nq_total, int32_t words, int32_t pitch_words, const QIndex& all,
+                      cudaStream_t st) {
+    const int64_t n_qtiles = (nq_total + SQ_TQ - 1) / SQ_TQ;
+    const size_t n_batches = (size_t)((nq_total + SQ_QB - 1) / SQ_QB);
+    R4D_CUDA(cudaMemsetAsync(all.any_dense, 0, n_batches * 4, st));
+    qindex_kernel<<<(unsigned)n_qtiles, QI_THREADS, 0, st>>>(qbits, nq_total, words, pitch_words, all); note_launch();
     R4D_CUDA(cudaGetLastError());
+    return R4D_OK;
+}
+
+// Clears the candidate counts of one batch.
+int sparseq_clear_batch(const QIndex& qi, int64_t nq, int32_t n_stripes, cudaStream_t st) {
+    R4D_REQUIRE(nq <= SQ_QB, "jaccard query-index path: batch of %lld rows > %d", (long long)nq, SQ_QB);
+    R4D_CUDA(cudaMemsetAsync(qi.gcount, 0, align256((size_t)nq * 4) + (size_t)n_stripes * (size_t)nq, st));
     return R4D_OK;
 }
 
