@@ -15,9 +15,11 @@
 //   4. Non-zero pool words of a batch are collected (ballot prefix sums) and looked up: the entries with the same
 //      word id whose bit is set in the pool word are hits (query row, pool row).  Every word of the 8 rows has been
 //      seen, so the number of hits of a pair IS its intersection; the pair is emitted once.
-//   5. Emitted candidates go to the (stripe, query) partial list in global memory: slots are handed out lock-free by
-//      a CAS on a per-row counter in shared memory (all lanes in parallel); only a candidate that finds the list
-//      full takes the per-row lock and replaces the worst entry if it ranks before it.
+//   5. Emitted candidates go to the query's own contiguous array in global memory (slot = one global atomicAdd, all
+//      lanes in parallel; the merge kernel reads it coalesced).  Only when that array is full (> 1 024 candidates of a
+//      query in one batch) do they go to the (stripe, query) list of the CTA: slots handed out lock-free by a CAS on a
+//      per-row counter in shared memory, and a candidate that finds that list full takes the per-row lock and
+//      replaces the worst entry if it ranks before it.
 // Zero-score candidates are never produced here: they only matter as the lowest-index filler of a short list, which
 // the merge kernel adds (jaccard.cu, jaccard_merge_kernel `n_fill`).
 //
@@ -236,10 +238,13 @@ struct ListState {
     uint32_t pub;    // u8 per group row: slots whose entry is stored (fast path)
 };
 
-// Hand the candidates of the lanes with `keep` set to their (stripe, query) partial list in global memory.
-// Fast path, all lanes in parallel: a CAS on the row's slot counter hands out an empty slot; the entry is stored and
-// then published (counter `pub`).  A candidate that finds all k slots taken goes through the per-row lock: wait until
-// the k entries are published, replace the worst one if the candidate ranks before it.
+// Store the candidates of the lanes with `keep` set, all lanes in parallel.
+//  1. The query's own contiguous array glist[q][SQ_GC]: a global atomicAdd on gcount[q] hands out the slot.
+//  2. Array full: the (stripe, query) list of this CTA (k slots).  A CAS on the row's slot counter in shared memory
+//     hands out an empty slot; the entry is stored and then published (counter `pub`).
+//  3. That list full as well: the per-row lock — wait until its k entries are published, replace the worst one if the
+//     candidate ranks before it.
+// top-k(all candidates) is contained in glist[q] + the per-stripe top-k of the rest, so the merge stays exact.
 __device__ __noinline__ void append_candidates(const SparseParams& prm, bool keep, uint32_t rr, uint32_t inter, uint32_t pcard,
                                                int32_t idx, int t0, int stripe, const ListState ls) {
     const int lane = threadIdx.x & 31;
