@@ -5,10 +5,11 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Workloads (BASELINE.json configs[3] and [4]), synthetic data, fixed TOTAL size (strong
-scaling: the pool is sharded row-wise over the N ranks, queries replicated, local top-K lists all-gathered over NCCL
+scaling: the pool is sharded row-wise over the N ranks, queries replicated, local top-K lists exchanged over NVLink
 and merged):
   jaccard : 1,000,000-set pool x 100,000 queries, 20,000-node vocab (W = 625 words), K = 10.
-            A step = one 8,192-query batch scored against the WHOLE 1M pool + top-K (+ all-gather + merge).
+            A step = ONE r4d_jaccard_topk call of 32,768 queries against the WHOLE 1M pool + top-K (+ exchange + merge);
+            the library serves it as four 8,192-query launch sequences, each streaming the pool's bitsets once.
   dense   : 10,000,000 x 768 pool embeddings x 100,000 queries, K = 10, exp(-lambda|dt|) epilogue, bf16 tensor cores.
             A step = one 8,192-query batch against the whole 10M pool.
 One JSON line: the Jaccard scorer is the headline (`value`), the dense scorer is reported under "dense".
