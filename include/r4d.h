@@ -214,6 +214,20 @@ int64_t r4d_format_int_rows(const int32_t* rows, int64_t nq, int64_t n, int64_t 
 int64_t r4d_format_lut_rows(const int32_t* codes, int64_t nq, int64_t n, int64_t ld, const char* lut_blob,
                             const int64_t* lut_off, int32_t n_codes, char* out, size_t cap);
 
+/* ---------------------------------------------------------------- host-side text readers (consumer half)
+ * [host] pointers.  The generator's dataloader reads the index / score files back with
+ *   [list(map(int, l.split())) for l in f.read().splitlines() if len(l) > 0 and not l.isspace()]   (and float)
+ * (dataloader/generator.py:32-48).  These calls parse the whole file text at once, multi-threaded: rows = lines holding at
+ * least one field, CSR offsets row_off[n_rows + 1] into values[].  strtoll / strtod semantics (correctly rounded:
+ * identical to Python's int() / float() for everything the writers above emit; Python-only spellings such as
+ * underscores are rejected with R4D_E_ARG).  Return the number of rows (>= 0) or a negative error code;
+ * R4D_E_WORKSPACE when cap_rows / cap_fields (from r4d_parse_rows_count) are too small. */
+int64_t r4d_parse_rows_count(const char* text, size_t len, int64_t* n_fields);
+int64_t r4d_parse_int_rows(const char* text, size_t len, int64_t* row_off, int64_t* values, int64_t cap_rows,
+                           int64_t cap_fields);
+int64_t r4d_parse_float_rows(const char* text, size_t len, int64_t* row_off, double* values, int64_t cap_rows,
+                             int64_t cap_fields);
+
 #ifdef __cplusplus
 }
 #endif
