@@ -1,0 +1,47 @@
+"""CPU: the bench.py output contract.  The reference arm (`--impl reference`, the oracle port on the host cores) prints
+exactly one JSON line with the agreed keys; the committed N=1 line of our arm (profiles/r1_bench_n1.json, produced on a
+B200) carries roofline / cpu_baseline / e2e / clocks / gpu_launches in the agreed shape."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"}
+
+
+def test_reference_arm_prints_one_json_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and BASE_KEYS <= set(d)
+    assert d["value"] > 0 and d["unit"] == "pairs/s" and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["config"]["workload"].startswith("synthetic Jaccard top-K")
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_committed_bench_line_has_the_contract_shape():
+    d = json.load(open(os.path.join(ROOT, "profiles", "r1_bench_n1.json")))
+    assert BASE_KEYS | {"roofline", "gpu_launches", "clocks"} <= set(d)
+    assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["gpu_launches"] > 0 and d["data"] == "synthetic"
+    rf = d["roofline"]
+    assert rf["bound"] in ("hbm", "tensor") and rf["unit"] in ("GB/s", "TFLOP/s")
+    assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9 and 0 < rf["frac"] <= 1.0
+    assert rf["traffic"] is None or rf["traffic"] >= rf["algorithmic_bytes"]        # DRAM bytes cannot undercut the stream
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
+    assert e["value"] < d["value"]                                                   # copies included: never faster
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["sample"]
+    c = d["clocks"]
+    assert c["sm_mhz"] and c["sm_max_mhz"] and not ({"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(c["reasons"]))
+    assert "model" not in d["config"] and d["config"]["workload"]
+    dn = d["dense"]
+    assert dn["roofline"]["bound"] == "tensor" and dn["e2e"]["value"] > 0 and dn["gpu_launches"] > 0
