@@ -65,7 +65,7 @@ int r4d_set_option(const char* key, int value);
 
 /* Measurement aid for the roofline figures (bench.py): after r4d_set_option("kernel_timing", 1) the library brackets
  * every launch of its dominant kernels with CUDA events on the launch stream; this call waits for the recorded
- * events, returns their summed duration and count, and clears them.  kernel: "jaccard_qindex" | "dense_pair". */
+ * events, returns their summed duration and count, and clears them.  kernel: "jaccard_qindex" | "jaccard_postings" | "dense_pair". */
 int r4d_profile_read(const char* kernel, double* total_ms, int64_t* launches);
 /* Kernels this library has enqueued since it was loaded (every <<<>>> of its own; memsets and copies not counted). */
 int64_t r4d_kernel_launches(void);
@@ -126,6 +126,40 @@ int r4d_jaccard_topk_scatter(const uint32_t* qbits, const uint32_t* qcard, int64
                              const uint32_t* pcard, int64_t np, int32_t words, int32_t pitch_words, int32_t k,
                              int32_t zero_diag, int64_t query_base, int64_t pool_base, void* const* peer_base,
                              int32_t world, int32_t rank, void* workspace, size_t workspace_bytes, r4d_stream_t stream);
+
+/* ---------------------------------------------------------------- Jaccard scorer over pool-side postings
+ * Same replacement of occurrence_matrix + np.argsort(-row)[:k] (retrieval_data_annotation.py:36-41, :97-103) for SPARSE
+ * sets: instead of streaming the pool's bitset rows, an inverted index of the pool (node id -> rows holding it) names
+ * exactly the pairs that share an id; every other pair scores 0 and only matters as a lowest-index filler.  Results are
+ * bit-identical to r4d_jaccard_topk.  n_bits <= 65 535.
+ *
+ * r4d_postings_build: pool bitsets (r4d_bitset_encode) -> index blob [dev], 256-byte aligned, of
+ * r4d_postings_index_bytes(np, n_bits, nnz) bytes (0 = unsupported shape), nnz = total set bits of the pool = sum of
+ * pcard.  The first 8 bytes of the blob are {uint32 magic, uint32 status}; status != 0 after the build means nnz was too
+ * small (the index is unusable).  Built once per pool (shard); ~2 passes over the bitsets. */
+size_t r4d_postings_index_bytes(int64_t np, int32_t n_bits, int64_t nnz);
+size_t r4d_postings_build_workspace_bytes(int64_t np, int32_t n_bits);
+int r4d_postings_build(const uint32_t* pbits, const uint32_t* pcard, int64_t np, int32_t n_bits, int32_t pitch_words,
+                       int64_t nnz, void* index, size_t index_bytes, void* workspace, size_t workspace_bytes,
+                       r4d_stream_t stream);
+
+/* Fused scorer + top-K over the postings.  Queries arrive as CSR id lists q_ids[q_off[q] .. q_off[q+1]) [dev] (ids outside
+ * [0, n_bits) are ignored, duplicates inside a row collapse: Python set() semantics, retrieval_data_annotation.py:12-13);
+ * no query bitsets are needed.  index / pcard / np / n_bits / nnz as given to r4d_postings_build.  Outputs as
+ * r4d_jaccard_topk: [nq][k] exact counts + GLOBAL pool index pool_base+p, order (score desc, index asc), rows short of k
+ * padded with (0, 1, R4D_IDX_NONE).  Any set size and skew is served exactly (queries too dense for the per-warp hash
+ * tables are completed by a per-window counting kernel). */
+size_t r4d_jaccard_topk_postings_workspace_bytes(int64_t nq);
+int r4d_jaccard_topk_postings(const int32_t* q_ids, const int64_t* q_off, int64_t nq, const void* index,
+                              const uint32_t* pcard, int64_t np, int32_t n_bits, int64_t nnz, int32_t k, int32_t zero_diag,
+                              int64_t query_base, int64_t pool_base, uint32_t* top_inter, uint32_t* top_union,
+                              int32_t* top_idx, void* workspace, size_t workspace_bytes, r4d_stream_t stream);
+/* Fused exchange variant (see r4d_jaccard_topk_scatter): the final lists go to slot `rank` of every peer's gather buffer. */
+int r4d_jaccard_topk_postings_scatter(const int32_t* q_ids, const int64_t* q_off, int64_t nq, const void* index,
+                                      const uint32_t* pcard, int64_t np, int32_t n_bits, int64_t nnz, int32_t k,
+                                      int32_t zero_diag, int64_t query_base, int64_t pool_base, void* const* peer_base,
+                                      int32_t world, int32_t rank, void* workspace, size_t workspace_bytes,
+                                      r4d_stream_t stream);
 
 /* ---------------------------------------------------------------- ranking of score matrices
  * Full descending STABLE ranking of every row: order[q][:] = np.argsort(-scores[q], kind='stable').

@@ -631,11 +631,8 @@ static bool skip_zero_spans() { return options().jaccard_skip_zero != 0; }
 template <int MODE, int NCW, bool SKIP>
 static int launch_ncw(const CUtensorMap& tm_q, const CUtensorMap& tm_p, const JaccardParams& prm, cudaStream_t st) {
     const size_t smem = smem_bytes_for(MODE);
-    static bool attr_done = false;  // one flag per template instantiation
-    if (!attr_done) {
-        R4D_CUDA(cudaFuncSetAttribute(jaccard_kernel<MODE, NCW, SKIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
+    static SmemOptIn opt_in;  // one per template instantiation, keyed by device inside
+    if (int rc = ensure_dyn_smem(jaccard_kernel<MODE, NCW, SKIP>, smem, opt_in)) return rc;
     const int64_t n_items = (int64_t)prm.n_qtiles * prm.n_stripes;
     int grid = num_sms();
     if (n_items < grid) grid = (int)n_items;

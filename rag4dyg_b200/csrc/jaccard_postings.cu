@@ -1,0 +1,779 @@
+// jaccard_postings.cu — fused Jaccard top-K as a sparse x sparse join over POOL-SIDE POSTINGS.
+//
+// Replaces occurrence_matrix + np.argsort(-row)[:k] (retrieval_data_annotation.py:36-41, :97-103) for SPARSE sets
+// (label sets: 2.2 of 20 000 ids): only pairs that share an id can score > 0, and an inverted index of the pool
+// names exactly those pairs.  Where the query-index kernel (jaccard_sparse.cu) still streams every pool bitset row
+// once per 8 192 queries (2.5 GB per pass at C4), this path touches only the ~110 postings of each of a query's ids.
+//
+//   pool state (built once per pool shard from its bitsets, r4d_postings_build):
+//     post[]   8-byte entries {pool row, |pool set|}, grouped by (node id, row window): bucket b = id * n_win + (row >> win_shift)
+//     off[]    bucket offsets (exclusive scan of the bucket sizes); an id's whole posting list is the contiguous
+//              range off[id * n_win] .. off[(id + 1) * n_win], and any run of windows of it is contiguous too
+//   r4d_jaccard_topk_postings (queries arrive as CSR id lists; duplicates inside a row collapse, like Python's set()):
+//     postings_light_kernel   one WARP per query.  The (<= 64) distinct ids of the query select their posting ranges;
+//                             every posting is inserted into the warp's 512-slot hash table in shared memory
+//                             (64-bit CAS claims a slot for a pool row, a 32-bit atomic add counts further hits), so a
+//                             slot's count IS |Q n P| and union = |Q| + |P| - count needs no second look at the pool.
+//                             The table is scanned into a warp-level sorted top-K list (exact rational compare).
+//                             A query with more postings than one table holds walks the pool's row windows in
+//                             several passes (disjoint row ranges => a pair never spans two passes).
+//     postings_heavy_kernel   one CTA per query the light kernel handed over (more than 64 ids, more passes than
+//                             windows, a hot window): the query becomes a bitmap over the ids, every window of the pool
+//                             gets one 16-bit counter per row in shared memory, postings increment them, a scan turns
+//                             non-zero counters into candidates.  Any set size, any skew; slower.
+//   Both write the final [nq][k] lists themselves (zero-score fillers included), or store them into the peers' gather
+//   buffers (fused exchange) — no candidate ever goes through global memory.
+//
+// Exactness: counts are integers, ranking is the same (inter * union' vs inter' * union, index) comparator as everywhere
+// else; results are bit-identical to the bitset kernels (tests/test_gpu_postings.py).
+#include "jaccard_common.cuh"
+
+namespace r4d {
+
+constexpr int PJ_WIN_SHIFT_MIN = 13;            // 8 192 pool rows per window
+constexpr int PJ_WIN_SHIFT_MAX = 15;            // heavy kernel: a window's 16-bit counters fill 64 KB of shared memory
+constexpr int64_t PJ_MAX_BUCKETS = 48ll << 20;  // (id, window) buckets: at most 192 MB of offsets
+constexpr int PJ_MAX_BITS = 65535;              // ids fit 16 bits; a heavy counter (<= |Q n P| <= 65 535) cannot wrap
+constexpr int PJ_LOG_T = 9;
+constexpr int PJ_T = 1 << PJ_LOG_T;             // slots of a warp's hash table (8 B each)
+constexpr int PJ_CAP = 224;                     // postings planned per pass (load factor <= ~0.45)
+constexpr int PJ_IDS = 64;                      // distinct ids of a light query: two per lane
+constexpr int PJ_LIGHT_WARPS = 8;
+constexpr int PJ_CHUNK = 8;                     // queries a warp takes per grab of the work counter
+constexpr int PJ_HEAVY_THREADS = 256;
+constexpr int PJ_HEAVY_UID = 2048;              // distinct ids of a heavy query enumerated in shared memory
+constexpr uint32_t PJ_MAGIC = 0x52344450u;      // "R4DP"
+
+struct PostingsHeader {   // first 256 bytes of the index blob (device memory)
+    uint32_t magic, status;   // status != 0: the build overflowed nnz_cap (index unusable)
+    int64_t np, nnz_cap;
+    int32_t n_bits, win_shift, n_win, pad;
+};
+
+struct PostingsLayout {
+    int win_shift, n_win;
+    int64_t n_buckets;
+    size_t off_at, post_at, total;
+    bool ok;
+};
+
+static PostingsLayout postings_layout(int64_t np, int32_t n_bits, int64_t nnz) {
+    PostingsLayout L{};
+    L.ok = np >= 0 && n_bits > 0 && n_bits <= PJ_MAX_BITS && nnz >= 0 && nnz < ((int64_t)1 << 32) && np < ((int64_t)1 << 31);
+    if (!L.ok) return L;
+    int ws = PJ_WIN_SHIFT_MIN;
+    auto wins = [&](int s) { return np == 0 ? (int64_t)1 : ((np + ((int64_t)1 << s) - 1) >> s); };
+    while (ws < PJ_WIN_SHIFT_MAX && wins(ws) * n_bits > PJ_MAX_BUCKETS) ++ws;
+    L.win_shift = ws;
+    L.n_win = (int)wins(ws);
+    L.n_buckets = (int64_t)L.n_win * n_bits;
+    if (L.n_buckets > PJ_MAX_BUCKETS) {
+        L.ok = false;
+        return L;
+    }
+    L.off_at = 256;
+    L.post_at = L.off_at + (((size_t)(L.n_buckets + 1) * 4 + 255) / 256) * 256;
+    L.total = L.post_at + (size_t)(nnz > 0 ? nnz : 1) * 8;
+    return L;
+}
+
+// ---------------------------------------------------------------------------- index build
+// One warp per pool row: every set bit is one posting.  COUNT: bucket sizes (atomicAdd into off[b + 1]);
+// FILL: slot = off[b] + atomicAdd(cursor[b]).  The order inside a bucket is arbitrary; every consumer is order independent.
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+postings_scan_rows_kernel(const uint32_t* __restrict__ pbits, const uint32_t* __restrict__ pcard, int64_t np,
+                          int32_t words, int32_t pitch_words, int32_t n_bits, int32_t win_shift, int32_t n_win,
+                          uint32_t* __restrict__ off, uint32_t* __restrict__ cursor, uint2* __restrict__ post,
+                          int64_t nnz_cap, PostingsHeader* __restrict__ hdr) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wpg = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < np; row += wpg) {
+        const uint32_t* r = pbits + row * pitch_words;
+        const uint32_t win = (uint32_t)(row >> win_shift);
+        const uint32_t card = FILL ? pcard[row] : 0u;
+        for (int w0 = 0; w0 < words; w0 += 4 * 32) {   // four independent loads in flight per lane
+            uint32_t v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int w = w0 + j * 32 + lane;
+                v[j] = w < words ? r[w] : 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint32_t x = v[j];
+                const int w = w0 + j * 32 + lane;
+                while (x) {
+                    const int b = __ffs(x) - 1;
+                    x &= x - 1;
+                    const int32_t id = w * 32 + b;
+                    if (id >= n_bits) break;
+                    const int64_t bucket = (int64_t)id * n_win + win;
+                    if (!FILL) {
+                        atomicAdd(off + bucket + 1, 1u);
+                    } else {
+                        const uint32_t at = off[bucket] + atomicAdd(cursor + bucket, 1u);
+                        if ((int64_t)at < nnz_cap)
+                            post[at] = make_uint2((uint32_t)row, card);
+                        else
+                            hdr->status = 1u;
+                    }
+                }
+            }
+        }
+    }
+}
+
+__global__ void postings_header_kernel(PostingsHeader* hdr, const PostingsHeader h) { *hdr = h; }
+
+// In-place inclusive scan of x[0 .. n) (uint32), three launches: block sums, scan of the sums, rescan + offset.
+constexpr int SCAN_THREADS = 256, SCAN_PER_THREAD = 16, SCAN_TILE = SCAN_THREADS * SCAN_PER_THREAD;
+
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* warp_tot /*[8] smem*/, uint32_t& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    uint32_t base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+        const uint32_t t = warp_tot[w];
+        if (w < warp) base += t;
+        tot += t;
+    }
+    __syncthreads();
+    total = tot;
+    return base + inc - v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tile_sums_kernel(const uint32_t* __restrict__ x, int64_t n,
+                                                                      uint32_t* __restrict__ tile_sum) {
+    __shared__ uint32_t wt[SCAN_THREADS / 32];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+    uint32_t s = 0;
+    for (int i = threadIdx.x; i < SCAN_TILE; i += SCAN_THREADS)
+        if (base + i < n) s += x[base + i];
+    uint32_t tot;
+    block_excl_scan(s, wt, tot);
+    if (threadIdx.x == 0) tile_sum[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_sums_kernel(uint32_t* __restrict__ tile_sum, int64_t n_tiles) {
+    __shared__ uint32_t wt[SCAN_THREADS / 32];
+    uint32_t carry = 0;
+    for (int64_t t0 = 0; t0 < n_tiles; t0 += SCAN_THREADS) {
+        const int64_t t = t0 + threadIdx.x;
+        const uint32_t v = t < n_tiles ? tile_sum[t] : 0u;
+        uint32_t tot;
+        const uint32_t ex = block_excl_scan(v, wt, tot);
+        if (t < n_tiles) tile_sum[t] = carry + ex;   // exclusive prefix of the tile sums
+        carry += tot;
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(uint32_t* __restrict__ x, int64_t n,
+                                                                  const uint32_t* __restrict__ tile_excl) {
+    __shared__ uint32_t wt[SCAN_THREADS / 32];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_PER_THREAD;
+    uint32_t v[SCAN_PER_THREAD], s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_PER_THREAD; ++i) {
+        v[i] = base + i < n ? x[base + i] : 0u;
+        s += v[i];
+    }
+    uint32_t tot;
+    uint32_t run = block_excl_scan(s, wt, tot) + tile_excl[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < SCAN_PER_THREAD; ++i) {
+        run += v[i];
+        if (base + i < n) x[base + i] = run;
+    }
+}
+
+// ---------------------------------------------------------------------------- scoring kernels
+struct PJParams {
+    const int32_t* q_ids;
+    const int64_t* q_off;
+    int64_t nq;
+    const uint32_t* off;
+    const uint2* post;
+    const uint32_t* pcard;
+    int64_t np;
+    int32_t n_bits, win_shift, n_win, k, zero_diag, n_fill;
+    int64_t query_base, pool_base;
+    uint32_t* out_inter;
+    uint32_t* out_union;
+    int32_t* out_idx;
+    uint32_t* heavy_list;   // [nq] queries handed to the heavy kernel
+    uint32_t* counters;     // [0] light work counter, [1] heavy queries, [2] heavy work counter
+    PeerOut peers;
+    int64_t q_out_off, nq_total;   // fused exchange: row offset / rows of the whole call
+};
+
+// Candidate with a 32-bit exact compare: valid while inter * union < 2^32 (light path: inter <= 64, union < 2^17).
+struct PEntry {
+    uint32_t inter, uni;
+    int32_t idx;
+    __device__ __forceinline__ static PEntry worst() { return PEntry{0u, 1u, R4D_IDX_NONE}; }
+    __device__ __forceinline__ static bool better(const PEntry& a, const PEntry& b) {
+        const uint32_t l = a.inter * b.uni, r = b.inter * a.uni;
+        return (l > r) || (l == r && a.idx < b.idx);
+    }
+    __device__ __forceinline__ PEntry shfl(int src) const {
+        return PEntry{__shfl_sync(0xffffffffu, inter, src), __shfl_sync(0xffffffffu, uni, src),
+                      __shfl_sync(0xffffffffu, idx, src)};
+    }
+    __device__ __forceinline__ PEntry shfl_up1() const {
+        return PEntry{__shfl_up_sync(0xffffffffu, inter, 1), __shfl_up_sync(0xffffffffu, uni, 1),
+                      __shfl_up_sync(0xffffffffu, idx, 1)};
+    }
+    __device__ __forceinline__ PEntry shfl_xor(int m) const {
+        return PEntry{__shfl_xor_sync(0xffffffffu, inter, m), __shfl_xor_sync(0xffffffffu, uni, m),
+                      __shfl_xor_sync(0xffffffffu, idx, m)};
+    }
+};
+
+// Zero-score fillers (pool rows 0 .. n_fill-1 unless listed already; they only matter while the k-th entry scores 0)
+// and the final store: plain [nq][k] planes, or slot `rank` of every peer's gather buffer (fused exchange).
+template <class E>
+__device__ __forceinline__ void pj_finish(WarpTopK<E>& tk, const PJParams& p, int64_t q, uint32_t cq) {
+    const int lane = threadIdx.x & 31;
+    if (p.n_fill > 0 && tk.kth.inter == 0u) {
+        const uint32_t cp = lane < p.n_fill ? p.pcard[lane] : 0u;
+        for (int i = 0; i < p.n_fill; ++i) {
+            const E c{0u, max(cq + __shfl_sync(0xffffffffu, cp, i), 1u), (int32_t)(p.pool_base + i)};
+            if (__ballot_sync(0xffffffffu, lane < p.k && tk.mine.idx == c.idx)) continue;
+            tk.insert(c);
+        }
+    }
+    if (lane < p.k) {
+        if (p.peers.world == 0) {
+            p.out_inter[q * p.k + lane] = tk.mine.inter;
+            p.out_union[q * p.k + lane] = tk.mine.uni;
+            p.out_idx[q * p.k + lane] = tk.mine.idx;
+        } else {
+            const int64_t nq_all = p.nq_total > 0 ? p.nq_total : p.nq;
+            const int64_t plane = (int64_t)p.peers.world * nq_all * p.k;
+            const int64_t at = ((int64_t)p.peers.rank * nq_all + p.q_out_off + q) * p.k + lane;
+            for (int r = 0; r < p.peers.world; ++r) {
+                uint32_t* dst = reinterpret_cast<uint32_t*>(p.peers.base[r]);
+                dst[at] = tk.mine.inter;
+                dst[plane + at] = tk.mine.uni;
+                dst[2 * plane + at] = (uint32_t)tk.mine.idx;
+            }
+        }
+    }
+}
+
+constexpr unsigned long long PJ_EMPTY = 0xffffffffffffffffull;
+
+// slot = {row : 32 | card : 24 | count : 8}; returns false when the table is full
+__device__ __forceinline__ bool pj_insert(unsigned long long* tab, uint32_t row, uint32_t card) {
+    uint32_t h = (row * 2654435761u) >> (32 - PJ_LOG_T);
+    const unsigned long long fresh = ((unsigned long long)row << 32) | (unsigned long long)((card << 8) | 1u);
+    for (int probe = 0; probe < PJ_T; ++probe) {
+        const unsigned long long old = atomicCAS(tab + h, PJ_EMPTY, fresh);
+        if (old == PJ_EMPTY) return true;
+        if ((uint32_t)(old >> 32) == row) {
+            atomicAdd(reinterpret_cast<unsigned int*>(tab + h), 1u);   // low word: card << 8 | count
+            return true;
+        }
+        h = (h + 1) & (PJ_T - 1);
+    }
+    return false;
+}
+
+struct PJWarpSmem {
+    unsigned long long tab[PJ_T];
+    uint32_t start[PJ_IDS];
+    uint32_t pref[PJ_IDS + 1];
+    int32_t ids[PJ_IDS];
+    uint32_t pad[3];
+};
+
+__global__ void __launch_bounds__(PJ_LIGHT_WARPS * 32, 4) postings_light_kernel(const PJParams p) {
+    extern __shared__ __align__(16) uint8_t pj_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    PJWarpSmem& sm = reinterpret_cast<PJWarpSmem*>(pj_smem)[warp];
+    const uint4 ones = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    auto clear_table = [&]() {
+        uint4* t4 = reinterpret_cast<uint4*>(sm.tab);
+#pragma unroll
+        for (int i = 0; i < PJ_T / 2 / 32; ++i) t4[i * 32 + lane] = ones;
+    };
+    auto hand_over = [&](int64_t q) {   // the heavy kernel serves this query
+        if (lane == 0) p.heavy_list[atomicAdd(p.counters + 1, 1u)] = (uint32_t)q;
+    };
+    clear_table();
+    bool table_clean = true;
+    for (;;) {
+        int64_t q0 = 0;
+        if (lane == 0) q0 = (int64_t)atomicAdd(p.counters + 0, (uint32_t)PJ_CHUNK);
+        q0 = __shfl_sync(0xffffffffu, q0, 0);
+        if (q0 >= p.nq) break;
+        // row offsets of the whole chunk with one load
+        int64_t my_off = 0;
+        if (lane <= PJ_CHUNK && q0 + lane <= p.nq) my_off = p.q_off[q0 + lane];
+        const int n_here = (int)min((int64_t)PJ_CHUNK, p.nq - q0);
+        for (int qi = 0; qi < n_here; ++qi) {
+            const int64_t q = q0 + qi;
+            const int64_t beg = __shfl_sync(0xffffffffu, my_off, qi), end = __shfl_sync(0xffffffffu, my_off, qi + 1);
+            const int64_t m_raw = end - beg;
+            if (m_raw > PJ_IDS) {
+                hand_over(q);
+                continue;
+            }
+            // ---- the query's distinct ids, at most two per lane (set semantics: duplicates collapse)
+            int32_t id0 = -1, id1 = -1;
+            if (lane < m_raw) id0 = p.q_ids[beg + lane];
+            if (lane + 32 < m_raw) id1 = p.q_ids[beg + 32 + lane];
+            if (id0 < 0 || id0 >= p.n_bits) id0 = -1;
+            if (id1 < 0 || id1 >= p.n_bits) id1 = -1;
+            if (m_raw <= 32) {
+                const uint32_t same = __match_any_sync(0xffffffffu, id0);
+                if (id0 >= 0 && (__ffs(same) - 1) != lane) id0 = -1;
+            } else {
+                sm.ids[lane] = id0;
+                sm.ids[lane + 32] = id1;
+                __syncwarp();
+                bool d0 = false, d1 = false;
+                for (int t = 0; t < (int)m_raw; ++t) {
+                    const int32_t v = sm.ids[t];
+                    d0 |= (t < lane) && (v == id0);
+                    d1 |= (t < lane + 32) && (v == id1);
+                }
+                if (d0) id0 = -1;
+                if (d1) id1 = -1;
+                __syncwarp();
+            }
+            const uint32_t cq = __popc(__ballot_sync(0xffffffffu, id0 >= 0)) + __popc(__ballot_sync(0xffffffffu, id1 >= 0));
+            const bool two = m_raw > 32;   // warp-uniform: the second id register is in use
+            // ---- whole posting lists: how many passes over the pool's row windows?
+            uint32_t s0 = 0, e0 = 0, s1 = 0, e1 = 0;
+            if (id0 >= 0) {
+                s0 = p.off[(int64_t)id0 * p.n_win];
+                e0 = p.off[(int64_t)(id0 + 1) * p.n_win];
+            }
+            if (two && id1 >= 0) {
+                s1 = p.off[(int64_t)id1 * p.n_win];
+                e1 = p.off[(int64_t)(id1 + 1) * p.n_win];
+            }
+            const uint32_t hits = __reduce_add_sync(0xffffffffu, (e0 - s0) + (e1 - s1));
+            const int passes = (int)((hits + PJ_CAP - 1) / PJ_CAP);
+            if (passes > p.n_win) {
+                hand_over(q);
+                continue;
+            }
+            WarpTopK<PEntry> tk;
+            tk.init(p.k);
+            bool failed = false, have_list = false;   // have_list: the sorted list holds entries of an earlier pass
+            const bool diag_on = p.zero_diag != 0;
+            const int64_t diag_row = p.query_base + q - p.pool_base;   // pool row forced to score 0
+            for (int ps = 0; ps < passes; ++ps) {
+                if (passes > 1) {   // this pass: windows [wlo, whi) of every list
+                    const int wlo = (int)((int64_t)ps * p.n_win / passes), whi = (int)((int64_t)(ps + 1) * p.n_win / passes);
+                    if (id0 >= 0) {
+                        s0 = p.off[(int64_t)id0 * p.n_win + wlo];
+                        e0 = p.off[(int64_t)id0 * p.n_win + whi];
+                    }
+                    if (two && id1 >= 0) {
+                        s1 = p.off[(int64_t)id1 * p.n_win + wlo];
+                        e1 = p.off[(int64_t)id1 * p.n_win + whi];
+                    }
+                }
+                // prefix sums of the list lengths (list j < 32: lane j's first id, list 32 + j: its second)
+                const uint32_t l0 = e0 - s0, l1 = two ? e1 - s1 : 0u;
+                uint32_t i0 = l0, i1 = l1;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
+                    if (lane >= o) {
+                        i0 += t0;
+                        i1 += t1;
+                    }
+                }
+                const uint32_t tot0 = __shfl_sync(0xffffffffu, i0, 31), tot1 = __shfl_sync(0xffffffffu, i1, 31);
+                const uint32_t n_hits = tot0 + tot1;
+                if (n_hits == 0) continue;
+                sm.start[lane] = s0;
+                sm.pref[lane] = i0 - l0;
+                sm.start[lane + 32] = s1;
+                sm.pref[lane + 32] = tot0 + i1 - l1;
+                if (lane == 0) sm.pref[PJ_IDS] = n_hits;
+                if (!table_clean) clear_table();
+                table_clean = false;
+                __syncwarp();
+                // ---- every posting of the pass goes into the hash table
+                const int n_lists = two ? PJ_IDS : 32;
+                bool ok = true;
+                for (uint32_t h0 = 0; h0 < n_hits; h0 += 32) {
+                    const uint32_t h = h0 + lane;
+                    if (h < n_hits) {
+                        int lo = 0, hi = n_lists;   // last list j with pref[j] <= h (empty lists share a prefix value)
+                        while (hi - lo > 1) {
+                            const int mid = (lo + hi) >> 1;
+                            if (sm.pref[mid] <= h) lo = mid; else hi = mid;
+                        }
+                        const uint2 e = p.post[sm.start[lo] + (h - sm.pref[lo])];
+                        if (!(diag_on && (int64_t)e.x == diag_row)) ok &= pj_insert(sm.tab, e.x, e.y);
+                    }
+                }
+                __syncwarp();
+                if (__ballot_sync(0xffffffffu, !ok)) {   // a hot window overflowed the table
+                    failed = true;
+                    break;
+                }
+                // ---- table -> sorted top-K list
+                auto slot_entry = [&](int i) {
+                    const unsigned long long s = sm.tab[i * 32 + lane];
+                    if (s == PJ_EMPTY) return PEntry::worst();
+                    const uint32_t lw = (uint32_t)s, cnt = lw & 0xffu, card = lw >> 8;
+                    return PEntry{cnt, cq + card - cnt, (int32_t)(p.pool_base + (int64_t)(uint32_t)(s >> 32))};
+                };
+                int32_t seeded = R4D_IDX_NONE;
+                if (!have_list) {
+                    // empty list: every lane finds the best of its 16 slots, a bitonic sort ranks the 32 lane-bests and the
+                    // first k of them seed the list (the others cannot be in the top k); the rest is inserted below only
+                    // if it beats the k-th
+                    PEntry lb = PEntry::worst();
+#pragma unroll 4
+                    for (int i = 0; i < PJ_T / 32; ++i) {
+                        const PEntry c = slot_entry(i);
+                        if (PEntry::better(c, lb)) lb = c;
+                    }
+                    PEntry v = lb;
+#pragma unroll
+                    for (int k2 = 2; k2 <= 32; k2 <<= 1)
+#pragma unroll
+                        for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+                            const PEntry o = v.shfl_xor(j2);
+                            const bool want_better = ((lane & j2) == 0) == ((lane & k2) == 0);
+                            if (PEntry::better(o, v) == want_better && o.idx != v.idx) v = o;
+                        }
+                    if (lane < p.k) tk.mine = v;
+                    tk.refresh_kth();
+                    seeded = lb.idx;
+                    have_list = true;
+                }
+#pragma unroll 2
+                for (int i = 0; i < PJ_T / 32; ++i) {
+                    PEntry c = slot_entry(i);
+                    uint32_t m = __ballot_sync(0xffffffffu, c.idx != seeded && PEntry::better(c, tk.kth));
+                    while (m) {
+                        const int src = __ffs(m) - 1;
+                        m &= m - 1;
+                        tk.insert(c.shfl(src));
+                    }
+                }
+                __syncwarp();
+            }
+            if (failed) {
+                hand_over(q);
+                continue;
+            }
+            pj_finish(tk, p, q, cq);
+        }
+    }
+}
+
+struct PJHeavySmem {
+    uint32_t cnt[(1 << PJ_WIN_SHIFT_MAX) / 2];   // one 16-bit counter per row of the window
+    uint32_t ubits[(PJ_MAX_BITS + 32) / 32];     // the query as a bitmap over the ids
+    uint16_t uid[PJ_HEAVY_UID];                  // its distinct ids, enumerated (when they fit)
+    uint32_t lst_inter[PJ_HEAVY_THREADS / 32][32], lst_uni[PJ_HEAVY_THREADS / 32][32];
+    int32_t lst_idx[PJ_HEAVY_THREADS / 32][32];
+    uint32_t n_uid, cq, work;
+};
+
+__global__ void __launch_bounds__(PJ_HEAVY_THREADS) postings_heavy_kernel(const PJParams p) {
+    extern __shared__ __align__(16) uint8_t pj_smem[];
+    PJHeavySmem& sm = *reinterpret_cast<PJHeavySmem*>(pj_smem);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = PJ_HEAVY_THREADS / 32;
+    const uint32_t n_heavy = p.counters[1];
+    const int win_rows = 1 << p.win_shift;
+    const int n_uw = (p.n_bits + 31) / 32;
+    for (int i = tid; i < win_rows / 2; i += PJ_HEAVY_THREADS) sm.cnt[i] = 0u;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) sm.work = atomicAdd(p.counters + 2, 1u);
+        __syncthreads();
+        const uint32_t hq = sm.work;
+        if (hq >= n_heavy) break;
+        const int64_t q = p.heavy_list[hq];
+        const int64_t beg = p.q_off[q], end = p.q_off[q + 1];
+        // ---- the query as a set: bitmap over the ids, |Q| = its popcount, distinct ids enumerated
+        for (int i = tid; i < n_uw; i += PJ_HEAVY_THREADS) sm.ubits[i] = 0u;
+        if (tid == 0) {
+            sm.n_uid = 0u;
+            sm.cq = 0u;
+        }
+        __syncthreads();
+        for (int64_t e = beg + tid; e < end; e += PJ_HEAVY_THREADS) {
+            const int32_t id = p.q_ids[e];
+            if (id >= 0 && id < p.n_bits) {
+                const uint32_t bit = 1u << (id & 31);
+                const uint32_t old = atomicOr(&sm.ubits[id >> 5], bit);
+                if (!(old & bit)) {
+                    atomicAdd(&sm.cq, 1u);
+                    const uint32_t at = atomicAdd(&sm.n_uid, 1u);
+                    if (at < (uint32_t)PJ_HEAVY_UID) sm.uid[at] = (uint16_t)id;
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t cq = sm.cq;
+        const bool listed = sm.n_uid <= (uint32_t)PJ_HEAVY_UID;
+        const int64_t diag_row = p.zero_diag ? p.query_base + q - p.pool_base : -1;
+        WarpTopK<JEntry> tk;
+        tk.init(p.k);
+        for (int w = 0; w < p.n_win; ++w) {
+            // ---- postings of window w: one warp per id, lanes stride its bucket
+            auto walk = [&](int32_t id) {
+                const uint32_t s = p.off[(int64_t)id * p.n_win + w], e = p.off[(int64_t)id * p.n_win + w + 1];
+                for (uint32_t t = s + lane; t < e; t += 32) {
+                    const uint32_t r = p.post[t].x & (uint32_t)(win_rows - 1);
+                    atomicAdd(&sm.cnt[r >> 1], 1u << (16 * (r & 1)));
+                }
+            };
+            if (listed) {
+                for (uint32_t i = warp; i < sm.n_uid; i += NW) walk((int32_t)sm.uid[i]);
+            } else {
+                for (int wi = warp; wi < n_uw; wi += NW) {
+                    uint32_t x = sm.ubits[wi];
+                    while (x) {
+                        const int b = __ffs(x) - 1;
+                        x &= x - 1;
+                        walk(wi * 32 + b);
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- non-zero counters are the candidates of this window (the counters are cleared on the way)
+            const int64_t row0 = (int64_t)w << p.win_shift;
+            uint4* c4 = reinterpret_cast<uint4*>(sm.cnt);
+            for (int i0 = 0; i0 < win_rows / 8; i0 += PJ_HEAVY_THREADS) {
+                const int i = i0 + tid;
+                uint4 v = c4[i];
+                const bool nz = (v.x | v.y | v.z | v.w) != 0u;
+                if (!__ballot_sync(0xffffffffu, nz)) continue;
+                if (nz) c4[i] = make_uint4(0u, 0u, 0u, 0u);
+                const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t c = (wv[j >> 1] >> (16 * (j & 1))) & 0xffffu;
+                    const int64_t row = row0 + (int64_t)i * 8 + j;
+                    JEntry cand = JEntry::worst();
+                    if (c != 0u && row != diag_row && row < p.np)
+                        cand = JEntry{c, cq + p.pcard[row] - c, (int32_t)(p.pool_base + row)};
+                    uint32_t m = __ballot_sync(0xffffffffu, cand.inter != 0u && JEntry::better(cand, tk.kth));
+                    while (m) {
+                        const int src = __ffs(m) - 1;
+                        m &= m - 1;
+                        tk.insert(cand.shfl(src));
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // ---- merge the warps' lists: warp 0 inserts the others' entries
+        sm.lst_inter[warp][lane] = tk.mine.inter;
+        sm.lst_uni[warp][lane] = tk.mine.uni;
+        sm.lst_idx[warp][lane] = tk.mine.idx;
+        __syncthreads();
+        if (warp == 0) {
+            for (int w2 = 1; w2 < NW; ++w2) {
+                const JEntry c{sm.lst_inter[w2][lane], sm.lst_uni[w2][lane], sm.lst_idx[w2][lane]};
+                uint32_t m = __ballot_sync(0xffffffffu, lane < p.k && c.inter != 0u && JEntry::better(c, tk.kth));
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    tk.insert(c.shfl(src));
+                }
+            }
+            pj_finish(tk, p, q, cq);
+        }
+    }
+}
+
+}  // namespace r4d
+
+extern "C" {
+
+size_t r4d_postings_index_bytes(int64_t np, int32_t n_bits, int64_t nnz) {
+    const r4d::PostingsLayout L = r4d::postings_layout(np, n_bits, nnz);
+    return L.ok ? L.total : 0;
+}
+
+size_t r4d_postings_build_workspace_bytes(int64_t np, int32_t n_bits) {
+    const r4d::PostingsLayout L = r4d::postings_layout(np, n_bits, 0);
+    if (!L.ok) return 0;
+    const size_t tiles = (size_t)((L.n_buckets + r4d::SCAN_TILE - 1) / r4d::SCAN_TILE);
+    return ((size_t)L.n_buckets * 4 + 255) / 256 * 256 + (tiles + 1) * 4 + 256;
+}
+
+int r4d_postings_build(const uint32_t* pbits, const uint32_t* pcard, int64_t np, int32_t n_bits, int32_t pitch_words,
+                       int64_t nnz, void* index, size_t index_bytes, void* workspace, size_t workspace_bytes,
+                       r4d_stream_t stream) {
+    using namespace r4d;
+    const PostingsLayout L = postings_layout(np, n_bits, nnz);
+    R4D_REQUIRE(L.ok, "postings_build: unsupported shape (np=%lld, n_bits=%d [max %d], nnz=%lld)", (long long)np, n_bits,
+                PJ_MAX_BITS, (long long)nnz);
+    const int32_t words = (n_bits + 31) / 32;
+    R4D_REQUIRE(pitch_words >= words, "postings_build: pitch_words=%d < words=%d", pitch_words, words);
+    R4D_REQUIRE(index && (reinterpret_cast<uintptr_t>(index) & 255) == 0, "postings_build: index must be 256-byte aligned");
+    R4D_REQUIRE(np == 0 || (pbits && pcard), "postings_build: null pointer");
+    if (index_bytes < L.total) {
+        set_error("postings_build: index %zu B < required %zu B", index_bytes, L.total);
+        return R4D_E_WORKSPACE;
+    }
+    const size_t need_ws = r4d_postings_build_workspace_bytes(np, n_bits);
+    if (!workspace || workspace_bytes < need_ws) {
+        set_error("postings_build: workspace %zu B < required %zu B", workspace_bytes, need_ws);
+        return R4D_E_WORKSPACE;
+    }
+    cudaStream_t st = as_stream(stream);
+    uint8_t* base = reinterpret_cast<uint8_t*>(index);
+    PostingsHeader* hdr = reinterpret_cast<PostingsHeader*>(base);
+    uint32_t* off = reinterpret_cast<uint32_t*>(base + L.off_at);
+    uint2* post = reinterpret_cast<uint2*>(base + L.post_at);
+    uint32_t* cursor = reinterpret_cast<uint32_t*>(workspace);
+    uint32_t* tile_sum = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(workspace) + ((size_t)L.n_buckets * 4 + 255) / 256 * 256);
+    PostingsHeader h{};
+    h.magic = PJ_MAGIC;
+    h.status = 0;
+    h.np = np;
+    h.nnz_cap = nnz;
+    h.n_bits = n_bits;
+    h.win_shift = L.win_shift;
+    h.n_win = L.n_win;
+    R4D_CUDA(cudaMemsetAsync(base, 0, L.post_at, st));   // header + offsets
+    postings_header_kernel<<<1, 1, 0, st>>>(hdr, h); note_launch();
+    R4D_CUDA(cudaMemsetAsync(cursor, 0, (size_t)L.n_buckets * 4, st));
+    if (np == 0) return R4D_OK;
+    int64_t blocks = (np + 7) / 8;
+    const int64_t cap = (int64_t)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    postings_scan_rows_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(pbits, pcard, np, words, pitch_words, n_bits, L.win_shift,
+                                                                     L.n_win, off, cursor, post, nnz, hdr);
+    note_launch();
+    const int64_t n_scan = L.n_buckets;   // inclusive scan of off[1 .. n_buckets]
+    const int64_t tiles = (n_scan + SCAN_TILE - 1) / SCAN_TILE;
+    scan_tile_sums_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(off + 1, n_scan, tile_sum); note_launch();
+    scan_sums_kernel<<<1, SCAN_THREADS, 0, st>>>(tile_sum, tiles); note_launch();
+    scan_apply_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(off + 1, n_scan, tile_sum); note_launch();
+    postings_scan_rows_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(pbits, pcard, np, words, pitch_words, n_bits, L.win_shift,
+                                                                    L.n_win, off, cursor, post, nnz, hdr);
+    note_launch();
+    R4D_CUDA(cudaGetLastError());
+    return R4D_OK;
+}
+
+size_t r4d_jaccard_topk_postings_workspace_bytes(int64_t nq) {
+    return 256 + (size_t)(nq > 0 ? nq : 0) * 4;
+}
+
+static int postings_topk_impl(const int32_t* q_ids, const int64_t* q_off, int64_t nq, const void* index,
+                              const uint32_t* pcard, int64_t np, int32_t n_bits, int64_t nnz, int32_t k, int32_t zero_diag,
+                              int64_t query_base, int64_t pool_base, uint32_t* top_inter, uint32_t* top_union,
+                              int32_t* top_idx, const r4d::PeerOut& peers, void* workspace, size_t workspace_bytes,
+                              r4d_stream_t stream) {
+    using namespace r4d;
+    const PostingsLayout L = postings_layout(np, n_bits, nnz);
+    R4D_REQUIRE(L.ok, "jaccard_topk_postings: unsupported shape (np=%lld, n_bits=%d [max %d])", (long long)np, n_bits, PJ_MAX_BITS);
+    R4D_REQUIRE(nq >= 0 && nq < ((int64_t)1 << 31), "jaccard_topk_postings: nq=%lld", (long long)nq);
+    R4D_REQUIRE(k >= 1 && k <= R4D_TOPK_MAX, "jaccard_topk_postings: k=%d out of range [1, %d]", k, R4D_TOPK_MAX);
+    R4D_REQUIRE(pool_base >= 0 && pool_base + np < (int64_t)R4D_IDX_NONE, "jaccard_topk_postings: pool_base+np exceeds int32");
+    if (nq == 0) return R4D_OK;
+    R4D_REQUIRE(q_off && index && (np == 0 || pcard), "jaccard_topk_postings: null pointer");
+    R4D_REQUIRE(peers.world > 0 || (top_inter && top_union && top_idx), "jaccard_topk_postings: null output");
+    const size_t need = r4d_jaccard_topk_postings_workspace_bytes(nq);
+    if (!workspace || workspace_bytes < need) {
+        set_error("jaccard_topk_postings: workspace %zu B < required %zu B", workspace_bytes, need);
+        return R4D_E_WORKSPACE;
+    }
+    R4D_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "jaccard_topk_postings: workspace must be 16-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    const uint8_t* base = reinterpret_cast<const uint8_t*>(index);
+    PJParams prm{};
+    prm.q_ids = q_ids;
+    prm.q_off = q_off;
+    prm.nq = nq;
+    prm.off = reinterpret_cast<const uint32_t*>(base + L.off_at);
+    prm.post = reinterpret_cast<const uint2*>(base + L.post_at);
+    prm.pcard = pcard;
+    prm.np = np;
+    prm.n_bits = n_bits;
+    prm.win_shift = L.win_shift;
+    prm.n_win = L.n_win;
+    prm.k = k;
+    prm.zero_diag = zero_diag;
+    prm.n_fill = (int32_t)(np < k ? np : k);
+    prm.query_base = query_base;
+    prm.pool_base = pool_base;
+    prm.out_inter = top_inter;
+    prm.out_union = top_union;
+    prm.out_idx = top_idx;
+    prm.counters = reinterpret_cast<uint32_t*>(workspace);
+    prm.heavy_list = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(workspace) + 256);
+    prm.peers = peers;
+    prm.q_out_off = 0;
+    prm.nq_total = nq;
+    R4D_CUDA(cudaMemsetAsync(workspace, 0, 256, st));
+    {
+        static SmemOptIn opt_in;
+        const size_t smem = sizeof(PJWarpSmem) * PJ_LIGHT_WARPS;
+        if (int rc = ensure_dyn_smem(postings_light_kernel, smem, opt_in)) return rc;
+        int64_t grid = (nq + (int64_t)PJ_LIGHT_WARPS * PJ_CHUNK - 1) / ((int64_t)PJ_LIGHT_WARPS * PJ_CHUNK);
+        const int64_t cap = (int64_t)num_sms() * 4;
+        if (grid > cap) grid = cap;
+        prof_begin(PROF_JACCARD_POSTINGS, st);
+        postings_light_kernel<<<(unsigned)grid, PJ_LIGHT_WARPS * 32, smem, st>>>(prm); note_launch();
+        prof_end(PROF_JACCARD_POSTINGS, st);
+    }
+    {
+        static SmemOptIn opt_in;
+        const size_t smem = sizeof(PJHeavySmem);
+        if (int rc = ensure_dyn_smem(postings_heavy_kernel, smem, opt_in)) return rc;
+        int64_t grid = (int64_t)num_sms() * 2;
+        if (grid > nq) grid = nq;
+        postings_heavy_kernel<<<(unsigned)grid, PJ_HEAVY_THREADS, smem, st>>>(prm); note_launch();
+    }
+    R4D_CUDA(cudaGetLastError());
+    return R4D_OK;
+}
+
+int r4d_jaccard_topk_postings(const int32_t* q_ids, const int64_t* q_off, int64_t nq, const void* index,
+                              const uint32_t* pcard, int64_t np, int32_t n_bits, int64_t nnz, int32_t k, int32_t zero_diag,
+                              int64_t query_base, int64_t pool_base, uint32_t* top_inter, uint32_t* top_union,
+                              int32_t* top_idx, void* workspace, size_t workspace_bytes, r4d_stream_t stream) {
+    r4d::PeerOut none{};
+    return postings_topk_impl(q_ids, q_off, nq, index, pcard, np, n_bits, nnz, k, zero_diag, query_base, pool_base, top_inter,
+                              top_union, top_idx, none, workspace, workspace_bytes, stream);
+}
+
+int r4d_jaccard_topk_postings_scatter(const int32_t* q_ids, const int64_t* q_off, int64_t nq, const void* index,
+                                      const uint32_t* pcard, int64_t np, int32_t n_bits, int64_t nnz, int32_t k,
+                                      int32_t zero_diag, int64_t query_base, int64_t pool_base, void* const* peer_base,
+                                      int32_t world, int32_t rank, void* workspace, size_t workspace_bytes,
+                                      r4d_stream_t stream) {
+    using namespace r4d;
+    R4D_REQUIRE(peer_base && world >= 1 && world <= R4D_MAX_PEERS && rank >= 0 && rank < world,
+                "fused exchange: world=%d rank=%d (max %d peers)", world, rank, R4D_MAX_PEERS);
+    PeerOut po{};
+    po.world = world;
+    po.rank = rank;
+    for (int r = 0; r < world; ++r) {
+        R4D_REQUIRE(peer_base[r] != nullptr, "fused exchange: null peer pointer %d", r);
+        po.base[r] = peer_base[r];
+    }
+    return postings_topk_impl(q_ids, q_off, nq, index, pcard, np, n_bits, nnz, k, zero_diag, query_base, pool_base, nullptr,
+                              nullptr, nullptr, po, workspace, workspace_bytes, stream);
+}
+
+}  // extern "C"

@@ -1014,11 +1014,8 @@ int sparseq_topk_launch(const uint32_t* pbits, const uint32_t* qcard, const uint
         case 6: kern = jaccard_qindex_kernel<6>; break;
         default: break;
     }
-    static bool attr_done[7] = {false, false, false, false, false, false, false};
-    if (!attr_done[nu]) {
-        R4D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SQ_SM_TOTAL));
-        attr_done[nu] = true;
-    }
+    static SmemOptIn opt_in[7];   // per kernel instantiation, keyed by device inside
+    if (int rc = ensure_dyn_smem(kern, SQ_SM_TOTAL, opt_in[nu])) return rc;
     int grid = num_sms();
     if (n_stripes < grid) grid = n_stripes;
     prof_begin(PROF_JACCARD_QINDEX, st);

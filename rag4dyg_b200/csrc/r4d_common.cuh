@@ -57,9 +57,25 @@ struct PeerOut {
 
 static inline cudaStream_t as_stream(r4d_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: one flag per (call site, device),
+// so a process that drives several GPUs opts every one of them in before its first launch there.
+struct SmemOptIn {
+    bool done[64] = {};
+};
+template <class K>
+static inline int ensure_dyn_smem(K kern, size_t bytes, SmemOptIn& once) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = -1;
+    if (dev >= 0 && dev < 64 && once.done[dev]) return R4D_OK;
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", __FILE__, __LINE__);
+    if (dev >= 0 && dev < 64) once.done[dev] = true;
+    return R4D_OK;
+}
+
 // Measurement aid: with the option "kernel_timing" set, a dominant kernel's launch is bracketed by CUDA events on its
 // own stream (prof_begin / prof_end around the <<<>>>); r4d_profile_read sums the elapsed times.
-enum ProfKernel { PROF_JACCARD_QINDEX = 0, PROF_DENSE_PAIR = 1, PROF_KERNELS = 2 };
+enum ProfKernel { PROF_JACCARD_QINDEX = 0, PROF_DENSE_PAIR = 1, PROF_JACCARD_POSTINGS = 2, PROF_KERNELS = 3 };
 void prof_begin(ProfKernel k, cudaStream_t st);
 void prof_end(ProfKernel k, cudaStream_t st);
 

@@ -144,6 +144,7 @@ int r4d_profile_read(const char* kernel, double* total_ms, int64_t* launches) {
     int k = -1;
     if (!strcmp(kernel, "jaccard_qindex")) k = PROF_JACCARD_QINDEX;
     else if (!strcmp(kernel, "dense_pair")) k = PROF_DENSE_PAIR;
+    else if (!strcmp(kernel, "jaccard_postings")) k = PROF_JACCARD_POSTINGS;
     R4D_REQUIRE(k >= 0, "r4d_profile_read: unknown kernel '%s'", kernel);
     std::lock_guard<std::mutex> lk(g_prof_mu);
     ProfState& p = g_prof[k];

@@ -13,6 +13,7 @@ from ._lib import (DENSE_COS_DECAY, DENSE_HALF_COS, DENSE_HALF_COS_DECAY, PREC_B
 
 __all__ = [
     "BitsetMatrix", "encode_bitsets", "jaccard_full", "jaccard_topk", "jaccard_topk_merge", "jaccard_topk_scatter", "dense_topk_scatter", "rank_rows", "topk_rows",
+    "PostingsIndex", "build_postings", "jaccard_topk_postings", "jaccard_topk_postings_scatter",
     "triplet_mine", "triplet_sample", "DensePlanes", "dense_prepare", "dense_topk", "dense_full", "dense_topk_merge", "meanpool_prepare", "R4D_IDX_NONE",
     "R4D_TOPK_MAX", "DENSE_HALF_COS", "DENSE_COS_DECAY", "DENSE_HALF_COS_DECAY", "PREC_BF16", "PREC_BF16X3",
     "launch_count", "reset_launch_count",
@@ -143,6 +144,88 @@ def jaccard_topk_scatter(q, p, k, peer_ptrs, world, rank, zero_diag=False, query
                                        q.pitch_words, k, int(bool(zero_diag)), query_base, pool_base, peer_ptrs, world,
                                        rank, _ptr(workspace), workspace.numel(), _stream()), "r4d_jaccard_topk_scatter")
     _count(2 if nq and np_ else (1 if nq else 0))
+
+
+@dataclass
+class PostingsIndex:
+    """Inverted index of a pool (shard): node id -> pool rows holding it, in HBM (r4d_postings_build).  State of the
+    pool like its bitsets; built once."""
+    blob: torch.Tensor      # uint8, the index blob
+    card: torch.Tensor      # int32 [n_rows], |set| per pool row (shared with the BitsetMatrix)
+    n_rows: int
+    n_bits: int
+    nnz: int
+
+    @property
+    def device(self):
+        return self.blob.device
+
+
+def build_postings(p):
+    """BitsetMatrix of the pool (shard) -> PostingsIndex.  r4d_postings_build.  One-time pool set-up: reads the exact
+    posting count (sum of the cardinalities) and the build status back, i.e. synchronises."""
+    lib = _lib.load()
+    dev = p.bits.device
+    with torch.cuda.device(dev):
+        nnz = int(p.card.sum(dtype=torch.int64).item()) if p.n_rows else 0
+        need = lib.r4d_postings_index_bytes(p.n_rows, p.n_bits, nnz)
+        if need == 0:
+            raise R4DError(f"postings index: unsupported shape (rows={p.n_rows}, n_bits={p.n_bits}, postings={nnz}); "
+                           "use the bitset path (jaccard_topk)")
+        blob = torch.empty((need,), dtype=torch.uint8, device=dev)
+        ws = torch.empty((lib.r4d_postings_build_workspace_bytes(p.n_rows, p.n_bits),), dtype=torch.uint8, device=dev)
+        check(lib.r4d_postings_build(_ptr(p.bits), _ptr(p.card), p.n_rows, p.n_bits, p.pitch_words, nnz, _ptr(blob),
+                                     blob.numel(), _ptr(ws), ws.numel(), _stream()), "r4d_postings_build")
+        status = int(blob[4:8].view(torch.int32).item())
+        if status != 0:
+            raise R4DError("postings index: build overflowed its capacity (cardinalities do not match the bitsets)")
+    return PostingsIndex(blob, p.card, p.n_rows, p.n_bits, nnz)
+
+
+def _postings_args(q_ids, q_off, index):
+    q_ids = _dev_tensor(q_ids, torch.int32, "q_ids")
+    q_off = _dev_tensor(q_off, torch.int64, "q_off")
+    if q_ids.device != index.device or q_off.device != index.device:
+        raise R4DError("jaccard_topk_postings: queries and index live on different devices")
+    nq = q_off.numel() - 1
+    if nq < 0:
+        raise R4DError("q_off must hold nq+1 offsets")
+    return q_ids, q_off, nq
+
+
+def jaccard_topk_postings(q_ids, q_off, index, k, zero_diag=False, query_base=0, pool_base=0, workspace=None, out=None):
+    """Fused Jaccard scorer + top-K over pool postings: queries as CSR id lists (int32 ids, int64 offsets, CUDA),
+    (inter, union, idx) int32 [nq, k] in the canonical order.  r4d_jaccard_topk_postings."""
+    lib = _lib.load()
+    q_ids, q_off, nq = _postings_args(q_ids, q_off, index)
+    dev = index.device
+    with torch.cuda.device(dev):
+        need = lib.r4d_jaccard_topk_postings_workspace_bytes(nq)
+        if workspace is None or workspace.numel() < need:
+            workspace = torch.empty((need,), dtype=torch.uint8, device=dev)
+        if out is None:
+            out = tuple(torch.empty((nq, k), dtype=torch.int32, device=dev) for _ in range(3))
+        check(lib.r4d_jaccard_topk_postings(_ptr(q_ids), _ptr(q_off), nq, _ptr(index.blob), _ptr(index.card), index.n_rows,
+                                            index.n_bits, index.nnz, k, int(bool(zero_diag)), query_base, pool_base,
+                                            _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(workspace), workspace.numel(),
+                                            _stream()), "r4d_jaccard_topk_postings")
+    return out
+
+
+def jaccard_topk_postings_scatter(q_ids, q_off, index, k, peer_ptrs, world, rank, zero_diag=False, query_base=0,
+                                  pool_base=0, workspace=None):
+    """Fused exchange variant: final lists go to slot `rank` of every peer's gather buffer [3][world][nq][k]."""
+    lib = _lib.load()
+    q_ids, q_off, nq = _postings_args(q_ids, q_off, index)
+    dev = index.device
+    with torch.cuda.device(dev):
+        need = lib.r4d_jaccard_topk_postings_workspace_bytes(nq)
+        if workspace is None or workspace.numel() < need:
+            workspace = torch.empty((need,), dtype=torch.uint8, device=dev)
+        check(lib.r4d_jaccard_topk_postings_scatter(_ptr(q_ids), _ptr(q_off), nq, _ptr(index.blob), _ptr(index.card),
+                                                    index.n_rows, index.n_bits, index.nnz, k, int(bool(zero_diag)),
+                                                    query_base, pool_base, peer_ptrs, world, rank, _ptr(workspace),
+                                                    workspace.numel(), _stream()), "r4d_jaccard_topk_postings_scatter")
 
 
 def jaccard_topk_merge(inter, uni, idx, k_out):

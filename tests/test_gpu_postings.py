@@ -1,0 +1,126 @@
+"""GPU parity of the postings path (r4d_postings_build + r4d_jaccard_topk_postings) vs the CPU oracle and vs the
+bitset path.  Bit-exact: integer counts, canonical (score desc, index asc) order."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import random_sets, to_csr
+from oracle import jaccard_oracle as jo
+
+pytestmark = pytest.mark.gpu
+
+from rag4dyg_b200 import engine, set_encoder  # noqa: E402
+
+
+def run_postings(q, p, n_bits, k, zero_diag=False, query_base=0, pool_base=0):
+    bp = set_encoder.encode_csr(*to_csr(p), n_bits)
+    index = engine.build_postings(bp)
+    qi, qo = to_csr(q)
+    if qi.size == 0:
+        qi = np.zeros(1, np.int32)
+    ti, tu, tx = engine.jaccard_topk_postings(torch.as_tensor(qi).cuda(), torch.as_tensor(qo).cuda(), index, k,
+                                              zero_diag=zero_diag, query_base=query_base, pool_base=pool_base)
+    return ti.cpu().numpy().astype(np.int64), tu.cpu().numpy().astype(np.int64), tx.cpu().numpy(), bp, index
+
+
+def check(q, p, n_bits, k, zero_diag=False, query_base=0, pool_base=0):
+    ti, tu, tx, bp, index = run_postings(q, p, n_bits, k, zero_diag, query_base, pool_base)
+    oi, ou, ox = jo.c_topk(*to_csr(q), *to_csr(p), k, zero_diag=zero_diag, query_base=query_base, pool_base=pool_base)
+    assert np.array_equal(tx, ox), f"indices differ in rows {np.nonzero((tx != ox).any(1))[0][:5]}"
+    assert np.array_equal(ti, oi)
+    assert np.array_equal(tu, ou)
+    return bp, index
+
+
+@pytest.mark.parametrize("nq,npool,n_bits,mean,k,zero_diag", [
+    (3, 5, 40, 3, 10, False),            # pool shorter than k -> padded with R4D_IDX_NONE
+    (130, 1000, 1000, 2.2, 10, False),
+    (257, 3000, 20000, 2.2, 10, False),
+    (300, 20000, 20000, 2.2, 10, False),  # three row windows
+    (100, 2000, 20000, 20, 7, False),
+    (500, 500, 300, 3, 10, True),        # train x train with the diagonal zeroed
+    (64, 5000, 4749, 2.2, 32, False),
+    (40, 700, 64, 12, 1, False),         # tiny vocabulary: long posting lists, several passes / heavy queries
+    (200, 30000, 500, 3, 10, False),     # ~180 postings per id over 4 windows: multi-pass light queries
+])
+def test_postings_topk_bit_exact(nq, npool, n_bits, mean, k, zero_diag):
+    rng = np.random.default_rng(nq + npool + k)
+    p = random_sets(rng, npool, n_bits, mean=mean, max_len=min(64, n_bits), p_empty=0.05, dup=True)
+    q = p[:nq] if zero_diag else random_sets(rng, nq, n_bits, mean=mean, max_len=min(64, n_bits), p_empty=0.05, dup=True)
+    check(q, p, n_bits, k, zero_diag)
+
+
+def test_postings_equals_bitset_path():
+    rng = np.random.default_rng(21)
+    n_bits = 20000
+    p = random_sets(rng, 50000, n_bits, mean=2.2)
+    q = random_sets(rng, 3000, n_bits, mean=2.2, p_empty=0.02, dup=True)
+    ti, tu, tx, bp, _ = run_postings(q, p, n_bits, 10)
+    bq = set_encoder.encode_csr(*to_csr(q), n_bits)
+    ri, ru, rx = engine.jaccard_topk(bq, bp, 10)
+    assert np.array_equal(tx, rx.cpu().numpy())
+    assert np.array_equal(ti, ri.cpu().numpy()) and np.array_equal(tu, ru.cpu().numpy())
+
+
+def test_postings_heavy_queries_and_hot_ids():
+    """Queries with more than 64 ids, a hot id held by a third of the pool, and light queries next to them."""
+    rng = np.random.default_rng(5)
+    n_bits, npool = 3000, 20000
+    p = random_sets(rng, npool, n_bits, mean=4, max_len=64)
+    for i in range(0, npool, 3):
+        p[i] = p[i] + [7]                      # hot id: ~6 700 postings
+    q = random_sets(rng, 60, n_bits, mean=3, max_len=64, p_empty=0.05, dup=True)
+    q[3] = list(rng.choice(n_bits, 200, replace=False))          # > 64 ids -> heavy kernel
+    q[10] = [7, 7, 11]                                             # hot id -> several passes
+    q[11] = list(range(0, 2600))                                   # > 2 048 distinct ids: heavy kernel without the id list
+    q[12] = list(rng.choice(n_bits, 70, replace=True)) + [7]
+    check(q, p, n_bits, 10)
+
+
+def test_postings_hot_window_falls_back_exactly():
+    """All postings of an id inside ONE row window: the light kernel's table overflows and hands the query over."""
+    rng = np.random.default_rng(9)
+    n_bits, npool = 5000, 9000
+    p = random_sets(rng, npool, n_bits, mean=2.2)
+    for i in range(100, 900):
+        p[i] = [42] + p[i][:1]                 # 800 postings of id 42, all in window 0
+    q = [[42], [42, 43], [1, 2, 3], []]
+    check(q, p, n_bits, 10)
+
+
+def test_postings_bases_and_diag_offsets():
+    rng = np.random.default_rng(13)
+    n_bits = 800
+    p = random_sets(rng, 1200, n_bits, mean=3)
+    check(p[100:400], p, n_bits, 10, zero_diag=True, query_base=1100, pool_base=1000)
+    check(random_sets(rng, 50, n_bits, mean=3), p, n_bits, 5, pool_base=123456)
+
+
+def test_postings_empty_inputs():
+    n_bits = 100
+    bp = set_encoder.encode_csr(*to_csr([[1, 2], [3]]), n_bits)
+    index = engine.build_postings(bp)
+    ti, tu, tx = engine.jaccard_topk_postings(torch.zeros(1, dtype=torch.int32).cuda(), torch.zeros(1, dtype=torch.int64).cuda(),
+                                              index, 4)
+    assert ti.shape == (0, 4)
+    # a pool of empty sets: every score 0, fillers in index order
+    check([[1], []], [[], [], []], n_bits, 2)
+
+
+def test_postings_shard_invariance():
+    rng = np.random.default_rng(17)
+    n_bits, npool, k = 2000, 20001, 10
+    p = random_sets(rng, npool, n_bits, mean=2.2)
+    q = random_sets(rng, 150, n_bits, mean=2.2)
+    oi, ou, ox = jo.c_topk(*to_csr(q), *to_csr(p), k)
+    bounds = [0, 7000, 7001, 15000, npool]
+    parts = []
+    qi, qo = to_csr(q)
+    dq, do = torch.as_tensor(qi).cuda(), torch.as_tensor(qo).cuda()
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        index = engine.build_postings(set_encoder.encode_csr(*to_csr(p[a:b]), n_bits))
+        parts.append(engine.jaccard_topk_postings(dq, do, index, k, pool_base=a))
+    mi, mu, mx = engine.jaccard_topk_merge(torch.stack([x[0] for x in parts]), torch.stack([x[1] for x in parts]),
+                                           torch.stack([x[2] for x in parts]), k)
+    assert np.array_equal(mx.cpu().numpy(), ox)
+    assert np.array_equal(mi.cpu().numpy(), oi) and np.array_equal(mu.cpu().numpy(), ou)
