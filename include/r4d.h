@@ -60,7 +60,8 @@ int r4d_device_ok(void);
  *   "dense_stripes"     [0]  same for the dense CTA-pair kernel
  *   "kernel_timing"     [0]  record CUDA events around the dominant kernels (see r4d_profile_read)
  *   "stripe_interleave" [0]  dense pair kernel: 1 = stripe s owns pool tiles s, s+S, s+2S, ... (measured: same
- *                            time, 1.7x the DRAM reads), 0 = contiguous stripes */
+ *                            time, 1.7x the DRAM reads), 0 = contiguous stripes
+ *   "postings_log_t"    [0]  postings path: 0 = automatic, 9 / 10 = force 512- / 1 024-slot per-warp hash tables */
 int r4d_set_option(const char* key, int value);
 
 /* Measurement aid for the roofline figures (bench.py): after r4d_set_option("kernel_timing", 1) the library brackets
@@ -145,17 +146,19 @@ int r4d_postings_build(const uint32_t* pbits, const uint32_t* pcard, int64_t np,
 
 /* Fused scorer + top-K over the postings.  Queries arrive as CSR id lists q_ids[q_off[q] .. q_off[q+1]) [dev] (ids outside
  * [0, n_bits) are ignored, duplicates inside a row collapse: Python set() semantics, retrieval_data_annotation.py:12-13);
- * no query bitsets are needed.  index / pcard / np / n_bits / nnz as given to r4d_postings_build.  Outputs as
+ * no query bitsets are needed; q_nnz = q_off[nq] (length of q_ids, known to the host) only sizes the hash tables.
+ * index / pcard / np / n_bits / nnz as given to r4d_postings_build.  Outputs as
  * r4d_jaccard_topk: [nq][k] exact counts + GLOBAL pool index pool_base+p, order (score desc, index asc), rows short of k
  * padded with (0, 1, R4D_IDX_NONE).  Any set size and skew is served exactly (queries too dense for the per-warp hash
  * tables are completed by a per-window counting kernel). */
 size_t r4d_jaccard_topk_postings_workspace_bytes(int64_t nq);
-int r4d_jaccard_topk_postings(const int32_t* q_ids, const int64_t* q_off, int64_t nq, const void* index,
+int r4d_jaccard_topk_postings(const int32_t* q_ids, const int64_t* q_off, int64_t nq, int64_t q_nnz, const void* index,
                               const uint32_t* pcard, int64_t np, int32_t n_bits, int64_t nnz, int32_t k, int32_t zero_diag,
                               int64_t query_base, int64_t pool_base, uint32_t* top_inter, uint32_t* top_union,
                               int32_t* top_idx, void* workspace, size_t workspace_bytes, r4d_stream_t stream);
 /* Fused exchange variant (see r4d_jaccard_topk_scatter): the final lists go to slot `rank` of every peer's gather buffer. */
-int r4d_jaccard_topk_postings_scatter(const int32_t* q_ids, const int64_t* q_off, int64_t nq, const void* index,
+int r4d_jaccard_topk_postings_scatter(const int32_t* q_ids, const int64_t* q_off, int64_t nq, int64_t q_nnz,
+                                      const void* index,
                                       const uint32_t* pcard, int64_t np, int32_t n_bits, int64_t nnz, int32_t k,
                                       int32_t zero_diag, int64_t query_base, int64_t pool_base, void* const* peer_base,
                                       int32_t world, int32_t rank, void* workspace, size_t workspace_bytes,

@@ -34,9 +34,11 @@ constexpr int PJ_WIN_SHIFT_MIN = 13;            // 8 192 pool rows per window
 constexpr int PJ_WIN_SHIFT_MAX = 15;            // heavy kernel: a window's 16-bit counters fill 64 KB of shared memory
 constexpr int64_t PJ_MAX_BUCKETS = 48ll << 20;  // (id, window) buckets: at most 192 MB of offsets
 constexpr int PJ_MAX_BITS = 65535;              // ids fit 16 bits; a heavy counter (<= |Q n P| <= 65 535) cannot wrap
-constexpr int PJ_LOG_T = 9;
-constexpr int PJ_T = 1 << PJ_LOG_T;             // slots of a warp's hash table (8 B each)
-constexpr int PJ_CAP = 224;                     // postings planned per pass (load factor <= ~0.45)
+// A warp's hash table has 1 << LOG_T slots of 8 B (LOG_T = 9 or 10); a pass plans for a load factor of ~0.44.
+// 512 slots keep 32 warps per SM resident (label-like sets: one pass per query); 1 024 slots halve the number of passes
+// of a query whose posting lists are long (history-like sets).
+constexpr int PJ_LOG_T_SMALL = 9, PJ_LOG_T_LARGE = 10;
+__host__ __device__ constexpr int pj_cap(int log_t) { return (7 << log_t) / 16; }   // postings planned per pass
 constexpr int PJ_IDS = 64;                      // distinct ids of a light query: two per lane
 constexpr int PJ_LIGHT_WARPS = 8;
 constexpr int PJ_CHUNK = 8;                     // queries a warp takes per grab of the work counter
@@ -213,6 +215,7 @@ struct PJParams {
     uint32_t* counters;     // [0] light work counter, [1] heavy queries, [2] heavy work counter
     PeerOut peers;
     int64_t q_out_off, nq_total;   // fused exchange: row offset / rows of the whole call
+    int32_t chunk;                 // queries a light warp takes per grab of the work counter (<= PJ_CHUNK)
 };
 
 // Candidate with a 32-bit exact compare: valid while inter * union < 2^32 (light path: inter <= 64, union < 2^17).
@@ -271,35 +274,43 @@ __device__ __forceinline__ void pj_finish(WarpTopK<E>& tk, const PJParams& p, in
 }
 
 constexpr unsigned long long PJ_EMPTY = 0xffffffffffffffffull;
+constexpr int PJ_OWN = 16;   // table slots a lane may claim per pass before the pass falls back to scanning the whole table
 
-// slot = {row : 32 | card : 24 | count : 8}; returns false when the table is full
-__device__ __forceinline__ bool pj_insert(unsigned long long* tab, uint32_t row, uint32_t card) {
-    uint32_t h = (row * 2654435761u) >> (32 - PJ_LOG_T);
+// slot = {row : 32 | card : 24 | count : 8}.  Returns the claimed slot (>= 0) when this call created the entry, -1 when it
+// counted one more hit of an existing entry, -2 when the table is full.
+template <int LOG_T>
+__device__ __forceinline__ int pj_insert(unsigned long long* tab, uint32_t row, uint32_t card) {
+    constexpr int PJ_T = 1 << LOG_T;
+    uint32_t h = (row * 2654435761u) >> (32 - LOG_T);
     const unsigned long long fresh = ((unsigned long long)row << 32) | (unsigned long long)((card << 8) | 1u);
     for (int probe = 0; probe < PJ_T; ++probe) {
         const unsigned long long old = atomicCAS(tab + h, PJ_EMPTY, fresh);
-        if (old == PJ_EMPTY) return true;
+        if (old == PJ_EMPTY) return (int)h;
         if ((uint32_t)(old >> 32) == row) {
             atomicAdd(reinterpret_cast<unsigned int*>(tab + h), 1u);   // low word: card << 8 | count
-            return true;
+            return -1;
         }
         h = (h + 1) & (PJ_T - 1);
     }
-    return false;
+    return -2;
 }
 
+template <int LOG_T>
 struct PJWarpSmem {
-    unsigned long long tab[PJ_T];
+    unsigned long long tab[1 << LOG_T];
     uint32_t start[PJ_IDS];
     uint32_t pref[PJ_IDS + 1];
     int32_t ids[PJ_IDS];
+    uint16_t own[PJ_OWN * 32];   // own[i * 32 + lane]: i-th slot claimed by the lane in this pass
     uint32_t pad[3];
 };
 
-__global__ void __launch_bounds__(PJ_LIGHT_WARPS * 32, 4) postings_light_kernel(const PJParams p) {
+template <int LOG_T>
+__global__ void __launch_bounds__(PJ_LIGHT_WARPS * 32, LOG_T == PJ_LOG_T_SMALL ? 4 : 2) postings_light_kernel(const PJParams p) {
     extern __shared__ __align__(16) uint8_t pj_smem[];
+    constexpr int PJ_T = 1 << LOG_T, PJ_CAP = pj_cap(LOG_T);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    PJWarpSmem& sm = reinterpret_cast<PJWarpSmem*>(pj_smem)[warp];
+    PJWarpSmem<LOG_T>& sm = reinterpret_cast<PJWarpSmem<LOG_T>*>(pj_smem)[warp];
     const uint4 ones = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
     auto clear_table = [&]() {
         uint4* t4 = reinterpret_cast<uint4*>(sm.tab);
@@ -311,15 +322,16 @@ __global__ void __launch_bounds__(PJ_LIGHT_WARPS * 32, 4) postings_light_kernel(
     };
     clear_table();
     bool table_clean = true;
+    const int chunk = p.chunk;
     for (;;) {
         int64_t q0 = 0;
-        if (lane == 0) q0 = (int64_t)atomicAdd(p.counters + 0, (uint32_t)PJ_CHUNK);
+        if (lane == 0) q0 = (int64_t)atomicAdd(p.counters + 0, (uint32_t)chunk);
         q0 = __shfl_sync(0xffffffffu, q0, 0);
         if (q0 >= p.nq) break;
         // row offsets of the whole chunk with one load
         int64_t my_off = 0;
-        if (lane <= PJ_CHUNK && q0 + lane <= p.nq) my_off = p.q_off[q0 + lane];
-        const int n_here = (int)min((int64_t)PJ_CHUNK, p.nq - q0);
+        if (lane <= chunk && q0 + lane <= p.nq) my_off = p.q_off[q0 + lane];
+        const int n_here = (int)min((int64_t)chunk, p.nq - q0);
         for (int qi = 0; qi < n_here; ++qi) {
             const int64_t q = q0 + qi;
             const int64_t beg = __shfl_sync(0xffffffffu, my_off, qi), end = __shfl_sync(0xffffffffu, my_off, qi + 1);
@@ -374,9 +386,10 @@ __global__ void __launch_bounds__(PJ_LIGHT_WARPS * 32, 4) postings_light_kernel(
             bool failed = false, have_list = false;   // have_list: the sorted list holds entries of an earlier pass
             const bool diag_on = p.zero_diag != 0;
             const int64_t diag_row = p.query_base + q - p.pool_base;   // pool row forced to score 0
+            const int w_base = passes > 1 ? p.n_win / passes : 0, w_rem = passes > 1 ? p.n_win - w_base * passes : 0;
             for (int ps = 0; ps < passes; ++ps) {
-                if (passes > 1) {   // this pass: windows [wlo, whi) of every list
-                    const int wlo = (int)((int64_t)ps * p.n_win / passes), whi = (int)((int64_t)(ps + 1) * p.n_win / passes);
+                if (passes > 1) {   // this pass: windows [wlo, whi) of every list (balanced split of the n_win windows)
+                    const int wlo = ps * w_base + min(ps, w_rem), whi = (ps + 1) * w_base + min(ps + 1, w_rem);
                     if (id0 >= 0) {
                         s0 = p.off[(int64_t)id0 * p.n_win + wlo];
                         e0 = p.off[(int64_t)id0 * p.n_win + whi];
@@ -386,9 +399,48 @@ __global__ void __launch_bounds__(PJ_LIGHT_WARPS * 32, 4) postings_light_kernel(
                         e1 = p.off[(int64_t)id1 * p.n_win + whi];
                     }
                 }
-                // prefix sums of the list lengths (list j < 32: lane j's first id, list 32 + j: its second)
                 const uint32_t l0 = e0 - s0, l1 = two ? e1 - s1 : 0u;
-                uint32_t i0 = l0, i1 = l1;
+                if (!__ballot_sync(0xffffffffu, (l0 | l1) != 0u)) continue;
+                if (!table_clean) clear_table();
+                table_clean = false;
+                // every posting of the pass goes into the hash table; a lane remembers the slots it claimed
+                int n_own = 0, bad = 0;   // bad: 1 = table full, 2 = more than PJ_OWN claims (scan the whole table instead)
+                auto put = [&](const uint2 e) {
+                    if (diag_on && (int64_t)e.x == diag_row) return;
+                    const int r = pj_insert<LOG_T>(sm.tab, e.x, e.y);
+                    if (r >= 0) {
+                        if (n_own < PJ_OWN) sm.own[n_own * 32 + lane] = (uint16_t)r; else bad |= 2;
+                        ++n_own;
+                    } else if (r == -2) {
+                        bad |= 1;
+                    }
+                };
+                // ---- (a) the full 32-entry blocks of every list, list by list: coalesced, no search
+                const uint32_t f0 = l0 & ~31u, f1 = l1 & ~31u;
+                __syncwarp();
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t mask = __ballot_sync(0xffffffffu, (half ? f1 : f0) != 0u);
+                    while (mask) {
+                        const int j = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const uint32_t s = __shfl_sync(0xffffffffu, half ? s1 : s0, j);
+                        const uint32_t f = __shfl_sync(0xffffffffu, half ? f1 : f0, j);
+                        for (uint32_t t0 = 0; t0 < f; t0 += 128) {   // up to four loads in flight per lane
+                            uint2 e[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                if (t0 + u * 32 < f) e[u] = p.post[s + t0 + u * 32 + lane];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                if (t0 + u * 32 < f) put(e[u]);
+                        }
+                    }
+                    if (!two) break;
+                }
+                // ---- (b) the remainders (< 32 entries per list), flattened: prefix sums + a search per posting
+                const uint32_t r0 = l0 - f0, r1 = l1 - f1;
+                uint32_t i0 = r0, i1 = r1;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
                     const uint32_t t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
@@ -398,52 +450,52 @@ __global__ void __launch_bounds__(PJ_LIGHT_WARPS * 32, 4) postings_light_kernel(
                     }
                 }
                 const uint32_t tot0 = __shfl_sync(0xffffffffu, i0, 31), tot1 = __shfl_sync(0xffffffffu, i1, 31);
-                const uint32_t n_hits = tot0 + tot1;
-                if (n_hits == 0) continue;
-                sm.start[lane] = s0;
-                sm.pref[lane] = i0 - l0;
-                sm.start[lane + 32] = s1;
-                sm.pref[lane + 32] = tot0 + i1 - l1;
-                if (lane == 0) sm.pref[PJ_IDS] = n_hits;
-                if (!table_clean) clear_table();
-                table_clean = false;
-                __syncwarp();
-                // ---- every posting of the pass goes into the hash table
-                const int n_lists = two ? PJ_IDS : 32;
-                bool ok = true;
-                for (uint32_t h0 = 0; h0 < n_hits; h0 += 32) {
-                    const uint32_t h = h0 + lane;
-                    if (h < n_hits) {
-                        int lo = 0, hi = n_lists;   // last list j with pref[j] <= h (empty lists share a prefix value)
-                        while (hi - lo > 1) {
-                            const int mid = (lo + hi) >> 1;
-                            if (sm.pref[mid] <= h) lo = mid; else hi = mid;
+                const uint32_t n_rem = tot0 + tot1;
+                if (n_rem != 0) {
+                    sm.start[lane] = s0 + f0;
+                    sm.pref[lane] = i0 - r0;
+                    sm.start[lane + 32] = s1 + f1;
+                    sm.pref[lane + 32] = tot0 + i1 - r1;
+                    __syncwarp();
+                    const int n_lists = two ? PJ_IDS : 32;
+                    for (uint32_t h0 = 0; h0 < n_rem; h0 += 32) {
+                        const uint32_t h = h0 + lane;
+                        if (h < n_rem) {
+                            int lo = 0, hi = n_lists;   // last list j with pref[j] <= h (empty lists share a prefix value)
+                            while (hi - lo > 1) {
+                                const int mid = (lo + hi) >> 1;
+                                if (sm.pref[mid] <= h) lo = mid; else hi = mid;
+                            }
+                            put(p.post[sm.start[lo] + (h - sm.pref[lo])]);
                         }
-                        const uint2 e = p.post[sm.start[lo] + (h - sm.pref[lo])];
-                        if (!(diag_on && (int64_t)e.x == diag_row)) ok &= pj_insert(sm.tab, e.x, e.y);
                     }
                 }
                 __syncwarp();
-                if (__ballot_sync(0xffffffffu, !ok)) {   // a hot window overflowed the table
+                const uint32_t any_bad = __reduce_or_sync(0xffffffffu, (uint32_t)bad);
+                if (any_bad & 1u) {   // a hot window overflowed the table
                     failed = true;
                     break;
                 }
-                // ---- table -> sorted top-K list
-                auto slot_entry = [&](int i) {
-                    const unsigned long long s = sm.tab[i * 32 + lane];
+                // ---- candidates -> sorted top-K list.  A candidate is a slot claimed in this pass: lane L looks at its own
+                // claims (or, if some lane claimed more than PJ_OWN slots, at slots L, L + 32, ... of the whole table)
+                const bool scan_all = (any_bad & 2u) != 0u;
+                const int n_cand = scan_all ? PJ_T / 32 : __reduce_max_sync(0xffffffffu, n_own);
+                auto cand = [&](int i) {
+                    unsigned long long s = PJ_EMPTY;
+                    if (scan_all) s = sm.tab[i * 32 + lane];
+                    else if (i < n_own) s = sm.tab[sm.own[i * 32 + lane]];
                     if (s == PJ_EMPTY) return PEntry::worst();
                     const uint32_t lw = (uint32_t)s, cnt = lw & 0xffu, card = lw >> 8;
                     return PEntry{cnt, cq + card - cnt, (int32_t)(p.pool_base + (int64_t)(uint32_t)(s >> 32))};
                 };
                 int32_t seeded = R4D_IDX_NONE;
                 if (!have_list) {
-                    // empty list: every lane finds the best of its 16 slots, a bitonic sort ranks the 32 lane-bests and the
+                    // empty list: every lane finds the best of its candidates, a bitonic sort ranks the 32 lane-bests and the
                     // first k of them seed the list (the others cannot be in the top k); the rest is inserted below only
                     // if it beats the k-th
                     PEntry lb = PEntry::worst();
-#pragma unroll 4
-                    for (int i = 0; i < PJ_T / 32; ++i) {
-                        const PEntry c = slot_entry(i);
+                    for (int i = 0; i < n_cand; ++i) {
+                        const PEntry c = cand(i);
                         if (PEntry::better(c, lb)) lb = c;
                     }
                     PEntry v = lb;
@@ -460,9 +512,8 @@ __global__ void __launch_bounds__(PJ_LIGHT_WARPS * 32, 4) postings_light_kernel(
                     seeded = lb.idx;
                     have_list = true;
                 }
-#pragma unroll 2
-                for (int i = 0; i < PJ_T / 32; ++i) {
-                    PEntry c = slot_entry(i);
+                for (int i = 0; i < n_cand; ++i) {
+                    const PEntry c = cand(i);
                     uint32_t m = __ballot_sync(0xffffffffu, c.idx != seeded && PEntry::better(c, tk.kth));
                     while (m) {
                         const int src = __ffs(m) - 1;
@@ -481,12 +532,17 @@ __global__ void __launch_bounds__(PJ_LIGHT_WARPS * 32, 4) postings_light_kernel(
     }
 }
 
+constexpr int PJ_HWIN_SHIFT = PJ_WIN_SHIFT_MAX;   // the heavy kernel walks the pool 32 768 rows at a time (several index windows)
+
 struct PJHeavySmem {
-    uint32_t cnt[(1 << PJ_WIN_SHIFT_MAX) / 2];   // one 16-bit counter per row of the window
+    uint32_t cnt[(1 << PJ_HWIN_SHIFT) / 2];      // one 16-bit counter per row of the window
     uint32_t ubits[(PJ_MAX_BITS + 32) / 32];     // the query as a bitmap over the ids
     uint16_t uid[PJ_HEAVY_UID];                  // its distinct ids, enumerated (when they fit)
+    uint32_t seg_start[PJ_HEAVY_UID];            // per enumerated id: its postings inside the current window
+    uint32_t seg_pref[PJ_HEAVY_UID + 8];         // exclusive prefix sums of the segment lengths
     uint32_t lst_inter[PJ_HEAVY_THREADS / 32][32], lst_uni[PJ_HEAVY_THREADS / 32][32];
     int32_t lst_idx[PJ_HEAVY_THREADS / 32][32];
+    uint32_t warp_tot[PJ_HEAVY_THREADS / 32];
     uint32_t n_uid, cq, work;
 };
 
@@ -495,10 +551,13 @@ __global__ void __launch_bounds__(PJ_HEAVY_THREADS) postings_heavy_kernel(const 
     PJHeavySmem& sm = *reinterpret_cast<PJHeavySmem*>(pj_smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = PJ_HEAVY_THREADS / 32;
+    static_assert(PJ_HEAVY_THREADS == SCAN_THREADS, "block_excl_scan is written for SCAN_THREADS threads");
     const uint32_t n_heavy = p.counters[1];
-    const int win_rows = 1 << p.win_shift;
+    constexpr int HW_ROWS = 1 << PJ_HWIN_SHIFT;
+    const int wins_per_hw = 1 << (PJ_HWIN_SHIFT - p.win_shift);
+    const int n_hwin = (p.n_win + wins_per_hw - 1) / wins_per_hw;
     const int n_uw = (p.n_bits + 31) / 32;
-    for (int i = tid; i < win_rows / 2; i += PJ_HEAVY_THREADS) sm.cnt[i] = 0u;
+    for (int i = tid; i < HW_ROWS / 2; i += PJ_HEAVY_THREADS) sm.cnt[i] = 0u;
     for (;;) {
         __syncthreads();
         if (tid == 0) sm.work = atomicAdd(p.counters + 2, 1u);
@@ -528,54 +587,94 @@ __global__ void __launch_bounds__(PJ_HEAVY_THREADS) postings_heavy_kernel(const 
         }
         __syncthreads();
         const uint32_t cq = sm.cq;
-        const bool listed = sm.n_uid <= (uint32_t)PJ_HEAVY_UID;
+        const int n_uid = (int)sm.n_uid;
+        const bool listed = n_uid <= PJ_HEAVY_UID;
         const int64_t diag_row = p.zero_diag ? p.query_base + q - p.pool_base : -1;
         WarpTopK<JEntry> tk;
         tk.init(p.k);
-        for (int w = 0; w < p.n_win; ++w) {
-            // ---- postings of window w: one warp per id, lanes stride its bucket
-            auto walk = [&](int32_t id) {
-                const uint32_t s = p.off[(int64_t)id * p.n_win + w], e = p.off[(int64_t)id * p.n_win + w + 1];
-                for (uint32_t t = s + lane; t < e; t += 32) {
-                    const uint32_t r = p.post[t].x & (uint32_t)(win_rows - 1);
-                    atomicAdd(&sm.cnt[r >> 1], 1u << (16 * (r & 1)));
-                }
+        for (int g = 0; g < n_hwin; ++g) {
+            const int wlo = g * wins_per_hw, whi = min(wlo + wins_per_hw, p.n_win);
+            auto count = [&](uint32_t row) {
+                const uint32_t r = row & (uint32_t)(HW_ROWS - 1);
+                atomicAdd(&sm.cnt[r >> 1], 1u << (16 * (r & 1)));
             };
             if (listed) {
-                for (uint32_t i = warp; i < sm.n_uid; i += NW) walk((int32_t)sm.uid[i]);
+                // ---- the ids' postings inside this window: segments, their prefix sums, then one thread per posting
+                constexpr int PER = PJ_HEAVY_UID / PJ_HEAVY_THREADS;
+                uint32_t len[PER], sum = 0;
+#pragma unroll
+                for (int j = 0; j < PER; ++j) {
+                    const int i = tid * PER + j;
+                    len[j] = 0u;
+                    if (i < n_uid) {
+                        const int64_t b = (int64_t)sm.uid[i] * p.n_win;
+                        const uint32_t s = p.off[b + wlo];
+                        sm.seg_start[i] = s;
+                        len[j] = p.off[b + whi] - s;
+                    }
+                    sum += len[j];
+                }
+                uint32_t total;
+                uint32_t run = block_excl_scan(sum, sm.warp_tot, total);
+#pragma unroll
+                for (int j = 0; j < PER; ++j) {
+                    const int i = tid * PER + j;
+                    if (i < n_uid) sm.seg_pref[i] = run;
+                    run += len[j];
+                }
+                __syncthreads();
+                for (uint32_t h = tid; h < total; h += PJ_HEAVY_THREADS) {
+                    int lo = 0, hi = n_uid;   // last segment with pref <= h (empty segments share a prefix value)
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        if (sm.seg_pref[mid] <= h) lo = mid; else hi = mid;
+                    }
+                    count(p.post[sm.seg_start[lo] + (h - sm.seg_pref[lo])].x);
+                }
             } else {
+                // more distinct ids than the list holds: one warp per set bit of the bitmap, lanes stride its bucket
                 for (int wi = warp; wi < n_uw; wi += NW) {
                     uint32_t x = sm.ubits[wi];
                     while (x) {
                         const int b = __ffs(x) - 1;
                         x &= x - 1;
-                        walk(wi * 32 + b);
+                        const int64_t bk = (int64_t)(wi * 32 + b) * p.n_win;
+                        const uint32_t s = p.off[bk + wlo], e = p.off[bk + whi];
+                        for (uint32_t t = s + lane; t < e; t += 32) count(p.post[t].x);
                     }
                 }
             }
             __syncthreads();
             // ---- non-zero counters are the candidates of this window (the counters are cleared on the way)
-            const int64_t row0 = (int64_t)w << p.win_shift;
+            const int64_t row0 = (int64_t)g << PJ_HWIN_SHIFT;
             uint4* c4 = reinterpret_cast<uint4*>(sm.cnt);
-            for (int i0 = 0; i0 < win_rows / 8; i0 += PJ_HEAVY_THREADS) {
+            for (int i0 = 0; i0 < HW_ROWS / 8; i0 += PJ_HEAVY_THREADS) {
                 const int i = i0 + tid;
+                if (row0 + (int64_t)i0 * 8 >= p.np) break;
                 uint4 v = c4[i];
                 const bool nz = (v.x | v.y | v.z | v.w) != 0u;
                 if (!__ballot_sync(0xffffffffu, nz)) continue;
                 if (nz) c4[i] = make_uint4(0u, 0u, 0u, 0u);
                 const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+                // a candidate with count c scores at most c / |Q| (|P| >= c): only those that could still enter the list
+                // fetch |P|; the (up to eight) fetches of a thread are issued together
+                JEntry cand[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const uint32_t c = (wv[j >> 1] >> (16 * (j & 1))) & 0xffffu;
                     const int64_t row = row0 + (int64_t)i * 8 + j;
-                    JEntry cand = JEntry::worst();
-                    if (c != 0u && row != diag_row && row < p.np)
-                        cand = JEntry{c, cq + p.pcard[row] - c, (int32_t)(p.pool_base + row)};
-                    uint32_t m = __ballot_sync(0xffffffffu, cand.inter != 0u && JEntry::better(cand, tk.kth));
+                    cand[j] = JEntry::worst();
+                    if (c != 0u && row != diag_row && row < p.np &&
+                        (uint64_t)c * tk.kth.uni >= (uint64_t)tk.kth.inter * cq)
+                        cand[j] = JEntry{c, cq + p.pcard[row] - c, (int32_t)(p.pool_base + row)};
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    uint32_t m = __ballot_sync(0xffffffffu, cand[j].inter != 0u && JEntry::better(cand[j], tk.kth));
                     while (m) {
                         const int src = __ffs(m) - 1;
                         m &= m - 1;
-                        tk.insert(cand.shfl(src));
+                        tk.insert(cand[j].shfl(src));
                     }
                 }
             }
@@ -678,7 +777,7 @@ size_t r4d_jaccard_topk_postings_workspace_bytes(int64_t nq) {
     return 256 + (size_t)(nq > 0 ? nq : 0) * 4;
 }
 
-static int postings_topk_impl(const int32_t* q_ids, const int64_t* q_off, int64_t nq, const void* index,
+static int postings_topk_impl(const int32_t* q_ids, const int64_t* q_off, int64_t nq, int64_t q_nnz, const void* index,
                               const uint32_t* pcard, int64_t np, int32_t n_bits, int64_t nnz, int32_t k, int32_t zero_diag,
                               int64_t query_base, int64_t pool_base, uint32_t* top_inter, uint32_t* top_union,
                               int32_t* top_idx, const r4d::PeerOut& peers, void* workspace, size_t workspace_bytes,
@@ -726,14 +825,23 @@ static int postings_topk_impl(const int32_t* q_ids, const int64_t* q_off, int64_
     prm.nq_total = nq;
     R4D_CUDA(cudaMemsetAsync(workspace, 0, 256, st));
     {
-        static SmemOptIn opt_in;
-        const size_t smem = sizeof(PJWarpSmem) * PJ_LIGHT_WARPS;
-        if (int rc = ensure_dyn_smem(postings_light_kernel, smem, opt_in)) return rc;
-        int64_t grid = (nq + (int64_t)PJ_LIGHT_WARPS * PJ_CHUNK - 1) / ((int64_t)PJ_LIGHT_WARPS * PJ_CHUNK);
-        const int64_t cap = (int64_t)num_sms() * 4;
+        // table size: expected postings per query = (ids per query) x (postings per id), both known on the host
+        const double per_query = (double)(q_nnz > 0 ? q_nnz : 0) / (double)nq * ((double)nnz / (double)n_bits);
+        const bool large = options().postings_log_t == PJ_LOG_T_LARGE ||
+                           (options().postings_log_t != PJ_LOG_T_SMALL && per_query > 4.0 * pj_cap(PJ_LOG_T_SMALL));
+        static SmemOptIn opt_in[2];
+        const size_t smem = (large ? sizeof(PJWarpSmem<PJ_LOG_T_LARGE>) : sizeof(PJWarpSmem<PJ_LOG_T_SMALL>)) * PJ_LIGHT_WARPS;
+        void (*kern)(const PJParams) = large ? postings_light_kernel<PJ_LOG_T_LARGE> : postings_light_kernel<PJ_LOG_T_SMALL>;
+        if (int rc = ensure_dyn_smem(kern, smem, opt_in[large ? 1 : 0])) return rc;
+        // every warp should find several grabs of work: small calls take fewer queries per grab
+        const int64_t cap = (int64_t)num_sms() * (large ? 2 : 4);   // resident CTAs per SM (shared memory)
+        int64_t chunk = nq / (cap * PJ_LIGHT_WARPS * 4);
+        chunk = chunk < 1 ? 1 : (chunk > PJ_CHUNK ? PJ_CHUNK : chunk);
+        prm.chunk = (int32_t)chunk;
+        int64_t grid = (nq + PJ_LIGHT_WARPS * chunk - 1) / (PJ_LIGHT_WARPS * chunk);
         if (grid > cap) grid = cap;
         prof_begin(PROF_JACCARD_POSTINGS, st);
-        postings_light_kernel<<<(unsigned)grid, PJ_LIGHT_WARPS * 32, smem, st>>>(prm); note_launch();
+        kern<<<(unsigned)grid, PJ_LIGHT_WARPS * 32, smem, st>>>(prm); note_launch();
         prof_end(PROF_JACCARD_POSTINGS, st);
     }
     {
@@ -748,16 +856,16 @@ static int postings_topk_impl(const int32_t* q_ids, const int64_t* q_off, int64_
     return R4D_OK;
 }
 
-int r4d_jaccard_topk_postings(const int32_t* q_ids, const int64_t* q_off, int64_t nq, const void* index,
+int r4d_jaccard_topk_postings(const int32_t* q_ids, const int64_t* q_off, int64_t nq, int64_t q_nnz, const void* index,
                               const uint32_t* pcard, int64_t np, int32_t n_bits, int64_t nnz, int32_t k, int32_t zero_diag,
                               int64_t query_base, int64_t pool_base, uint32_t* top_inter, uint32_t* top_union,
                               int32_t* top_idx, void* workspace, size_t workspace_bytes, r4d_stream_t stream) {
     r4d::PeerOut none{};
-    return postings_topk_impl(q_ids, q_off, nq, index, pcard, np, n_bits, nnz, k, zero_diag, query_base, pool_base, top_inter,
+    return postings_topk_impl(q_ids, q_off, nq, q_nnz, index, pcard, np, n_bits, nnz, k, zero_diag, query_base, pool_base, top_inter,
                               top_union, top_idx, none, workspace, workspace_bytes, stream);
 }
 
-int r4d_jaccard_topk_postings_scatter(const int32_t* q_ids, const int64_t* q_off, int64_t nq, const void* index,
+int r4d_jaccard_topk_postings_scatter(const int32_t* q_ids, const int64_t* q_off, int64_t nq, int64_t q_nnz, const void* index,
                                       const uint32_t* pcard, int64_t np, int32_t n_bits, int64_t nnz, int32_t k,
                                       int32_t zero_diag, int64_t query_base, int64_t pool_base, void* const* peer_base,
                                       int32_t world, int32_t rank, void* workspace, size_t workspace_bytes,
@@ -772,7 +880,7 @@ int r4d_jaccard_topk_postings_scatter(const int32_t* q_ids, const int64_t* q_off
         R4D_REQUIRE(peer_base[r] != nullptr, "fused exchange: null peer pointer %d", r);
         po.base[r] = peer_base[r];
     }
-    return postings_topk_impl(q_ids, q_off, nq, index, pcard, np, n_bits, nnz, k, zero_diag, query_base, pool_base, nullptr,
+    return postings_topk_impl(q_ids, q_off, nq, q_nnz, index, pcard, np, n_bits, nnz, k, zero_diag, query_base, pool_base, nullptr,
                               nullptr, nullptr, po, workspace, workspace_bytes, stream);
 }
 

@@ -177,6 +177,7 @@ int r4d_set_option(const char* key, int value) {
     else if (!strcmp(key, "jaccard_stripes")) slot = &o.jaccard_stripes;
     else if (!strcmp(key, "dense_stripes")) slot = &o.dense_stripes;
     else if (!strcmp(key, "kernel_timing")) slot = &o.kernel_timing;
+    else if (!strcmp(key, "postings_log_t")) slot = &o.postings_log_t;
     if (!slot || (slot == &o.jaccard_warps && value != 8 && value != 16)) {
         r4d::set_error("r4d_set_option: unknown key or bad value (%s = %d)", key, value);
         return R4D_E_ARG;

@@ -205,7 +205,7 @@ def jaccard_topk_postings(q_ids, q_off, index, k, zero_diag=False, query_base=0,
             workspace = torch.empty((need,), dtype=torch.uint8, device=dev)
         if out is None:
             out = tuple(torch.empty((nq, k), dtype=torch.int32, device=dev) for _ in range(3))
-        check(lib.r4d_jaccard_topk_postings(_ptr(q_ids), _ptr(q_off), nq, _ptr(index.blob), _ptr(index.card), index.n_rows,
+        check(lib.r4d_jaccard_topk_postings(_ptr(q_ids), _ptr(q_off), nq, q_ids.numel(), _ptr(index.blob), _ptr(index.card), index.n_rows,
                                             index.n_bits, index.nnz, k, int(bool(zero_diag)), query_base, pool_base,
                                             _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(workspace), workspace.numel(),
                                             _stream()), "r4d_jaccard_topk_postings")
@@ -222,7 +222,7 @@ def jaccard_topk_postings_scatter(q_ids, q_off, index, k, peer_ptrs, world, rank
         need = lib.r4d_jaccard_topk_postings_workspace_bytes(nq)
         if workspace is None or workspace.numel() < need:
             workspace = torch.empty((need,), dtype=torch.uint8, device=dev)
-        check(lib.r4d_jaccard_topk_postings_scatter(_ptr(q_ids), _ptr(q_off), nq, _ptr(index.blob), _ptr(index.card),
+        check(lib.r4d_jaccard_topk_postings_scatter(_ptr(q_ids), _ptr(q_off), nq, q_ids.numel(), _ptr(index.blob), _ptr(index.card),
                                                     index.n_rows, index.n_bits, index.nnz, k, int(bool(zero_diag)),
                                                     query_base, pool_base, peer_ptrs, world, rank, _ptr(workspace),
                                                     workspace.numel(), _stream()), "r4d_jaccard_topk_postings_scatter")
