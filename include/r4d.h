@@ -41,7 +41,8 @@ typedef void* r4d_stream_t; /* cudaStream_t */
 #define R4D_DENSE_HALF_COS_DECAY 2 /* ((cos+1)/2) * exp(-lambda*|dt|)                              */
 /* dense contraction precision */
 #define R4D_PREC_BF16 0   /* one tcgen05 kind::f16 pass on bf16-rounded operands                  */
-#define R4D_PREC_BF16X3 1 /* hi/lo bf16 split of both operands, all four products, fp32 accumulate    */
+#define R4D_PREC_BF16X3 1 /* hi/lo bf16 split of both operands, fp32 accumulate: hi.hi + hi.lo + lo.hi on the
+                             CTA-pair top-K kernel (k <= 16), all four products elsewhere; <= 1e-5 of fp32    */
 
 int r4d_version(void);
 const char* r4d_last_error(void);

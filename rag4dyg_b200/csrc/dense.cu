@@ -465,10 +465,11 @@ size_t r4d_dense_topk_workspace_bytes(int64_t nq, int64_t np, int32_t k) {
     // it supports (multiples of 64 up to 768)
     if (k <= 16)
         for (int d = 64; d <= 768; d += 64)
-            if (dense2_supported(nq, np, d, R4D_PREC_BF16, k)) {
-                const size_t n2 = dense2_workspace_bytes(nq, np, d, k);
-                if (n2 > need) need = n2;
-            }
+            for (int x3 = 0; x3 < 2; ++x3)
+                if (dense2_supported(nq, np, d, x3 ? R4D_PREC_BF16X3 : R4D_PREC_BF16, k)) {
+                    const size_t n2 = dense2_workspace_bytes(nq, np, d, k, x3 != 0);
+                    if (n2 > need) need = n2;
+                }
     return need;
 }
 
@@ -498,7 +499,8 @@ static int dense_topk_impl(const void* q_hi, const void* q_lo, int64_t nq, const
     R4D_REQUIRE(peers.world > 0 || (top_score && top_idx), "dense_topk: null output");
     if (np > 0 && dense2_supported(nq, np, d_pad, prec, k)) {
         // throughput path: CTA pairs (cta_group::2), resident query tile, register top-K (dense2.cu)
-        const size_t need2 = dense2_workspace_bytes(nq, np, d_pad, k);
+        const bool x3 = prec == R4D_PREC_BF16X3;
+        const size_t need2 = dense2_workspace_bytes(nq, np, d_pad, k, x3);
         if (workspace_bytes < need2 || !workspace) {
             set_error("dense_topk: workspace %zu B < required %zu B", workspace_bytes, need2);
             return R4D_E_WORKSPACE;
@@ -506,8 +508,8 @@ static int dense_topk_impl(const void* q_hi, const void* q_lo, int64_t nq, const
         int32_t n_lists = 0;
         float* ps = reinterpret_cast<float*>(workspace);
         int32_t* pi = reinterpret_cast<int32_t*>(ps + (need2 - 256) / 8);
-        rc = dense2_topk(q_hi, nq, p_hi, np, d_pad, q_time, p_time, lambda, mode, k, pool_base, ps, pi, &n_lists,
-                         as_stream(stream));
+        rc = dense2_topk(q_hi, x3 ? q_lo : nullptr, nq, p_hi, x3 ? p_lo : nullptr, np, d_pad, q_time, p_time, lambda, mode, k,
+                         pool_base, ps, pi, &n_lists, as_stream(stream));
         if (rc) return rc;
         return dense_merge_launch(ps, pi, n_lists, nq, k, k, top_score, top_idx, peers, stream);
     }

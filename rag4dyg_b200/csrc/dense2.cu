@@ -16,7 +16,8 @@
 // bound (measured: no gain over dense.cu), so wide D uses QRES = false: the pair streams both k-blocks (64 B/clk/SM,
 // 7-stage ring) and still halves the pool traffic per MMA.
 //
-// Supports: PREC_BF16, top-K with k <= 16.  Everything else goes through dense.cu.
+// Supports: PREC_BF16 and PREC_BF16X3 (three products: hi.hi + hi.lo + lo.hi, streamed operands), top-K with k <= 16.
+// Everything else goes through dense.cu.
 #include <cmath>
 #include <cstdlib>
 
@@ -32,6 +33,7 @@ constexpr int D2_KMAX = 16;  // top-K width served by this kernel (wider K -> de
 struct Dense2Params {
     int64_t nq, np;
     int32_t n_kblocks;
+    int32_t n_segs;   // 1: bf16 single pass; 3: BF16X3 = q_hi.p_hi + q_hi.p_lo + q_lo.p_hi accumulated in the same TMEM tile
     int32_t mode;
     int32_t k;
     int32_t n_stages;
@@ -114,6 +116,7 @@ __device__ __forceinline__ void tc_commit_2sm_mc(uint64_t* bar) {
 template <int DPN, bool QRES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D2_THREADS, 1)
 dense2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_p,
+              const __grid_constant__ CUtensorMap tm_qlo, const __grid_constant__ CUtensorMap tm_plo,
               const Dense2Params prm) {
     constexpr int P_TILE_BYTES_ = (DPN / 2) * DKB * 2;
     constexpr int P_STAGE_BYTES = P_TILE_BYTES_ + (QRES ? 0 : Q_TILE_BYTES);  // streamed Q k-block sits after the P tile
@@ -143,6 +146,10 @@ dense2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tm_q);
         tma_prefetch_desc(&tm_p);
+        if (prm.n_segs > 1) {
+            tma_prefetch_desc(&tm_qlo);
+            tma_prefetch_desc(&tm_plo);
+        }
         for (int s = 0; s < 8; ++s) {
             mbar_init(&full_bar[s], 2);
             mbar_init(&empty_bar[s], 1);
@@ -189,16 +196,21 @@ dense2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                                         qtile * DQ);
                 }
                 for (int pt = pt0; pt < pt_lim; pt += pt_step) {
-                    for (int kb = 0; kb < prm.n_kblocks; ++kb) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
-                        const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[stage]), 0);
-                        const uint32_t sdst = smem_u32(stages + (size_t)stage * P_STAGE_BYTES);
-                        mbar_arrive_expect_tx_cluster(full_leader, (uint32_t)P_STAGE_BYTES);
-                        tma_load_2d_2sm(sdst, &tm_p, full_leader, kb * DKB, pt * DPN + (int)rank * (DPN / 2));
-                        if (!QRES) tma_load_2d_2sm(sdst + P_TILE_BYTES_, &tm_q, full_leader, kb * DKB, qtile * DQ);
-                        if (++stage == prm.n_stages) {
-                            stage = 0;
-                            phase ^= 1;
+                    // split precision: segment 0 = q_hi.p_hi, 1 = q_hi.p_lo, 2 = q_lo.p_hi (streamed operands only)
+                    for (int seg = 0; seg < prm.n_segs; ++seg) {
+                        const CUtensorMap* mp = seg == 1 ? &tm_plo : &tm_p;
+                        const CUtensorMap* mq = seg == 2 ? &tm_qlo : &tm_q;
+                        for (int kb = 0; kb < prm.n_kblocks; ++kb) {
+                            mbar_wait(&empty_bar[stage], phase ^ 1);
+                            const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[stage]), 0);
+                            const uint32_t sdst = smem_u32(stages + (size_t)stage * P_STAGE_BYTES);
+                            mbar_arrive_expect_tx_cluster(full_leader, (uint32_t)P_STAGE_BYTES);
+                            tma_load_2d_2sm(sdst, mp, full_leader, kb * DKB, pt * DPN + (int)rank * (DPN / 2));
+                            if (!QRES) tma_load_2d_2sm(sdst + P_TILE_BYTES_, mq, full_leader, kb * DKB, qtile * DQ);
+                            if (++stage == prm.n_stages) {
+                                stage = 0;
+                                phase ^= 1;
+                            }
                         }
                     }
                 }
@@ -227,7 +239,8 @@ dense2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                     mbar_wait(&tempty_bar[buf], ((tile_seq >> 1) & 1u) ^ 1u);
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + buf * DPN;
-                    for (int kb = 0; kb < prm.n_kblocks; ++kb) {
+                    const int n_vk = prm.n_kblocks * prm.n_segs;   // k-blocks of all segments accumulate into one tile
+                    for (int kb = 0; kb < n_vk; ++kb) {
                         mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
                         const uint32_t sbase = smem_u32(stages + (size_t)stage * P_STAGE_BYTES);
@@ -363,7 +376,7 @@ struct Dense2Plan {
     size_t smem;
 };
 
-static Dense2Plan dense2_plan(int64_t nq, int64_t np, int32_t d_pad, int32_t k) {
+static Dense2Plan dense2_plan(int64_t nq, int64_t np, int32_t d_pad, int32_t k, bool x3 = false) {
     Dense2Plan pl{};
     pl.ok = false;
     if (k > D2_KMAX || nq <= 0 || np <= 0) return pl;
@@ -374,7 +387,7 @@ static Dense2Plan dense2_plan(int64_t nq, int64_t np, int32_t d_pad, int32_t k) 
     const long q_bytes = (long)n_kblocks * Q_TILE_BYTES;
     const int force = options().dense_pair_qres;  // -1 auto, 0 never resident
     const long avail_res = total - fixed - q_bytes;
-    pl.qres = avail_res >= 4 * 16384 && force != 0;
+    pl.qres = avail_res >= 4 * 16384 && force != 0 && !x3;   // split precision streams hi and lo planes of both operands
     if (pl.qres) {
         pl.n_stages = (int)(avail_res / 16384);
     } else {
@@ -415,19 +428,20 @@ static Dense2Plan dense2_plan(int64_t nq, int64_t np, int32_t d_pad, int32_t k) 
 
 // exported to dense.cu
 bool dense2_supported(int64_t nq, int64_t np, int32_t d_pad, int32_t prec, int32_t k) {
-    if (!options().dense_pair_kernel || prec != R4D_PREC_BF16) return false;
-    return dense2_plan(nq, np, d_pad, k).ok;
+    if (!options().dense_pair_kernel || (prec != R4D_PREC_BF16 && prec != R4D_PREC_BF16X3)) return false;
+    return dense2_plan(nq, np, d_pad, k, prec == R4D_PREC_BF16X3).ok;
 }
 
-size_t dense2_workspace_bytes(int64_t nq, int64_t np, int32_t d_pad, int32_t k) {
-    const Dense2Plan pl = dense2_plan(nq, np, d_pad, k);
+size_t dense2_workspace_bytes(int64_t nq, int64_t np, int32_t d_pad, int32_t k, bool x3) {
+    const Dense2Plan pl = dense2_plan(nq, np, d_pad, k, x3);
     return (size_t)pl.n_stripes * 2 * (size_t)nq * (size_t)k * 8 + 256;
 }
 
-int dense2_topk(const void* q_hi, int64_t nq, const void* p_hi, int64_t np, int32_t d_pad, const float* q_time,
-                const float* p_time, float lambda, int32_t mode, int32_t k, int64_t pool_base, float* part_score,
-                int32_t* part_idx, int32_t* n_lists_out, cudaStream_t st) {
-    const Dense2Plan pl = dense2_plan(nq, np, d_pad, k);
+int dense2_topk(const void* q_hi, const void* q_lo, int64_t nq, const void* p_hi, const void* p_lo, int64_t np, int32_t d_pad,
+                const float* q_time, const float* p_time, float lambda, int32_t mode, int32_t k, int64_t pool_base,
+                float* part_score, int32_t* part_idx, int32_t* n_lists_out, cudaStream_t st) {
+    const bool x3 = q_lo != nullptr && p_lo != nullptr;
+    const Dense2Plan pl = dense2_plan(nq, np, d_pad, k, x3);
     if (!pl.ok) {
         set_error("dense2: unsupported shape");
         return R4D_E_ARG;
@@ -441,10 +455,20 @@ int dense2_topk(const void* q_hi, int64_t nq, const void* p_hi, int64_t np, int3
     if ((rc = make_tmap_2d(&tm_p, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p_hi, d_pad, np, rs, DKB, pl.dpn / 2,
                            CU_TENSOR_MAP_SWIZZLE_128B)))
         return rc;
+    CUtensorMap tm_qlo = tm_q, tm_plo = tm_p;
+    if (x3) {
+        if ((rc = make_tmap_2d(&tm_qlo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, q_lo, d_pad, nq, rs, DKB, DQ,
+                               CU_TENSOR_MAP_SWIZZLE_128B)))
+            return rc;
+        if ((rc = make_tmap_2d(&tm_plo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p_lo, d_pad, np, rs, DKB, pl.dpn / 2,
+                               CU_TENSOR_MAP_SWIZZLE_128B)))
+            return rc;
+    }
     Dense2Params prm{};
     prm.nq = nq;
     prm.np = np;
     prm.n_kblocks = d_pad / DKB;
+    prm.n_segs = x3 ? 3 : 1;
     prm.mode = mode;
     prm.k = k;
     prm.n_stages = pl.n_stages;
@@ -466,11 +490,11 @@ int dense2_topk(const void* q_hi, int64_t nq, const void* p_hi, int64_t np, int3
     if (pl.qres) {
         R4D_CUDA(cudaFuncSetAttribute(dense2_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         prof_begin(PROF_DENSE_PAIR, st);
-        dense2_kernel<256, true><<<2 * n_clusters, D2_THREADS, smem, st>>>(tm_q, tm_p, prm); note_launch();
+        dense2_kernel<256, true><<<2 * n_clusters, D2_THREADS, smem, st>>>(tm_q, tm_p, tm_qlo, tm_plo, prm); note_launch();
     } else {
         R4D_CUDA(cudaFuncSetAttribute(dense2_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         prof_begin(PROF_DENSE_PAIR, st);
-        dense2_kernel<256, false><<<2 * n_clusters, D2_THREADS, smem, st>>>(tm_q, tm_p, prm); note_launch();
+        dense2_kernel<256, false><<<2 * n_clusters, D2_THREADS, smem, st>>>(tm_q, tm_p, tm_qlo, tm_plo, prm); note_launch();
     }
     prof_end(PROF_DENSE_PAIR, st);
     R4D_CUDA(cudaGetLastError());

@@ -91,9 +91,10 @@ static __device__ __noinline__ float list_insert(float* ls, int32_t* li, int k, 
 
 // dense2.cu (CTA-pair kernel) entry points used by the C ABI in dense.cu
 bool dense2_supported(int64_t nq, int64_t np, int32_t d_pad, int32_t prec, int32_t k);
-size_t dense2_workspace_bytes(int64_t nq, int64_t np, int32_t d_pad, int32_t k);
-int dense2_topk(const void* q_hi, int64_t nq, const void* p_hi, int64_t np, int32_t d_pad, const float* q_time,
-                const float* p_time, float lambda, int32_t mode, int32_t k, int64_t pool_base, float* part_score,
-                int32_t* part_idx, int32_t* n_lists_out, cudaStream_t st);
+size_t dense2_workspace_bytes(int64_t nq, int64_t np, int32_t d_pad, int32_t k, bool x3);
+// q_lo / p_lo non-null selects the split-precision (BF16X3) contraction
+int dense2_topk(const void* q_hi, const void* q_lo, int64_t nq, const void* p_hi, const void* p_lo, int64_t np, int32_t d_pad,
+                const float* q_time, const float* p_time, float lambda, int32_t mode, int32_t k, int64_t pool_base,
+                float* part_score, int32_t* part_idx, int32_t* n_lists_out, cudaStream_t st);
 
 }  // namespace r4d

@@ -7,9 +7,14 @@
 //   r4d_parse_rows_count : rows (lines that are neither empty nor all whitespace) and fields (whitespace separated)
 //   r4d_parse_int_rows   : CSR row offsets + int64 values   (strtoll, base 10)
 //   r4d_parse_float_rows : CSR row offsets + float64 values (strtod: correctly rounded, so == Python's float(text))
-// The accepted number syntax is C's, which covers everything the writers of this path emit (decimal integers;
-// str(np.float64) / "%.4f" floats incl. exponents, nan, inf); Python-only forms (underscores, non-ASCII digits) are
-// rejected with R4D_E_ARG.
+// The accepted number syntax is C's ("C" locale), which covers everything the writers of this path emit (decimal
+// integers; str(np.float64) / "%.4f" floats incl. exponents, nan, inf); Python-only forms (underscores, non-ASCII
+// digits) are rejected with R4D_E_ARG.  Line structure follows Python's text mode + str.splitlines() on ASCII input:
+// \n, \r, \r\n, \v, \f, \x1c, \x1d, \x1e end a line; space, \t and \x1f separate fields (str.split()).  Non-ASCII
+// bytes (where Python knows further separators: \x85, U+2028, U+2029, Unicode spaces) are rejected with R4D_E_ARG —
+// the writers of this path never produce them.
+#include <locale.h>
+
 #include <cerrno>
 #include <cstdlib>
 #include <cstring>
@@ -20,33 +25,42 @@
 
 namespace r4d {
 
-static inline bool is_space(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\v' || c == '\f'; }
+static inline bool is_space(char c) { return c == ' ' || c == '\t' || c == '\x1f'; }
+static inline bool is_line_end(char c) {
+    return c == '\n' || c == '\r' || c == '\v' || c == '\f' || c == '\x1c' || c == '\x1d' || c == '\x1e';
+}
 
 struct Line {
     const char* beg;
     const char* end;  // exclusive, the '\n' is not part of the line
 };
 
-// lines that hold at least one field, with their field counts
-static void split_lines(const char* text, size_t len, std::vector<Line>& lines, std::vector<int64_t>& fields) {
+// lines that hold at least one field, with their field counts; false when the text holds a non-ASCII byte
+static bool split_lines(const char* text, size_t len, std::vector<Line>& lines, std::vector<int64_t>& fields) {
     const char* p = text;
     const char* const stop = text + len;
     while (p < stop) {
-        const char* nl = static_cast<const char*>(memchr(p, '\n', (size_t)(stop - p)));
-        const char* e = nl ? nl : stop;
         int64_t n = 0;
         bool in_field = false;
-        for (const char* c = p; c < e; ++c) {
+        const char* c = p;
+        for (; c < stop && !is_line_end(*c); ++c) {
+            if (static_cast<unsigned char>(*c) >= 0x80) return false;
             const bool sp = is_space(*c);
             if (!sp && !in_field) ++n;
             in_field = !sp;
         }
         if (n > 0) {
-            lines.push_back(Line{p, e});
+            lines.push_back(Line{p, c});
             fields.push_back(n);
         }
-        p = nl ? nl + 1 : stop;
+        p = c < stop ? c + 1 : stop;
     }
+    return true;
+}
+
+static locale_t c_locale() {
+    static locale_t loc = newlocale(LC_ALL_MASK, "C", (locale_t)0);
+    return loc;
 }
 
 template <class T>
@@ -139,7 +153,7 @@ bool parse_field<double>(const char* b, const char* e, double* out) {
     if (memchr(tmp, 'x', n) || memchr(tmp, 'X', n) || memchr(tmp, 'p', n) || memchr(tmp, 'P', n) || memchr(tmp, '(', n))
         return false;  // C-only forms (hex floats, nan(...)) that Python's float() rejects
     char* endp = nullptr;
-    const double v = strtod(tmp, &endp);
+    const double v = strtod_l(tmp, &endp, c_locale());   // Python's float() ignores LC_NUMERIC; so does this
     if (endp != tmp + n) return false;
     *out = v;
     return true;
@@ -150,7 +164,10 @@ static int64_t parse_rows(const char* text, size_t len, int64_t* row_off, T* val
     if ((!text && len) || !row_off || (!values && cap_fields > 0)) return R4D_E_ARG;
     std::vector<Line> lines;
     std::vector<int64_t> fields;
-    split_lines(text, len, lines, fields);
+    if (!split_lines(text, len, lines, fields)) {
+        set_error("parse_rows: non-ASCII byte in the text (only ASCII index / score files are accepted)");
+        return R4D_E_ARG;
+    }
     const int64_t n_rows = (int64_t)lines.size();
     int64_t total = 0;
     for (int64_t n : fields) total += n;
@@ -206,7 +223,10 @@ int64_t r4d_parse_rows_count(const char* text, size_t len, int64_t* n_fields) {
     if ((!text && len) || !n_fields) return R4D_E_ARG;
     std::vector<r4d::Line> lines;
     std::vector<int64_t> fields;
-    r4d::split_lines(text, len, lines, fields);
+    if (!r4d::split_lines(text, len, lines, fields)) {
+        r4d::set_error("parse_rows_count: non-ASCII byte in the text (only ASCII index / score files are accepted)");
+        return R4D_E_ARG;
+    }
     int64_t total = 0;
     for (int64_t n : fields) total += n;
     *n_fields = total;

@@ -3,6 +3,7 @@
 Every function here takes CUDA tensors, passes raw device pointers + the current CUDA stream to libr4d.so and returns
 CUDA tensors.  Nothing is computed in Python/torch: a missing library or device raises (no CPU fallback).
 """
+import functools
 from dataclasses import dataclass
 
 import torch
@@ -40,6 +41,36 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def _device_of(x):
+    if isinstance(x, torch.Tensor):
+        return x.device
+    for attr in ("bits", "hi", "blob"):          # BitsetMatrix / DensePlanes / PostingsIndex
+        t = getattr(x, attr, None)
+        if isinstance(t, torch.Tensor):
+            return t.device
+    return None
+
+
+def _on_input_device(fn):
+    """Run `fn` with the CUDA device of its tensor arguments current (kernels, streams and the per-device shared-memory
+    opt-ins all follow the current device); inputs on different GPUs raise instead of launching on the wrong one."""
+    @functools.wraps(fn)
+    def wrapped(*args, **kw):
+        dev = None
+        for a in list(args) + list(kw.values()):
+            d = _device_of(a)
+            if d is not None and d.type == "cuda":
+                if dev is None:
+                    dev = d
+                elif d != dev:
+                    raise R4DError(f"{fn.__name__}: inputs live on different devices ({dev} vs {d})")
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kw)
+        with torch.cuda.device(dev):
+            return fn(*args, **kw)
+    return wrapped
+
+
 def _ptr(t):
     return 0 if t is None else t.data_ptr()
 
@@ -72,6 +103,7 @@ class BitsetMatrix:
         return BitsetMatrix(self.bits[start:stop], self.card[start:stop], self.n_bits, self.words, self.pitch_words)
 
 
+@_on_input_device
 def encode_bitsets(bit_pos, row_off, n_bits):
     """CSR (int32 bit positions, int64 row offsets; CUDA tensors) -> BitsetMatrix.  r4d_bitset_encode."""
     lib = _lib.load()
@@ -96,6 +128,7 @@ def _check_pair(q, p):
         raise R4DError("query and pool bitsets must share the same universe (words/pitch differ)")
 
 
+@_on_input_device
 def jaccard_full(q, p, zero_diag=False, want_score=True, query_base=0, pool_base=0):
     """All-pairs intersection counts (int32 [nq, np]) and float64 Jaccard scores.  r4d_jaccard_full."""
     lib = _lib.load()
@@ -111,6 +144,7 @@ def jaccard_full(q, p, zero_diag=False, want_score=True, query_base=0, pool_base
     return inter, score
 
 
+@_on_input_device
 def jaccard_topk(q, p, k, zero_diag=False, query_base=0, pool_base=0, workspace=None):
     """Fused scorer + top-K: (inter, union, idx) int32 [nq, k], order (score desc, idx asc).  r4d_jaccard_topk."""
     lib = _lib.load()
@@ -130,6 +164,7 @@ def jaccard_topk(q, p, k, zero_diag=False, query_base=0, pool_base=0, workspace=
     return top_inter, top_union, top_idx
 
 
+@_on_input_device
 def jaccard_topk_scatter(q, p, k, peer_ptrs, world, rank, zero_diag=False, query_base=0, pool_base=0, workspace=None):
     """Fused exchange: local fused top-K whose final lists are stored straight into slot `rank` of every peer's
     gather buffer [3][world][nq][k] over NVLink.  peer_ptrs: ctypes array of `world` device pointers.
@@ -161,6 +196,7 @@ class PostingsIndex:
         return self.blob.device
 
 
+@_on_input_device
 def build_postings(p):
     """BitsetMatrix of the pool (shard) -> PostingsIndex.  r4d_postings_build.  One-time pool set-up: reads the exact
     posting count (sum of the cardinalities) and the build status back, i.e. synchronises."""
@@ -193,6 +229,7 @@ def _postings_args(q_ids, q_off, index):
     return q_ids, q_off, nq
 
 
+@_on_input_device
 def jaccard_topk_postings(q_ids, q_off, index, k, zero_diag=False, query_base=0, pool_base=0, workspace=None, out=None):
     """Fused Jaccard scorer + top-K over pool postings: queries as CSR id lists (int32 ids, int64 offsets, CUDA),
     (inter, union, idx) int32 [nq, k] in the canonical order.  r4d_jaccard_topk_postings."""
@@ -212,6 +249,7 @@ def jaccard_topk_postings(q_ids, q_off, index, k, zero_diag=False, query_base=0,
     return out
 
 
+@_on_input_device
 def jaccard_topk_postings_scatter(q_ids, q_off, index, k, peer_ptrs, world, rank, zero_diag=False, query_base=0,
                                   pool_base=0, workspace=None):
     """Fused exchange variant: final lists go to slot `rank` of every peer's gather buffer [3][world][nq][k]."""
@@ -228,6 +266,7 @@ def jaccard_topk_postings_scatter(q_ids, q_off, index, k, peer_ptrs, world, rank
                                                     workspace.numel(), _stream()), "r4d_jaccard_topk_postings_scatter")
 
 
+@_on_input_device
 def jaccard_topk_merge(inter, uni, idx, k_out):
     """Merge candidate lists [n_lists, nq, k_in] -> [nq, k_out].  r4d_jaccard_topk_merge."""
     lib = _lib.load()
@@ -245,6 +284,7 @@ def jaccard_topk_merge(inter, uni, idx, k_out):
     return o_i, o_u, o_x
 
 
+@_on_input_device
 def rank_rows(scores):
     """order[q] = argsort(-scores[q], stable) as int32 [nq, n].  float64 or float32 CUDA matrix."""
     lib = _lib.load()
@@ -265,6 +305,7 @@ def rank_rows(scores):
     return order
 
 
+@_on_input_device
 def topk_rows(scores, k):
     """Top-k of each row of an explicit float64 matrix: (scores f64 [nq,k], idx int32 [nq,k])."""
     lib = _lib.load()
@@ -278,6 +319,7 @@ def topk_rows(scores, k):
     return ts, ti
 
 
+@_on_input_device
 def triplet_mine(out, inn, thr, neg_num):
     """Device part of save_train_annotation: (n_pos [n], neg [n, neg_num], n_neg [n]) int32."""
     lib = _lib.load()
@@ -296,6 +338,7 @@ def triplet_mine(out, inn, thr, neg_num):
     return n_pos, neg, n_neg
 
 
+@_on_input_device
 def triplet_sample(pos_row, row_start, neg, n_neg, seed):
     """Counter-based negative choice per positive pair (r4d_triplet_sample): int32 [n_pairs]."""
     lib = _lib.load()
@@ -330,6 +373,7 @@ class DensePlanes:
                            self.prec)
 
 
+@_on_input_device
 def dense_prepare(x, prec=PREC_BF16X3):
     """fp32 [n, d] -> row-normalised bf16 planes.  r4d_dense_prepare."""
     lib = _lib.load()
@@ -343,6 +387,7 @@ def dense_prepare(x, prec=PREC_BF16X3):
     return DensePlanes(hi, lo, d, d_pad, prec)
 
 
+@_on_input_device
 def meanpool_prepare(hidden, prec=PREC_BF16X3, want_mean=False):
     """hidden fp32 [B, L, D] -> (DensePlanes of the L2-normalised mean over L, fp32 means or None).
     r4d_meanpool_prepare: replaces torch.mean(h, dim=1) + per-batch normalisation (train_retriever.py:420,433)."""
@@ -373,6 +418,7 @@ def _check_dense(q, p, q_time, p_time, mode):
             raise R4DError("dense: time vectors must have one entry per row")
 
 
+@_on_input_device
 def dense_topk(q, p, k, mode=DENSE_HALF_COS, q_time=None, p_time=None, lam=0.0, pool_base=0, workspace=None):
     """Fused tcgen05 contraction + epilogue + top-K: (score f32 [nq,k], idx int32 [nq,k]).  r4d_dense_topk."""
     lib = _lib.load()
@@ -391,6 +437,7 @@ def dense_topk(q, p, k, mode=DENSE_HALF_COS, q_time=None, p_time=None, lam=0.0, 
     return ts, ti
 
 
+@_on_input_device
 def dense_topk_scatter(q, p, k, peer_ptrs, world, rank, mode=DENSE_HALF_COS, q_time=None, p_time=None, lam=0.0,
                        pool_base=0, workspace=None):
     """Fused exchange for the dense scorer: peers' buffers are [2][world][nq][k] (float32 scores, int32 indices).
@@ -407,6 +454,7 @@ def dense_topk_scatter(q, p, k, peer_ptrs, world, rank, mode=DENSE_HALF_COS, q_t
     _count(2 if nq and np_ else (1 if nq else 0))
 
 
+@_on_input_device
 def dense_full(q, p, mode=DENSE_HALF_COS, q_time=None, p_time=None, lam=0.0):
     """Full score rows f32 [nq, np].  r4d_dense_full."""
     lib = _lib.load()
@@ -419,6 +467,7 @@ def dense_full(q, p, mode=DENSE_HALF_COS, q_time=None, p_time=None, lam=0.0):
     return scores
 
 
+@_on_input_device
 def dense_topk_merge(score, idx, k_out):
     """Merge [n_lists, nq, k_in] dense candidate lists -> [nq, k_out]."""
     lib = _lib.load()

@@ -1,0 +1,128 @@
+"""Retrieval pool resident in HBM + the top-K call a user makes against it (Jaccard scorer).
+
+`JaccardPool` holds the state of one pool (shard): the bitsets (storage of record; the bitset kernels serve dense sets
+and full matrices), the cardinalities and — when the universe fits (n_bits <= 65 535) — the postings index that the
+sparse-set top-K path walks (r4d_postings_build).  It replaces what the reference rebuilds for every pair: `set(seq_j)`
+of every pool sample inside co_occurrence_ratio (retrieval_data_annotation.py:12-13).
+
+`topk` is the device-resident call; `HostTopK` is the same call for HOST buffers: the step's query id lists arrive in
+pinned host memory, results land in pinned host memory, and consecutive steps overlap (step i's device->host copy runs
+on a copy stream while step i+1 is scored).
+"""
+import torch
+
+from . import _lib, engine
+from ._lib import R4DError
+
+POSTINGS_MAX_BITS = 65535
+
+
+class JaccardPool:
+    def __init__(self, bits, pool_base=0, postings="auto"):
+        """bits: BitsetMatrix of the pool (shard) on the GPU.  postings: "auto" | True | False."""
+        self.bits = bits
+        self.pool_base = int(pool_base)
+        self.index = None
+        want = postings is True or (postings == "auto" and bits.n_bits <= POSTINGS_MAX_BITS)
+        if want:
+            try:
+                self.index = engine.build_postings(bits)
+            except R4DError:
+                if postings is True:
+                    raise
+        self._ws = None
+
+    @classmethod
+    def from_csr(cls, bit_pos, row_off, n_bits, device="cuda", pool_base=0, postings="auto"):
+        """Host CSR id lists (duplicates allowed) -> pool state in HBM (H2D + set encoder + postings build)."""
+        from . import set_encoder
+        return cls(set_encoder.encode_csr(bit_pos, row_off, n_bits, device), pool_base, postings)
+
+    @property
+    def n_rows(self):
+        return self.bits.n_rows
+
+    @property
+    def device(self):
+        return self.bits.bits.device
+
+    def workspace(self, nq, k):
+        lib = _lib.load()
+        need = (lib.r4d_jaccard_topk_postings_workspace_bytes(nq) if self.index is not None
+                else lib.r4d_jaccard_topk_workspace_bytes(nq, self.n_rows, k))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty((need,), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def topk(self, q_ids, q_off, k, zero_diag=False, query_base=0, out=None):
+        """Queries as CSR id lists on the device -> (inter, union, idx) int32 [nq, k], canonical order, GLOBAL indices.
+        Sparse path (postings) when the index exists, else set encoder + bitset kernels."""
+        nq = q_off.numel() - 1
+        if self.index is not None:
+            return engine.jaccard_topk_postings(q_ids, q_off, self.index, k, zero_diag=zero_diag, query_base=query_base,
+                                                pool_base=self.pool_base, workspace=self.workspace(nq, k), out=out)
+        q = engine.encode_bitsets(q_ids, q_off, self.bits.n_bits)
+        r = engine.jaccard_topk(q, self.bits, k, zero_diag=zero_diag, query_base=query_base, pool_base=self.pool_base,
+                                workspace=self.workspace(nq, k))
+        if out is not None:
+            for o, t in zip(out, r):
+                o.copy_(t)
+            return out
+        return r
+
+
+class HostTopK:
+    """Pipelined host-buffer front end of JaccardPool.topk: submit(q_ids, q_off) enqueues H2D -> top-K -> D2H and
+    returns a ticket; result(ticket) waits for that step only.  `depth` steps may be in flight (their buffers are
+    separate), so the copies of one step overlap the scoring of the next."""
+
+    def __init__(self, pool, k, max_queries, max_ids, depth=2):
+        self.pool, self.k, self.depth = pool, int(k), int(depth)
+        dev = pool.device
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.slots = []
+        for _ in range(self.depth):
+            self.slots.append({
+                "ids": torch.empty((max(1, max_ids),), dtype=torch.int32, device=dev),
+                "off": torch.empty((max_queries + 1,), dtype=torch.int64, device=dev),
+                "out": tuple(torch.empty((max_queries, self.k), dtype=torch.int32, device=dev) for _ in range(3)),
+                "host": tuple(torch.empty((max_queries, self.k), dtype=torch.int32).pin_memory() for _ in range(3)),
+                "scored": torch.cuda.Event(), "done": torch.cuda.Event(), "nq": 0, "busy": False,
+            })
+        self.step = 0
+
+    def submit(self, q_ids, q_off, zero_diag=False, query_base=0):
+        """q_ids int32 [nnz], q_off int64 [nq+1]: CPU tensors (pinned for an asynchronous copy)."""
+        s = self.slots[self.step % self.depth]
+        if s["busy"]:
+            raise R4DError("HostTopK: more than `depth` steps in flight; collect result() first")
+        nq, nnz = q_off.numel() - 1, q_ids.numel()
+        if nq > s["off"].numel() - 1 or nnz > s["ids"].numel():
+            raise R4DError("HostTopK: step larger than the buffers this object was created with")
+        ids, off = s["ids"][:max(nnz, 1)], s["off"][:nq + 1]
+        if nnz:
+            ids[:nnz].copy_(q_ids, non_blocking=True)
+        off.copy_(q_off, non_blocking=True)
+        out = tuple(o[:nq] for o in s["out"])
+        self.pool.topk(ids, off, self.k, zero_diag=zero_diag, query_base=query_base, out=out)
+        s["scored"].record()
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(s["scored"])
+            for h, o in zip(s["host"], out):
+                h[:nq].copy_(o, non_blocking=True)
+            s["done"].record()
+        s["nq"], s["busy"] = nq, True
+        ticket = self.step
+        self.step += 1
+        return ticket
+
+    def result(self, ticket):
+        s = self.slots[ticket % self.depth]
+        s["done"].synchronize()
+        s["busy"] = False
+        # the compute stream may reuse this slot's device buffers only after the copy has read them
+        torch.cuda.current_stream().wait_event(s["done"])
+        return tuple(h[:s["nq"]] for h in s["host"])
+
+    def bytes_per_step(self, nq, nnz):
+        return nnz * 4 + (nq + 1) * 8, nq * self.k * 12

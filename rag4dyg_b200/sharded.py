@@ -1,7 +1,11 @@
-"""Pool sharding across the GPUs of one node.
+"""Sharding across the GPUs of one node.
 
-One process per GPU.  The pool is split row-wise into `world` contiguous shards (pool_base = first global row of the
-shard); queries are replicated; every rank runs the fused scorer + top-K on its shard; ONE exchange follows: an
+One process per GPU.  Two ways to split the path:
+* QUERY sharding (`query_shard`, `jaccard_topk_query_sharded`): the pool state is replicated (C4: 2.56 GB of bitsets +
+  a 28 MB postings index per GPU), every rank scores its own contiguous slice of the queries; there is no data-path
+  collective at all (an optional all-gather returns the whole [Q, K] result to every rank).  The choice for Q >> N/G.
+* POOL sharding (everything else in this file): for pools that do not fit one GPU.  The pool is split row-wise into
+`world` contiguous shards (pool_base = first global row of the shard); queries are replicated; every rank runs the fused scorer + top-K on its shard; ONE exchange follows: an
 all-gather of the per-shard [Q, K] candidate lists (NCCL over NVLink/NVSwitch, gloo in CPU tests), then a local merge
 with the same exact comparator and (score desc, global index asc) tie rule, so the result does not depend on `world`.
 The reference has no multi-GPU code on this path (its DDP/DataParallel paths only wrap model training).
@@ -77,6 +81,50 @@ class P2PExchange:
         b = self.step & 1
         self.step += 1
         return self.bufs[b], self.hdls[b], self.ptrs[b]
+
+
+def query_shard(q_ids, q_off, rank=None, world=None):
+    """This rank's contiguous slice of CSR queries: (ids, offsets rebased to 0, first global query row)."""
+    nq = q_off.numel() - 1
+    a, b = my_shard(nq, rank, world)
+    o = q_off[a:b + 1]
+    return q_ids[int(o[0]):int(o[-1])].contiguous(), (o - o[0]).contiguous(), a
+
+
+def jaccard_topk_query_sharded(pool, q_ids, q_off, k, zero_diag=False, gather=False, group=None):
+    """Query-sharded Jaccard top-K.  pool: a JaccardPool holding the WHOLE pool on this rank; q_ids/q_off: the FULL
+    query set (CSR, CUDA tensors, the same on every rank).  Every rank scores rows my_shard(nq); returns its
+    (inter, union, idx) [Q/world, K] and the first global query row, or — gather=True — the whole [Q, K] result on
+    every rank (one all-gather of the outputs; needs equal slices, i.e. nq divisible by world)."""
+    ids, off, first = query_shard(q_ids, q_off, None if dist.is_initialized() else 0, None if dist.is_initialized() else 1)
+    parts = pool.topk(ids, off, k, zero_diag=zero_diag, query_base=first)
+    if not gather or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return parts, first
+    world = dist.get_world_size(group)
+    if (q_off.numel() - 1) % world:
+        raise engine.R4DError("jaccard_topk_query_sharded(gather=True): the query count must be divisible by the world size")
+    g = gather_candidates(parts, group)
+    return tuple(t.reshape(-1, t.shape[-1]) for t in g), 0
+
+
+def jaccard_pool_topk_sharded(pool_shard, q_ids, q_off, k, zero_diag=False, query_base=0, group=None, exchange=None):
+    """Pool-sharded Jaccard top-K over a JaccardPool shard (pool_shard.pool_base = first global row of the shard),
+    queries as CSR id lists replicated on every rank.  Local fused top-K (postings path when the shard has an index),
+    ONE exchange of [Q, K] candidates, merge.  exchange: a P2PExchange(nq, k, 3) selects the fused NVLink path (the
+    top-K kernel itself stores into every peer's gather buffer)."""
+    nq = q_off.numel() - 1
+    if exchange is not None and pool_shard.index is not None:
+        buf, hdl, ptrs = exchange.next()
+        engine.jaccard_topk_postings_scatter(q_ids, q_off, pool_shard.index, k, ptrs, exchange.world, exchange.rank,
+                                             zero_diag=zero_diag, query_base=query_base, pool_base=pool_shard.pool_base,
+                                             workspace=pool_shard.workspace(nq, k))
+        hdl.barrier()
+        return engine.jaccard_topk_merge(buf[0], buf[1], buf[2], k)
+    parts = pool_shard.topk(q_ids, q_off, k, zero_diag=zero_diag, query_base=query_base)
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return parts
+    gi, gu, gx = gather_candidates(parts, group)
+    return engine.jaccard_topk_merge(gi, gu, gx, k)
 
 
 def jaccard_topk_sharded(q, p_shard, k, pool_base, zero_diag=False, query_base=0, group=None, workspace=None,

@@ -69,6 +69,10 @@ def write_float_rows(path, mat, fmt=fmt_str, mode="w"):
     mat = np.asarray(mat)
     if mat.ndim != 2:
         raise ValueError("write_float_rows expects a 2-D array")
+    if mat.shape[1] == 0:                     # empty pool: ' '.join([]) + '\n' per row, like the reference
+        with open(path, mode + "b") as f:
+            f.write(b"\n" * mat.shape[0])
+        return
     codes, strings = _float_codes(mat, fmt)
     codes = np.ascontiguousarray(codes, dtype=np.int32)
     enc = [s.encode("ascii") for s in strings.tolist()]

@@ -94,3 +94,19 @@ def test_malformed_input_is_an_error(tmp_path):
         p.write_bytes(payload)
         with pytest.raises(_lib.R4DError):
             readers.read_float_rows(str(p))
+
+
+def test_line_structure_follows_python_text_mode_and_splitlines(tmp_path):
+    """Bare \\r, \\v, \\f, \\x1c-\\x1e end a line; \\x1f separates fields; non-ASCII bytes are rejected."""
+    p = tmp_path / "t.txt"
+    raw = b"1 2\r3 4\x0b5\x0c6 7\x1c8\x1d9\x1e10\x1f11 12\r\n\r\n13\n"
+    p.write_bytes(raw)
+    with open(p, encoding="utf-8") as f:                 # the reference's read: universal newlines, then splitlines()
+        text = f.read()
+    got = readers.read_int_rows(str(p))
+    assert readers.as_lists(got) == _ref_parse(text, int)
+    assert readers.as_lists(got) == [[1, 2], [3, 4], [5], [6, 7], [8], [9], [10, 11, 12], [13]]
+    for payload in ("1 2\x853\n".encode("utf-8"), "1 2\n".encode("utf-8"), "1\xa02\n".encode("utf-8")):
+        p.write_bytes(payload)
+        with pytest.raises(_lib.R4DError):
+            readers.read_int_rows(str(p))

@@ -81,3 +81,55 @@ def test_two_rank_gather_and_merge_matches_unsharded_oracle():
         assert pr.exitcode == 0
     ri, ru, rx = jo.c_topk(*to_csr(q), *to_csr(p), k)
     assert np.array_equal(ox, rx) and np.array_equal(oi, ri) and np.array_equal(ou, ru)
+
+
+class _OraclePool:
+    """Stand-in for JaccardPool on CPU (the scorer has no CPU implementation): same .topk signature, oracle inside."""
+
+    def __init__(self, p):
+        self.p = to_csr(p)
+
+    def topk(self, q_ids, q_off, k, zero_diag=False, query_base=0, out=None):
+        li, lu, lx = jo.c_topk(q_ids.numpy(), q_off.numpy(), *self.p, k, zero_diag=zero_diag, query_base=query_base)
+        return (torch.from_numpy(li.astype(np.int32)), torch.from_numpy(lu.astype(np.int32)), torch.from_numpy(lx))
+
+
+def _qworker(rank, world, port, q, p, k, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        qi, qo = to_csr(q)
+        qi, qo = torch.from_numpy(qi), torch.from_numpy(qo)
+        ids, off, first = sharded.query_shard(qi, qo)
+        a, b = sharded.my_shard(len(q))
+        assert first == a and off.numel() == b - a + 1 and int(off[0]) == 0 and int(off[-1]) == ids.numel()
+        # train x train with the diagonal zeroed: the slice must carry its global query row (query_base)
+        (gi, gu, gx), base = sharded.jaccard_topk_query_sharded(_OraclePool(p), qi, qo, k, zero_diag=True, gather=True)
+        assert base == 0 and gx.shape == (len(q), k)
+        if rank == 0:
+            ret.put((gi.numpy(), gu.numpy(), gx.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_query_sharding_matches_unsharded_oracle():
+    rng = np.random.default_rng(43)
+    p = random_sets(rng, 300, 150, mean=3, p_empty=0.05)
+    q = p[:64]                                   # queries = pool rows: zero_diag needs the global row of every query
+    k = 10
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    procs = [ctx.Process(target=_qworker, args=(r, 2, port, q, p, k, ret)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    gi, gu, gx = ret.get(timeout=120)
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    ri, ru, rx = jo.c_topk(*to_csr(q), *to_csr(p), k, zero_diag=True)
+    assert np.array_equal(gx, rx) and np.array_equal(gi, ri) and np.array_equal(gu, ru)

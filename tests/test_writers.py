@@ -47,3 +47,12 @@ def test_empty(tmp_path):
     assert p.read_text() == ""
     writers.write_int_rows(str(p), np.zeros((2, 0), dtype=np.int32))
     assert p.read_text() == "\n\n"
+
+
+def test_float_rows_with_zero_columns(tmp_path):
+    """An empty pool: the reference writes ' '.join([]) + '\\n' per query row; index and score files must agree."""
+    p = tmp_path / "z.txt"
+    writers.write_float_rows(str(p), np.zeros((3, 0), dtype=np.float64))
+    assert p.read_text() == "\n\n\n"
+    writers.write_float_rows(str(p), np.zeros((0, 0), dtype=np.float64))
+    assert p.read_text() == ""

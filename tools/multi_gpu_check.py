@@ -41,6 +41,22 @@ def main():
         oi, ou, ox = jo.c_topk(*to_csr(q[:200]), *to_csr(p), k)
         ok &= np.array_equal(got[2][:200].cpu().numpy(), ox) and np.array_equal(got[0][:200].cpu().numpy(), oi)
         print(f"[multi_gpu_check] world={world} jaccard sharded == single-GPU == oracle: {ok}", flush=True)
+    # postings path: pool-sharded over NCCL, and query-sharded (pool replicated, no collective, outputs gathered)
+    from rag4dyg_b200.jaccard_pool import JaccardPool
+    qi, qo = to_csr(q)
+    dqi, dqo = torch.as_tensor(qi).to(dev), torch.as_tensor(qo).to(dev)
+    shard = JaccardPool.from_csr(*to_csr(p[lo:hi]), n_bits, dev, pool_base=lo, postings=True)
+    got_p = sharded.jaccard_pool_topk_sharded(shard, dqi, dqo, k)
+    same_p = all(torch.equal(a, b) for a, b in zip(got, got_p))
+    ok &= same_p
+    print(f"[multi_gpu_check] world={world} rank={rank} postings pool-sharded (NCCL) == single-GPU: {same_p}", flush=True)
+    nq_even = nq - nq % world
+    whole = JaccardPool.from_csr(*to_csr(p), n_bits, dev, postings=True)
+    eqi, eqo = to_csr(q[:nq_even])
+    got_q, _ = sharded.jaccard_topk_query_sharded(whole, torch.as_tensor(eqi).to(dev), torch.as_tensor(eqo).to(dev), k, gather=True)
+    same_q = all(torch.equal(a[:nq_even], b) for a, b in zip(got, got_q))
+    ok &= same_q
+    print(f"[multi_gpu_check] world={world} rank={rank} query-sharded == single-GPU == oracle: {same_q}", flush=True)
     # fused exchange: final lists stored into every peer's buffer over NVLink, one barrier, local merge
     p2p_ok = True
     try:
@@ -49,6 +65,10 @@ def main():
             got2 = sharded.jaccard_topk_sharded(bq, bp_shard, k, pool_base=lo, exchange=ex)
             p2p_ok &= all(torch.equal(a, b) for a, b in zip(got, got2))
         print(f"[multi_gpu_check] world={world} rank={rank} jaccard fused P2P exchange == NCCL path: {p2p_ok}", flush=True)
+        for _ in range(3):
+            got3 = sharded.jaccard_pool_topk_sharded(shard, dqi, dqo, k, exchange=ex)
+            p2p_ok &= all(torch.equal(a, b) for a, b in zip(got, got3))
+        print(f"[multi_gpu_check] world={world} rank={rank} postings fused P2P exchange == NCCL path: {p2p_ok}", flush=True)
     except Exception as e:  # symmetric memory unavailable on this box: report, do not fail the NCCL verdict
         print(f"[multi_gpu_check] world={world} rank={rank} fused P2P exchange unavailable: {type(e).__name__}: {e}", flush=True)
         ex = None
