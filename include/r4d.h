@@ -192,6 +192,29 @@ int r4d_triplet_mine_f64(const double* out, const double* in, int64_t n, int64_t
                          int32_t neg_num, int32_t* n_pos, int32_t* neg /*[n][neg_num]*/, int32_t* n_neg,
                          r4d_stream_t stream);
 
+/* The same mining straight from the OUT (label) and IN (history) BITSETS of the train pool — no [n, n] matrix in HBM
+ * (replaces occurrence_matrix x 2 + the loop of retrieval_data_annotation.py:53-71 in one pass).
+ * zero_diag != 0 forces both scores of the pairs (i, i) to 0, as :172-173 does before the mining.
+ *   positives: every (i, j) with out[i,j] > thr is APPENDED, in no particular order, as
+ *              pos_key[t] = i << 32 | j and pos_counts[t] = |A_i n A_j| << 32 | |A_i u A_j| (OUT sets), t < pos_cap;
+ *              *pos_total [dev] receives the number of positives found (if > pos_cap: call again with larger buffers);
+ *              n_pos[i] their number per row.  Sorting the keys gives np.where's row-major order (:54).
+ *   negatives: neg / n_neg as r4d_triplet_mine_f64, plus the OUT counts of every negative (neg_inter, neg_union
+ *              [n][neg_num]; 0 / 1 for unused slots), so that out[i, neg] = neg_inter / neg_union needs no matrix.
+ * Scores compare as exact rationals; out[i,j] > thr is evaluated on double(inter) / double(union) like the reference.
+ * Bitset rows as produced by r4d_bitset_encode (16-byte aligned, pitch a multiple of 4 words, zero padded). */
+int r4d_triplet_mine(const uint32_t* obits, const uint32_t* ocard, int32_t owords, int32_t opitch, const uint32_t* ibits,
+                     const uint32_t* icard, int32_t iwords, int32_t ipitch, int64_t n, double thr, int32_t neg_num,
+                     int32_t zero_diag, int32_t* n_pos, int64_t* pos_key, int64_t* pos_counts, int64_t pos_cap,
+                     int64_t* pos_total, int32_t* neg, uint32_t* neg_inter, uint32_t* neg_union, int32_t* n_neg,
+                     r4d_stream_t stream);
+
+/* HOST function (no GPU work): replays `n_calls` consecutive np.random.choice(a) calls (:79) of numpy's legacy global
+ * RandomState on its MT19937 state — key[624] and *pos as returned by np.random.get_state() — for arrays of
+ * sizes[t] >= 1 elements: choice[t] = the index numpy would pick; key / *pos are advanced exactly as numpy advances
+ * them (a one-element array consumes no randomness; otherwise masked rejection sampling on 32-bit outputs). */
+int r4d_mt19937_choice_replay(uint32_t* key, int32_t* pos, const int32_t* sizes, int64_t n_calls, int32_t* choice);
+
 /* Counter-based replacement of the sequential np.random.choice (:79) — NOT bit-compatible with numpy's RNG, offered
  * as the deterministic device-side mode of SURVEY.md 8f-2.  For positive pair t (row pos_row[t], its rank within the
  * row = t - row_start[row]): choice[t] = neg[row][splitmix64(seed, row, rank) % n_neg[row]] (or -1 if n_neg == 0).

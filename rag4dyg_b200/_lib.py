@@ -56,6 +56,9 @@ PROTOTYPES = {
     "r4d_rank_rows_f32": (_c.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _sz, _vp]),
     "r4d_topk_rows_f64": (_c.c_int, [_vp, _i64, _i64, _i64, _i32, _vp, _vp, _vp]),
     "r4d_triplet_mine_f64": (_c.c_int, [_vp, _vp, _i64, _i64, _f64, _i32, _vp, _vp, _vp, _vp]),
+    "r4d_triplet_mine": (_c.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _i32, _i32, _i64, _f64, _i32, _i32, _vp, _vp, _vp, _i64, _vp,
+                                    _vp, _vp, _vp, _vp, _vp]),
+    "r4d_mt19937_choice_replay": (_c.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "r4d_triplet_sample": (_c.c_int, [_vp, _vp, _i64, _vp, _vp, _i32, _c.c_uint64, _vp, _vp]),
     "r4d_dense_dpad": (_i32, [_i32]),
     "r4d_dense_prepare": (_c.c_int, [_vp, _i64, _i32, _i64, _i32, _vp, _vp, _vp]),

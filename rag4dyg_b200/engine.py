@@ -15,7 +15,7 @@ from ._lib import (DENSE_COS_DECAY, DENSE_HALF_COS, DENSE_HALF_COS_DECAY, PREC_B
 __all__ = [
     "BitsetMatrix", "encode_bitsets", "jaccard_full", "jaccard_topk", "jaccard_topk_merge", "jaccard_topk_scatter", "dense_topk_scatter", "rank_rows", "topk_rows",
     "PostingsIndex", "build_postings", "jaccard_topk_postings", "jaccard_topk_postings_scatter",
-    "triplet_mine", "triplet_sample", "DensePlanes", "dense_prepare", "dense_topk", "dense_full", "dense_topk_merge", "meanpool_prepare", "R4D_IDX_NONE",
+    "triplet_mine", "triplet_mine_bits", "triplet_sample", "DensePlanes", "dense_prepare", "dense_topk", "dense_full", "dense_topk_merge", "meanpool_prepare", "R4D_IDX_NONE",
     "R4D_TOPK_MAX", "DENSE_HALF_COS", "DENSE_COS_DECAY", "DENSE_HALF_COS_DECAY", "PREC_BF16", "PREC_BF16X3",
     "launch_count", "reset_launch_count",
 ]
@@ -336,6 +336,38 @@ def triplet_mine(out, inn, thr, neg_num):
                                    _stream()), "r4d_triplet_mine_f64")
     _count(1 if n else 0)
     return n_pos, neg, n_neg
+
+
+@_on_input_device
+def triplet_mine_bits(b_out, b_in, thr, neg_num, zero_diag=True, pos_cap=None):
+    """save_train_annotation's device half from the OUT / IN bitsets of the train pool (r4d_triplet_mine; no [n, n] matrix).
+    Returns a dict: n_pos [n], pos_row / pos_col [P] (row-major order, like np.where per row), pos_inter / pos_union [P]
+    (OUT counts), neg / neg_inter / neg_union [n, neg_num], n_neg [n].  Synchronises once (number of positives)."""
+    lib = _lib.load()
+    n = b_out.n_rows
+    if b_in.n_rows != n:
+        raise R4DError("triplet_mine_bits: the OUT and IN bitsets must describe the same rows")
+    dev = b_out.bits.device
+    i32 = dict(dtype=torch.int32, device=dev)
+    n_pos, n_neg = torch.empty((n,), **i32), torch.empty((n,), **i32)
+    neg, neg_i, neg_u = (torch.empty((n, neg_num), **i32) for _ in range(3))
+    total = torch.zeros((1,), dtype=torch.int64, device=dev)
+    cap = int(pos_cap) if pos_cap is not None else max(1 << 16, 16 * n)
+    while True:
+        key = torch.empty((max(cap, 1),), dtype=torch.int64, device=dev)
+        cnt = torch.empty((max(cap, 1),), dtype=torch.int64, device=dev)
+        check(lib.r4d_triplet_mine(_ptr(b_out.bits), _ptr(b_out.card), b_out.words, b_out.pitch_words, _ptr(b_in.bits),
+                                   _ptr(b_in.card), b_in.words, b_in.pitch_words, n, float(thr), neg_num,
+                                   int(bool(zero_diag)), _ptr(n_pos), _ptr(key), _ptr(cnt), cap, _ptr(total), _ptr(neg),
+                                   _ptr(neg_i), _ptr(neg_u), _ptr(n_neg), _stream()), "r4d_triplet_mine")
+        found = int(total.item())
+        if found <= cap:
+            break
+        cap = found                                   # rare: more positives than the first guess; mine again
+    key, order = torch.sort(key[:found])
+    cnt = cnt[:found][order]
+    return {"n_pos": n_pos, "pos_row": key >> 32, "pos_col": key & 0xFFFFFFFF, "pos_inter": cnt >> 32,
+            "pos_union": cnt & 0xFFFFFFFF, "neg": neg, "neg_inter": neg_i, "neg_union": neg_u, "n_neg": n_neg}
 
 
 @_on_input_device

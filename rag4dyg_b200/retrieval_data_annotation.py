@@ -87,28 +87,43 @@ def _to_device_f64(m):
     return torch.from_numpy(np.ascontiguousarray(m, dtype=np.float64)).to(_DEVICE)
 
 
+def _replay_choice(sizes):
+    """np.random.choice(a) for consecutive arrays of the given lengths, on numpy's legacy GLOBAL RandomState: returns
+    the chosen positions and leaves the global stream exactly where the reference's per-triplet calls (:79) would
+    (r4d_mt19937_choice_replay; one native loop instead of one Python call per triplet)."""
+    import ctypes
+    from . import _lib
+    sizes = np.ascontiguousarray(sizes, dtype=np.int32)
+    if sizes.size and int(sizes.min()) <= 0:
+        raise ValueError("'a' cannot be empty unless no samples are taken")   # np.random.choice([]) in the reference
+    st = np.random.get_state()
+    if st[0] != "MT19937":
+        raise _lib.R4DError(f"unsupported global bit generator {st[0]!r}")
+    key = np.array(st[1], dtype=np.uint32)
+    pos = ctypes.c_int32(int(st[2]))
+    pick = np.empty(sizes.size, dtype=np.int32)
+    _lib.check(_lib.load().r4d_mt19937_choice_replay(key.ctypes.data, ctypes.addressof(pos), sizes.ctypes.data, sizes.size,
+                                                     pick.ctypes.data), "r4d_mt19937_choice_replay")
+    np.random.set_state((st[0], key, pos.value, st[3], st[4]))
+    return pick
+
+
 def _write_triplets(save_file, save_file_score, n_rows, pos_rows, pos_cols, pos_scores, neg, n_neg, neg_scores):
-    """Host tail of save_train_annotation: dialog truncation, np.random.choice replay, text output (:72-85)."""
-    cnt = 0
+    """Host tail of save_train_annotation: dialog truncation, np.random.choice replay, text output (:72-85).
+    pos_* list the positives in row-major order; neg / neg_scores [n, neg_num], n_neg [n]."""
     is_dialog = "dialog" in dataset  # noqa: F821  module global set by main(), exactly like the reference (:73)
-    starts = np.searchsorted(pos_rows, np.arange(n_rows + 1))
-    with open(save_file, "w") as f, open(save_file_score, "w") as g:
-        for i in range(n_rows):
-            lo, hi = starts[i], starts[i + 1]
-            if hi == lo:
-                continue
-            if is_dialog:
-                hi = min(hi, lo + 4)
-            cand = neg[i, : n_neg[i]]
-            cand_scores = neg_scores[i]
-            for t in range(lo, hi):
-                neg_i = np.random.choice(cand)
-                s_neg = cand_scores[int(np.nonzero(cand == neg_i)[0][0])]
-                f.write(f"{i} {pos_cols[t]} {neg_i}\n")
-                g.write(f"{i} {writers.fmt_str(pos_scores[t])} {writers.fmt_str(s_neg)}\n")
-                cnt += 1
+    pos_rows = np.asarray(pos_rows, dtype=np.int64)
+    if is_dialog:                    # pos_indices[:4]: the first four positives of every row
+        starts = np.searchsorted(pos_rows, np.arange(n_rows + 1))
+        keep = (np.arange(pos_rows.size) - starts[pos_rows]) < 4
+        pos_rows, pos_cols, pos_scores = pos_rows[keep], np.asarray(pos_cols)[keep], np.asarray(pos_scores)[keep]
+    pick = _replay_choice(np.asarray(n_neg)[pos_rows])          # one np.random.choice per written triplet, in file order
+    neg_i = np.asarray(neg)[pos_rows, pick]
+    s_neg = np.asarray(neg_scores)[pos_rows, pick]
+    writers.write_int_rows(save_file, np.stack([pos_rows, np.asarray(pos_cols, dtype=np.int64), neg_i.astype(np.int64)], axis=1))
+    writers.write_triplet_scores(save_file_score, pos_rows, pos_scores, s_neg)
     print("Number of original instances:", n_rows)
-    print("Number of positive samples:", cnt)
+    print("Number of positive samples:", int(pos_rows.size))
 
 
 def _device_sampled_triplets(out_d, pos, neg, n_neg, save_file, save_file_score, seed):
@@ -230,14 +245,16 @@ def annotate(dataset_name, timestamp, threshold, neg_num=5, topk=10, timing=None
     b_train_in = set_encoder.encode_sequences(train_in, uni_in, _DEVICE)
     tm.mark("universe+csr+encode")
 
-    # subsystem 2: Jaccard matrices (diagonals zeroed as :172-173)
-    _, s_train_out = engine.jaccard_full(b_train_out, b_train_out, zero_diag=True)
-    _, s_train_in = engine.jaccard_full(b_train_in, b_train_in, zero_diag=True)
-    tm.mark("jaccard train matrices (GPU)")
-    _mine_and_write(s_train_out, s_train_in, os.path.join(save_path, "train_index.retrieval"),
-                    os.path.join(save_path, "train_score.retrieval"), threshold, neg_num)
-    del s_train_in
-    tm.mark("triplet mining (GPU) + numpy RNG replay + write")
+    # subsystem 2 + triplets: positives and hard / fill negatives straight from the OUT and IN bitsets (both diagonals
+    # zeroed as :172-173); no [N, N] matrix exists at any point
+    m = engine.triplet_mine_bits(b_train_out, b_train_in, threshold, neg_num, zero_diag=True)
+    tm.mark("triplet mining from bitsets (GPU)")
+    _write_triplets(os.path.join(save_path, "train_index.retrieval"), os.path.join(save_path, "train_score.retrieval"),
+                    b_train_out.n_rows, m["pos_row"].cpu().numpy(), m["pos_col"].cpu().numpy(),
+                    writers.jaccard_scores_f64(m["pos_inter"].cpu().numpy(), m["pos_union"].cpu().numpy()),
+                    m["neg"].cpu().numpy(), m["n_neg"].cpu().numpy(),
+                    writers.jaccard_scores_f64(m["neg_inter"].cpu().numpy(), m["neg_union"].cpu().numpy()))
+    tm.mark("numpy RNG replay + write triplets")
 
     for name, b in (("test", b_test_out), ("val", b_val_out)):
         _, s = engine.jaccard_full(b, b_train_out, zero_diag=False)

@@ -74,8 +74,14 @@ def write_float_rows(path, mat, fmt=fmt_str, mode="w"):
             f.write(b"\n" * mat.shape[0])
         return
     codes, strings = _float_codes(mat, fmt)
+    write_lut_rows(path, codes, strings.tolist(), mode)
+
+
+def write_lut_rows(path, codes, strings, mode="w"):
+    """Rows of table entries: line r == ' '.join(strings[c] for c in codes[r]).  Assembled by r4d_format_lut_rows."""
+    lib = _lib.load()
     codes = np.ascontiguousarray(codes, dtype=np.int32)
-    enc = [s.encode("ascii") for s in strings.tolist()]
+    enc = [s.encode("ascii") for s in strings]
     off = np.zeros(len(enc) + 1, dtype=np.int64)
     np.cumsum([len(e) for e in enc], out=off[1:])
     blob = b"".join(enc)
@@ -93,6 +99,21 @@ def write_float_rows(path, mat, fmt=fmt_str, mode="w"):
             if got < 0:
                 raise _lib.R4DError(f"r4d_format_lut_rows failed ({got}): {_lib.last_error()}")
             f.write(memoryview(buf)[:got])
+
+
+def write_triplet_scores(path, rows, s_pos, s_neg, fmt=fmt_str):
+    """train_score.retrieval: one line f"{i} {out[i, pos]} {out[i, neg]}" per triplet (retrieval_data_annotation.py:81).
+    One table holds the decimal row numbers and every distinct score formatted once by `fmt`."""
+    rows = np.asarray(rows, dtype=np.int64)
+    scores = np.stack([np.asarray(s_pos, dtype=np.float64), np.asarray(s_neg, dtype=np.float64)], axis=1)
+    if rows.size == 0:
+        open(path, "w").close()
+        return
+    s_codes, s_strings = _float_codes(scores, fmt)
+    n_row_strings = int(rows.max()) + 1
+    table = [str(i) for i in range(n_row_strings)] + s_strings.tolist()
+    codes = np.concatenate([rows[:, None], s_codes + n_row_strings], axis=1)
+    write_lut_rows(path, codes, table)
 
 
 def jaccard_scores_f64(inter, union):

@@ -78,3 +78,41 @@ def test_triplet_mining(n, neg_num):
     for i in range(n):
         assert n_neg[i] == len(rn[i])
         assert neg[i, : n_neg[i]].tolist() == rn[i], i
+
+
+@pytest.mark.parametrize("n,vo,vi,mean_o,mean_i,thr,neg_num", [
+    (50, 40, 60, 2.0, 6.0, 0.8, 5),        # one anchor block + a ragged tile
+    (333, 120, 300, 2.2, 8.0, 0.8, 5),
+    (1000, 300, 2500, 1.5, 20.0, 0.8, 3),  # several 64-word chunks of history sets
+    (700, 30, 80, 2.0, 5.0, 0.3, 5),       # small universe: many positives and ties
+    (257, 64, 64, 3.0, 3.0, 0.0, 7),       # thr = 0: every intersecting pair is a positive -> fill negatives only
+])
+def test_triplet_mining_from_bitsets(n, vo, vi, mean_o, mean_i, thr, neg_num):
+    """r4d_triplet_mine (OUT / IN bitsets, no matrix) == the reference's walk on the float64 matrices (:53-71)."""
+    from conftest import random_sets, to_csr
+    from rag4dyg_b200 import set_encoder
+    rng = np.random.default_rng(n + neg_num)
+    s_out = random_sets(rng, n, vo, mean=mean_o, max_len=min(64, vo), p_empty=0.03, dup=True)
+    s_in = random_sets(rng, n, vi, mean=mean_i, max_len=min(64, vi), p_empty=0.01, dup=True)
+    s_out[5] = list(s_out[4])                  # identical label sets: score 1.0 both ways
+    out_m = jo.scores_from_counts(*jo.counts_matrix(s_out, s_out))
+    in_m = jo.scores_from_counts(*jo.counts_matrix(s_in, s_in))
+    np.fill_diagonal(out_m, 0)
+    np.fill_diagonal(in_m, 0)
+    b_out = set_encoder.encode_csr(*to_csr(s_out), vo)
+    b_in = set_encoder.encode_csr(*to_csr(s_in), vi)
+    for cap in (None, 7):                      # 7: the positives overflow the first buffer and the call is repeated
+        m = engine.triplet_mine_bits(b_out, b_in, thr, neg_num, zero_diag=True, pos_cap=cap)
+        rp, rn = ref_mine(out_m, in_m, thr, neg_num)
+        assert np.array_equal(m["n_pos"].cpu().numpy(), rp)
+        rows, cols = np.nonzero(out_m > thr)       # row-major, like np.where per row
+        assert np.array_equal(m["pos_row"].cpu().numpy(), rows) and np.array_equal(m["pos_col"].cpu().numpy(), cols)
+        pi, pu = m["pos_inter"].cpu().numpy(), m["pos_union"].cpu().numpy()
+        assert np.array_equal(pi / pu, out_m[rows, cols])                      # bit-identical float64 scores
+        neg, n_neg = m["neg"].cpu().numpy(), m["n_neg"].cpu().numpy()
+        ni, nu = m["neg_inter"].cpu().numpy(), m["neg_union"].cpu().numpy()
+        for i in range(n):
+            assert n_neg[i] == len(rn[i])
+            assert neg[i, : n_neg[i]].tolist() == rn[i], i
+            assert np.array_equal(ni[i, : n_neg[i]] / nu[i, : n_neg[i]], out_m[i, rn[i]])
+            assert (neg[i, n_neg[i]:] == -1).all()
