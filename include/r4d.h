@@ -41,8 +41,8 @@ typedef void* r4d_stream_t; /* cudaStream_t */
 #define R4D_DENSE_HALF_COS_DECAY 2 /* ((cos+1)/2) * exp(-lambda*|dt|)                              */
 /* dense contraction precision */
 #define R4D_PREC_BF16 0   /* one tcgen05 kind::f16 pass on bf16-rounded operands                  */
-#define R4D_PREC_BF16X3 1 /* hi/lo bf16 split of both operands, fp32 accumulate: hi.hi + hi.lo + lo.hi on the
-                             CTA-pair top-K kernel (k <= 16), all four products elsewhere; <= 1e-5 of fp32    */
+#define R4D_PREC_BF16X3 1 /* hi/lo bf16 split of both operands, three products (hi.hi + hi.lo + lo.hi), fp32
+                             accumulate: <= 1e-5 of the reference's fp32 scores                                */
 
 int r4d_version(void);
 const char* r4d_last_error(void);
@@ -264,6 +264,18 @@ int r4d_meanpool_prepare(const float* hidden, int64_t batch, int32_t len, int32_
 /* Merge [n_lists][nq][k_in] dense candidate lists into [nq][k_out] (score desc, index asc). */
 int r4d_dense_topk_merge(const float* score, const int32_t* idx, int32_t n_lists, int64_t nq, int32_t k_in,
                          int32_t k_out, float* out_score, int32_t* out_idx, r4d_stream_t stream);
+
+/* ---------------------------------------------------------------- device-side text assembly
+ * The same files (retrieval_data_annotation.py:88-103, train/train_retriever.py:357-368) assembled in HBM from device
+ * arrays: line q == ' '.join(field(vals[q][j]) for j in range(n)) + '\n', where field(v) = the decimal text of v
+ * (lut_off == NULL) or the string lut_blob[lut_off[v] : lut_off[v + 1]] of a caller-built table (one entry per distinct
+ * float, formatted by the reference's own formatter).  Two calls: _sizes fills row_off [nq + 1] (int64, dev; row_off[nq]
+ * = file size) and *status (dev, nullable: 1 if a code was out of range); the second writes row_off[nq] bytes to `text`
+ * (dev).  vals [nq][ld] int32, lut_blob / lut_off device pointers. */
+int r4d_format_rows_device_sizes(const int32_t* vals, int64_t nq, int64_t n, int64_t ld, const int64_t* lut_off,
+                                 int32_t n_codes, int64_t* row_off, int32_t* status, r4d_stream_t stream);
+int r4d_format_rows_device(const int32_t* vals, int64_t nq, int64_t n, int64_t ld, const char* lut_blob, const int64_t* lut_off,
+                           int32_t n_codes, const int64_t* row_off, char* text, r4d_stream_t stream);
 
 /* ---------------------------------------------------------------- host-side text formatters
  * [host] pointers.  Produce the exact bytes of ' '.join(str(x) for x in row) + '\n' per row

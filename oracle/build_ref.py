@@ -3,7 +3,7 @@
     python oracle/build_ref.py          (also run by __graft_entry__.build() when /root/reference is mounted)
 
 The reference's hot path is one pure-Python file, /root/reference/retrieval_data_annotation.py; "building" it is
-py_compile.  The result, oracle/_ref/retrieval_data_annotation.pyc, is a build output (git-ignored, travels to the GPU
+py_compile.  The result, oracle/_ref/retrieval_data_annotation.bytecode, is a build output (git-ignored, travels to the GPU
 box with the snapshot like the repo's own .so files); no reference SOURCE is copied into the repo.  bench.py's
 `--impl reference` arm and `cpu_baseline` leg import `occurrence_matrix` from it unchanged (oracle/ref_loader.py) and
 report kind = "reference"; tests use it to pin the restatement in oracle/jaccard_oracle.py.
@@ -27,7 +27,7 @@ def build(verbose=False):
         if not os.path.exists(src):
             continue
         os.makedirs(out_dir, exist_ok=True)
-        dst = os.path.join(out_dir, name + "c")
+        dst = os.path.join(out_dir, name[:-3] + ".bytecode")   # not "*.pyc": snapshot tools tend to drop those
         if not os.path.exists(dst) or os.path.getmtime(dst) < os.path.getmtime(src):
             py_compile.compile(src, cfile=dst, doraise=True)
         done.append(dst)

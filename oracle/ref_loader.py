@@ -13,7 +13,7 @@ def load(name="retrieval_data_annotation"):
     been built (the reference tree was not mounted at build time)."""
     if name in _cache:
         return _cache[name]
-    path = os.path.join(HERE, "_ref", name + ".pyc")
+    path = os.path.join(HERE, "_ref", name + ".bytecode")
     mod = None
     if os.path.exists(path):
         try:
@@ -21,7 +21,7 @@ def load(name="retrieval_data_annotation"):
             spec = importlib.util.spec_from_loader(loader.name, loader)
             mod = importlib.util.module_from_spec(spec)
             loader.exec_module(mod)
-        except Exception:   # e.g. a .pyc of another interpreter version
+        except Exception:   # e.g. bytecode of another interpreter version
             mod = None
     _cache[name] = mod
     return mod

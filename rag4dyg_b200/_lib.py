@@ -76,6 +76,8 @@ PROTOTYPES = {
     "r4d_format_int_rows_bound": (_sz, [_i64, _i64]),
     "r4d_format_int_rows": (_i64, [_vp, _i64, _i64, _i64, _vp, _sz]),
     "r4d_format_lut_rows": (_i64, [_vp, _i64, _i64, _i64, _vp, _vp, _i32, _vp, _sz]),
+    "r4d_format_rows_device_sizes": (_c.c_int, [_vp, _i64, _i64, _i64, _vp, _i32, _vp, _vp, _vp]),
+    "r4d_format_rows_device": (_c.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _i32, _vp, _vp, _vp]),
     "r4d_parse_rows_count": (_i64, [_vp, _sz, _vp]),
     "r4d_parse_int_rows": (_i64, [_vp, _sz, _vp, _vp, _i64, _i64]),
     "r4d_parse_float_rows": (_i64, [_vp, _sz, _vp, _vp, _i64, _i64]),

@@ -33,7 +33,7 @@ constexpr int D2_KMAX = 16;  // top-K width served by this kernel (wider K -> de
 struct Dense2Params {
     int64_t nq, np;
     int32_t n_kblocks;
-    int32_t n_segs;   // 1: bf16 single pass; 3: BF16X3 = q_hi.p_hi + q_hi.p_lo + q_lo.p_hi accumulated in the same TMEM tile
+    int32_t n_segs;   // 1: bf16 single pass; 3: BF16X3 = q_hi.p_hi + q_hi.p_lo + q_lo.p_hi per k-block, one TMEM tile
     int32_t mode;
     int32_t k;
     int32_t n_stages;
@@ -196,11 +196,12 @@ dense2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                                         qtile * DQ);
                 }
                 for (int pt = pt0; pt < pt_lim; pt += pt_step) {
-                    // split precision: segment 0 = q_hi.p_hi, 1 = q_hi.p_lo, 2 = q_lo.p_hi (streamed operands only)
-                    for (int seg = 0; seg < prm.n_segs; ++seg) {
-                        const CUtensorMap* mp = seg == 1 ? &tm_plo : &tm_p;
-                        const CUtensorMap* mq = seg == 2 ? &tm_qlo : &tm_q;
-                        for (int kb = 0; kb < prm.n_kblocks; ++kb) {
+                    // split precision: per k-block the products q_hi.p_hi, q_hi.p_lo, q_lo.p_hi in this order — the
+                    // same sequence of K = 16 MMA steps as dense.cu issues, so both kernels accumulate identically
+                    for (int kb = 0; kb < prm.n_kblocks; ++kb) {
+                        for (int seg = 0; seg < prm.n_segs; ++seg) {
+                            const CUtensorMap* mp = seg == 1 ? &tm_plo : &tm_p;
+                            const CUtensorMap* mq = seg == 2 ? &tm_qlo : &tm_q;
                             mbar_wait(&empty_bar[stage], phase ^ 1);
                             const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[stage]), 0);
                             const uint32_t sdst = smem_u32(stages + (size_t)stage * P_STAGE_BYTES);

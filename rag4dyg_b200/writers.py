@@ -116,6 +116,86 @@ def write_triplet_scores(path, rows, s_pos, s_neg, fmt=fmt_str):
     write_lut_rows(path, codes, table)
 
 
+# ---------------------------------------------------------------------------------------------- device-side assembly
+_PIN = {}     # two reusable pinned staging buffers per process (allocating pinned memory costs more than the copy)
+_PIN_BYTES = 32 << 20
+
+
+def _drain_to_file(f, text_dev):
+    """Device text -> file through two pinned staging buffers: the copy of chunk i + 1 overlaps the write of chunk i."""
+    import torch
+    if "bufs" not in _PIN:
+        _PIN["bufs"] = [torch.empty(_PIN_BYTES, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        _PIN["ev"] = [torch.cuda.Event() for _ in range(2)]
+    bufs, evs = _PIN["bufs"], _PIN["ev"]
+    total = text_dev.numel()
+    chunks = [(a, min(a + _PIN_BYTES, total)) for a in range(0, total, _PIN_BYTES)]
+    for i, (a, b) in enumerate(chunks[:1]):
+        bufs[0][:b - a].copy_(text_dev[a:b], non_blocking=True)
+        evs[0].record()
+    for i, (a, b) in enumerate(chunks):
+        if i + 1 < len(chunks):
+            a2, b2 = chunks[i + 1]
+            bufs[(i + 1) & 1][:b2 - a2].copy_(text_dev[a2:b2], non_blocking=True)
+            evs[(i + 1) & 1].record()
+        evs[i & 1].synchronize()
+        f.write(memoryview(bufs[i & 1].numpy())[:b - a])
+
+
+def _format_rows_device(vals, lut_blob=None, lut_off=None):
+    """int32 CUDA matrix (+ optional device string table) -> uint8 CUDA tensor holding the file's bytes."""
+    import torch
+    lib = _lib.load()
+    if not (isinstance(vals, torch.Tensor) and vals.is_cuda and vals.dtype == torch.int32 and vals.dim() == 2):
+        raise _lib.R4DError("device text assembly expects a 2-D int32 CUDA tensor")
+    vals = vals.contiguous()
+    nq, n = vals.shape
+    dev = vals.device
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream().cuda_stream
+        row_off = torch.empty((nq + 1,), dtype=torch.int64, device=dev)
+        status = torch.zeros((1,), dtype=torch.int32, device=dev)
+        n_codes = 0 if lut_off is None else lut_off.numel() - 1
+        p_off = 0 if lut_off is None else lut_off.data_ptr()
+        p_blob = 0 if lut_blob is None else lut_blob.data_ptr()
+        _lib.check(lib.r4d_format_rows_device_sizes(vals.data_ptr(), nq, n, n, p_off, n_codes, row_off.data_ptr(),
+                                                    status.data_ptr(), st), "r4d_format_rows_device_sizes")
+        total = int(row_off[-1].item())
+        if int(status.item()) != 0:
+            raise _lib.R4DError("device text assembly: a code lies outside the string table")
+        text = torch.empty((max(total, 1),), dtype=torch.uint8, device=dev)
+        _lib.check(lib.r4d_format_rows_device(vals.data_ptr(), nq, n, n, p_blob, p_off, n_codes, row_off.data_ptr(),
+                                              text.data_ptr(), st), "r4d_format_rows_device")
+    return text[:total]
+
+
+def write_int_rows_device(path, rows, mode="w"):
+    """write_int_rows for an int32 CUDA matrix: the text is assembled on the GPU (r4d_format_rows_device)."""
+    text = _format_rows_device(rows)
+    with open(path, mode + "b") as f:
+        _drain_to_file(f, text)
+
+
+def write_float_rows_device(path, mat, fmt=fmt_str, mode="w"):
+    """write_float_rows for a float64 / float32 CUDA matrix: distinct values are found on the device, each is formatted
+    once on the host with `fmt` (the reference's own formatter), the rows are assembled on the GPU."""
+    import torch
+    if mat.shape[1] == 0:
+        with open(path, mode + "b") as f:
+            f.write(b"\n" * mat.shape[0])
+        return
+    raw = mat.contiguous().view(torch.int64 if mat.dtype == torch.float64 else torch.int32)     # bit patterns: -0.0 != 0.0
+    uniq, inv = torch.unique(raw, return_inverse=True)
+    vals = uniq.cpu().numpy().view(np.float64 if mat.dtype == torch.float64 else np.float32)
+    enc = [fmt(v).encode("ascii") for v in vals]
+    off = np.zeros(len(enc) + 1, dtype=np.int64)
+    np.cumsum([len(e) for e in enc], out=off[1:])
+    blob = torch.frombuffer(bytearray(b"".join(enc) or b"\0"), dtype=torch.uint8).to(mat.device)
+    text = _format_rows_device(inv.to(torch.int32), blob, torch.from_numpy(off).to(mat.device))
+    with open(path, mode + "b") as f:
+        _drain_to_file(f, text)
+
+
 def jaccard_scores_f64(inter, union):
     """Exact float64 Jaccard from integer counts: identical to Python's len(inter)/len(union) (:14); 0/0 -> 0."""
     inter = np.asarray(inter).astype(np.float64)

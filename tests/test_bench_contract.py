@@ -24,7 +24,7 @@ def test_reference_arm_prints_one_json_line():
     assert d["config"]["workload"].startswith("synthetic Jaccard top-K")
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
-    if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "retrieval_data_annotation.pyc")):
+    if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "retrieval_data_annotation.bytecode")):
         assert cb["kind"] == "reference"          # the unmodified reference functions are what is timed
     assert cb["per_core"]["value"] > 0 and d["extrapolated"] is True and d["sample_pairs_per_step"] > 0
     import bench

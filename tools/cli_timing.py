@@ -12,7 +12,7 @@ from rag4dyg_b200 import retrieval_data_annotation as rda
 out = {}
 man = json.load(open(os.path.join(ROOT, "tests", "golden", "manifest.json")))
 torch.zeros(1, device="cuda"); torch.cuda.synchronize()       # CUDA context creation is not part of the stage
-for ds, T in (("UCI_13", "12"), ("hepth", "11"), ("dialog", "15"), ("UCI_13", "12")):
+for ds, T in (("UCI_13", "12"), ("hepth", "11"), ("dialog", "15"), ("UCI_13", "12"), ("hepth", "11"), ("dialog", "15")):
     with tempfile.TemporaryDirectory() as d:
         raw = lzma.decompress(open(os.path.join(ROOT, "tests", "golden", f"inputs_{ds}.tar.xz"), "rb").read())
         tarfile.open(fileobj=io.BytesIO(raw)).extractall(d, filter="data")
