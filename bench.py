@@ -352,11 +352,12 @@ def main():
 
     flush_buf = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
 
-    def timed(step_fn, sampler=None, steps=None, flush=False, keep_running_ms=1200.0):
+    def timed(step_fn, sampler=None, steps=None, flush=False, sampled=False, keep_running_ms=1200.0):
         """W warm-up steps, then `steps` (default K) timed steps between barrier+synchronize; device time by CUDA
         events on the launch stream, max over ranks.  flush=True: L2 is flushed before every timed step and each step
         has its own event pair (the flush is not timed); else one event pair brackets all steps (inputs larger than
-        L2).  Returns (ms summed over the steps, launches, clocks)."""
+        L2).  sampled=True on EVERY rank of a run whose rank 0 samples clocks (all ranks then run the same number of
+        extra steps and barriers).  Returns (ms summed over the steps, launches, clocks)."""
         n = K if steps is None else steps
         for i in range(W):
             step_fn(i)
@@ -380,7 +381,7 @@ def main():
         launches = engine.launch_count()
         ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev))
         clocks = None
-        if sampler:
+        if sampler or sampled:
             # nvidia-smi samples every 100 ms: when the timed region is shorter than ~1.2 s the SAME step keeps running
             # (untimed) until the sampler has seen that much load; the step count is derived from the max-over-ranks
             # time, so every rank runs the same number
@@ -390,6 +391,7 @@ def main():
                 for i in range(extra):
                     step_fn(W + n + i)
                 barrier()
+        if sampler:
             clocks = sampler.stop()
             clocks["sampled_over"] = (f"the {n} timed steps" if extra == 0 else
                                       f"the {n} timed steps + {extra} further identical steps run right after them "
@@ -429,7 +431,7 @@ def main():
             pool.topk(dq, do, TOPK, out=res)
 
         sampler = ClockSampler(local_rank) if rank == 0 else None
-        ms, launches, clocks = timed(step_resident, sampler, flush=True)
+        ms, launches, clocks = timed(step_resident, sampler, flush=True, sampled=True)
         pairs_per_step = nq * n_pool * world
         value = pairs_per_step * K / (ms * 1e-3)
         verified = {"headline": all_ranks_true(verify(res, q_ids, q_off, 0) and verify(res, q_ids, q_off, nq - 16))}
@@ -691,12 +693,12 @@ def main():
         peak_sust = peaks.get("bf16_tflops_sustained")
         hold = {}
 
-        def measure(qp, pool, mode, lam, steps, sampler=None):
+        def measure(qp, pool, mode, lam, steps, sampler=None, sampled=False):
             def dstep(i):
                 b = i % n_batches
                 hold["r"] = sharded.dense_topk_sharded(qp[b], pool, TOPK, pool_base=lo, mode=mode, q_time=q_times[b],
                                                        p_time=p_time, lam=lam, workspace=ws, exchange=dex)
-            return timed(dstep, sampler, steps=steps)
+            return timed(dstep, sampler, steps=steps, sampled=sampled)
 
         def kernel_ms(qp, pool, mode, lam, steps):
             _lib.set_option("kernel_timing", 1)
@@ -713,7 +715,7 @@ def main():
         mode = engine.DENSE_COS_DECAY
         # ---- headline dense line: the reference's precision (split bf16: q_hi.p_hi + q_hi.p_lo + q_lo.p_hi, fp32 accumulate)
         sampler = ClockSampler(local_rank) if rank == 0 else None
-        d_ms, d_launch, d_clocks = measure(q3, pool3, mode, DENSE_LAMBDA, K, sampler)
+        d_ms, d_launch, d_clocks = measure(q3, pool3, mode, DENSE_LAMBDA, K, sampler, sampled=True)
         d_value = pairs * K / (d_ms * 1e-3)
         # verified: 8 queries of the last batch x the first rows of this rank's shard vs the fp32 torch oracle (tolerance-aware)
         b_last = (W + K - 1) % n_batches
