@@ -6,24 +6,34 @@ position map reproduces the set algebra exactly, so the universe is simply "ever
 first-appearance order; with the shipped data that is the dataset vocabulary plus the T+1 time tokens.
 The device half (scatter-OR + popcount) is r4d_bitset_encode.
 """
+import itertools
+
 import numpy as np
 import torch
 
 from . import engine
 
 
+def _flatten(seqs):
+    """(flat token list, row lengths int64 [n]) of list[list[token]] with co_occurrence_ratio's argument quirks."""
+    rows = [_as_list(seq) for seq in seqs]
+    lens = np.fromiter((len(r) for r in rows), dtype=np.int64, count=len(rows))
+    return list(itertools.chain.from_iterable(rows)), lens
+
+
 class Universe:
-    """Injective token -> bit-position map shared by every list that will be compared."""
+    """Injective token -> bit-position map shared by every list that will be compared (first-appearance order)."""
 
     def __init__(self):
         self.pos = {}
 
     def add(self, seqs):
+        flat, _ = _flatten(seqs)
         pos = self.pos
-        for seq in seqs:
-            for tok in _as_list(seq):
-                if tok not in pos:
-                    pos[tok] = len(pos)
+        # dict.fromkeys: the distinct tokens in order of appearance, at C speed; the Python loop only sees DISTINCT tokens
+        for tok in dict.fromkeys(flat):
+            if tok not in pos:
+                pos[tok] = len(pos)
         return self
 
     @property
@@ -41,15 +51,14 @@ def _as_list(seq):
 
 
 def to_csr(seqs, universe):
-    """list[list[token]] -> (bit_pos int32 [nnz], row_off int64 [n+1]) numpy arrays (duplicates kept)."""
-    pos = universe.pos
-    row_off = np.zeros(len(seqs) + 1, dtype=np.int64)
-    flat = []
-    for i, seq in enumerate(seqs):
-        s = _as_list(seq)
-        flat.extend(pos[t] for t in s)
-        row_off[i + 1] = len(flat)
-    return np.asarray(flat, dtype=np.int32), row_off
+    """list[list[token]] -> (bit_pos int32 [nnz], row_off int64 [n+1]) numpy arrays (duplicates kept).
+    The per-token dict lookups run inside map() / np.fromiter (no Python-level loop body)."""
+    flat, lens = _flatten(seqs)
+    row_off = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens, out=row_off[1:])
+    if not flat:
+        return np.zeros(0, dtype=np.int32), row_off
+    return np.fromiter(map(universe.pos.__getitem__, flat), dtype=np.int32, count=len(flat)), row_off
 
 
 def encode_csr(bit_pos, row_off, n_bits, device="cuda"):
