@@ -307,6 +307,8 @@ def main():
 
     _lib.require_device()  # fail loudly: no CPU fallback
     torch.cuda.set_device(local_rank)
+    from rag4dyg_b200 import numa
+    placement = numa.bind_to_gpu_node(local_rank) if world > 1 else {"node": None, "why": "single process"}
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -505,10 +507,12 @@ def main():
             ep_ms = max_over_ranks(e0.elapsed_time(e1))
             h2d, d2h = hk.bytes_per_step(nq, int(q_ids.numel()))
             e2e = {"value": pairs_per_step * K / (e_ms * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d * world,
+                   "host_placement": placement,
                    "d2h_bytes_per_step": d2h * world, "ms_per_step": e_ms / K,
                    "what": "JaccardPool/HostTopK (the Python host API over the r4d C ABI), HOST buffers: the step's query CSR id "
-                           "lists in pinned host memory -> H2D -> fused Jaccard top-K over the pool's postings -> D2H of [Q,K] "
-                           "(inter, union, idx) into pinned host buffers, one step at a time, L2 flushed between steps; the pool "
+                           "lists in pinned host memory -> H2D -> fused Jaccard top-K over the pool's postings, four row ranges whose D2H "
+                           "of [Q,K] (inter, union, idx) into pinned host buffers overlaps the next range's scoring; one step at a "
+                           "time, L2 flushed between steps; the pool "
                            "(bitsets + postings index) is state resident in HBM, like the pool embeddings of the dense scorer",
                    "pipelined": {"value": pairs_per_step * K / (ep_ms * 1e-3), "unit": "pairs/s", "ms_per_step": ep_ms / K,
                                  "what": "same call, two steps in flight (step i's device->host copy overlaps step i+1's "

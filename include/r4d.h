@@ -147,7 +147,8 @@ int r4d_postings_build(const uint32_t* pbits, const uint32_t* pcard, int64_t np,
 
 /* Fused scorer + top-K over the postings.  Queries arrive as CSR id lists q_ids[q_off[q] .. q_off[q+1]) [dev] (ids outside
  * [0, n_bits) are ignored, duplicates inside a row collapse: Python set() semantics, retrieval_data_annotation.py:12-13);
- * no query bitsets are needed; q_nnz = q_off[nq] (length of q_ids, known to the host) only sizes the hash tables.
+ * no query bitsets are needed.  q_off may be a row range of a larger CSR (its values index q_ids absolutely);
+ * q_nnz = q_off[nq] - q_off[0], the number of ids of the nq rows (known to the host), only sizes the hash tables.
  * index / pcard / np / n_bits / nnz as given to r4d_postings_build.  Outputs as
  * r4d_jaccard_topk: [nq][k] exact counts + GLOBAL pool index pool_base+p, order (score desc, index asc), rows short of k
  * padded with (0, 1, R4D_IDX_NONE).  Any set size and skew is served exactly (queries too dense for the per-warp hash

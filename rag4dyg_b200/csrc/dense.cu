@@ -464,7 +464,7 @@ size_t r4d_dense_topk_workspace_bytes(int64_t nq, int64_t np, int32_t k) {
     size_t need = (size_t)pl.n_stripes * 2 * (size_t)nq * (size_t)k * 8 + 256;
     // the CTA-pair kernel (dense2.cu) plans its own stripes; d_pad is not known here, so bound it over the widths
     // it supports (multiples of 64 up to 768)
-    if (k <= 16)
+    if (k <= R4D_TOPK_MAX)
         for (int d = 64; d <= 768; d += 64)
             for (int x3 = 0; x3 < 2; ++x3)
                 if (dense2_supported(nq, np, d, x3 ? R4D_PREC_BF16X3 : R4D_PREC_BF16, k)) {
@@ -507,10 +507,10 @@ static int dense_topk_impl(const void* q_hi, const void* q_lo, int64_t nq, const
             return R4D_E_WORKSPACE;
         }
         int32_t n_lists = 0;
-        float* ps = reinterpret_cast<float*>(workspace);
-        int32_t* pi = reinterpret_cast<int32_t*>(ps + (need2 - 256) / 8);
+        float* ps = nullptr;
+        int32_t* pi = nullptr;
         rc = dense2_topk(q_hi, x3 ? q_lo : nullptr, nq, p_hi, x3 ? p_lo : nullptr, np, d_pad, q_time, p_time, lambda, mode, k,
-                         pool_base, ps, pi, &n_lists, as_stream(stream));
+                         pool_base, workspace, &ps, &pi, &n_lists, as_stream(stream));
         if (rc) return rc;
         return dense_merge_launch(ps, pi, n_lists, nq, k, k, top_score, top_idx, peers, stream);
     }

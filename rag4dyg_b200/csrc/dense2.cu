@@ -16,8 +16,8 @@
 // bound (measured: no gain over dense.cu), so wide D uses QRES = false: the pair streams both k-blocks (64 B/clk/SM,
 // 7-stage ring) and still halves the pool traffic per MMA.
 //
-// Supports: PREC_BF16 and PREC_BF16X3 (three products: hi.hi + hi.lo + lo.hi, streamed operands), top-K with k <= 16.
-// Everything else goes through dense.cu.
+// Supports: PREC_BF16 and PREC_BF16X3 (three products: hi.hi + hi.lo + lo.hi, streamed operands), top-K with k <= 32.
+// Full score rows (r4d_dense_full) and shapes whose lists leave fewer than 3 stages go through dense.cu.
 #include <cmath>
 #include <cstdlib>
 
@@ -28,11 +28,13 @@ namespace r4d {
 constexpr int D2_THREADS = 320;
 constexpr int D2_EPI_WARPS = 8;
 constexpr int D2_EPI_THREADS = 256;
-constexpr int D2_KMAX = 16;  // top-K width served by this kernel (wider K -> dense.cu)
+constexpr int D2_KMAX = R4D_TOPK_MAX;  // every top-K width of the ABI: the per-thread lists of k = 32 (64 KB) still leave 5 stages
 
 struct Dense2Params {
     int64_t nq, np;
     int32_t n_kblocks;
+    int32_t* progress;   // [n_items] tiles issued per work item (walker throttle, see the producer); nullptr = off
+    int32_t window;      // tiles a walker may lead the slowest concurrent walker of its pool stripe
     int32_t n_segs;   // 1: bf16 single pass; 3: BF16X3 = q_hi.p_hi + q_hi.p_lo + q_lo.p_hi per k-block, one TMEM tile
     int32_t mode;
     int32_t k;
@@ -113,6 +115,15 @@ __device__ __forceinline__ void tc_commit_2sm_mc(uint64_t* bar) {
 // QRES: true  = this CTA's query tile (128 x D) stays resident in smem for the whole work item (32 B/clk/SM streamed);
 //              needs D small enough to leave >= 4 pool stages (D <= 512).
 //       false = the query k-block is streamed next to the pool k-block (64 B/clk/SM, deep ring) — wide D.
+__device__ __forceinline__ void st_relaxed_i32(int32_t* p, int32_t v) {
+    asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int32_t ld_relaxed_i32(const int32_t* p) {
+    int32_t v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 template <int DPN, bool QRES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D2_THREADS, 1)
 dense2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_p,
@@ -176,26 +187,50 @@ dense2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     const int cluster_id = blockIdx.x >> 1;
 
     if (warp == 0) {
-        // ------------------------------------------------------------ TMA producer (both CTAs)
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0, item_seq = 0;
-            const uint32_t qfull_leader = mapa_shared(smem_u32(qfull_bar), 0);
-            for (int item = cluster_id; item < n_items; item += n_clusters, ++item_seq) {
-                const int stripe = item / prm.n_qpairs;
-                const int pt_step = prm.interleave ? prm.n_stripes : 1;
-                const int pt0 = prm.interleave ? stripe : stripe * prm.ptiles_per_stripe;
-                const int pt_lim = prm.interleave ? prm.n_ptiles : min(pt0 + prm.ptiles_per_stripe, prm.n_ptiles);
-                const int qtile = (item - stripe * prm.n_qpairs) * 2 + (int)rank;
-                if (QRES) {
-                    // resident query tile: wait until the previous item's MMAs have released it
-                    mbar_wait(qempty_bar, (item_seq & 1u) ^ 1u);
-                    mbar_arrive_expect_tx_cluster(qfull_leader, (uint32_t)(prm.n_kblocks * Q_TILE_BYTES));
-                    for (int kb = 0; kb < prm.n_kblocks; ++kb)
-                        tma_load_2d_2sm(smem_u32(q_res + (size_t)kb * Q_TILE_BYTES), &tm_q, qfull_leader, kb * DKB,
-                                        qtile * DQ);
+        // ------------------------------------------------------------ TMA producer (both CTAs; lane 0 issues)
+        // Walker throttle: the n_qpairs work items of one pool stripe read the same pool tiles.  Left alone they drift
+        // apart (a walker that falls out of the L2 window sees DRAM latency and falls further back) and every tile is
+        // fetched from HBM ~12 times (ncu, round 1/2).  Every 2 tiles a walker publishes its tile count and waits while
+        // it leads the slowest walker of the same stripe and round by more than `window` tiles, so a stripe's
+        // walkers share one L2-resident window and the pool crosses HBM about once.  Deadlock-free: the slowest walker
+        // of the earliest unfinished round never waits, and that round's items are all running (a cluster takes its
+        // items in order); the wait is bounded anyway.
+        int stage = 0;
+        uint32_t phase = 0, item_seq = 0;
+        const uint32_t qfull_leader = mapa_shared(smem_u32(qfull_bar), 0);
+        for (int item = cluster_id; item < n_items; item += n_clusters, ++item_seq) {
+            const int stripe = item / prm.n_qpairs;
+            const int pt_step = prm.interleave ? prm.n_stripes : 1;
+            const int pt0 = prm.interleave ? stripe : stripe * prm.ptiles_per_stripe;
+            const int pt_lim = prm.interleave ? prm.n_ptiles : min(pt0 + prm.ptiles_per_stripe, prm.n_ptiles);
+            const int qtile = (item - stripe * prm.n_qpairs) * 2 + (int)rank;
+            if (QRES && lane == 0) {
+                // resident query tile: wait until the previous item's MMAs have released it
+                mbar_wait(qempty_bar, (item_seq & 1u) ^ 1u);
+                mbar_arrive_expect_tx_cluster(qfull_leader, (uint32_t)(prm.n_kblocks * Q_TILE_BYTES));
+                for (int kb = 0; kb < prm.n_kblocks; ++kb)
+                    tma_load_2d_2sm(smem_u32(q_res + (size_t)kb * Q_TILE_BYTES), &tm_q, qfull_leader, kb * DKB,
+                                    qtile * DQ);
+            }
+            const int round_first = (item / n_clusters) * n_clusters;      // items running concurrently with this one
+            const int peer0 = stripe * prm.n_qpairs;
+            int tiles_done = 0;
+            for (int pt = pt0; pt < pt_lim; pt += pt_step, ++tiles_done) {
+                if (prm.progress != nullptr && (tiles_done & 1) == 0) {
+                    if (lane == 0 && leader) st_relaxed_i32(prm.progress + item, tiles_done);
+                    for (int spin = 0; spin < 20000; ++spin) {
+                        int slowest = 0x7fffffff;
+                        for (int pl = lane; pl < prm.n_qpairs; pl += 32) {
+                            const int it = peer0 + pl;
+                            if (it >= round_first && it < round_first + n_clusters && it < n_items)
+                                slowest = min(slowest, ld_relaxed_i32(prm.progress + it));
+                        }
+                        slowest = __reduce_min_sync(0xffffffffu, slowest);
+                        if (tiles_done - slowest <= prm.window) break;
+                        __nanosleep(256);
+                    }
                 }
-                for (int pt = pt0; pt < pt_lim; pt += pt_step) {
+                if (lane == 0) {
                     // split precision: per k-block the products q_hi.p_hi, q_hi.p_lo, q_lo.p_hi in this order — the
                     // same sequence of K = 16 MMA steps as dense.cu issues, so both kernels accumulate identically
                     for (int kb = 0; kb < prm.n_kblocks; ++kb) {
@@ -215,7 +250,9 @@ dense2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                         }
                     }
                 }
+                __syncwarp();
             }
+            if (prm.progress != nullptr && lane == 0 && leader) st_relaxed_i32(prm.progress + item, 0x7fffffff);   // done
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer (leader CTA, one lane)
@@ -433,20 +470,30 @@ bool dense2_supported(int64_t nq, int64_t np, int32_t d_pad, int32_t prec, int32
     return dense2_plan(nq, np, d_pad, k, prec == R4D_PREC_BF16X3).ok;
 }
 
+// workspace: part_score [n_lists][nq][k] f32 | part_idx [n_lists][nq][k] i32 | progress [n_items] i32 (256-byte aligned)
+static size_t dense2_lists_bytes(const Dense2Plan& pl, int64_t nq, int32_t k) {
+    return (((size_t)pl.n_stripes * 2 * (size_t)nq * (size_t)k * 4) + 255) / 256 * 256;
+}
 size_t dense2_workspace_bytes(int64_t nq, int64_t np, int32_t d_pad, int32_t k, bool x3) {
     const Dense2Plan pl = dense2_plan(nq, np, d_pad, k, x3);
-    return (size_t)pl.n_stripes * 2 * (size_t)nq * (size_t)k * 8 + 256;
+    return 2 * dense2_lists_bytes(pl, nq, k) + ((size_t)pl.n_qpairs * pl.n_stripes * 4 + 255) / 256 * 256 + 256;
 }
 
 int dense2_topk(const void* q_hi, const void* q_lo, int64_t nq, const void* p_hi, const void* p_lo, int64_t np, int32_t d_pad,
                 const float* q_time, const float* p_time, float lambda, int32_t mode, int32_t k, int64_t pool_base,
-                float* part_score, int32_t* part_idx, int32_t* n_lists_out, cudaStream_t st) {
+                void* workspace, float** part_score_out, int32_t** part_idx_out, int32_t* n_lists_out, cudaStream_t st) {
     const bool x3 = q_lo != nullptr && p_lo != nullptr;
     const Dense2Plan pl = dense2_plan(nq, np, d_pad, k, x3);
     if (!pl.ok) {
         set_error("dense2: unsupported shape");
         return R4D_E_ARG;
     }
+    const size_t lists = dense2_lists_bytes(pl, nq, k);
+    float* part_score = reinterpret_cast<float*>(workspace);
+    int32_t* part_idx = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(workspace) + lists);
+    int32_t* progress = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(workspace) + 2 * lists);
+    *part_score_out = part_score;
+    *part_idx_out = part_idx;
     CUtensorMap tm_q, tm_p;
     int rc;
     const uint64_t rs = (uint64_t)d_pad * 2;
@@ -486,6 +533,10 @@ int dense2_topk(const void* q_hi, const void* q_lo, int64_t nq, const void* p_hi
     prm.part_idx = part_idx;
     const size_t smem = pl.smem;
     const int64_t n_items = (int64_t)pl.n_qpairs * pl.n_stripes;
+    // walker throttle (option "dense_walker_window": tiles; 0 = off): only useful when several walkers share a stripe
+    prm.window = options().dense_walker_window;
+    prm.progress = (prm.window > 0 && pl.n_qpairs > 1) ? progress : nullptr;
+    if (prm.progress) R4D_CUDA(cudaMemsetAsync(progress, 0, (size_t)n_items * 4, st));
     int n_clusters = num_sms() / 2;
     if (n_items < n_clusters) n_clusters = (int)n_items;
     if (pl.qres) {

@@ -95,6 +95,6 @@ size_t dense2_workspace_bytes(int64_t nq, int64_t np, int32_t d_pad, int32_t k, 
 // q_lo / p_lo non-null selects the split-precision (BF16X3) contraction
 int dense2_topk(const void* q_hi, const void* q_lo, int64_t nq, const void* p_hi, const void* p_lo, int64_t np, int32_t d_pad,
                 const float* q_time, const float* p_time, float lambda, int32_t mode, int32_t k, int64_t pool_base,
-                float* part_score, int32_t* part_idx, int32_t* n_lists_out, cudaStream_t st);
+                void* workspace, float** part_score_out, int32_t** part_idx_out, int32_t* n_lists_out, cudaStream_t st);
 
 }  // namespace r4d

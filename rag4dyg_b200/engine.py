@@ -230,9 +230,11 @@ def _postings_args(q_ids, q_off, index):
 
 
 @_on_input_device
-def jaccard_topk_postings(q_ids, q_off, index, k, zero_diag=False, query_base=0, pool_base=0, workspace=None, out=None):
+def jaccard_topk_postings(q_ids, q_off, index, k, zero_diag=False, query_base=0, pool_base=0, workspace=None, out=None,
+                          q_nnz=None):
     """Fused Jaccard scorer + top-K over pool postings: queries as CSR id lists (int32 ids, int64 offsets, CUDA),
-    (inter, union, idx) int32 [nq, k] in the canonical order.  r4d_jaccard_topk_postings."""
+    (inter, union, idx) int32 [nq, k] in the canonical order.  r4d_jaccard_topk_postings.
+    q_nnz: number of ids the nq rows hold, when q_off is a row range of a larger CSR (a sizing hint only)."""
     lib = _lib.load()
     q_ids, q_off, nq = _postings_args(q_ids, q_off, index)
     dev = index.device
@@ -242,7 +244,8 @@ def jaccard_topk_postings(q_ids, q_off, index, k, zero_diag=False, query_base=0,
             workspace = torch.empty((need,), dtype=torch.uint8, device=dev)
         if out is None:
             out = tuple(torch.empty((nq, k), dtype=torch.int32, device=dev) for _ in range(3))
-        check(lib.r4d_jaccard_topk_postings(_ptr(q_ids), _ptr(q_off), nq, q_ids.numel(), _ptr(index.blob), _ptr(index.card), index.n_rows,
+        check(lib.r4d_jaccard_topk_postings(_ptr(q_ids), _ptr(q_off), nq, q_ids.numel() if q_nnz is None else int(q_nnz),
+                                            _ptr(index.blob), _ptr(index.card), index.n_rows,
                                             index.n_bits, index.nnz, k, int(bool(zero_diag)), query_base, pool_base,
                                             _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(workspace), workspace.numel(),
                                             _stream()), "r4d_jaccard_topk_postings")

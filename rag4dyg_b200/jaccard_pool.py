@@ -6,8 +6,8 @@ sparse-set top-K path walks (r4d_postings_build).  It replaces what the referenc
 of every pool sample inside co_occurrence_ratio (retrieval_data_annotation.py:12-13).
 
 `topk` is the device-resident call; `HostTopK` is the same call for HOST buffers: the step's query id lists arrive in
-pinned host memory, results land in pinned host memory, and consecutive steps overlap (step i's device->host copy runs
-on a copy stream while step i+1 is scored).
+pinned host memory, results land in pinned host memory; device->host copies run on a copy stream and overlap the
+scoring of the next row range / the next step.
 """
 import torch
 
@@ -54,13 +54,15 @@ class JaccardPool:
             self._ws = torch.empty((need,), dtype=torch.uint8, device=self.device)
         return self._ws
 
-    def topk(self, q_ids, q_off, k, zero_diag=False, query_base=0, out=None):
+    def topk(self, q_ids, q_off, k, zero_diag=False, query_base=0, out=None, q_nnz=None):
         """Queries as CSR id lists on the device -> (inter, union, idx) int32 [nq, k], canonical order, GLOBAL indices.
-        Sparse path (postings) when the index exists, else set encoder + bitset kernels."""
+        Sparse path (postings) when the index exists, else set encoder + bitset kernels.  q_off may be a row range of a
+        larger CSR (offsets stay absolute into q_ids); q_nnz then tells how many ids the range holds (sizing hint)."""
         nq = q_off.numel() - 1
         if self.index is not None:
             return engine.jaccard_topk_postings(q_ids, q_off, self.index, k, zero_diag=zero_diag, query_base=query_base,
-                                                pool_base=self.pool_base, workspace=self.workspace(nq, k), out=out)
+                                                pool_base=self.pool_base, workspace=self.workspace(nq, k), out=out,
+                                                q_nnz=q_nnz)
         q = engine.encode_bitsets(q_ids, q_off, self.bits.n_bits)
         r = engine.jaccard_topk(q, self.bits, k, zero_diag=zero_diag, query_base=query_base, pool_base=self.pool_base,
                                 workspace=self.workspace(nq, k))
@@ -73,11 +75,13 @@ class JaccardPool:
 
 class HostTopK:
     """Pipelined host-buffer front end of JaccardPool.topk: submit(q_ids, q_off) enqueues H2D -> top-K -> D2H and
-    returns a ticket; result(ticket) waits for that step only.  `depth` steps may be in flight (their buffers are
-    separate), so the copies of one step overlap the scoring of the next."""
+    returns a ticket; result(ticket) waits for that step only.  Inside a step the queries are scored in `chunks` row
+    ranges: the device->host copy of a range runs on a copy stream while the next range is scored, so a step costs
+    about H2D + scoring + the last range's copy.  `depth` steps may be in flight (their buffers are separate), so the
+    tail copy of one step also overlaps the scoring of the next."""
 
-    def __init__(self, pool, k, max_queries, max_ids, depth=2):
-        self.pool, self.k, self.depth = pool, int(k), int(depth)
+    def __init__(self, pool, k, max_queries, max_ids, depth=2, chunks=4):
+        self.pool, self.k, self.depth, self.chunks = pool, int(k), int(depth), max(1, int(chunks))
         dev = pool.device
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.slots = []
@@ -87,7 +91,7 @@ class HostTopK:
                 "off": torch.empty((max_queries + 1,), dtype=torch.int64, device=dev),
                 "out": tuple(torch.empty((max_queries, self.k), dtype=torch.int32, device=dev) for _ in range(3)),
                 "host": tuple(torch.empty((max_queries, self.k), dtype=torch.int32).pin_memory() for _ in range(3)),
-                "scored": torch.cuda.Event(), "done": torch.cuda.Event(), "nq": 0, "busy": False,
+                "scored": [torch.cuda.Event() for _ in range(self.chunks)], "done": torch.cuda.Event(), "nq": 0, "busy": False,
             })
         self.step = 0
 
@@ -103,13 +107,19 @@ class HostTopK:
         if nnz:
             ids[:nnz].copy_(q_ids, non_blocking=True)
         off.copy_(q_off, non_blocking=True)
-        out = tuple(o[:nq] for o in s["out"])
-        self.pool.topk(ids, off, self.k, zero_diag=zero_diag, query_base=query_base, out=out)
-        s["scored"].record()
+        n_chunks = min(self.chunks, max(1, nq // 4096))            # small steps are not worth splitting
+        bounds = [nq * c // n_chunks for c in range(n_chunks + 1)]
+        for c in range(n_chunks):
+            a, b = bounds[c], bounds[c + 1]
+            # row range [a, b): the offsets stay absolute into `ids`, so only the offset and output views move
+            self.pool.topk(ids, off[a:b + 1], self.k, zero_diag=zero_diag, query_base=query_base + a,
+                           out=tuple(o[a:b] for o in s["out"]), q_nnz=int(q_off[b]) - int(q_off[a]))
+            s["scored"][c].record()
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(s["scored"][c])
+                for h, o in zip(s["host"], s["out"]):
+                    h[a:b].copy_(o[a:b], non_blocking=True)
         with torch.cuda.stream(self.copy_stream):
-            self.copy_stream.wait_event(s["scored"])
-            for h, o in zip(s["host"], out):
-                h[:nq].copy_(o, non_blocking=True)
             s["done"].record()
         s["nq"], s["busy"] = nq, True
         ticket = self.step

@@ -124,3 +124,26 @@ def test_postings_shard_invariance():
                                            torch.stack([x[2] for x in parts]), k)
     assert np.array_equal(mx.cpu().numpy(), ox)
     assert np.array_equal(mi.cpu().numpy(), oi) and np.array_equal(mu.cpu().numpy(), ou)
+
+
+@pytest.mark.parametrize("zero_diag", [False, True])
+def test_host_topk_row_ranges_equal_one_call(zero_diag):
+    """HostTopK scores a step in row ranges (offsets stay absolute, query_base moves with the range) and overlaps their
+    device->host copies: the result must equal one device-resident call, for two steps in flight."""
+    from rag4dyg_b200.jaccard_pool import HostTopK, JaccardPool
+    rng = np.random.default_rng(9)
+    n_bits, npool, nq, k = 5000, 30000, 18000, 10
+    p = random_sets(rng, npool, n_bits, mean=2.2, p_empty=0.02, dup=True)
+    q = p[:nq] if zero_diag else random_sets(rng, nq, n_bits, mean=2.2, p_empty=0.02, dup=True)
+    pool = JaccardPool.from_csr(*to_csr(p), n_bits)
+    qi, qo = to_csr(q)
+    tq, to = torch.as_tensor(qi).pin_memory(), torch.as_tensor(qo).pin_memory()
+    ref = pool.topk(tq.cuda(), to.cuda(), k, zero_diag=zero_diag)
+    hk = HostTopK(pool, k, nq, qi.size, depth=2, chunks=4)
+    t0 = hk.submit(tq, to, zero_diag=zero_diag)
+    t1 = hk.submit(tq, to, zero_diag=zero_diag)
+    for t in (t0, t1):
+        got = hk.result(t)
+        assert all(torch.equal(g, r.cpu()) for g, r in zip(got, ref))
+    oi, ou, ox = jo.c_topk(qi, qo, *to_csr(p), k, zero_diag=zero_diag)
+    assert np.array_equal(ref[2].cpu().numpy(), ox) and np.array_equal(ref[0].cpu().numpy(), oi)
