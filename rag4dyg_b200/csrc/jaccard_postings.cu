@@ -243,8 +243,11 @@ struct PEntry {
 
 // Zero-score fillers (pool rows 0 .. n_fill-1 unless listed already; they only matter while the k-th entry scores 0)
 // and the final store: plain [nq][k] planes, or slot `rank` of every peer's gather buffer (fused exchange).
+// stage != nullptr (light kernel, plain output, k <= PJ_OBUF_K): the list goes to the warp's staging buffer [3][chunk][k];
+// the rows of a whole chunk of consecutive queries are then written out together (pj_flush_chunk).
 template <class E>
-__device__ __forceinline__ void pj_finish(WarpTopK<E>& tk, const PJParams& p, int64_t q, uint32_t cq) {
+__device__ __forceinline__ void pj_finish(WarpTopK<E>& tk, const PJParams& p, int64_t q, uint32_t cq, uint32_t* stage = nullptr,
+                                          int stage_row = 0, int stage_rows = 0) {
     const int lane = threadIdx.x & 31;
     if (p.n_fill > 0 && tk.kth.inter == 0u) {
         const uint32_t cp = lane < p.n_fill ? p.pcard[lane] : 0u;
@@ -253,6 +256,14 @@ __device__ __forceinline__ void pj_finish(WarpTopK<E>& tk, const PJParams& p, in
             if (__ballot_sync(0xffffffffu, lane < p.k && tk.mine.idx == c.idx)) continue;
             tk.insert(c);
         }
+    }
+    if (stage != nullptr) {
+        if (lane < p.k) {
+            stage[stage_row * p.k + lane] = tk.mine.inter;
+            stage[(stage_rows + stage_row) * p.k + lane] = tk.mine.uni;
+            stage[(2 * stage_rows + stage_row) * p.k + lane] = (uint32_t)tk.mine.idx;
+        }
+        return;
     }
     if (lane < p.k) {
         if (p.peers.world == 0) {
@@ -274,6 +285,7 @@ __device__ __forceinline__ void pj_finish(WarpTopK<E>& tk, const PJParams& p, in
 }
 
 constexpr unsigned long long PJ_EMPTY = 0xffffffffffffffffull;
+constexpr int PJ_OBUF_K = 12;   // lists up to this width are staged per chunk (wider ones are stored row by row)
 constexpr int PJ_OWN = 16;   // table slots a lane may claim per pass before the pass falls back to scanning the whole table
 
 // slot = {row : 32 | card : 24 | count : 8}.  Returns the claimed slot (>= 0) when this call created the entry, -1 when it
@@ -302,6 +314,7 @@ struct PJWarpSmem {
     uint32_t pref[PJ_IDS + 1];
     int32_t ids[PJ_IDS];
     uint16_t own[PJ_OWN * 32];   // own[i * 32 + lane]: i-th slot claimed by the lane in this pass
+    uint32_t obuf[3 * PJ_CHUNK * PJ_OBUF_K];   // finished lists of the chunk's queries: [plane][row][k], flushed together
     uint32_t pad[3];
 };
 
@@ -332,6 +345,10 @@ __global__ void __launch_bounds__(PJ_LIGHT_WARPS * 32, LOG_T == PJ_LOG_T_SMALL ?
         int64_t my_off = 0;
         if (lane <= chunk && q0 + lane <= p.nq) my_off = p.q_off[q0 + lane];
         const int n_here = (int)min((int64_t)chunk, p.nq - q0);
+        // plain output of narrow lists: the chunk's rows are contiguous in every output plane, so they are staged in
+        // shared memory and written out together — n_here * k consecutive words per plane instead of k-word pieces
+        // (full sectors in HBM; when the caller's buffers are pinned HOST memory, far fewer and larger PCIe writes)
+        const bool staged = p.peers.world == 0 && p.k <= PJ_OBUF_K;
         for (int qi = 0; qi < n_here; ++qi) {
             const int64_t q = q0 + qi;
             const int64_t beg = __shfl_sync(0xffffffffu, my_off, qi), end = __shfl_sync(0xffffffffu, my_off, qi + 1);
@@ -527,7 +544,19 @@ __global__ void __launch_bounds__(PJ_LIGHT_WARPS * 32, LOG_T == PJ_LOG_T_SMALL ?
                 hand_over(q);
                 continue;
             }
-            pj_finish(tk, p, q, cq);
+            pj_finish(tk, p, q, cq, staged ? sm.obuf : nullptr, qi, n_here);
+        }
+        if (staged) {
+            // rows of queries handed to the heavy kernel hold stale words here; that kernel runs afterwards and rewrites them
+            __syncwarp();
+            const int n_words = n_here * p.k;
+            const int64_t at = q0 * p.k;
+            for (int i = lane; i < n_words; i += 32) {
+                p.out_inter[at + i] = sm.obuf[i];
+                p.out_union[at + i] = sm.obuf[n_words + i];
+                p.out_idx[at + i] = (int32_t)sm.obuf[2 * n_words + i];
+            }
+            __syncwarp();
         }
     }
 }
@@ -836,6 +865,16 @@ static int postings_topk_impl(const int32_t* q_ids, const int64_t* q_off, int64_
         // every warp should find several grabs of work: small calls take fewer queries per grab
         const int64_t cap = (int64_t)num_sms() * (large ? 2 : 4);   // resident CTAs per SM (shared memory)
         int64_t chunk = nq / (cap * PJ_LIGHT_WARPS * 4);
+        if (top_idx != nullptr && peers.world == 0 && k <= PJ_OBUF_K) {
+            // results going straight to pinned HOST memory: the largest chunks make the fewest, widest PCIe writes
+            cudaPointerAttributes attr{};
+            if (cudaPointerGetAttributes(&attr, top_idx) == cudaSuccess) {
+                if (attr.type == cudaMemoryTypeHost) chunk = PJ_CHUNK;
+            } else {
+                (void)cudaGetLastError();
+            }
+        }
+        if (options().postings_chunk > 0) chunk = options().postings_chunk;
         chunk = chunk < 1 ? 1 : (chunk > PJ_CHUNK ? PJ_CHUNK : chunk);
         prm.chunk = (int32_t)chunk;
         int64_t grid = (nq + PJ_LIGHT_WARPS * chunk - 1) / (PJ_LIGHT_WARPS * chunk);

@@ -244,6 +244,12 @@ def jaccard_topk_postings(q_ids, q_off, index, k, zero_diag=False, query_base=0,
             workspace = torch.empty((need,), dtype=torch.uint8, device=dev)
         if out is None:
             out = tuple(torch.empty((nq, k), dtype=torch.int32, device=dev) for _ in range(3))
+        else:
+            # device tensors, or PINNED host tensors (device-addressable: the kernel then stores over PCIe directly)
+            for o in out:
+                if not (o.dtype == torch.int32 and o.is_contiguous() and tuple(o.shape) == (nq, k) and
+                        (o.is_cuda or o.is_pinned())):
+                    raise R4DError("jaccard_topk_postings: `out` must be contiguous int32 [nq, k] CUDA or pinned host tensors")
         check(lib.r4d_jaccard_topk_postings(_ptr(q_ids), _ptr(q_off), nq, q_ids.numel() if q_nnz is None else int(q_nnz),
                                             _ptr(index.blob), _ptr(index.card), index.n_rows,
                                             index.n_bits, index.nnz, k, int(bool(zero_diag)), query_base, pool_base,

@@ -74,14 +74,18 @@ class JaccardPool:
 
 
 class HostTopK:
-    """Pipelined host-buffer front end of JaccardPool.topk: submit(q_ids, q_off) enqueues H2D -> top-K -> D2H and
-    returns a ticket; result(ticket) waits for that step only.  Inside a step the queries are scored in `chunks` row
-    ranges: the device->host copy of a range runs on a copy stream while the next range is scored, so a step costs
-    about H2D + scoring + the last range's copy.  `depth` steps may be in flight (their buffers are separate), so the
-    tail copy of one step also overlaps the scoring of the next."""
+    """Host-buffer front end of JaccardPool.topk: submit(q_ids, q_off) enqueues H2D -> top-K -> results in pinned host
+    memory and returns a ticket; result(ticket) waits for that step only; `depth` steps may be in flight.
 
-    def __init__(self, pool, k, max_queries, max_ids, depth=2, chunks=4):
+    direct=True (default, postings path): the top-K kernel stores its [Q, K] lists STRAIGHT into the pinned host
+    buffers (pinned memory is device-addressable under unified addressing), so the device->host transfer is spread over
+    the kernel's run time as posted PCIe writes — there is no separate copy, and a step costs H2D + scoring.
+    direct=False: results land in HBM and are copied out on a copy stream, in `chunks` row ranges so that the copy of
+    one range overlaps the scoring of the next (also the path for pools without a postings index)."""
+
+    def __init__(self, pool, k, max_queries, max_ids, depth=2, chunks=1, direct=True):
         self.pool, self.k, self.depth, self.chunks = pool, int(k), int(depth), max(1, int(chunks))
+        self.direct = bool(direct) and pool.index is not None
         dev = pool.device
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.slots = []
@@ -89,7 +93,8 @@ class HostTopK:
             self.slots.append({
                 "ids": torch.empty((max(1, max_ids),), dtype=torch.int32, device=dev),
                 "off": torch.empty((max_queries + 1,), dtype=torch.int64, device=dev),
-                "out": tuple(torch.empty((max_queries, self.k), dtype=torch.int32, device=dev) for _ in range(3)),
+                "out": None if self.direct else tuple(torch.empty((max_queries, self.k), dtype=torch.int32, device=dev)
+                                                      for _ in range(3)),
                 "host": tuple(torch.empty((max_queries, self.k), dtype=torch.int32).pin_memory() for _ in range(3)),
                 "scored": [torch.cuda.Event() for _ in range(self.chunks)], "done": torch.cuda.Event(), "nq": 0, "busy": False,
             })
@@ -107,20 +112,25 @@ class HostTopK:
         if nnz:
             ids[:nnz].copy_(q_ids, non_blocking=True)
         off.copy_(q_off, non_blocking=True)
-        n_chunks = min(self.chunks, max(1, nq // 4096))            # small steps are not worth splitting
-        bounds = [nq * c // n_chunks for c in range(n_chunks + 1)]
-        for c in range(n_chunks):
-            a, b = bounds[c], bounds[c + 1]
-            # row range [a, b): the offsets stay absolute into `ids`, so only the offset and output views move
-            self.pool.topk(ids, off[a:b + 1], self.k, zero_diag=zero_diag, query_base=query_base + a,
-                           out=tuple(o[a:b] for o in s["out"]), q_nnz=int(q_off[b]) - int(q_off[a]))
-            s["scored"][c].record()
-            with torch.cuda.stream(self.copy_stream):
-                self.copy_stream.wait_event(s["scored"][c])
-                for h, o in zip(s["host"], s["out"]):
-                    h[a:b].copy_(o[a:b], non_blocking=True)
-        with torch.cuda.stream(self.copy_stream):
+        if self.direct:
+            self.pool.topk(ids, off, self.k, zero_diag=zero_diag, query_base=query_base,
+                           out=tuple(h[:nq] for h in s["host"]), q_nnz=nnz)
             s["done"].record()
+        else:
+            n_chunks = min(self.chunks, max(1, nq // 4096))            # small steps are not worth splitting
+            bounds = [nq * c // n_chunks for c in range(n_chunks + 1)]
+            for c in range(n_chunks):
+                a, b = bounds[c], bounds[c + 1]
+                # row range [a, b): the offsets stay absolute into `ids`, so only the offset and output views move
+                self.pool.topk(ids, off[a:b + 1], self.k, zero_diag=zero_diag, query_base=query_base + a,
+                               out=tuple(o[a:b] for o in s["out"]), q_nnz=int(q_off[b]) - int(q_off[a]))
+                s["scored"][c].record()
+                with torch.cuda.stream(self.copy_stream):
+                    self.copy_stream.wait_event(s["scored"][c])
+                    for h, o in zip(s["host"], s["out"]):
+                        h[a:b].copy_(o[a:b], non_blocking=True)
+            with torch.cuda.stream(self.copy_stream):
+                s["done"].record()
         s["nq"], s["busy"] = nq, True
         ticket = self.step
         self.step += 1
@@ -130,8 +140,9 @@ class HostTopK:
         s = self.slots[ticket % self.depth]
         s["done"].synchronize()
         s["busy"] = False
-        # the compute stream may reuse this slot's device buffers only after the copy has read them
-        torch.cuda.current_stream().wait_event(s["done"])
+        if not self.direct:
+            # the compute stream may reuse this slot's device buffers only after the copy has read them
+            torch.cuda.current_stream().wait_event(s["done"])
         return tuple(h[:s["nq"]] for h in s["host"])
 
     def bytes_per_step(self, nq, nnz):

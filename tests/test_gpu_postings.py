@@ -139,11 +139,12 @@ def test_host_topk_row_ranges_equal_one_call(zero_diag):
     qi, qo = to_csr(q)
     tq, to = torch.as_tensor(qi).pin_memory(), torch.as_tensor(qo).pin_memory()
     ref = pool.topk(tq.cuda(), to.cuda(), k, zero_diag=zero_diag)
-    hk = HostTopK(pool, k, nq, qi.size, depth=2, chunks=4)
-    t0 = hk.submit(tq, to, zero_diag=zero_diag)
-    t1 = hk.submit(tq, to, zero_diag=zero_diag)
-    for t in (t0, t1):
-        got = hk.result(t)
-        assert all(torch.equal(g, r.cpu()) for g, r in zip(got, ref))
+    for kw in (dict(direct=False, chunks=4), dict(direct=True)):          # copy-stream ranges / kernel stores to pinned host
+        hk = HostTopK(pool, k, nq, qi.size, depth=2, **kw)
+        t0 = hk.submit(tq, to, zero_diag=zero_diag)
+        t1 = hk.submit(tq, to, zero_diag=zero_diag)
+        for t in (t0, t1):
+            got = hk.result(t)
+            assert all(torch.equal(g, r.cpu()) for g, r in zip(got, ref)), kw
     oi, ou, ox = jo.c_topk(qi, qo, *to_csr(p), k, zero_diag=zero_diag)
     assert np.array_equal(ref[2].cpu().numpy(), ox) and np.array_equal(ref[0].cpu().numpy(), oi)
