@@ -73,6 +73,36 @@ class JaccardPool:
         return r
 
 
+class GraphTopK:
+    """One JaccardPool.topk call captured in a CUDA graph: replay() re-runs the whole launch sequence (counter memset +
+    scoring kernels) with a single graph launch.  For short steps (a few thousand queries per GPU) the Python / ctypes
+    launch path (~100 us) is longer than the kernels; the graph makes the step GPU-bound again.  The query buffers and
+    the outputs are fixed device tensors: refresh their CONTENTS (copy_) between replays, never rebind them."""
+
+    def __init__(self, pool, q_ids, q_off, k, zero_diag=False, query_base=0, out=None):
+        if pool.index is None:
+            raise R4DError("GraphTopK needs the postings path (a pool with an index)")
+        nq = q_off.numel() - 1
+        self.pool, self.q_ids, self.q_off, self.k = pool, q_ids, q_off, int(k)
+        self.out = out if out is not None else tuple(torch.empty((nq, self.k), dtype=torch.int32, device=pool.device)
+                                                     for _ in range(3))
+        pool.workspace(nq, self.k)
+        with torch.cuda.device(pool.device):
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):          # warm-up outside the capture: lazy module load, shared-memory opt-ins
+                pool.topk(q_ids, q_off, self.k, zero_diag=zero_diag, query_base=query_base, out=self.out)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                pool.topk(q_ids, q_off, self.k, zero_diag=zero_diag, query_base=query_base, out=self.out)
+
+    def replay(self):
+        self.graph.replay()
+        return self.out
+
+
 class HostTopK:
     """Host-buffer front end of JaccardPool.topk: submit(q_ids, q_off) enqueues H2D -> top-K -> results in pinned host
     memory and returns a ticket; result(ticket) waits for that step only; `depth` steps may be in flight.

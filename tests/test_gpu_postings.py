@@ -148,3 +148,30 @@ def test_host_topk_row_ranges_equal_one_call(zero_diag):
             assert all(torch.equal(g, r.cpu()) for g, r in zip(got, ref)), kw
     oi, ou, ox = jo.c_topk(qi, qo, *to_csr(p), k, zero_diag=zero_diag)
     assert np.array_equal(ref[2].cpu().numpy(), ox) and np.array_equal(ref[0].cpu().numpy(), oi)
+
+
+def test_graph_topk_replays_with_refreshed_queries():
+    """GraphTopK: the captured launch sequence re-run on new query CONTENTS (same buffers) equals a plain call."""
+    from rag4dyg_b200.jaccard_pool import GraphTopK, JaccardPool
+    rng = np.random.default_rng(17)
+    n_bits, npool, nq, k = 3000, 20000, 2000, 10
+    p = random_sets(rng, npool, n_bits, mean=2.2)
+    pool = JaccardPool.from_csr(*to_csr(p), n_bits)
+    qa = random_sets(rng, nq, n_bits, mean=2.2, max_len=8)
+    qb = random_sets(rng, nq, n_bits, mean=2.2, max_len=8)
+    cap = 8 * nq
+    ids = torch.zeros(cap, dtype=torch.int32, device="cuda")
+    off = torch.zeros(nq + 1, dtype=torch.int64, device="cuda")
+
+    def load(q):
+        qi, qo = to_csr(q)
+        ids[:qi.size].copy_(torch.as_tensor(qi))
+        off.copy_(torch.as_tensor(qo))
+        return qi, qo
+    qi, qo = load(qa)
+    g = GraphTopK(pool, ids, off, k)
+    for q in (qa, qb, qa):
+        qi, qo = load(q)
+        got = [t.cpu().numpy() for t in g.replay()]
+        oi, ou, ox = jo.c_topk(qi, qo, *to_csr(p), k)
+        assert np.array_equal(got[2], ox) and np.array_equal(got[0], oi) and np.array_equal(got[1], ou)
