@@ -797,6 +797,29 @@ def main():
             variants["decay_lambda_0.1"]["what"] = "cos*exp(-0.1|dt|) stress case (SURVEY C5), BF16X3"
             variants["bf16_single_pass"]["what"] = ("one bf16 product (<= 3e-3 of fp32: NARROWER than the reference's fp32 "
                                                     "SGEMM, so a comparison point, not the metric)")
+        whole = None
+        if aux:
+            # the WHOLE C5 workload once: all 100,000 queries against the whole pool = 12 batches of 8,192 + one of 1,696
+            # (the query batches are cycled; the last, shorter batch goes through the NCCL exchange at N > 1)
+            n_full, rem = QUERY_N // qs, QUERY_N % qs
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record()
+            for b in range(n_full):
+                sharded.dense_topk_sharded(q3[b % n_batches], pool3, TOPK, pool_base=lo, mode=mode, q_time=q_times[b % n_batches],
+                                           p_time=p_time, lam=DENSE_LAMBDA, workspace=ws, exchange=dex)
+            if rem:
+                sharded.dense_topk_sharded(q3[0].rows(0, rem), pool3, TOPK, pool_base=lo, mode=mode,
+                                           q_time=q_times[0][:rem].contiguous(), p_time=p_time, lam=DENSE_LAMBDA, workspace=ws)
+            e1.record()
+            barrier()
+            wall = time.perf_counter() - t0
+            w_ms = max_over_ranks(e0.elapsed_time(e1))
+            whole = {"what": f"all {QUERY_N:,} queries x the {n_pool:,}-row pool once ({n_full} batches of {qs:,} + one of {rem:,}), "
+                             f"BF16X3, decay epilogue, one pass, no warm-up between batches",
+                     "seconds": w_ms * 1e-3, "wall_seconds": wall, "value": QUERY_N * n_pool / (w_ms * 1e-3), "unit": "pairs/s",
+                     "tensor_TFLOPs_issued": 3 * 2.0 * D * QUERY_N * n_pool / (w_ms * 1e-3) / 1e12}
         d_cpu = None
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             torch.manual_seed(0)
@@ -825,7 +848,7 @@ def main():
                  "clocks": d_clocks, "verified": d_verified,
                  "verified_what": "8 queries x the first 200,000 pool rows: top-K of the BF16X3 kernel vs the fp32 torch oracle, "
                                   "tolerance-aware at 1e-5 (oracle/dense_oracle.py), on every rank",
-                 "variants": variants}
+                 "variants": variants, "whole_workload": whole}
         if out:
             out["dense"] = dense
             out["verified"] = bool(out["verified"] and d_verified)
