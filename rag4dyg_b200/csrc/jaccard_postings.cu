@@ -561,6 +561,306 @@ __global__ void __launch_bounds__(PJ_LIGHT_WARPS * 32, LOG_T == PJ_LOG_T_SMALL ?
     }
 }
 
+// ---------------------------------------------------------------------------- light kernel, register-resident variant
+// For label-like sets (a couple of hundred postings per query) the hash table of postings_light_kernel is mostly
+// overhead: a posting's row almost never repeats (two ids of a query rarely share a pool row), yet every posting pays a
+// CAS probe loop, a claimed-slot list and a table read-back.  Here a pass keeps its <= 256 postings IN REGISTERS, eight
+// per lane ({row, card << 8 | count}), and finds the rare repeats with a per-warp 8 192-bit filter in shared memory: a
+// posting whose filter bit was already set MAY repeat an earlier row; only those (a handful per query, false positives
+// included) are resolved, by broadcasting the row and letting every lane compare it with the live rows it holds — the
+// holder absorbs the count, the repeat dies.  Counts are exact; everything after that (candidate -> sorted top-K list,
+// passes over row windows for longer lists, hand-over to the heavy kernel) is the same as in postings_light_kernel.
+constexpr int PR_SLOTS = 8;               // postings a lane holds per pass
+constexpr int PR_CAP = PR_SLOTS * 32;     // postings per pass
+constexpr int PR_PLAN = 200;              // postings PLANNED per pass (row windows are not perfectly even)
+constexpr int PR_BM_WORDS = 256;          // 8 192-bit repeat filter per warp
+constexpr int PR_WARPS = 8;
+
+struct PRWarpSmem {
+    uint32_t bm[PR_BM_WORDS];
+    uint32_t start[PJ_IDS];
+    uint32_t pref[PJ_IDS + 1];
+    int32_t ids[PJ_IDS];
+    uint32_t obuf[3 * PJ_CHUNK * PJ_OBUF_K];
+    uint32_t pad[3];
+};
+
+__global__ void __launch_bounds__(PR_WARPS * 32, 4) postings_reg_kernel(const PJParams p) {
+    extern __shared__ __align__(16) uint8_t pj_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    PRWarpSmem& sm = reinterpret_cast<PRWarpSmem*>(pj_smem)[warp];
+    auto clear_filter = [&]() {
+        uint4* b4 = reinterpret_cast<uint4*>(sm.bm);
+#pragma unroll
+        for (int i = 0; i < PR_BM_WORDS / 4 / 32; ++i) b4[i * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
+    };
+    auto hand_over = [&](int64_t q) {   // the heavy kernel serves this query
+        if (lane == 0) p.heavy_list[atomicAdd(p.counters + 1, 1u)] = (uint32_t)q;
+    };
+    clear_filter();
+    bool filter_clean = true;
+    const int chunk = p.chunk;
+    for (;;) {
+        int64_t q0 = 0;
+        if (lane == 0) q0 = (int64_t)atomicAdd(p.counters + 0, (uint32_t)chunk);
+        q0 = __shfl_sync(0xffffffffu, q0, 0);
+        if (q0 >= p.nq) break;
+        int64_t my_off = 0;
+        if (lane <= chunk && q0 + lane <= p.nq) my_off = p.q_off[q0 + lane];
+        const int n_here = (int)min((int64_t)chunk, p.nq - q0);
+        const bool staged = p.peers.world == 0 && p.k <= PJ_OBUF_K;   // see postings_light_kernel
+        for (int qi = 0; qi < n_here; ++qi) {
+            const int64_t q = q0 + qi;
+            const int64_t beg = __shfl_sync(0xffffffffu, my_off, qi), end = __shfl_sync(0xffffffffu, my_off, qi + 1);
+            const int64_t m_raw = end - beg;
+            if (m_raw > PJ_IDS) {
+                hand_over(q);
+                continue;
+            }
+            // ---- the query's distinct ids, at most two per lane (set semantics: duplicates collapse)
+            int32_t id0 = -1, id1 = -1;
+            if (lane < m_raw) id0 = p.q_ids[beg + lane];
+            if (lane + 32 < m_raw) id1 = p.q_ids[beg + 32 + lane];
+            if (id0 < 0 || id0 >= p.n_bits) id0 = -1;
+            if (id1 < 0 || id1 >= p.n_bits) id1 = -1;
+            if (m_raw <= 32) {
+                const uint32_t same = __match_any_sync(0xffffffffu, id0);
+                if (id0 >= 0 && (__ffs(same) - 1) != lane) id0 = -1;
+            } else {
+                sm.ids[lane] = id0;
+                sm.ids[lane + 32] = id1;
+                __syncwarp();
+                bool d0 = false, d1 = false;
+                for (int t = 0; t < (int)m_raw; ++t) {
+                    const int32_t v = sm.ids[t];
+                    d0 |= (t < lane) && (v == id0);
+                    d1 |= (t < lane + 32) && (v == id1);
+                }
+                if (d0) id0 = -1;
+                if (d1) id1 = -1;
+                __syncwarp();
+            }
+            const uint32_t cq = __popc(__ballot_sync(0xffffffffu, id0 >= 0)) + __popc(__ballot_sync(0xffffffffu, id1 >= 0));
+            const bool two = m_raw > 32;   // warp-uniform: the second id register is in use
+            const bool few = m_raw <= 4;   // warp-uniform: the lists are found by three compares instead of a search
+            uint32_t s0 = 0, e0 = 0, s1 = 0, e1 = 0;
+            if (id0 >= 0) {
+                s0 = p.off[(int64_t)id0 * p.n_win];
+                e0 = p.off[(int64_t)(id0 + 1) * p.n_win];
+            }
+            if (two && id1 >= 0) {
+                s1 = p.off[(int64_t)id1 * p.n_win];
+                e1 = p.off[(int64_t)(id1 + 1) * p.n_win];
+            }
+            const uint32_t hits = __reduce_add_sync(0xffffffffu, (e0 - s0) + (e1 - s1));
+            const int passes = (int)((hits + PR_PLAN - 1) / PR_PLAN);
+            if (passes > p.n_win) {
+                hand_over(q);
+                continue;
+            }
+            WarpTopK<PEntry> tk;
+            tk.init(p.k);
+            bool failed = false, have_list = false;   // have_list: the sorted list holds entries of an earlier pass
+            const bool diag_on = p.zero_diag != 0;
+            const int64_t diag_row = p.query_base + q - p.pool_base;   // pool row forced to score 0
+            const int w_base = passes > 1 ? p.n_win / passes : 0, w_rem = passes > 1 ? p.n_win - w_base * passes : 0;
+            for (int ps = 0; ps < passes; ++ps) {
+                if (passes > 1) {   // this pass: windows [wlo, whi) of every list (balanced split of the n_win windows)
+                    const int wlo = ps * w_base + min(ps, w_rem), whi = (ps + 1) * w_base + min(ps + 1, w_rem);
+                    if (id0 >= 0) {
+                        s0 = p.off[(int64_t)id0 * p.n_win + wlo];
+                        e0 = p.off[(int64_t)id0 * p.n_win + whi];
+                    }
+                    if (two && id1 >= 0) {
+                        s1 = p.off[(int64_t)id1 * p.n_win + wlo];
+                        e1 = p.off[(int64_t)id1 * p.n_win + whi];
+                    }
+                }
+                // ---- the pass's postings as ONE sequence: posting g of the sequence goes to lane g % 32, slot g / 32
+                const uint32_t l0 = e0 - s0, l1 = two ? e1 - s1 : 0u;
+                uint32_t i0 = l0, i1 = l1;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
+                    if (lane >= o) {
+                        i0 += t0;
+                        i1 += t1;
+                    }
+                }
+                const uint32_t tot0 = __shfl_sync(0xffffffffu, i0, 31), tot1 = __shfl_sync(0xffffffffu, i1, 31);
+                const uint32_t n_post = tot0 + tot1;
+                if (n_post == 0u) continue;
+                if (n_post > (uint32_t)PR_CAP) {   // a hot window: more postings than the registers of a pass hold
+                    failed = true;
+                    break;
+                }
+                const uint32_t ex0 = i0 - l0, ex1 = tot0 + i1 - l1;   // first sequence position of the lane's lists
+                uint32_t b1 = 0, b2 = 0, b3 = 0, st0 = 0, st1 = 0, st2 = 0, st3 = 0;
+                if (few) {
+                    b1 = __shfl_sync(0xffffffffu, ex0, 1);
+                    b2 = __shfl_sync(0xffffffffu, ex0, 2);
+                    b3 = __shfl_sync(0xffffffffu, ex0, 3);
+                    st0 = __shfl_sync(0xffffffffu, s0, 0);
+                    st1 = __shfl_sync(0xffffffffu, s0, 1);
+                    st2 = __shfl_sync(0xffffffffu, s0, 2);
+                    st3 = __shfl_sync(0xffffffffu, s0, 3);
+                } else {
+                    sm.start[lane] = s0;
+                    sm.pref[lane] = ex0;
+                    sm.start[lane + 32] = s1;
+                    sm.pref[lane + 32] = ex1;
+                }
+                if (!filter_clean) clear_filter();
+                filter_clean = false;
+                __syncwarp();
+                const int n_it = (int)((n_post + 31u) >> 5);
+                const int n_lists = two ? PJ_IDS : 32;
+                uint2 ent[PR_SLOTS];
+#pragma unroll
+                for (int sl = 0; sl < PR_SLOTS; ++sl) {   // all loads of the pass in flight
+                    ent[sl] = make_uint2(0xffffffffu, 0u);
+                    const uint32_t g = (uint32_t)sl * 32u + (uint32_t)lane;
+                    if (sl < n_it && g < n_post) {
+                        uint32_t at;
+                        if (few) {
+                            // lists past the query's ids are empty and start at n_post: an empty list shares its start
+                            // with its successor, so counting "starts <= g" lands on the list that holds g
+                            const int li = (g >= b1) + (g >= b2) + (g >= b3);
+                            const uint32_t base = li == 0 ? 0u : (li == 1 ? b1 : (li == 2 ? b2 : b3));
+                            const uint32_t st = li == 0 ? st0 : (li == 1 ? st1 : (li == 2 ? st2 : st3));
+                            at = st + (g - base);
+                        } else {
+                            int lo = 0, hi = n_lists;   // last list j with pref[j] <= g (empty lists share a prefix value)
+                            while (hi - lo > 1) {
+                                const int mid = (lo + hi) >> 1;
+                                if (sm.pref[mid] <= g) lo = mid; else hi = mid;
+                            }
+                            at = sm.start[lo] + (g - sm.pref[lo]);
+                        }
+                        ent[sl] = p.post[at];
+                    }
+                }
+                uint32_t rrow[PR_SLOTS], rcc[PR_SLOTS];   // row; card << 8 | count (count 0: no posting here / merged away)
+                uint32_t flags = 0u;                      // bit sl: the posting may repeat an earlier row
+#pragma unroll
+                for (int sl = 0; sl < PR_SLOTS; ++sl) {
+                    rrow[sl] = ent[sl].x;
+                    rcc[sl] = 0u;
+                    const uint32_t g = (uint32_t)sl * 32u + (uint32_t)lane;
+                    if (sl < n_it && g < n_post && !(diag_on && (int64_t)ent[sl].x == diag_row)) {
+                        rcc[sl] = (ent[sl].y << 8) | 1u;
+                        const uint32_t h = (ent[sl].x * 2654435761u) >> 19;   // 13 bits
+                        const uint32_t bit = 1u << (h & 31u);
+                        if (atomicOr(&sm.bm[h >> 5], bit) & bit) flags |= 1u << sl;
+                    }
+                }
+                // Only the cheap per-slot work above and below is unrolled; everything with a large body (the resolution
+                // loop, the list insertions) exists ONCE and picks its slot with an 8-way select — the fully unrolled
+                // version was instruction-fetch bound (ncu: 7.3 of 12 stall cycles "no instruction").
+                auto sel8 = [&](const uint32_t (&a)[PR_SLOTS], int i) {
+                    uint32_t v = a[0];
+#pragma unroll
+                    for (int t = 1; t < PR_SLOTS; ++t) v = (i == t) ? a[t] : v;
+                    return v;
+                };
+                // ---- resolve the possible repeats (rare): the live holder of the same row absorbs the count
+                if (__ballot_sync(0xffffffffu, flags != 0u)) {
+#pragma unroll 1
+                    for (int sl = 0; sl < n_it; ++sl) {
+                        uint32_t m = __ballot_sync(0xffffffffu, (flags >> sl) & 1u);
+                        if (!m) continue;
+                        const uint32_t my_row = sel8(rrow, sl);
+                        while (m) {
+                            const int src = __ffs(m) - 1;
+                            m &= m - 1;
+                            const uint32_t drow = __shfl_sync(0xffffffffu, my_row, src);
+                            const uint32_t dcnt = __shfl_sync(0xffffffffu, sel8(rcc, sl), src) & 0xffu;   // counts move: re-read
+                            int hs = -1;
+#pragma unroll
+                            for (int t = 0; t < PR_SLOTS; ++t)
+                                if (rrow[t] == drow && (rcc[t] & 0xffu) != 0u && !(t == sl && lane == src)) hs = t;
+                            const uint32_t hm = __ballot_sync(0xffffffffu, hs >= 0);
+                            if (hm) {
+                                const bool owner = lane == __ffs(hm) - 1;
+#pragma unroll
+                                for (int t = 0; t < PR_SLOTS; ++t) {
+                                    if (owner && t == hs) rcc[t] += dcnt;
+                                    if (lane == src && t == sl) rcc[t] &= ~0xffu;
+                                }
+                            }
+                        }
+                    }
+                }
+                // ---- candidates (live postings) -> sorted top-K list
+                auto cand = [&](uint32_t row, uint32_t cc) {
+                    const uint32_t cnt = cc & 0xffu, card = cc >> 8;
+                    if (cnt == 0u) return PEntry::worst();
+                    return PEntry{cnt, cq + card - cnt, (int32_t)(p.pool_base + (int64_t)row)};
+                };
+                int32_t seeded = R4D_IDX_NONE;
+                if (!have_list) {
+                    // empty list: every lane finds the best of its candidates, a bitonic sort ranks the 32 lane-bests and the
+                    // first k of them seed the list (the others cannot be in the top k); the rest is inserted below only
+                    // if it beats the k-th
+                    PEntry lb = PEntry::worst();
+#pragma unroll
+                    for (int t = 0; t < PR_SLOTS; ++t) {
+                        const PEntry c = cand(rrow[t], rcc[t]);   // slots past n_it hold count 0 = worst()
+                        if (PEntry::better(c, lb)) lb = c;
+                    }
+                    PEntry v = lb;
+#pragma unroll
+                    for (int k2 = 2; k2 <= 32; k2 <<= 1)
+#pragma unroll
+                        for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+                            const PEntry o = v.shfl_xor(j2);
+                            const bool want_better = ((lane & j2) == 0) == ((lane & k2) == 0);
+                            if (PEntry::better(o, v) == want_better && o.idx != v.idx) v = o;
+                        }
+                    if (lane < p.k) tk.mine = v;
+                    tk.refresh_kth();
+                    seeded = lb.idx;
+                    have_list = true;
+                }
+                uint32_t todo = 0u;   // my slots whose candidate still beats the k-th entry
+#pragma unroll
+                for (int t = 0; t < PR_SLOTS; ++t) {
+                    const PEntry c = cand(rrow[t], rcc[t]);
+                    if (c.idx != seeded && PEntry::better(c, tk.kth)) todo |= 1u << t;
+                }
+#pragma unroll 1
+                for (;;) {
+                    const uint32_t any = __ballot_sync(0xffffffffu, todo != 0u);
+                    if (!any) break;
+                    const int src = __ffs(any) - 1;
+                    const int t = __ffs(todo) - 1;                  // meaningful in lane src only
+                    const PEntry c = cand(sel8(rrow, t), sel8(rcc, t));
+                    if (lane == src) todo &= todo - 1u;
+                    tk.insert(c.shfl(src));                         // a candidate the list has outgrown is dropped inside
+                }
+                __syncwarp();
+            }
+            if (failed) {
+                hand_over(q);
+                continue;
+            }
+            pj_finish(tk, p, q, cq, staged ? sm.obuf : nullptr, qi, n_here);
+        }
+        if (staged) {
+            // rows of queries handed to the heavy kernel hold stale words here; that kernel runs afterwards and rewrites them
+            __syncwarp();
+            const int n_words = n_here * p.k;
+            const int64_t at = q0 * p.k;
+            for (int i = lane; i < n_words; i += 32) {
+                p.out_inter[at + i] = sm.obuf[i];
+                p.out_union[at + i] = sm.obuf[n_words + i];
+                p.out_idx[at + i] = (int32_t)sm.obuf[2 * n_words + i];
+            }
+            __syncwarp();
+        }
+    }
+}
+
 constexpr int PJ_HWIN_SHIFT = PJ_WIN_SHIFT_MAX;   // the heavy kernel walks the pool 32 768 rows at a time (several index windows)
 
 struct PJHeavySmem {
@@ -858,10 +1158,15 @@ static int postings_topk_impl(const int32_t* q_ids, const int64_t* q_off, int64_
         const double per_query = (double)(q_nnz > 0 ? q_nnz : 0) / (double)nq * ((double)nnz / (double)n_bits);
         const bool large = options().postings_log_t == PJ_LOG_T_LARGE ||
                            (options().postings_log_t != PJ_LOG_T_SMALL && per_query > 4.0 * pj_cap(PJ_LOG_T_SMALL));
-        static SmemOptIn opt_in[2];
-        const size_t smem = (large ? sizeof(PJWarpSmem<PJ_LOG_T_LARGE>) : sizeof(PJWarpSmem<PJ_LOG_T_SMALL>)) * PJ_LIGHT_WARPS;
-        void (*kern)(const PJParams) = large ? postings_light_kernel<PJ_LOG_T_LARGE> : postings_light_kernel<PJ_LOG_T_SMALL>;
-        if (int rc = ensure_dyn_smem(kern, smem, opt_in[large ? 1 : 0])) return rc;
+        // label-like sets (the small-table regime) take the register-resident kernel; option "postings_kernel" = 1
+        // keeps the hash-table kernel for them too (comparison point)
+        const bool reg = !large && options().postings_kernel != 1;
+        static SmemOptIn opt_in[3];
+        const size_t smem = reg ? sizeof(PRWarpSmem) * PR_WARPS
+                                : (large ? sizeof(PJWarpSmem<PJ_LOG_T_LARGE>) : sizeof(PJWarpSmem<PJ_LOG_T_SMALL>)) * PJ_LIGHT_WARPS;
+        void (*kern)(const PJParams) = reg ? postings_reg_kernel
+                                           : (large ? postings_light_kernel<PJ_LOG_T_LARGE> : postings_light_kernel<PJ_LOG_T_SMALL>);
+        if (int rc = ensure_dyn_smem(kern, smem, opt_in[reg ? 2 : (large ? 1 : 0)])) return rc;
         // every warp should find several grabs of work: small calls take fewer queries per grab
         const int64_t cap = (int64_t)num_sms() * (large ? 2 : 4);   // resident CTAs per SM (shared memory)
         int64_t chunk = nq / (cap * PJ_LIGHT_WARPS * 4);

@@ -52,6 +52,7 @@ Options& options() {
         if (const char* e = getenv("R4D_DENSE_STRIPES")) v.dense_stripes = atoi(e);
         if (const char* e = getenv("R4D_DENSE_WALKER_WINDOW")) v.dense_walker_window = atoi(e);
         if (const char* e = getenv("R4D_POSTINGS_CHUNK")) v.postings_chunk = atoi(e);
+        if (const char* e = getenv("R4D_POSTINGS_KERNEL")) v.postings_kernel = atoi(e);
         return v;
     }();
     return o;
@@ -182,6 +183,7 @@ int r4d_set_option(const char* key, int value) {
     else if (!strcmp(key, "postings_log_t")) slot = &o.postings_log_t;
     else if (!strcmp(key, "dense_walker_window")) slot = &o.dense_walker_window;
     else if (!strcmp(key, "postings_chunk")) slot = &o.postings_chunk;
+    else if (!strcmp(key, "postings_kernel")) slot = &o.postings_kernel;
     if (!slot || (slot == &o.jaccard_warps && value != 8 && value != 16)) {
         r4d::set_error("r4d_set_option: unknown key or bad value (%s = %d)", key, value);
         return R4D_E_ARG;
