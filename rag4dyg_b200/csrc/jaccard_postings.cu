@@ -653,7 +653,8 @@ __global__ void __launch_bounds__(PR_WARPS * 32, 4) postings_reg_kernel(const PJ
                 e1 = p.off[(int64_t)(id1 + 1) * p.n_win];
             }
             const uint32_t hits = __reduce_add_sync(0xffffffffu, (e0 - s0) + (e1 - s1));
-            const int passes = (int)((hits + PR_PLAN - 1) / PR_PLAN);
+            // one pass holds PR_CAP postings exactly; only a split over row windows needs slack for uneven windows
+            const int passes = hits <= (uint32_t)PR_CAP ? 1 : (int)((hits + PR_PLAN - 1) / PR_PLAN);
             if (passes > p.n_win) {
                 hand_over(q);
                 continue;
@@ -1168,7 +1169,7 @@ static int postings_topk_impl(const int32_t* q_ids, const int64_t* q_off, int64_
                                            : (large ? postings_light_kernel<PJ_LOG_T_LARGE> : postings_light_kernel<PJ_LOG_T_SMALL>);
         if (int rc = ensure_dyn_smem(kern, smem, opt_in[reg ? 2 : (large ? 1 : 0)])) return rc;
         // every warp should find several grabs of work: small calls take fewer queries per grab
-        const int64_t cap = (int64_t)num_sms() * (large ? 2 : 4);   // resident CTAs per SM (shared memory)
+        const int64_t cap = (int64_t)num_sms() * (large ? 2 : 4);   // resident CTAs per SM (shared memory / registers)
         int64_t chunk = nq / (cap * PJ_LIGHT_WARPS * 4);
         if (top_idx != nullptr && peers.world == 0 && k <= PJ_OBUF_K) {
             // results going straight to pinned HOST memory: the largest chunks make the fewest, widest PCIe writes
