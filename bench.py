@@ -458,8 +458,8 @@ def main():
             "bound": "hbm", "achieved": survey_bytes / main_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
             "frac": survey_bytes / main_s / 1e9 / hbm_peak,
             "traffic": dram_traffic("jaccard_postings", queries=nq, pool=n_pool),
-            "kernel": "r4d::postings_light_kernel<9> (one warp per query: hash join of the query's posting lists in shared "
-                      "memory, exact counts, warp-level top-K)",
+            "kernel": "r4d::postings_reg_kernel (one warp per query: the query's posting lists joined in registers, repeat "
+                      "filter in shared memory, exact counts, warp-level top-K)",
             "kernel_ms": main_s * 1e3, "launches_timed": int(main_n),
             "algorithmic_bytes": survey_bytes,
             "algorithmic_bytes_what": "SURVEY 8(d): (N + Q) * 4W B of bitsets read once + Q*K*12 B written (W = 625 words) — the "
@@ -469,7 +469,7 @@ def main():
             "own_representation": {
                 "what": "bytes the postings representation itself has to touch per launch: 8 B per posting of every query id "
                         "+ bucket offsets + query CSR + [Q,K] output; the 28 MB index is L2 resident, the kernel is bound by "
-                        "issue slots / L2 latency, not by HBM (ncu: profiles/r2_ncu_postings_light.txt)",
+                        "issue slots / L2 latency, not by HBM (ncu: profiles/r2_ncu_postings_reg_benchcfg.txt)",
                 "bytes": own_bytes, "postings_visited": postings_touched, "achieved_GBps": own_bytes / main_s / 1e9,
                 "frac_hbm": own_bytes / main_s / 1e9 / hbm_peak,
                 "postings_per_s": postings_touched / main_s}}

@@ -175,3 +175,29 @@ def test_graph_topk_replays_with_refreshed_queries():
         got = [t.cpu().numpy() for t in g.replay()]
         oi, ou, ox = jo.c_topk(qi, qo, *to_csr(p), k)
         assert np.array_equal(got[2], ox) and np.array_equal(got[0], oi) and np.array_equal(got[1], ou)
+
+
+@pytest.mark.parametrize("npool,n_bits,mean,nq,k,self_queries", [
+    (3000, 200, 6, 400, 10, False),      # small vocabulary: many rows share several ids (true repeats), 2-3 passes
+    (30000, 30000, 20, 300, 10, True),   # queries = pool rows with up to 64 ids: one row repeats in EVERY list; > 32 ids
+    (30000, 30000, 20, 300, 12, False),  # general list search (5..64 ids), staged output at the widest staged k
+    (9000, 1500, 3, 2000, 7, True),      # two windows, forced-zero diagonal next to repeats
+])
+def test_register_kernel_repeats_and_passes(npool, n_bits, mean, nq, k, self_queries):
+    """The register-resident light kernel (label-like regime): repeat filter + resolution, few-list and searched list
+    lookup, several passes over row windows — bit-identical to the oracle and to the hash-table kernel."""
+    from rag4dyg_b200 import _lib
+    rng = np.random.default_rng(npool + k)
+    p = random_sets(rng, npool, n_bits, mean=mean, max_len=min(64, n_bits), p_empty=0.02, dup=True)
+    q = [list(x) for x in p[:nq]] if self_queries else random_sets(rng, nq, n_bits, mean=mean, max_len=min(64, n_bits),
+                                                                 p_empty=0.02, dup=True)
+    zero_diag = self_queries and k == 7
+    ti, tu, tx, bp, index = run_postings(q, p, n_bits, k, zero_diag=zero_diag)
+    oi, ou, ox = jo.c_topk(*to_csr(q), *to_csr(p), k, zero_diag=zero_diag)
+    assert np.array_equal(tx, ox) and np.array_equal(ti, oi) and np.array_equal(tu, ou)
+    prev = _lib.set_option("postings_kernel", 1)          # the hash-table kernel on the same call
+    try:
+        hi, hu, hx, _, _ = run_postings(q, p, n_bits, k, zero_diag=zero_diag)
+    finally:
+        _lib.set_option("postings_kernel", prev)
+    assert np.array_equal(hx, tx) and np.array_equal(hi, ti) and np.array_equal(hu, tu)
