@@ -653,9 +653,16 @@ __global__ void __launch_bounds__(PR_WARPS * 32, 4) postings_reg_kernel(const PJ
                 e1 = p.off[(int64_t)(id1 + 1) * p.n_win];
             }
             const uint32_t hits = __reduce_add_sync(0xffffffffu, (e0 - s0) + (e1 - s1));
-            // one pass holds PR_CAP postings exactly; only a split over row windows needs slack for uneven windows
-            const int passes = hits <= (uint32_t)PR_CAP ? 1 : (int)((hits + PR_PLAN - 1) / PR_PLAN);
-            if (passes > p.n_win) {
+            // One pass holds PR_CAP postings.  A query with more walks the pool's row windows, `wpp` windows per pass
+            // (planned for PR_PLAN postings: windows are not perfectly even); a pass that still overflows is halved until
+            // it fits — only a SINGLE window with more than PR_CAP postings sends the query to the heavy kernel.
+            const bool single = hits <= (uint32_t)PR_CAP;
+            int wpp = p.n_win;
+            if (!single) {
+                wpp = (int)(((uint64_t)PR_PLAN * (uint64_t)p.n_win) / (uint64_t)hits);
+                if (wpp < 1) wpp = 1;
+            }
+            if (!single && (uint64_t)hits > (uint64_t)PR_CAP * (uint64_t)p.n_win) {   // even one window per pass cannot fit
                 hand_over(q);
                 continue;
             }
@@ -664,34 +671,42 @@ __global__ void __launch_bounds__(PR_WARPS * 32, 4) postings_reg_kernel(const PJ
             bool failed = false, have_list = false;   // have_list: the sorted list holds entries of an earlier pass
             const bool diag_on = p.zero_diag != 0;
             const int64_t diag_row = p.query_base + q - p.pool_base;   // pool row forced to score 0
-            const int w_base = passes > 1 ? p.n_win / passes : 0, w_rem = passes > 1 ? p.n_win - w_base * passes : 0;
-            for (int ps = 0; ps < passes; ++ps) {
-                if (passes > 1) {   // this pass: windows [wlo, whi) of every list (balanced split of the n_win windows)
-                    const int wlo = ps * w_base + min(ps, w_rem), whi = (ps + 1) * w_base + min(ps + 1, w_rem);
-                    if (id0 >= 0) {
-                        s0 = p.off[(int64_t)id0 * p.n_win + wlo];
-                        e0 = p.off[(int64_t)id0 * p.n_win + whi];
+            for (int w = 0; w < p.n_win;) {
+                int wn = single ? p.n_win : min(w + wpp, p.n_win);
+                uint32_t l0, l1, i0, i1, tot0, tot1, n_post;
+                for (;;) {
+                    if (!single) {   // this pass: windows [w, wn) of every list
+                        if (id0 >= 0) {
+                            s0 = p.off[(int64_t)id0 * p.n_win + w];
+                            e0 = p.off[(int64_t)id0 * p.n_win + wn];
+                        }
+                        if (two && id1 >= 0) {
+                            s1 = p.off[(int64_t)id1 * p.n_win + w];
+                            e1 = p.off[(int64_t)id1 * p.n_win + wn];
+                        }
                     }
-                    if (two && id1 >= 0) {
-                        s1 = p.off[(int64_t)id1 * p.n_win + wlo];
-                        e1 = p.off[(int64_t)id1 * p.n_win + whi];
-                    }
-                }
-                // ---- the pass's postings as ONE sequence: posting g of the sequence goes to lane g % 32, slot g / 32
-                const uint32_t l0 = e0 - s0, l1 = two ? e1 - s1 : 0u;
-                uint32_t i0 = l0, i1 = l1;
+                    // ---- the pass's postings as ONE sequence: posting g of the sequence goes to lane g % 32, slot g / 32
+                    l0 = e0 - s0;
+                    l1 = two ? e1 - s1 : 0u;
+                    i0 = l0;
+                    i1 = l1;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
-                    if (lane >= o) {
-                        i0 += t0;
-                        i1 += t1;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
+                        if (lane >= o) {
+                            i0 += t0;
+                            i1 += t1;
+                        }
                     }
+                    tot0 = __shfl_sync(0xffffffffu, i0, 31);
+                    tot1 = __shfl_sync(0xffffffffu, i1, 31);
+                    n_post = tot0 + tot1;
+                    if (n_post <= (uint32_t)PR_CAP || wn - w <= 1) break;
+                    wn = w + ((wn - w) >> 1);   // too many postings for the registers of a pass: take half the windows
                 }
-                const uint32_t tot0 = __shfl_sync(0xffffffffu, i0, 31), tot1 = __shfl_sync(0xffffffffu, i1, 31);
-                const uint32_t n_post = tot0 + tot1;
+                w = wn;
                 if (n_post == 0u) continue;
-                if (n_post > (uint32_t)PR_CAP) {   // a hot window: more postings than the registers of a pass hold
+                if (n_post > (uint32_t)PR_CAP) {   // one hot window: more postings than a pass holds
                     failed = true;
                     break;
                 }
