@@ -10,18 +10,22 @@
 //     off[]    bucket offsets (exclusive scan of the bucket sizes); an id's whole posting list is the contiguous
 //              range off[id * n_win] .. off[(id + 1) * n_win], and any run of windows of it is contiguous too
 //   r4d_jaccard_topk_postings (queries arrive as CSR id lists; duplicates inside a row collapse, like Python's set()):
-//     postings_light_kernel   one WARP per query.  The (<= 64) distinct ids of the query select their posting ranges;
-//                             every posting is inserted into the warp's 512-slot hash table in shared memory
-//                             (64-bit CAS claims a slot for a pool row, a 32-bit atomic add counts further hits), so a
-//                             slot's count IS |Q n P| and union = |Q| + |P| - count needs no second look at the pool.
-//                             The table is scanned into a warp-level sorted top-K list (exact rational compare).
-//                             A query with more postings than one table holds walks the pool's row windows in
-//                             several passes (disjoint row ranges => a pair never spans two passes).
-//     postings_heavy_kernel   one CTA per query the light kernel handed over (more than 64 ids, more passes than
-//                             windows, a hot window): the query becomes a bitmap over the ids, every window of the pool
-//                             gets one 16-bit counter per row in shared memory, postings increment them, a scan turns
-//                             non-zero counters into candidates.  Any set size, any skew; slower.
-//   Both write the final [nq][k] lists themselves (zero-score fillers included), or store them into the peers' gather
+//     postings_reg_kernel     label-like sets (the headline): one WARP per query, the pass's <= 256 postings held in
+//                             REGISTERS, repeats of a pool row found with an 8 192-bit filter in shared memory and
+//                             resolved by a warp-wide compare; warp-level sorted top-K list (exact rational compare).
+//     postings_light_kernel   history-like sets (hundreds to thousands of postings per query): one WARP per query.  The
+//                             (<= 64) distinct ids of the query select their posting ranges; every posting is inserted
+//                             into the warp's 512 / 1 024-slot hash table in shared memory (64-bit CAS claims a slot for
+//                             a pool row, a 32-bit atomic add counts further hits), so a slot's count IS |Q n P| and
+//                             union = |Q| + |P| - count needs no second look at the pool.  The claimed slots are scanned
+//                             into the warp-level sorted top-K list.
+//                             Both walk the pool's row windows in several passes when a query has more postings than a
+//                             pass holds (disjoint row ranges => a pair never spans two passes).
+//     postings_heavy_kernel   one CTA per query the light kernels handed over (more than 64 ids, a row window with more
+//                             postings than a pass holds): the query becomes a bitmap over the ids, every window of the
+//                             pool gets one 16-bit counter per row in shared memory, postings increment them, a scan
+//                             turns non-zero counters into candidates.  Any set size, any skew; slower.
+//   All write the final [nq][k] lists themselves (zero-score fillers included), or store them into the peers' gather
 //   buffers (fused exchange) — no candidate ever goes through global memory.
 //
 // Exactness: counts are integers, ranking is the same (inter * union' vs inter' * union, index) comparator as everywhere
