@@ -64,7 +64,7 @@ def test_committed_bench_line_has_the_contract_shape():
 
 def test_committed_scaling_lines_are_weak_and_verified():
     base = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_n1.json")))
-    for n in (2, 8):
+    for n in (2, 4, 8):
         d = json.load(open(os.path.join(ROOT, "profiles", f"r2_bench_n{n}.json")))
         assert d["n_gpus"] == n and d["scaling"] == "weak" and d["verified"] is True
         assert "query-sharded" in d["config"]["parallelism"]
