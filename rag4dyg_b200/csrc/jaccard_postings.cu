@@ -48,7 +48,8 @@ constexpr int PJ_LIGHT_WARPS = 8;
 constexpr int PJ_CHUNK = 8;                     // queries a warp takes per grab of the work counter
 constexpr int PJ_HEAVY_THREADS = 256;
 constexpr int PJ_HEAVY_UID = 2048;              // distinct ids of a heavy query enumerated in shared memory
-constexpr uint32_t PJ_MAGIC = 0x52344450u;      // "R4DP"
+constexpr int PJ_BEST = 32;                      // per id: its 32 best postings by (|pool set| asc, row asc), one per lane
+constexpr uint32_t PJ_MAGIC = 0x52344451u;      // "R4DQ" (layout with the per-id best lists)
 
 struct PostingsHeader {   // first 256 bytes of the index blob (device memory)
     uint32_t magic, status;   // status != 0: the build overflowed nnz_cap (index unusable)
@@ -59,7 +60,7 @@ struct PostingsHeader {   // first 256 bytes of the index blob (device memory)
 struct PostingsLayout {
     int win_shift, n_win;
     int64_t n_buckets;
-    size_t off_at, post_at, total;
+    size_t off_at, post_at, best_at, total;
     bool ok;
 };
 
@@ -79,7 +80,8 @@ static PostingsLayout postings_layout(int64_t np, int32_t n_bits, int64_t nnz) {
     }
     L.off_at = 256;
     L.post_at = L.off_at + (((size_t)(L.n_buckets + 1) * 4 + 255) / 256) * 256;
-    L.total = L.post_at + (size_t)(nnz > 0 ? nnz : 1) * 8;
+    L.best_at = L.post_at + (((size_t)(nnz > 0 ? nnz : 1) * 8 + 255) / 256) * 256;
+    L.total = L.best_at + (size_t)n_bits * PJ_BEST * 8;
     return L;
 }
 
@@ -131,6 +133,49 @@ postings_scan_rows_kernel(const uint32_t* __restrict__ pbits, const uint32_t* __
 }
 
 __global__ void postings_header_kernel(PostingsHeader* hdr, const PostingsHeader h) { *hdr = h; }
+
+// best[id][0 .. PJ_BEST): the postings of `id` with the smallest (|pool set|, row), ascending, padded with
+// {0xffffffff, 0}.  A query that holds ONE id scores every pool row of that list 1 / |pool set| (intersection 1, union
+// |pool set|), so its top-K is simply the head of this list — no join at all (postings_reg_kernel).  One warp per id,
+// built once with the index.
+struct BestEntry {
+    uint32_t card, row;
+    __device__ __forceinline__ static BestEntry worst() { return BestEntry{0xffffffffu, 0xffffffffu}; }
+    __device__ __forceinline__ static bool better(const BestEntry& a, const BestEntry& b) {
+        return a.card < b.card || (a.card == b.card && a.row < b.row);
+    }
+    __device__ __forceinline__ BestEntry shfl(int src) const {
+        return BestEntry{__shfl_sync(0xffffffffu, card, src), __shfl_sync(0xffffffffu, row, src)};
+    }
+    __device__ __forceinline__ BestEntry shfl_up1() const {
+        return BestEntry{__shfl_up_sync(0xffffffffu, card, 1), __shfl_up_sync(0xffffffffu, row, 1)};
+    }
+};
+
+__global__ void __launch_bounds__(256) postings_best_kernel(const uint32_t* __restrict__ off, const uint2* __restrict__ post,
+                                                           int32_t n_bits, int32_t n_win, uint2* __restrict__ best) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wpg = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t id = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); id < n_bits; id += wpg) {
+        const uint32_t s = off[id * n_win], e = off[(id + 1) * n_win];
+        WarpTopK<BestEntry> tk;
+        tk.init(PJ_BEST);
+        for (uint32_t t0 = s; t0 < e; t0 += 32) {
+            BestEntry c = BestEntry::worst();
+            if (t0 + lane < e) {
+                const uint2 v = post[t0 + lane];
+                c = BestEntry{v.y, v.x};
+            }
+            uint32_t m = __ballot_sync(0xffffffffu, BestEntry::better(c, tk.kth));
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                tk.insert(c.shfl(src));
+            }
+        }
+        best[id * PJ_BEST + lane] = make_uint2(tk.mine.row, tk.mine.card == 0xffffffffu ? 0u : tk.mine.card);
+    }
+}
 
 // In-place inclusive scan of x[0 .. n) (uint32), three launches: block sums, scan of the sums, rescan + offset.
 constexpr int SCAN_THREADS = 256, SCAN_PER_THREAD = 16, SCAN_TILE = SCAN_THREADS * SCAN_PER_THREAD;
@@ -208,6 +253,7 @@ struct PJParams {
     int64_t nq;
     const uint32_t* off;
     const uint2* post;
+    const uint2* best;      // [n_bits][PJ_BEST] per-id best postings (nullptr: not used)
     const uint32_t* pcard;
     int64_t np;
     int32_t n_bits, win_shift, n_win, k, zero_diag, n_fill;
@@ -647,6 +693,30 @@ __global__ void __launch_bounds__(PR_WARPS * 32, 4) postings_reg_kernel(const PJ
             const uint32_t cq = __popc(__ballot_sync(0xffffffffu, id0 >= 0)) + __popc(__ballot_sync(0xffffffffu, id1 >= 0));
             const bool two = m_raw > 32;   // warp-uniform: the second id register is in use
             const bool few = m_raw <= 4;   // warp-uniform: the lists are found by three compares instead of a search
+            // ---- a query of ONE id needs no join: every row of the id's list scores 1 / |pool set|, and the index holds
+            // the head of that list in (|pool set| asc, row asc) = (score desc, index asc) order
+            if (cq == 1u && p.best != nullptr && p.k + (p.zero_diag ? 1 : 0) <= PJ_BEST) {
+                const uint32_t has = __ballot_sync(0xffffffffu, id0 >= 0) | 0u;
+                const int32_t id = has ? __shfl_sync(0xffffffffu, id0, __ffs(has) - 1)
+                                       : __shfl_sync(0xffffffffu, id1, __ffs(__ballot_sync(0xffffffffu, id1 >= 0)) - 1);
+                const uint2 e = p.best[(int64_t)id * PJ_BEST + lane];
+                const int64_t diag_row1 = p.query_base + q - p.pool_base;
+                const bool is_diag = p.zero_diag != 0 && e.x != 0xffffffffu && (int64_t)e.x == diag_row1;
+                const uint32_t dm = __ballot_sync(0xffffffffu, is_diag);
+                const int d_at = dm ? __ffs(dm) - 1 : 32;                       // the forced-zero row, if it is listed
+                const int from = lane < d_at ? lane : lane + 1;                 // close the gap it leaves
+                const uint32_t row = __shfl_sync(0xffffffffu, e.x, from & 31), card = __shfl_sync(0xffffffffu, e.y, from & 31);
+                const bool live = from < 32 && row != 0xffffffffu;
+                const int n_live = __popc(__ballot_sync(0xffffffffu, live));
+                if (n_live >= p.k) {   // (a shorter list falls through to the general path, which also adds the fillers)
+                    WarpTopK<PEntry> tk1;
+                    tk1.init(p.k);
+                    if (lane < p.k) tk1.mine = PEntry{1u, card, (int32_t)(p.pool_base + (int64_t)row)};
+                    tk1.refresh_kth();
+                    pj_finish(tk1, p, q, cq, staged ? sm.obuf : nullptr, qi, n_here);
+                    continue;
+                }
+            }
             uint32_t s0 = 0, e0 = 0, s1 = 0, e1 = 0;
             if (id0 >= 0) {
                 s0 = p.off[(int64_t)id0 * p.n_win];
@@ -1103,7 +1173,10 @@ int r4d_postings_build(const uint32_t* pbits, const uint32_t* pcard, int64_t np,
     R4D_CUDA(cudaMemsetAsync(base, 0, L.post_at, st));   // header + offsets
     postings_header_kernel<<<1, 1, 0, st>>>(hdr, h); note_launch();
     R4D_CUDA(cudaMemsetAsync(cursor, 0, (size_t)L.n_buckets * 4, st));
-    if (np == 0) return R4D_OK;
+    if (np == 0) {   // empty pool: every best list is empty
+        R4D_CUDA(cudaMemsetAsync(base + L.best_at, 0xff, (size_t)n_bits * PJ_BEST * 8, st));
+        return R4D_OK;
+    }
     int64_t blocks = (np + 7) / 8;
     const int64_t cap = (int64_t)num_sms() * 16;
     if (blocks > cap) blocks = cap;
@@ -1118,6 +1191,12 @@ int r4d_postings_build(const uint32_t* pbits, const uint32_t* pcard, int64_t np,
     postings_scan_rows_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(pbits, pcard, np, words, pitch_words, n_bits, L.win_shift,
                                                                     L.n_win, off, cursor, post, nnz, hdr);
     note_launch();
+    {
+        uint2* best = reinterpret_cast<uint2*>(base + L.best_at);
+        int64_t bb = ((int64_t)n_bits + 7) / 8;
+        if (bb > cap) bb = cap;
+        postings_best_kernel<<<(unsigned)bb, 256, 0, st>>>(off, post, n_bits, L.n_win, best); note_launch();
+    }
     R4D_CUDA(cudaGetLastError());
     return R4D_OK;
 }
@@ -1154,6 +1233,7 @@ static int postings_topk_impl(const int32_t* q_ids, const int64_t* q_off, int64_
     prm.nq = nq;
     prm.off = reinterpret_cast<const uint32_t*>(base + L.off_at);
     prm.post = reinterpret_cast<const uint2*>(base + L.post_at);
+    prm.best = options().postings_best ? reinterpret_cast<const uint2*>(base + L.best_at) : nullptr;
     prm.pcard = pcard;
     prm.np = np;
     prm.n_bits = n_bits;
