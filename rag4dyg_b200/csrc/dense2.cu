@@ -124,13 +124,18 @@ __device__ __forceinline__ int32_t ld_relaxed_i32(const int32_t* p) {
     return v;
 }
 
-template <int DPN, bool QRES>
+// X3C: split precision with COMBINED stages — one stage holds the hi AND lo planes of the pool half-tile and of the query
+// tile for one k-block (4 x 16 KB), and feeds all three products; the separate-stage form loads p_hi and q_hi twice
+// (L2 -> SM traffic 96 KB instead of 64 KB per k-block), which costs power the tensor pipe could use.
+template <int DPN, bool QRES, bool X3C>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(D2_THREADS, 1)
 dense2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_p,
               const __grid_constant__ CUtensorMap tm_qlo, const __grid_constant__ CUtensorMap tm_plo,
               const Dense2Params prm) {
     constexpr int P_TILE_BYTES_ = (DPN / 2) * DKB * 2;
-    constexpr int P_STAGE_BYTES = P_TILE_BYTES_ + (QRES ? 0 : Q_TILE_BYTES);  // streamed Q k-block sits after the P tile
+    static_assert(!(QRES && X3C), "combined split-precision stages stream both operands");
+    // streamed Q k-block sits after the P tile; X3C: [p_hi | q_hi | p_lo | q_lo]
+    constexpr int P_STAGE_BYTES = X3C ? 2 * (P_TILE_BYTES_ + Q_TILE_BYTES) : P_TILE_BYTES_ + (QRES ? 0 : Q_TILE_BYTES);
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* q_res = smem;                                              // [n_kblocks][128 x 64 bf16]  resident (QRES)
     uint8_t* stages = smem + (QRES ? (size_t)prm.n_kblocks * Q_TILE_BYTES : 0);  // [n_stages][stage]
@@ -230,7 +235,24 @@ dense2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                         __nanosleep(256);
                     }
                 }
-                if (lane == 0) {
+                if (lane == 0 && X3C) {
+                    for (int kb = 0; kb < prm.n_kblocks; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[stage]), 0);
+                        const uint32_t sdst = smem_u32(stages + (size_t)stage * P_STAGE_BYTES);
+                        mbar_arrive_expect_tx_cluster(full_leader, (uint32_t)P_STAGE_BYTES);
+                        const int prow = pt * DPN + (int)rank * (DPN / 2);
+                        tma_load_2d_2sm(sdst, &tm_p, full_leader, kb * DKB, prow);
+                        tma_load_2d_2sm(sdst + P_TILE_BYTES_, &tm_q, full_leader, kb * DKB, qtile * DQ);
+                        tma_load_2d_2sm(sdst + P_TILE_BYTES_ + Q_TILE_BYTES, &tm_plo, full_leader, kb * DKB, prow);
+                        tma_load_2d_2sm(sdst + 2 * P_TILE_BYTES_ + Q_TILE_BYTES, &tm_qlo, full_leader, kb * DKB, qtile * DQ);
+                        if (++stage == prm.n_stages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+                if (lane == 0 && !X3C) {
                     // split precision: per k-block the products q_hi.p_hi, q_hi.p_lo, q_lo.p_hi in this order — the
                     // same sequence of K = 16 MMA steps as dense.cu issues, so both kernels accumulate identically
                     for (int kb = 0; kb < prm.n_kblocks; ++kb) {
@@ -277,7 +299,7 @@ dense2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                     mbar_wait(&tempty_bar[buf], ((tile_seq >> 1) & 1u) ^ 1u);
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + buf * DPN;
-                    const int n_vk = prm.n_kblocks * prm.n_segs;   // k-blocks of all segments accumulate into one tile
+                    const int n_vk = X3C ? prm.n_kblocks : prm.n_kblocks * prm.n_segs;   // all segments accumulate into one tile
                     for (int kb = 0; kb < n_vk; ++kb) {
                         mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
@@ -288,6 +310,16 @@ dense2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                         for (int ks = 0; ks < DKB / 16; ++ks)
                             umma_bf16_2sm(tmem_d, qd + (uint64_t)(2 * ks), pd + (uint64_t)(2 * ks), idesc,
                                           (kb | ks) != 0 ? 1u : 0u);
+                        if (X3C) {   // + q_hi.p_lo + q_lo.p_hi from the same stage (same order as dense.cu)
+                            const uint64_t pl = make_smem_desc(sbase + P_TILE_BYTES_ + Q_TILE_BYTES);
+                            const uint64_t ql = make_smem_desc(sbase + 2 * P_TILE_BYTES_ + Q_TILE_BYTES);
+#pragma unroll
+                            for (int ks = 0; ks < DKB / 16; ++ks)
+                                umma_bf16_2sm(tmem_d, qd + (uint64_t)(2 * ks), pl + (uint64_t)(2 * ks), idesc, 1u);
+#pragma unroll
+                            for (int ks = 0; ks < DKB / 16; ++ks)
+                                umma_bf16_2sm(tmem_d, ql + (uint64_t)(2 * ks), pd + (uint64_t)(2 * ks), idesc, 1u);
+                        }
                         tc_commit_2sm_mc(&empty_bar[stage]);  // pool stage free in both CTAs
                         if (++stage == prm.n_stages) {
                             stage = 0;
@@ -410,6 +442,7 @@ dense2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
 struct Dense2Plan {
     int32_t n_qpairs, n_ptiles, n_stripes, ptiles_per_stripe, dpn, n_stages;
     bool qres;
+    bool x3c;   // split precision with combined 64 KB stages
     bool ok;
     size_t smem;
 };
@@ -426,14 +459,13 @@ static Dense2Plan dense2_plan(int64_t nq, int64_t np, int32_t d_pad, int32_t k, 
     const int force = options().dense_pair_qres;  // -1 auto, 0 never resident
     const long avail_res = total - fixed - q_bytes;
     pl.qres = avail_res >= 4 * 16384 && force != 0 && !x3;   // split precision streams hi and lo planes of both operands
-    if (pl.qres) {
-        pl.n_stages = (int)(avail_res / 16384);
-    } else {
-        pl.n_stages = (int)((total - fixed) / (16384 + Q_TILE_BYTES));
-    }
+    long stage_bytes = 16384 + (pl.qres ? 0 : Q_TILE_BYTES);
+    pl.x3c = x3 && options().dense_x3_combined && (total - fixed) / (2 * (16384 + Q_TILE_BYTES)) >= 3;
+    if (pl.x3c) stage_bytes = 2 * (16384 + Q_TILE_BYTES);
+    pl.n_stages = (int)((pl.qres ? avail_res : total - fixed) / stage_bytes);
     if (pl.n_stages > 8) pl.n_stages = 8;
     if (pl.n_stages < 3) return pl;
-    pl.smem = (size_t)fixed + (size_t)pl.n_stages * (16384 + (pl.qres ? 0 : Q_TILE_BYTES)) + (pl.qres ? (size_t)q_bytes : 0);
+    pl.smem = (size_t)fixed + (size_t)pl.n_stages * (size_t)stage_bytes + (pl.qres ? (size_t)q_bytes : 0);
     pl.n_qpairs = (int32_t)((nq + 2 * DQ - 1) / (2 * DQ));
     pl.n_ptiles = (int32_t)((np + pl.dpn - 1) / pl.dpn);
     // Stripe count by a small cost model: rounds(items / clusters) x (tile time + top-K warm-up per stripe).  A stripe
@@ -540,13 +572,17 @@ int dense2_topk(const void* q_hi, const void* q_lo, int64_t nq, const void* p_hi
     int n_clusters = num_sms() / 2;
     if (n_items < n_clusters) n_clusters = (int)n_items;
     if (pl.qres) {
-        R4D_CUDA(cudaFuncSetAttribute(dense2_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        R4D_CUDA(cudaFuncSetAttribute(dense2_kernel<256, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         prof_begin(PROF_DENSE_PAIR, st);
-        dense2_kernel<256, true><<<2 * n_clusters, D2_THREADS, smem, st>>>(tm_q, tm_p, tm_qlo, tm_plo, prm); note_launch();
+        dense2_kernel<256, true, false><<<2 * n_clusters, D2_THREADS, smem, st>>>(tm_q, tm_p, tm_qlo, tm_plo, prm); note_launch();
+    } else if (pl.x3c) {
+        R4D_CUDA(cudaFuncSetAttribute(dense2_kernel<256, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        prof_begin(PROF_DENSE_PAIR, st);
+        dense2_kernel<256, false, true><<<2 * n_clusters, D2_THREADS, smem, st>>>(tm_q, tm_p, tm_qlo, tm_plo, prm); note_launch();
     } else {
-        R4D_CUDA(cudaFuncSetAttribute(dense2_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        R4D_CUDA(cudaFuncSetAttribute(dense2_kernel<256, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         prof_begin(PROF_DENSE_PAIR, st);
-        dense2_kernel<256, false><<<2 * n_clusters, D2_THREADS, smem, st>>>(tm_q, tm_p, tm_qlo, tm_plo, prm); note_launch();
+        dense2_kernel<256, false, false><<<2 * n_clusters, D2_THREADS, smem, st>>>(tm_q, tm_p, tm_qlo, tm_plo, prm); note_launch();
     }
     prof_end(PROF_DENSE_PAIR, st);
     R4D_CUDA(cudaGetLastError());

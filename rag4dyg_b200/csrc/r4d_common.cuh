@@ -25,6 +25,7 @@ struct Options {
     int dense_stripes = 0;
     int stripe_interleave = 0;  // dense pair kernel: 1 = stripe s owns pool tiles s, s+S, ...; 0 = contiguous stripes
     int kernel_timing = 0;      // bracket the dominant kernels with CUDA events (r4d_profile_read)
+    int dense_x3_combined = 1;      // dense pair kernel, split precision: hi + lo planes of a k-block in ONE 64 KB stage
     int dense_walker_window = 4;    // dense pair kernel: tiles a walker may lead the slowest walker of its stripe (0 = off)
     int postings_best = 1;      // postings path: single-id queries read their top-K from the per-id best lists
     int postings_kernel = 0;    // postings path, label-like sets: 0 = register-resident kernel, 1 = hash-table kernel

@@ -182,6 +182,7 @@ int r4d_set_option(const char* key, int value) {
     else if (!strcmp(key, "kernel_timing")) slot = &o.kernel_timing;
     else if (!strcmp(key, "postings_log_t")) slot = &o.postings_log_t;
     else if (!strcmp(key, "dense_walker_window")) slot = &o.dense_walker_window;
+    else if (!strcmp(key, "dense_x3_combined")) slot = &o.dense_x3_combined;
     else if (!strcmp(key, "postings_chunk")) slot = &o.postings_chunk;
     else if (!strcmp(key, "postings_kernel")) slot = &o.postings_kernel;
     else if (!strcmp(key, "postings_best")) slot = &o.postings_best;
