@@ -54,7 +54,8 @@ constexpr uint32_t PJ_MAGIC = 0x52344451u;      // "R4DQ" (layout with the per-i
 struct PostingsHeader {   // first 256 bytes of the index blob (device memory)
     uint32_t magic, status;   // status != 0: the build overflowed nnz_cap (index unusable)
     int64_t np, nnz_cap;
-    int32_t n_bits, win_shift, n_win, pad;
+    int32_t n_bits, win_shift, n_win;
+    uint32_t max_bucket;   // most postings of one id inside one row window (written by the build)
 };
 
 struct PostingsLayout {
@@ -133,6 +134,15 @@ postings_scan_rows_kernel(const uint32_t* __restrict__ pbits, const uint32_t* __
 }
 
 __global__ void postings_header_kernel(PostingsHeader* hdr, const PostingsHeader h) { *hdr = h; }
+
+__global__ void __launch_bounds__(256) postings_max_bucket_kernel(const uint32_t* __restrict__ off, int64_t n_buckets,
+                                                                 PostingsHeader* __restrict__ hdr) {
+    uint32_t m = 0;
+    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_buckets; b += (int64_t)gridDim.x * blockDim.x)
+        m = max(m, off[b + 1] - off[b]);
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(&hdr->max_bucket, m);
+}
 
 // best[id][0 .. PJ_BEST): the postings of `id` with the smallest (|pool set|, row), ascending, padded with
 // {0xffffffff, 0}.  A query that holds ONE id scores every pool row of that list 1 / |pool set| (intersection 1, union
@@ -254,6 +264,7 @@ struct PJParams {
     const uint32_t* off;
     const uint2* post;
     const uint2* best;      // [n_bits][PJ_BEST] per-id best postings (nullptr: not used)
+    const PostingsHeader* hdr;
     const uint32_t* pcard;
     int64_t np;
     int32_t n_bits, win_shift, n_win, k, zero_diag, n_fill;
@@ -261,8 +272,14 @@ struct PJParams {
     uint32_t* out_inter;
     uint32_t* out_union;
     int32_t* out_idx;
-    uint32_t* heavy_list;   // [nq] queries handed to the heavy kernel
-    uint32_t* counters;     // [0] light work counter, [1] heavy queries, [2] heavy work counter
+    // Kernel chain of a call: first-stage light kernel (all queries) -> [hash-table kernel on the queries the register
+    // kernel handed over] -> heavy kernel on what is left.  Every stage takes its work from `work`, serves the queries
+    // in_list[0 .. *in_count) (in_list == nullptr: queries 0 .. nq-1) and appends what it cannot serve to hand_list.
+    const uint32_t* in_list;
+    const uint32_t* in_count;
+    uint32_t* work;
+    uint32_t* hand_list;
+    uint32_t* hand_count;
     PeerOut peers;
     int64_t q_out_off, nq_total;   // fused exchange: row offset / rows of the whole call
     int32_t chunk;                 // queries a light warp takes per grab of the work counter (<= PJ_CHUNK)
@@ -381,26 +398,30 @@ __global__ void __launch_bounds__(PJ_LIGHT_WARPS * 32, LOG_T == PJ_LOG_T_SMALL ?
         for (int i = 0; i < PJ_T / 2 / 32; ++i) t4[i * 32 + lane] = ones;
     };
     auto hand_over = [&](int64_t q) {   // the heavy kernel serves this query
-        if (lane == 0) p.heavy_list[atomicAdd(p.counters + 1, 1u)] = (uint32_t)q;
+        if (lane == 0) p.hand_list[atomicAdd(p.hand_count, 1u)] = (uint32_t)q;
     };
     clear_table();
     bool table_clean = true;
-    const int chunk = p.chunk;
+    // second stage of a chain: the queries are the ones the register kernel handed over, one per grab
+    const bool listed = p.in_list != nullptr;
+    const int64_t n_work = listed ? (int64_t)*p.in_count : p.nq;
+    const int chunk = listed ? 1 : p.chunk;
     for (;;) {
         int64_t q0 = 0;
-        if (lane == 0) q0 = (int64_t)atomicAdd(p.counters + 0, (uint32_t)chunk);
+        if (lane == 0) q0 = (int64_t)atomicAdd(p.work, (uint32_t)chunk);
         q0 = __shfl_sync(0xffffffffu, q0, 0);
-        if (q0 >= p.nq) break;
+        if (q0 >= n_work) break;
+        const int64_t q_first = listed ? (int64_t)p.in_list[q0] : q0;
         // row offsets of the whole chunk with one load
         int64_t my_off = 0;
-        if (lane <= chunk && q0 + lane <= p.nq) my_off = p.q_off[q0 + lane];
-        const int n_here = (int)min((int64_t)chunk, p.nq - q0);
+        if (lane <= chunk && q_first + lane <= p.nq) my_off = p.q_off[q_first + lane];
+        const int n_here = (int)min((int64_t)chunk, n_work - q0);
         // plain output of narrow lists: the chunk's rows are contiguous in every output plane, so they are staged in
         // shared memory and written out together — n_here * k consecutive words per plane instead of k-word pieces
         // (full sectors in HBM; when the caller's buffers are pinned HOST memory, far fewer and larger PCIe writes)
-        const bool staged = p.peers.world == 0 && p.k <= PJ_OBUF_K;
+        const bool staged = !listed && p.peers.world == 0 && p.k <= PJ_OBUF_K;
         for (int qi = 0; qi < n_here; ++qi) {
-            const int64_t q = q0 + qi;
+            const int64_t q = q_first + qi;
             const int64_t beg = __shfl_sync(0xffffffffu, my_off, qi), end = __shfl_sync(0xffffffffu, my_off, qi + 1);
             const int64_t m_raw = end - beg;
             if (m_raw > PJ_IDS) {
@@ -620,9 +641,11 @@ __global__ void __launch_bounds__(PJ_LIGHT_WARPS * 32, LOG_T == PJ_LOG_T_SMALL ?
 // included) are resolved, by broadcasting the row and letting every lane compare it with the live rows it holds — the
 // holder absorbs the count, the repeat dies.  Counts are exact; everything after that (candidate -> sorted top-K list,
 // passes over row windows for longer lists, hand-over to the heavy kernel) is the same as in postings_light_kernel.
-constexpr int PR_SLOTS = 8;               // postings a lane holds per pass
-constexpr int PR_CAP = PR_SLOTS * 32;     // postings per pass
-constexpr int PR_PLAN = 200;              // postings PLANNED per pass (row windows are not perfectly even)
+// Postings a lane holds per pass: 5 (160 per pass) keeps the unrolled per-slot code short — the kernel is instruction-fetch
+// sensitive: 8 slots ran 17 % slower on uniform ids — while 8 (256 per pass) serves pools with hot ids, where a single
+// row window of two hot lists would overflow the smaller pass (such queries then take the slow hand-over chain).  The
+// index header knows the largest (id, window) bucket; the kernel picks its body from it, uniformly for the whole grid.
+constexpr int PR_SLOTS_SMALL = 5, PR_SLOTS_LARGE = 8;
 constexpr int PR_BM_WORDS = 256;          // 8 192-bit repeat filter per warp
 constexpr int PR_WARPS = 8;
 
@@ -635,7 +658,10 @@ struct PRWarpSmem {
     uint32_t pad[3];
 };
 
-__global__ void __launch_bounds__(PR_WARPS * 32, 4) postings_reg_kernel(const PJParams p) {
+template <int PR_SLOTS>
+__device__ __forceinline__ void postings_reg_body(const PJParams& p) {
+    constexpr int PR_CAP = PR_SLOTS * 32;            // postings per pass
+    constexpr int PR_PLAN = PR_SLOTS * 27;           // postings PLANNED per pass (row windows are not perfectly even)
     extern __shared__ __align__(16) uint8_t pj_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     PRWarpSmem& sm = reinterpret_cast<PRWarpSmem*>(pj_smem)[warp];
@@ -645,14 +671,14 @@ __global__ void __launch_bounds__(PR_WARPS * 32, 4) postings_reg_kernel(const PJ
         for (int i = 0; i < PR_BM_WORDS / 4 / 32; ++i) b4[i * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
     };
     auto hand_over = [&](int64_t q) {   // the heavy kernel serves this query
-        if (lane == 0) p.heavy_list[atomicAdd(p.counters + 1, 1u)] = (uint32_t)q;
+        if (lane == 0) p.hand_list[atomicAdd(p.hand_count, 1u)] = (uint32_t)q;
     };
     clear_filter();
     bool filter_clean = true;
     const int chunk = p.chunk;
     for (;;) {
         int64_t q0 = 0;
-        if (lane == 0) q0 = (int64_t)atomicAdd(p.counters + 0, (uint32_t)chunk);
+        if (lane == 0) q0 = (int64_t)atomicAdd(p.work, (uint32_t)chunk);
         q0 = __shfl_sync(0xffffffffu, q0, 0);
         if (q0 >= p.nq) break;
         int64_t my_off = 0;
@@ -951,6 +977,13 @@ __global__ void __launch_bounds__(PR_WARPS * 32, 4) postings_reg_kernel(const PJ
     }
 }
 
+__global__ void __launch_bounds__(PR_WARPS * 32, 4) postings_reg_kernel(const PJParams p) {
+    if (2u * p.hdr->max_bucket > (uint32_t)(PR_SLOTS_SMALL * 32))
+        postings_reg_body<PR_SLOTS_LARGE>(p);
+    else
+        postings_reg_body<PR_SLOTS_SMALL>(p);
+}
+
 constexpr int PJ_HWIN_SHIFT = PJ_WIN_SHIFT_MAX;   // the heavy kernel walks the pool 32 768 rows at a time (several index windows)
 
 struct PJHeavySmem {
@@ -971,7 +1004,7 @@ __global__ void __launch_bounds__(PJ_HEAVY_THREADS) postings_heavy_kernel(const 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = PJ_HEAVY_THREADS / 32;
     static_assert(PJ_HEAVY_THREADS == SCAN_THREADS, "block_excl_scan is written for SCAN_THREADS threads");
-    const uint32_t n_heavy = p.counters[1];
+    const uint32_t n_heavy = *p.in_count;
     constexpr int HW_ROWS = 1 << PJ_HWIN_SHIFT;
     const int wins_per_hw = 1 << (PJ_HWIN_SHIFT - p.win_shift);
     const int n_hwin = (p.n_win + wins_per_hw - 1) / wins_per_hw;
@@ -979,11 +1012,11 @@ __global__ void __launch_bounds__(PJ_HEAVY_THREADS) postings_heavy_kernel(const 
     for (int i = tid; i < HW_ROWS / 2; i += PJ_HEAVY_THREADS) sm.cnt[i] = 0u;
     for (;;) {
         __syncthreads();
-        if (tid == 0) sm.work = atomicAdd(p.counters + 2, 1u);
+        if (tid == 0) sm.work = atomicAdd(p.work, 1u);
         __syncthreads();
         const uint32_t hq = sm.work;
         if (hq >= n_heavy) break;
-        const int64_t q = p.heavy_list[hq];
+        const int64_t q = p.in_list[hq];
         const int64_t beg = p.q_off[q], end = p.q_off[q + 1];
         // ---- the query as a set: bitmap over the ids, |Q| = its popcount, distinct ids enumerated
         for (int i = tid; i < n_uw; i += PJ_HEAVY_THREADS) sm.ubits[i] = 0u;
@@ -1196,13 +1229,14 @@ int r4d_postings_build(const uint32_t* pbits, const uint32_t* pcard, int64_t np,
         int64_t bb = ((int64_t)n_bits + 7) / 8;
         if (bb > cap) bb = cap;
         postings_best_kernel<<<(unsigned)bb, 256, 0, st>>>(off, post, n_bits, L.n_win, best); note_launch();
+        postings_max_bucket_kernel<<<(unsigned)cap, 256, 0, st>>>(off, L.n_buckets, hdr); note_launch();
     }
     R4D_CUDA(cudaGetLastError());
     return R4D_OK;
 }
 
 size_t r4d_jaccard_topk_postings_workspace_bytes(int64_t nq) {
-    return 256 + (size_t)(nq > 0 ? nq : 0) * 4;
+    return 256 + (size_t)(nq > 0 ? nq : 0) * 8;   // counters + two hand-over lists
 }
 
 static int postings_topk_impl(const int32_t* q_ids, const int64_t* q_off, int64_t nq, int64_t q_nnz, const void* index,
@@ -1233,6 +1267,7 @@ static int postings_topk_impl(const int32_t* q_ids, const int64_t* q_off, int64_
     prm.nq = nq;
     prm.off = reinterpret_cast<const uint32_t*>(base + L.off_at);
     prm.post = reinterpret_cast<const uint2*>(base + L.post_at);
+    prm.hdr = reinterpret_cast<const PostingsHeader*>(base);
     prm.best = options().postings_best ? reinterpret_cast<const uint2*>(base + L.best_at) : nullptr;
     prm.pcard = pcard;
     prm.np = np;
@@ -1247,8 +1282,12 @@ static int postings_topk_impl(const int32_t* q_ids, const int64_t* q_off, int64_
     prm.out_inter = top_inter;
     prm.out_union = top_union;
     prm.out_idx = top_idx;
-    prm.counters = reinterpret_cast<uint32_t*>(workspace);
-    prm.heavy_list = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(workspace) + 256);
+    // workspace: counters [64] | list A [nq] | list B [nq]
+    //   counters[0] work of the first stage, [1] entries of list A, [2] work of the heavy kernel,
+    //   counters[3] work of the second (hash-table) stage, [4] entries of list B
+    uint32_t* counters = reinterpret_cast<uint32_t*>(workspace);
+    uint32_t* list_a = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(workspace) + 256);
+    uint32_t* list_b = list_a + nq;
     prm.peers = peers;
     prm.q_out_off = 0;
     prm.nq_total = nq;
@@ -1284,17 +1323,48 @@ static int postings_topk_impl(const int32_t* q_ids, const int64_t* q_off, int64_
         prm.chunk = (int32_t)chunk;
         int64_t grid = (nq + PJ_LIGHT_WARPS * chunk - 1) / (PJ_LIGHT_WARPS * chunk);
         if (grid > cap) grid = cap;
+        // first stage: every query; what it cannot serve goes to list A
+        prm.in_list = nullptr;
+        prm.in_count = nullptr;
+        prm.work = counters + 0;
+        prm.hand_list = list_a;
+        prm.hand_count = counters + 1;
         prof_begin(PROF_JACCARD_POSTINGS, st);
         kern<<<(unsigned)grid, PJ_LIGHT_WARPS * 32, smem, st>>>(prm); note_launch();
         prof_end(PROF_JACCARD_POSTINGS, st);
-    }
-    {
-        static SmemOptIn opt_in;
-        const size_t smem = sizeof(PJHeavySmem);
-        if (int rc = ensure_dyn_smem(postings_heavy_kernel, smem, opt_in)) return rc;
-        int64_t grid = (int64_t)num_sms() * 2;
-        if (grid > nq) grid = nq;
-        postings_heavy_kernel<<<(unsigned)grid, PJ_HEAVY_THREADS, smem, st>>>(prm); note_launch();
+        const uint32_t* heavy_in = list_a;
+        const uint32_t* heavy_count = counters + 1;
+        if (reg) {
+            // second stage: the register kernel's hand-overs (a row window with more postings than its registers hold)
+            // are served by the hash-table kernel, whose 512-slot tables take several times as many per pass;
+            // what even that cannot serve goes to list B.  An empty list A costs one idle launch (~3 us).
+            static SmemOptIn opt_in2;
+            const size_t smem2 = sizeof(PJWarpSmem<PJ_LOG_T_SMALL>) * PJ_LIGHT_WARPS;
+            if (int rc = ensure_dyn_smem(postings_light_kernel<PJ_LOG_T_SMALL>, smem2, opt_in2)) return rc;
+            PJParams p2 = prm;
+            p2.in_list = list_a;
+            p2.in_count = counters + 1;
+            p2.work = counters + 3;
+            p2.hand_list = list_b;
+            p2.hand_count = counters + 4;
+            int64_t grid2 = (int64_t)num_sms() * 2;
+            if (grid2 > (nq + PJ_LIGHT_WARPS - 1) / PJ_LIGHT_WARPS) grid2 = (nq + PJ_LIGHT_WARPS - 1) / PJ_LIGHT_WARPS;
+            postings_light_kernel<PJ_LOG_T_SMALL><<<(unsigned)grid2, PJ_LIGHT_WARPS * 32, smem2, st>>>(p2); note_launch();
+            heavy_in = list_b;
+            heavy_count = counters + 4;
+        }
+        static SmemOptIn opt_in_h;
+        const size_t smem_h = sizeof(PJHeavySmem);
+        if (int rc = ensure_dyn_smem(postings_heavy_kernel, smem_h, opt_in_h)) return rc;
+        PJParams ph = prm;
+        ph.in_list = heavy_in;
+        ph.in_count = heavy_count;
+        ph.work = counters + 2;
+        ph.hand_list = nullptr;
+        ph.hand_count = nullptr;
+        int64_t grid_h = (int64_t)num_sms() * 2;
+        if (grid_h > nq) grid_h = nq;
+        postings_heavy_kernel<<<(unsigned)grid_h, PJ_HEAVY_THREADS, smem_h, st>>>(ph); note_launch();
     }
     R4D_CUDA(cudaGetLastError());
     return R4D_OK;

@@ -21,5 +21,5 @@ for kern in (1, 0):
     for _ in range(10): pool.topk(dq, do, 10, out=out)
     e1.record(); torch.cuda.synchronize()
     ms, n = _lib.profile_read("jaccard_postings"); _lib.set_option("kernel_timing", 0)
-    heavy = int(pool._ws[4:8].view(torch.int32).item())
-    print(f"postings_kernel={kern}: call {e0.elapsed_time(e1) / 10:.3f} ms, light kernel {ms / n:.3f} ms, heavy queries {heavy}", flush=True)
+    c = pool._ws[:32].view(torch.int32).cpu().tolist()
+    print(f"postings_kernel={kern}: call {e0.elapsed_time(e1) / 10:.3f} ms, first-stage kernel {ms / n:.3f} ms, handed over {c[1]}, to the heavy kernel {c[4] if kern == 0 else c[1]}", flush=True)
