@@ -689,7 +689,7 @@ __device__ __forceinline__ void postings_reg_body(const PJParams& p) {
             const int64_t q = q0 + qi;
             const int64_t beg = __shfl_sync(0xffffffffu, my_off, qi), end = __shfl_sync(0xffffffffu, my_off, qi + 1);
             const int64_t m_raw = end - beg;
-            if (m_raw > PJ_IDS) {
+            if (m_raw > 32) {   // more ids than lanes: the hash-table kernel (second stage) holds two ids per lane
                 hand_over(q);
                 continue;
             }
@@ -717,7 +717,7 @@ __device__ __forceinline__ void postings_reg_body(const PJParams& p) {
                 __syncwarp();
             }
             const uint32_t cq = __popc(__ballot_sync(0xffffffffu, id0 >= 0)) + __popc(__ballot_sync(0xffffffffu, id1 >= 0));
-            const bool two = m_raw > 32;   // warp-uniform: the second id register is in use
+            constexpr bool two = false;    // (this kernel keeps one id per lane; the shared code below folds away)
             const bool few = m_raw <= 4;   // warp-uniform: the lists are found by three compares instead of a search
             // ---- a query of ONE id needs no join: every row of the id's list scores 1 / |pool set|, and the index holds
             // the head of that list in (|pool set| asc, row asc) = (score desc, index asc) order
