@@ -977,11 +977,16 @@ __device__ __forceinline__ void postings_reg_body(const PJParams& p) {
     }
 }
 
-__global__ void __launch_bounds__(PR_WARPS * 32, 4) postings_reg_kernel(const PJParams p) {
-    if (2u * p.hdr->max_bucket > (uint32_t)(PR_SLOTS_SMALL * 32))
-        postings_reg_body<PR_SLOTS_LARGE>(p);
-    else
-        postings_reg_body<PR_SLOTS_SMALL>(p);
+// Two kernels, one of which exits at once (an idle launch costs ~3 us): each body gets its own register budget, and the
+// short 5-slot body fits 5 CTAs per SM.
+__device__ __forceinline__ bool pr_wants_large(const PJParams& p) {
+    return 2u * p.hdr->max_bucket > (uint32_t)(PR_SLOTS_SMALL * 32);
+}
+__global__ void __launch_bounds__(PR_WARPS * 32, 6) postings_reg_kernel(const PJParams p) {
+    if (!pr_wants_large(p)) postings_reg_body<PR_SLOTS_SMALL>(p);
+}
+__global__ void __launch_bounds__(PR_WARPS * 32, 4) postings_reg_large_kernel(const PJParams p) {
+    if (pr_wants_large(p)) postings_reg_body<PR_SLOTS_LARGE>(p);
 }
 
 constexpr int PJ_HWIN_SHIFT = PJ_WIN_SHIFT_MAX;   // the heavy kernel walks the pool 32 768 rows at a time (several index windows)
@@ -1307,7 +1312,7 @@ static int postings_topk_impl(const int32_t* q_ids, const int64_t* q_off, int64_
                                            : (large ? postings_light_kernel<PJ_LOG_T_LARGE> : postings_light_kernel<PJ_LOG_T_SMALL>);
         if (int rc = ensure_dyn_smem(kern, smem, opt_in[reg ? 2 : (large ? 1 : 0)])) return rc;
         // every warp should find several grabs of work: small calls take fewer queries per grab
-        const int64_t cap = (int64_t)num_sms() * (large ? 2 : 4);   // resident CTAs per SM (shared memory / registers)
+        const int64_t cap = (int64_t)num_sms() * (reg ? 6 : (large ? 2 : 4));   // resident CTAs per SM (shared memory / registers)
         int64_t chunk = nq / (cap * PJ_LIGHT_WARPS * 4);
         if (top_idx != nullptr && peers.world == 0 && k <= PJ_OBUF_K) {
             // results going straight to pinned HOST memory: the largest chunks make the fewest, widest PCIe writes
@@ -1331,6 +1336,12 @@ static int postings_topk_impl(const int32_t* q_ids, const int64_t* q_off, int64_
         prm.hand_count = counters + 1;
         prof_begin(PROF_JACCARD_POSTINGS, st);
         kern<<<(unsigned)grid, PJ_LIGHT_WARPS * 32, smem, st>>>(prm); note_launch();
+        if (reg) {   // the 8-slot body for pools with hot (id, window) buckets; exits at once otherwise (and vice versa)
+            static SmemOptIn opt_in_l;
+            if (int rc = ensure_dyn_smem(postings_reg_large_kernel, smem, opt_in_l)) return rc;
+            const int64_t cap_l = (int64_t)num_sms() * 4;
+            postings_reg_large_kernel<<<(unsigned)(grid > cap_l ? cap_l : grid), PR_WARPS * 32, smem, st>>>(prm); note_launch();
+        }
         prof_end(PROF_JACCARD_POSTINGS, st);
         const uint32_t* heavy_in = list_a;
         const uint32_t* heavy_count = counters + 1;
