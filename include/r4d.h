@@ -158,6 +158,16 @@ int r4d_jaccard_topk_postings(const int32_t* q_ids, const int64_t* q_off, int64_
                               const uint32_t* pcard, int64_t np, int32_t n_bits, int64_t nnz, int32_t k, int32_t zero_diag,
                               int64_t query_base, int64_t pool_base, uint32_t* top_inter, uint32_t* top_union,
                               int32_t* top_idx, void* workspace, size_t workspace_bytes, r4d_stream_t stream);
+/* Packed results — for [nq][k] lists that cross PCIe (HostTopK stores them straight into pinned host memory): 8 bytes per
+ * entry instead of 12.  top_pair[q][j] = inter << 16 | |pool set| (both <= 65 535 because n_bits is), top_idx as above,
+ * q_card[q] = |query set| (distinct valid ids of the row).  The consumer recovers union = q_card + |pool set| - inter, so
+ * the score inter / union (retrieval_data_annotation.py:18) is the same rational; a padding entry (idx R4D_IDX_NONE)
+ * packs as 0 and stands for (0, 1).  Same kernels, same order, same exactness as r4d_jaccard_topk_postings. */
+int r4d_jaccard_topk_postings_packed(const int32_t* q_ids, const int64_t* q_off, int64_t nq, int64_t q_nnz, const void* index,
+                                     const uint32_t* pcard, int64_t np, int32_t n_bits, int64_t nnz, int32_t k,
+                                     int32_t zero_diag, int64_t query_base, int64_t pool_base, uint32_t* top_pair,
+                                     int32_t* top_idx, uint32_t* q_card, void* workspace, size_t workspace_bytes,
+                                     r4d_stream_t stream);
 /* Fused exchange variant (see r4d_jaccard_topk_scatter): the final lists go to slot `rank` of every peer's gather buffer. */
 int r4d_jaccard_topk_postings_scatter(const int32_t* q_ids, const int64_t* q_off, int64_t nq, int64_t q_nnz,
                                       const void* index,

@@ -272,6 +272,10 @@ struct PJParams {
     uint32_t* out_inter;
     uint32_t* out_union;
     int32_t* out_idx;
+    // Packed results (r4d_jaccard_topk_postings_packed; out_qcard != nullptr): out_inter holds `inter << 16 | |pool set|`
+    // per entry, out_qcard[q] = |query set|, out_union is not written: 8 bytes per entry instead of 12 for results that
+    // cross PCIe.  union = |query set| + |pool set| - inter; a padding entry (idx R4D_IDX_NONE) packs as 0.
+    uint32_t* out_qcard;
     // Kernel chain of a call: first-stage light kernel (all queries) -> [hash-table kernel on the queries the register
     // kernel handed over] -> heavy kernel on what is left.  Every stage takes its work from `work`, serves the queries
     // in_list[0 .. *in_count) (in_list == nullptr: queries 0 .. nq-1) and appends what it cannot serve to hand_list.
@@ -313,8 +317,8 @@ struct PEntry {
 // stage != nullptr (light kernel, plain output, k <= PJ_OBUF_K): the list goes to the warp's staging buffer [3][chunk][k];
 // the rows of a whole chunk of consecutive queries are then written out together (pj_flush_chunk).
 template <class E>
-__device__ __forceinline__ void pj_finish(WarpTopK<E>& tk, const PJParams& p, int64_t q, uint32_t cq, uint32_t* stage = nullptr,
-                                          int stage_row = 0, int stage_rows = 0) {
+__device__ __forceinline__ void pj_finish(WarpTopK<E>& tk, const PJParams& p, int64_t q, uint32_t cq, const bool packed,
+                                          uint32_t* stage = nullptr, int stage_row = 0, int stage_rows = 0) {
     const int lane = threadIdx.x & 31;
     if (p.n_fill > 0 && tk.kth.inter == 0u) {
         const uint32_t cp = lane < p.n_fill ? p.pcard[lane] : 0u;
@@ -324,19 +328,24 @@ __device__ __forceinline__ void pj_finish(WarpTopK<E>& tk, const PJParams& p, in
             tk.insert(c);
         }
     }
+    // packed entry: |pool set| = union + inter - |query set| (also for the fillers: an empty pair has union 1 = "|pool set| 1")
+    const uint32_t first = !packed ? tk.mine.inter
+                                   : (tk.mine.idx == R4D_IDX_NONE ? 0u : (tk.mine.inter << 16) | (tk.mine.uni + tk.mine.inter - cq));
     if (stage != nullptr) {
         if (lane < p.k) {
-            stage[stage_row * p.k + lane] = tk.mine.inter;
-            stage[(stage_rows + stage_row) * p.k + lane] = tk.mine.uni;
+            stage[stage_row * p.k + lane] = first;
+            if (!packed) stage[(stage_rows + stage_row) * p.k + lane] = tk.mine.uni;
             stage[(2 * stage_rows + stage_row) * p.k + lane] = (uint32_t)tk.mine.idx;
         }
+        if (packed && lane == 0) stage[stage_rows * p.k + stage_row] = cq;   // the union plane's place holds |query set|
         return;
     }
     if (lane < p.k) {
         if (p.peers.world == 0) {
-            p.out_inter[q * p.k + lane] = tk.mine.inter;
-            p.out_union[q * p.k + lane] = tk.mine.uni;
+            p.out_inter[q * p.k + lane] = first;
+            if (!packed) p.out_union[q * p.k + lane] = tk.mine.uni;
             p.out_idx[q * p.k + lane] = tk.mine.idx;
+            if (packed && lane == 0) p.out_qcard[q] = cq;
         } else {
             const int64_t nq_all = p.nq_total > 0 ? p.nq_total : p.nq;
             const int64_t plane = (int64_t)p.peers.world * nq_all * p.k;
@@ -349,6 +358,24 @@ __device__ __forceinline__ void pj_finish(WarpTopK<E>& tk, const PJParams& p, in
             }
         }
     }
+}
+
+// The finished lists of a chunk's consecutive queries, staged as [plane][row][k] (pj_finish), go out together: n_here * k
+// consecutive words per plane.  The store loop walks the 128-byte line grid of the destination (a warp-wide store that
+// straddles two lines becomes two partial writes — in HBM two partial sectors, over PCIe two short TLPs).
+__device__ __forceinline__ void pj_flush_chunk(const PJParams& p, const uint32_t* stage, int64_t q0, int n_here,
+                                               const bool packed) {
+    const int lane = threadIdx.x & 31;
+    const int n_words = n_here * p.k;
+    const int64_t at = q0 * p.k;
+    const int mis = (int)((reinterpret_cast<uintptr_t>(p.out_idx + at) >> 2) & 31);   // planes of one call are aligned alike
+    for (int i = lane - mis; i < n_words; i += 32)
+        if (i >= 0) {
+            p.out_inter[at + i] = stage[i];
+            if (!packed) p.out_union[at + i] = stage[n_words + i];
+            p.out_idx[at + i] = (int32_t)stage[2 * n_words + i];
+        }
+    if (packed && lane < n_here) p.out_qcard[q0 + lane] = stage[n_words + lane];
 }
 
 constexpr unsigned long long PJ_EMPTY = 0xffffffffffffffffull;
@@ -391,6 +418,7 @@ __global__ void __launch_bounds__(PJ_LIGHT_WARPS * 32, LOG_T == PJ_LOG_T_SMALL ?
     constexpr int PJ_T = 1 << LOG_T, PJ_CAP = pj_cap(LOG_T);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     PJWarpSmem<LOG_T>& sm = reinterpret_cast<PJWarpSmem<LOG_T>*>(pj_smem)[warp];
+    const bool packed = p.out_qcard != nullptr;
     const uint4 ones = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
     auto clear_table = [&]() {
         uint4* t4 = reinterpret_cast<uint4*>(sm.tab);
@@ -615,18 +643,12 @@ __global__ void __launch_bounds__(PJ_LIGHT_WARPS * 32, LOG_T == PJ_LOG_T_SMALL ?
                 hand_over(q);
                 continue;
             }
-            pj_finish(tk, p, q, cq, staged ? sm.obuf : nullptr, qi, n_here);
+            pj_finish(tk, p, q, cq, packed, staged ? sm.obuf : nullptr, qi, n_here);
         }
         if (staged) {
             // rows of queries handed to the heavy kernel hold stale words here; that kernel runs afterwards and rewrites them
             __syncwarp();
-            const int n_words = n_here * p.k;
-            const int64_t at = q0 * p.k;
-            for (int i = lane; i < n_words; i += 32) {
-                p.out_inter[at + i] = sm.obuf[i];
-                p.out_union[at + i] = sm.obuf[n_words + i];
-                p.out_idx[at + i] = (int32_t)sm.obuf[2 * n_words + i];
-            }
+            pj_flush_chunk(p, sm.obuf, q0, n_here, packed);
             __syncwarp();
         }
     }
@@ -658,8 +680,9 @@ struct PRWarpSmem {
     uint32_t pad[3];
 };
 
-template <int PR_SLOTS>
+template <int PR_SLOTS, bool PACKED>
 __device__ __forceinline__ void postings_reg_body(const PJParams& p) {
+    constexpr bool packed = PACKED;   // packed results are a kernel variant of their own: the plain one pays nothing for them
     constexpr int PR_CAP = PR_SLOTS * 32;            // postings per pass
     constexpr int PR_PLAN = PR_SLOTS * 27;           // postings PLANNED per pass (row windows are not perfectly even)
     extern __shared__ __align__(16) uint8_t pj_smem[];
@@ -739,7 +762,7 @@ __device__ __forceinline__ void postings_reg_body(const PJParams& p) {
                     tk1.init(p.k);
                     if (lane < p.k) tk1.mine = PEntry{1u, card, (int32_t)(p.pool_base + (int64_t)row)};
                     tk1.refresh_kth();
-                    pj_finish(tk1, p, q, cq, staged ? sm.obuf : nullptr, qi, n_here);
+                    pj_finish(tk1, p, q, cq, packed, staged ? sm.obuf : nullptr, qi, n_here);
                     continue;
                 }
             }
@@ -960,18 +983,12 @@ __device__ __forceinline__ void postings_reg_body(const PJParams& p) {
                 hand_over(q);
                 continue;
             }
-            pj_finish(tk, p, q, cq, staged ? sm.obuf : nullptr, qi, n_here);
+            pj_finish(tk, p, q, cq, packed, staged ? sm.obuf : nullptr, qi, n_here);
         }
         if (staged) {
             // rows of queries handed to the heavy kernel hold stale words here; that kernel runs afterwards and rewrites them
             __syncwarp();
-            const int n_words = n_here * p.k;
-            const int64_t at = q0 * p.k;
-            for (int i = lane; i < n_words; i += 32) {
-                p.out_inter[at + i] = sm.obuf[i];
-                p.out_union[at + i] = sm.obuf[n_words + i];
-                p.out_idx[at + i] = (int32_t)sm.obuf[2 * n_words + i];
-            }
+            pj_flush_chunk(p, sm.obuf, q0, n_here, packed);
             __syncwarp();
         }
     }
@@ -982,11 +999,13 @@ __device__ __forceinline__ void postings_reg_body(const PJParams& p) {
 __device__ __forceinline__ bool pr_wants_large(const PJParams& p) {
     return 2u * p.hdr->max_bucket > (uint32_t)(PR_SLOTS_SMALL * 32);
 }
+template <bool PACKED>
 __global__ void __launch_bounds__(PR_WARPS * 32, 6) postings_reg_kernel(const PJParams p) {
-    if (!pr_wants_large(p)) postings_reg_body<PR_SLOTS_SMALL>(p);
+    if (!pr_wants_large(p)) postings_reg_body<PR_SLOTS_SMALL, PACKED>(p);
 }
+template <bool PACKED>
 __global__ void __launch_bounds__(PR_WARPS * 32, 4) postings_reg_large_kernel(const PJParams p) {
-    if (pr_wants_large(p)) postings_reg_body<PR_SLOTS_LARGE>(p);
+    if (pr_wants_large(p)) postings_reg_body<PR_SLOTS_LARGE, PACKED>(p);
 }
 
 constexpr int PJ_HWIN_SHIFT = PJ_WIN_SHIFT_MAX;   // the heavy kernel walks the pool 32 768 rows at a time (several index windows)
@@ -1152,7 +1171,7 @@ __global__ void __launch_bounds__(PJ_HEAVY_THREADS) postings_heavy_kernel(const 
                     tk.insert(c.shfl(src));
                 }
             }
-            pj_finish(tk, p, q, cq);
+            pj_finish(tk, p, q, cq, p.out_qcard != nullptr);
         }
     }
 }
@@ -1247,8 +1266,8 @@ size_t r4d_jaccard_topk_postings_workspace_bytes(int64_t nq) {
 static int postings_topk_impl(const int32_t* q_ids, const int64_t* q_off, int64_t nq, int64_t q_nnz, const void* index,
                               const uint32_t* pcard, int64_t np, int32_t n_bits, int64_t nnz, int32_t k, int32_t zero_diag,
                               int64_t query_base, int64_t pool_base, uint32_t* top_inter, uint32_t* top_union,
-                              int32_t* top_idx, const r4d::PeerOut& peers, void* workspace, size_t workspace_bytes,
-                              r4d_stream_t stream) {
+                              int32_t* top_idx, uint32_t* q_card, const r4d::PeerOut& peers, void* workspace,
+                              size_t workspace_bytes, r4d_stream_t stream) {
     using namespace r4d;
     const PostingsLayout L = postings_layout(np, n_bits, nnz);
     R4D_REQUIRE(L.ok, "jaccard_topk_postings: unsupported shape (np=%lld, n_bits=%d [max %d])", (long long)np, n_bits, PJ_MAX_BITS);
@@ -1257,7 +1276,7 @@ static int postings_topk_impl(const int32_t* q_ids, const int64_t* q_off, int64_
     R4D_REQUIRE(pool_base >= 0 && pool_base + np < (int64_t)R4D_IDX_NONE, "jaccard_topk_postings: pool_base+np exceeds int32");
     if (nq == 0) return R4D_OK;
     R4D_REQUIRE(q_off && index && (np == 0 || pcard), "jaccard_topk_postings: null pointer");
-    R4D_REQUIRE(peers.world > 0 || (top_inter && top_union && top_idx), "jaccard_topk_postings: null output");
+    R4D_REQUIRE(peers.world > 0 || (top_inter && (top_union || q_card) && top_idx), "jaccard_topk_postings: null output");
     const size_t need = r4d_jaccard_topk_postings_workspace_bytes(nq);
     if (!workspace || workspace_bytes < need) {
         set_error("jaccard_topk_postings: workspace %zu B < required %zu B", workspace_bytes, need);
@@ -1287,6 +1306,7 @@ static int postings_topk_impl(const int32_t* q_ids, const int64_t* q_off, int64_
     prm.out_inter = top_inter;
     prm.out_union = top_union;
     prm.out_idx = top_idx;
+    prm.out_qcard = q_card;
     // workspace: counters [64] | list A [nq] | list B [nq]
     //   counters[0] work of the first stage, [1] entries of list A, [2] work of the heavy kernel,
     //   counters[3] work of the second (hash-table) stage, [4] entries of list B
@@ -1305,12 +1325,13 @@ static int postings_topk_impl(const int32_t* q_ids, const int64_t* q_off, int64_
         // label-like sets (the small-table regime) take the register-resident kernel; option "postings_kernel" = 1
         // keeps the hash-table kernel for them too (comparison point)
         const bool reg = !large && options().postings_kernel != 1;
-        static SmemOptIn opt_in[3];
+        const bool packed = q_card != nullptr;
+        static SmemOptIn opt_in[4];
         const size_t smem = reg ? sizeof(PRWarpSmem) * PR_WARPS
                                 : (large ? sizeof(PJWarpSmem<PJ_LOG_T_LARGE>) : sizeof(PJWarpSmem<PJ_LOG_T_SMALL>)) * PJ_LIGHT_WARPS;
-        void (*kern)(const PJParams) = reg ? postings_reg_kernel
+        void (*kern)(const PJParams) = reg ? (packed ? postings_reg_kernel<true> : postings_reg_kernel<false>)
                                            : (large ? postings_light_kernel<PJ_LOG_T_LARGE> : postings_light_kernel<PJ_LOG_T_SMALL>);
-        if (int rc = ensure_dyn_smem(kern, smem, opt_in[reg ? 2 : (large ? 1 : 0)])) return rc;
+        if (int rc = ensure_dyn_smem(kern, smem, opt_in[reg ? (packed ? 3 : 2) : (large ? 1 : 0)])) return rc;
         // every warp should find several grabs of work: small calls take fewer queries per grab
         const int64_t cap = (int64_t)num_sms() * (reg ? 6 : (large ? 2 : 4));   // resident CTAs per SM (shared memory / registers)
         int64_t chunk = nq / (cap * PJ_LIGHT_WARPS * 4);
@@ -1337,10 +1358,11 @@ static int postings_topk_impl(const int32_t* q_ids, const int64_t* q_off, int64_
         prof_begin(PROF_JACCARD_POSTINGS, st);
         kern<<<(unsigned)grid, PJ_LIGHT_WARPS * 32, smem, st>>>(prm); note_launch();
         if (reg) {   // the 8-slot body for pools with hot (id, window) buckets; exits at once otherwise (and vice versa)
-            static SmemOptIn opt_in_l;
-            if (int rc = ensure_dyn_smem(postings_reg_large_kernel, smem, opt_in_l)) return rc;
+            static SmemOptIn opt_in_l[2];
+            void (*kern_l)(const PJParams) = packed ? postings_reg_large_kernel<true> : postings_reg_large_kernel<false>;
+            if (int rc = ensure_dyn_smem(kern_l, smem, opt_in_l[packed ? 1 : 0])) return rc;
             const int64_t cap_l = (int64_t)num_sms() * 4;
-            postings_reg_large_kernel<<<(unsigned)(grid > cap_l ? cap_l : grid), PR_WARPS * 32, smem, st>>>(prm); note_launch();
+            kern_l<<<(unsigned)(grid > cap_l ? cap_l : grid), PR_WARPS * 32, smem, st>>>(prm); note_launch();
         }
         prof_end(PROF_JACCARD_POSTINGS, st);
         const uint32_t* heavy_in = list_a;
@@ -1387,7 +1409,18 @@ int r4d_jaccard_topk_postings(const int32_t* q_ids, const int64_t* q_off, int64_
                               int32_t* top_idx, void* workspace, size_t workspace_bytes, r4d_stream_t stream) {
     r4d::PeerOut none{};
     return postings_topk_impl(q_ids, q_off, nq, q_nnz, index, pcard, np, n_bits, nnz, k, zero_diag, query_base, pool_base, top_inter,
-                              top_union, top_idx, none, workspace, workspace_bytes, stream);
+                              top_union, top_idx, nullptr, none, workspace, workspace_bytes, stream);
+}
+
+int r4d_jaccard_topk_postings_packed(const int32_t* q_ids, const int64_t* q_off, int64_t nq, int64_t q_nnz, const void* index,
+                                     const uint32_t* pcard, int64_t np, int32_t n_bits, int64_t nnz, int32_t k,
+                                     int32_t zero_diag, int64_t query_base, int64_t pool_base, uint32_t* top_pair,
+                                     int32_t* top_idx, uint32_t* q_card, void* workspace, size_t workspace_bytes,
+                                     r4d_stream_t stream) {
+    r4d::PeerOut none{};
+    R4D_REQUIRE(nq <= 0 || q_card != nullptr, "jaccard_topk_postings_packed: null q_card");
+    return postings_topk_impl(q_ids, q_off, nq, q_nnz, index, pcard, np, n_bits, nnz, k, zero_diag, query_base, pool_base, top_pair,
+                              nullptr, top_idx, q_card, none, workspace, workspace_bytes, stream);
 }
 
 int r4d_jaccard_topk_postings_scatter(const int32_t* q_ids, const int64_t* q_off, int64_t nq, int64_t q_nnz, const void* index,
@@ -1406,7 +1439,7 @@ int r4d_jaccard_topk_postings_scatter(const int32_t* q_ids, const int64_t* q_off
         po.base[r] = peer_base[r];
     }
     return postings_topk_impl(q_ids, q_off, nq, q_nnz, index, pcard, np, n_bits, nnz, k, zero_diag, query_base, pool_base, nullptr,
-                              nullptr, nullptr, po, workspace, workspace_bytes, stream);
+                              nullptr, nullptr, nullptr, po, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

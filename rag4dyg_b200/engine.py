@@ -259,6 +259,46 @@ def jaccard_topk_postings(q_ids, q_off, index, k, zero_diag=False, query_base=0,
 
 
 @_on_input_device
+def jaccard_topk_postings_packed(q_ids, q_off, index, k, zero_diag=False, query_base=0, pool_base=0, workspace=None, out=None,
+                                 q_nnz=None):
+    """The same top-K with PACKED results (r4d_jaccard_topk_postings_packed): out = (pair int32 [nq, k] holding
+    inter << 16 | |pool set|, idx int32 [nq, k], q_card int32 [nq]); CUDA or pinned host tensors.  8 bytes per entry instead
+    of 12 — for results that cross PCIe.  `unpack_topk` recovers (inter, union, idx)."""
+    lib = _lib.load()
+    q_ids, q_off, nq = _postings_args(q_ids, q_off, index)
+    dev = index.device
+    with torch.cuda.device(dev):
+        need = lib.r4d_jaccard_topk_postings_workspace_bytes(nq)
+        if workspace is None or workspace.numel() < need:
+            workspace = torch.empty((need,), dtype=torch.uint8, device=dev)
+        if out is None:
+            out = (torch.empty((nq, k), dtype=torch.int32, device=dev), torch.empty((nq, k), dtype=torch.int32, device=dev),
+                   torch.empty((nq,), dtype=torch.int32, device=dev))
+        else:
+            for o, shape in zip(out, ((nq, k), (nq, k), (nq,))):
+                if not (o.dtype == torch.int32 and o.is_contiguous() and tuple(o.shape) == shape and
+                        (o.is_cuda or o.is_pinned())):
+                    raise R4DError("jaccard_topk_postings_packed: `out` must be contiguous int32 ([nq, k], [nq, k], [nq]) "
+                                   "CUDA or pinned host tensors")
+        check(lib.r4d_jaccard_topk_postings_packed(_ptr(q_ids), _ptr(q_off), nq, q_ids.numel() if q_nnz is None else int(q_nnz),
+                                                   _ptr(index.blob), _ptr(index.card), index.n_rows,
+                                                   index.n_bits, index.nnz, k, int(bool(zero_diag)), query_base, pool_base,
+                                                   _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(workspace),
+                                                   workspace.numel(), _stream()), "r4d_jaccard_topk_postings_packed")
+    return out
+
+
+def unpack_topk(pair, idx, q_card):
+    """(pair, idx, q_card) of jaccard_topk_postings_packed -> (inter, union, idx) int32 [nq, k], the planes
+    jaccard_topk_postings writes: inter = pair >> 16, union = q_card + (pair & 0xffff) - inter; padding entries
+    (idx == 0x7fffffff) are (0, 1)."""
+    inter = (pair >> 16) & 0xffff
+    union = q_card.unsqueeze(1) + (pair & 0xffff) - inter
+    union = torch.where(idx == 0x7FFFFFFF, torch.ones_like(union), union)
+    return inter, union, idx
+
+
+@_on_input_device
 def jaccard_topk_postings_scatter(q_ids, q_off, index, k, peer_ptrs, world, rank, zero_diag=False, query_base=0,
                                   pool_base=0, workspace=None):
     """Fused exchange variant: final lists go to slot `rank` of every peer's gather buffer [3][world][nq][k]."""

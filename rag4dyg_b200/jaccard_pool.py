@@ -72,6 +72,16 @@ class JaccardPool:
             return out
         return r
 
+    def topk_packed(self, q_ids, q_off, k, zero_diag=False, query_base=0, out=None, q_nnz=None):
+        """`topk` with packed results: (pair = inter << 16 | |pool set| [nq, k], idx [nq, k], q_card = |query set| [nq]),
+        8 bytes per entry instead of 12 (postings path only; `engine.unpack_topk` gives the three planes back)."""
+        if self.index is None:
+            raise R4DError("topk_packed needs the postings path (a pool with an index)")
+        nq = q_off.numel() - 1
+        return engine.jaccard_topk_postings_packed(q_ids, q_off, self.index, k, zero_diag=zero_diag, query_base=query_base,
+                                                   pool_base=self.pool_base, workspace=self.workspace(nq, k), out=out,
+                                                   q_nnz=q_nnz)
+
 
 class GraphTopK:
     """One JaccardPool.topk call captured in a CUDA graph: replay() re-runs the whole launch sequence (counter memset +
@@ -111,11 +121,17 @@ class HostTopK:
     buffers (pinned memory is device-addressable under unified addressing), so the device->host transfer is spread over
     the kernel's run time as posted PCIe writes — there is no separate copy, and a step costs H2D + scoring.
     direct=False: results land in HBM and are copied out on a copy stream, in `chunks` row ranges so that the copy of
-    one range overlaps the scoring of the next (also the path for pools without a postings index)."""
+    one range overlaps the scoring of the next (also the path for pools without a postings index).
+    packed=True (direct mode): the lists cross PCIe in the packed form of r4d_jaccard_topk_postings_packed — 8 bytes per
+    entry instead of 12; result() then returns (pair, idx, q_card) and `HostTopK.unpack` turns them into the three
+    planes on the host (score = inter / union is the same rational either way)."""
 
-    def __init__(self, pool, k, max_queries, max_ids, depth=2, chunks=1, direct=True):
+    def __init__(self, pool, k, max_queries, max_ids, depth=2, chunks=1, direct=True, packed=False):
         self.pool, self.k, self.depth, self.chunks = pool, int(k), int(depth), max(1, int(chunks))
         self.direct = bool(direct) and pool.index is not None
+        self.packed = bool(packed)
+        if self.packed and not self.direct:
+            raise R4DError("HostTopK: packed results need direct mode (a pool with a postings index)")
         dev = pool.device
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.slots = []
@@ -125,7 +141,10 @@ class HostTopK:
                 "off": torch.empty((max_queries + 1,), dtype=torch.int64, device=dev),
                 "out": None if self.direct else tuple(torch.empty((max_queries, self.k), dtype=torch.int32, device=dev)
                                                       for _ in range(3)),
-                "host": tuple(torch.empty((max_queries, self.k), dtype=torch.int32).pin_memory() for _ in range(3)),
+                "host": ((torch.empty((max_queries, self.k), dtype=torch.int32).pin_memory(),
+                          torch.empty((max_queries, self.k), dtype=torch.int32).pin_memory(),
+                          torch.empty((max_queries,), dtype=torch.int32).pin_memory()) if self.packed else
+                         tuple(torch.empty((max_queries, self.k), dtype=torch.int32).pin_memory() for _ in range(3))),
                 "scored": [torch.cuda.Event() for _ in range(self.chunks)], "done": torch.cuda.Event(), "nq": 0, "busy": False,
             })
         self.step = 0
@@ -143,8 +162,8 @@ class HostTopK:
             ids[:nnz].copy_(q_ids, non_blocking=True)
         off.copy_(q_off, non_blocking=True)
         if self.direct:
-            self.pool.topk(ids, off, self.k, zero_diag=zero_diag, query_base=query_base,
-                           out=tuple(h[:nq] for h in s["host"]), q_nnz=nnz)
+            call = self.pool.topk_packed if self.packed else self.pool.topk
+            call(ids, off, self.k, zero_diag=zero_diag, query_base=query_base, out=tuple(h[:nq] for h in s["host"]), q_nnz=nnz)
             s["done"].record()
         else:
             n_chunks = min(self.chunks, max(1, nq // 4096))            # small steps are not worth splitting
@@ -175,5 +194,10 @@ class HostTopK:
             torch.cuda.current_stream().wait_event(s["done"])
         return tuple(h[:s["nq"]] for h in s["host"])
 
+    @staticmethod
+    def unpack(result):
+        """(pair, idx, q_card) of a packed step -> (inter, union, idx) int32 [nq, k]."""
+        return engine.unpack_topk(*result)
+
     def bytes_per_step(self, nq, nnz):
-        return nnz * 4 + (nq + 1) * 8, nq * self.k * 12
+        return nnz * 4 + (nq + 1) * 8, (nq * self.k * 8 + nq * 4) if self.packed else nq * self.k * 12

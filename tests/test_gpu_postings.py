@@ -18,8 +18,13 @@ def run_postings(q, p, n_bits, k, zero_diag=False, query_base=0, pool_base=0):
     qi, qo = to_csr(q)
     if qi.size == 0:
         qi = np.zeros(1, np.int32)
-    ti, tu, tx = engine.jaccard_topk_postings(torch.as_tensor(qi).cuda(), torch.as_tensor(qo).cuda(), index, k,
-                                              zero_diag=zero_diag, query_base=query_base, pool_base=pool_base)
+    dqi, dqo = torch.as_tensor(qi).cuda(), torch.as_tensor(qo).cuda()
+    ti, tu, tx = engine.jaccard_topk_postings(dqi, dqo, index, k, zero_diag=zero_diag, query_base=query_base, pool_base=pool_base)
+    # the packed form of the same call (8 bytes per entry) must decode to exactly these planes, whatever kernel served a row
+    packed = engine.jaccard_topk_postings_packed(dqi, dqo, index, k, zero_diag=zero_diag, query_base=query_base,
+                                                 pool_base=pool_base)
+    ui, uu, ux = engine.unpack_topk(*packed)
+    assert torch.equal(ux, tx) and torch.equal(ui, ti) and torch.equal(uu, tu), "packed results differ from the planes"
     return ti.cpu().numpy().astype(np.int64), tu.cpu().numpy().astype(np.int64), tx.cpu().numpy(), bp, index
 
 
@@ -139,15 +144,40 @@ def test_host_topk_row_ranges_equal_one_call(zero_diag):
     qi, qo = to_csr(q)
     tq, to = torch.as_tensor(qi).pin_memory(), torch.as_tensor(qo).pin_memory()
     ref = pool.topk(tq.cuda(), to.cuda(), k, zero_diag=zero_diag)
-    for kw in (dict(direct=False, chunks=4), dict(direct=True)):          # copy-stream ranges / kernel stores to pinned host
+    # copy-stream ranges / kernel stores to pinned host / the same with packed lists
+    for kw in (dict(direct=False, chunks=4), dict(direct=True), dict(direct=True, packed=True)):
         hk = HostTopK(pool, k, nq, qi.size, depth=2, **kw)
         t0 = hk.submit(tq, to, zero_diag=zero_diag)
         t1 = hk.submit(tq, to, zero_diag=zero_diag)
         for t in (t0, t1):
             got = hk.result(t)
+            if hk.packed:
+                assert got[2].shape == (nq,) and hk.bytes_per_step(nq, qi.size)[1] == nq * k * 8 + nq * 4
+                got = HostTopK.unpack(got)
             assert all(torch.equal(g, r.cpu()) for g, r in zip(got, ref)), kw
     oi, ou, ox = jo.c_topk(qi, qo, *to_csr(p), k, zero_diag=zero_diag)
     assert np.array_equal(ref[2].cpu().numpy(), ox) and np.array_equal(ref[0].cpu().numpy(), oi)
+
+
+def test_packed_results_from_every_kernel_of_the_chain():
+    """Packed lists through the hash-table kernel as first stage (option postings_kernel = 1), with hand-overs to the
+    heavy kernel, a pool shorter than k (padding entries) and empty-vs-empty pairs (union forced to 1)."""
+    from rag4dyg_b200 import _lib
+    rng = np.random.default_rng(33)
+    n_bits = 600
+    p = random_sets(rng, 4000, n_bits, mean=3, p_empty=0.1, dup=True)
+    q = random_sets(rng, 300, n_bits, mean=3, p_empty=0.1, dup=True)
+    q[5] = list(range(0, 500))                 # heavy kernel
+    q[6] = list(rng.choice(n_bits, 100))       # > 64 ids
+    _lib.set_option("postings_kernel", 1)
+    try:
+        check(q, p, n_bits, 10)
+        check(q[:40], p[:6], n_bits, 10)       # padding entries
+        check([[], [1]], [[], [], [2]], n_bits, 3)
+    finally:
+        _lib.set_option("postings_kernel", 0)
+    check(q[:40], p[:6], n_bits, 10)
+    check([[], [1]], [[], [], [2]], n_bits, 3)
 
 
 def test_graph_topk_replays_with_refreshed_queries():
