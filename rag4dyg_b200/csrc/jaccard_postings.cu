@@ -284,6 +284,12 @@ struct PJParams {
     uint32_t* work;
     uint32_t* hand_list;
     uint32_t* hand_count;
+    // Head kernel: queries with more than big_ids ids (listed by postings_big_scan_kernel) are served FIRST, one per grab:
+    // they take many times the average query's time, and a long query that starts last is the tail of the launch.
+    const uint32_t* big_list;
+    const uint32_t* big_count;
+    uint32_t* big_work;
+    int32_t big_ids;
     PeerOut peers;
     int64_t q_out_off, nq_total;   // fused exchange: row offset / rows of the whole call
     int32_t chunk;                 // queries a light warp takes per grab of the work counter (<= PJ_CHUNK)
@@ -360,22 +366,40 @@ __device__ __forceinline__ void pj_finish(WarpTopK<E>& tk, const PJParams& p, in
     }
 }
 
+__constant__ uint32_t ph_inv[33] = {   // ceil(2^32 / m): t / m = umulhi(t, ph_inv[m]) for t < 2^16
+    0u, 0u, 2147483648u, 1431655766u, 1073741824u, 858993460u, 715827883u, 613566757u, 536870912u, 477218589u, 429496730u,
+    390451573u, 357913942u, 330382100u, 306783379u, 286331154u, 268435456u, 252645136u, 238609295u, 226050911u, 214748365u,
+    204522253u, 195225787u, 186737709u, 178956971u, 171798692u, 165191050u, 159072863u, 153391690u, 148102321u, 143165577u,
+    138547333u, 134217728u};
+
 // The finished lists of a chunk's consecutive queries, staged as [plane][row][k] (pj_finish), go out together: n_here * k
 // consecutive words per plane.  The store loop walks the 128-byte line grid of the destination (a warp-wide store that
 // straddles two lines becomes two partial writes — in HBM two partial sectors, over PCIe two short TLPs).
 __device__ __forceinline__ void pj_flush_chunk(const PJParams& p, const uint32_t* stage, int64_t q0, int n_here,
-                                               const bool packed) {
+                                               const bool packed, const uint32_t skip = 0u) {
     const int lane = threadIdx.x & 31;
     const int n_words = n_here * p.k;
     const int64_t at = q0 * p.k;
     const int mis = (int)((reinterpret_cast<uintptr_t>(p.out_idx + at) >> 2) & 31);   // planes of one call are aligned alike
-    for (int i = lane - mis; i < n_words; i += 32)
-        if (i >= 0) {
-            p.out_inter[at + i] = stage[i];
-            if (!packed) p.out_union[at + i] = stage[n_words + i];
-            p.out_idx[at + i] = (int32_t)stage[2 * n_words + i];
-        }
-    if (packed && lane < n_here) p.out_qcard[q0 + lane] = stage[n_words + lane];
+    if (skip == 0u) {
+        for (int i = lane - mis; i < n_words; i += 32)
+            if (i >= 0) {
+                p.out_inter[at + i] = stage[i];
+                if (!packed) p.out_union[at + i] = stage[n_words + i];
+                p.out_idx[at + i] = (int32_t)stage[2 * n_words + i];
+            }
+    } else {   // rows of the chunk that another warp has written already (bit r of `skip`) are left alone
+        const uint32_t inv = ph_inv[p.k];
+        for (int i = lane - mis; i < n_words; i += 32)
+            if (i >= 0) {
+                const uint32_t r = p.k == 1 ? (uint32_t)i : __umulhi((uint32_t)i, inv);
+                if ((skip >> r) & 1u) continue;
+                p.out_inter[at + i] = stage[i];
+                if (!packed) p.out_union[at + i] = stage[n_words + i];
+                p.out_idx[at + i] = (int32_t)stage[2 * n_words + i];
+            }
+    }
+    if (packed && lane < n_here && !((skip >> lane) & 1u)) p.out_qcard[q0 + lane] = stage[n_words + lane];
 }
 
 constexpr unsigned long long PJ_EMPTY = 0xffffffffffffffffull;
@@ -698,18 +722,22 @@ __device__ __forceinline__ void postings_reg_body(const PJParams& p) {
     };
     clear_filter();
     bool filter_clean = true;
-    const int chunk = p.chunk;
+    // later stage of a chain: the queries are the ones the head kernel handed over, one per grab
+    const bool listed = p.in_list != nullptr;
+    const int64_t n_work = listed ? (int64_t)*p.in_count : p.nq;
+    const int chunk = listed ? 1 : p.chunk;
     for (;;) {
         int64_t q0 = 0;
         if (lane == 0) q0 = (int64_t)atomicAdd(p.work, (uint32_t)chunk);
         q0 = __shfl_sync(0xffffffffu, q0, 0);
-        if (q0 >= p.nq) break;
+        if (q0 >= n_work) break;
+        const int64_t q_first = listed ? (int64_t)p.in_list[q0] : q0;
         int64_t my_off = 0;
-        if (lane <= chunk && q0 + lane <= p.nq) my_off = p.q_off[q0 + lane];
-        const int n_here = (int)min((int64_t)chunk, p.nq - q0);
-        const bool staged = p.peers.world == 0 && p.k <= PJ_OBUF_K;   // see postings_light_kernel
+        if (lane <= chunk && q_first + lane <= p.nq) my_off = p.q_off[q_first + lane];
+        const int n_here = (int)min((int64_t)chunk, n_work - q0);
+        const bool staged = !listed && p.peers.world == 0 && p.k <= PJ_OBUF_K;   // see postings_light_kernel
         for (int qi = 0; qi < n_here; ++qi) {
-            const int64_t q = q0 + qi;
+            const int64_t q = q_first + qi;
             const int64_t beg = __shfl_sync(0xffffffffu, my_off, qi), end = __shfl_sync(0xffffffffu, my_off, qi + 1);
             const int64_t m_raw = end - beg;
             if (m_raw > 32) {   // more ids than lanes: the hash-table kernel (second stage) holds two ids per lane
@@ -1006,6 +1034,293 @@ __global__ void __launch_bounds__(PR_WARPS * 32, 6) postings_reg_kernel(const PJ
 template <bool PACKED>
 __global__ void __launch_bounds__(PR_WARPS * 32, 4) postings_reg_large_kernel(const PJParams p) {
     if (pr_wants_large(p)) postings_reg_body<PR_SLOTS_LARGE, PACKED>(p);
+}
+
+// ---------------------------------------------------------------------------- first stage for label-like sets: heads + repeat check
+// A pool row that holds exactly ONE of the query's m ids scores 1 / (m + |pool set| - 1): among such rows the ranking is
+// (|pool set| asc, row asc) — the order the per-id best lists are kept in.  So the top-K over the single-hit rows is the
+// merge of the m list heads, and the join only has to find the rows that hold SEVERAL of the query's ids (rare: two ids of a
+// query seldom share a pool row).  Per query:
+//   1. stream the rows of all postings, list by list, through a per-warp 16 384-bit Bloom filter in shared memory (two bits
+//      of one word per row: one ATOMS.OR); a posting whose bits were already set MAY repeat an earlier row — it is noted
+//      (rarely: for a few hundred postings the false-positive rate is ~1e-3).  Nothing is kept in registers, there are no
+//      passes over row windows, no candidate handling per posting;
+//   2. every noted row is counted exactly: one lane per (row, id) pair looks the row up in the id's (row window) bucket;
+//      rows with a count >= 2 are the multi-hit rows (with |pool set| from the posting);
+//   3. the m heads (32 entries each, one coalesced load) lose the multi-hit rows and the forced-zero row, and are merged
+//      by a 5-stage bitonic network per list (two sorted 16-entry lists -> sorted 32); the multi-hit rows are inserted
+//      with their exact score.  A head that is left with fewer than k entries although its list is longer than the head
+//      cannot vouch for the k best single-hit rows of its id: the query goes to the next stage.
+// Queries this kernel cannot serve (more than 32 ids, more than PH_MAX_HITS postings, more than PH_MULTI multi-hit rows,
+// a probed bucket with more than PH_MAX_BUCKET entries, a depleted head) are handed to the register kernel.  k <= 16.
+constexpr int PH_BM_WORDS = 512;     // 16 384-bit repeat filter per warp
+constexpr int PH_FLAG = 64;          // noted rows buffered (resolved in batches, whenever more than half of them are in use)
+constexpr int PH_MULTI = 32;         // multi-hit rows per query
+constexpr int PH_MAX_HITS = 4096;    // postings streamed per query
+constexpr int PH_MAX_BUCKET = 64;    // bucket entries scanned per probe
+constexpr int PH_K = 16;             // the merge network ranks two sorted 16-entry lists
+constexpr int PH_WARPS = 8;
+constexpr int PH_BIG_IDS = 8;         // queries with more ids are served first
+
+struct PHWarpSmem {
+    uint32_t bm[PH_BM_WORDS];
+    int32_t ids[32];
+    uint32_t frow[PH_FLAG];    // noted rows
+    uint32_t fcnt[PH_FLAG];    // ids of the query each of them holds
+    uint32_t fcard[PH_FLAG];   // |pool set|
+    uint32_t mrow[PH_MULTI], mcnt[PH_MULTI], mcard[PH_MULTI];   // the multi-hit rows among them
+    uint32_t obuf[3 * PJ_CHUNK * PJ_OBUF_K];
+};
+
+__global__ void __launch_bounds__(256) postings_big_scan_kernel(const int64_t* __restrict__ q_off, int64_t nq, int32_t big_ids,
+                                                               uint32_t* __restrict__ list, uint32_t* __restrict__ count) {
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = q_off[q + 1] - q_off[q];
+        if (m > (int64_t)big_ids && m <= 32) list[atomicAdd(count, 1u)] = (uint32_t)q;
+    }
+}
+
+template <bool PACKED>
+__global__ void __launch_bounds__(PH_WARPS * 32, 6) postings_head_kernel(const PJParams p) {
+    constexpr bool packed = PACKED;
+    extern __shared__ __align__(16) uint8_t pj_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    PHWarpSmem& sm = reinterpret_cast<PHWarpSmem*>(pj_smem)[warp];
+    const uint32_t lt = (1u << lane) - 1u;
+    constexpr uint32_t FULL = 0xffffffffu, NONE = 0xffffffffu;
+    constexpr unsigned long long DEAD = ~0ull;
+    auto clear_filter = [&]() {
+        uint4* b4 = reinterpret_cast<uint4*>(sm.bm);
+#pragma unroll
+        for (int i = 0; i < PH_BM_WORDS / 4 / 32; ++i) b4[i * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
+    };
+    auto hand_over = [&](int64_t q) {
+        if (lane == 0) p.hand_list[atomicAdd(p.hand_count, 1u)] = (uint32_t)q;
+    };
+    clear_filter();
+    bool filter_clean = true;
+    bool big_phase = p.big_list != nullptr;   // first the long queries, one per grab; then everything else in chunks
+    for (;;) {
+        int64_t q0 = 0;
+        int chunk = p.chunk;
+        if (big_phase) {
+            uint32_t g = 0;
+            if (lane == 0) g = atomicAdd(p.big_work, 1u);
+            g = __shfl_sync(FULL, g, 0);
+            if (g >= *p.big_count) {
+                big_phase = false;
+                continue;
+            }
+            q0 = (int64_t)p.big_list[g];
+            chunk = 1;
+        } else {
+            if (lane == 0) q0 = (int64_t)atomicAdd(p.work, (uint32_t)chunk);
+            q0 = __shfl_sync(FULL, q0, 0);
+            if (q0 >= p.nq) break;
+        }
+        const bool staged = !big_phase && p.peers.world == 0 && p.k <= PJ_OBUF_K;   // see postings_light_kernel
+        int64_t my_off = 0;
+        if (lane <= chunk && q0 + lane <= p.nq) my_off = p.q_off[q0 + lane];
+        const int n_here = (int)min((int64_t)chunk, p.nq - q0);
+        uint32_t skip = 0u;
+        for (int qi = 0; qi < n_here; ++qi) {
+            const int64_t q = q0 + qi;
+            const int64_t beg = __shfl_sync(FULL, my_off, qi), end = __shfl_sync(FULL, my_off, qi + 1);
+            const int64_t m_raw = end - beg;
+            if (m_raw > 32) {
+                hand_over(q);
+                continue;
+            }
+            if (!big_phase && p.big_list != nullptr && m_raw > (int64_t)p.big_ids) {   // served in the first phase
+                skip |= 1u << qi;
+                continue;
+            }
+            // ---- the query's distinct ids (set semantics: duplicates collapse), the j-th of them in lane j
+            int32_t id = -1;
+            if (lane < m_raw) id = p.q_ids[beg + lane];
+            if (id < 0 || id >= p.n_bits) id = -1;
+            {
+                const uint32_t same = __match_any_sync(FULL, id);
+                if (id >= 0 && (__ffs(same) - 1) != lane) id = -1;
+            }
+            const uint32_t act = __ballot_sync(FULL, id >= 0);
+            const uint32_t cq = __popc(act);
+            if (act & (act + 1u)) {   // not a prefix of the lanes yet
+                __syncwarp();
+                if (id >= 0) sm.ids[__popc(act & lt)] = id;
+                __syncwarp();
+                id = lane < (int)cq ? sm.ids[lane] : -1;
+            }
+            uint32_t s = 0, len = 0;
+            if (id >= 0) {
+                s = p.off[(int64_t)id * p.n_win];
+                len = p.off[(int64_t)(id + 1) * p.n_win] - s;
+            }
+            const int64_t diag_row = p.query_base + q - p.pool_base;   // pool row forced to score 0
+            const uint32_t diag = (p.zero_diag != 0 && diag_row >= 0 && diag_row < p.np) ? (uint32_t)diag_row : NONE;
+            uint32_t n_flag = 0, n_multi = 0;
+            if (cq >= 2u) {
+                const uint32_t hits = __reduce_add_sync(FULL, len);
+                if (hits > (uint32_t)PH_MAX_HITS) {
+                    hand_over(q);
+                    continue;
+                }
+                if (hits != 0u) {
+                    if (!filter_clean) clear_filter();
+                    filter_clean = false;
+                    __syncwarp();
+                }
+                const uint32_t inv = ph_inv[cq];   // t / cq = umulhi(t, inv) for t < 2^16
+                // ---- 2. the noted rows, counted exactly: lane <-> (row j, id i), the row is looked up in the id's (row
+                // window) bucket; rows with a count >= 2 (never the forced-zero row) join the multi-hit list.  Runs
+                // whenever the noted rows pile up and once at the end.  false: the query must be handed over.
+                auto resolve = [&]() -> bool {
+                    __syncwarp();
+                    for (uint32_t j = lane; j < n_flag; j += 32u) sm.fcnt[j] = 0u;
+                    __syncwarp();
+                    const uint32_t n_probe = n_flag * cq;
+                    bool bad = false;
+                    for (uint32_t t0 = 0; t0 < n_probe; t0 += 32u) {
+                        const uint32_t t = t0 + (uint32_t)lane;
+                        const bool on = t < n_probe;
+                        const uint32_t j = on ? __umulhi(t, inv) : 0u, i = on ? t - j * cq : 0u;
+                        const int32_t pid = __shfl_sync(FULL, id, (int)i);
+                        if (on) {
+                            const uint32_t r = sm.frow[j];
+                            const int64_t b = (int64_t)pid * p.n_win + (int64_t)(r >> p.win_shift);
+                            const uint32_t bs = p.off[b], be = p.off[b + 1];
+                            if (be - bs > (uint32_t)PH_MAX_BUCKET) {
+                                bad = true;   // a hot bucket
+                            } else {
+                                for (uint32_t u = bs; u < be; ++u) {
+                                    const uint2 v = p.post[u];
+                                    if (v.x == r) {
+                                        atomicAdd(&sm.fcnt[j], 1u);
+                                        sm.fcard[j] = v.y;
+                                        break;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    for (uint32_t j0 = 0; j0 < n_flag; j0 += 32u) {
+                        const uint32_t j = j0 + (uint32_t)lane;
+                        const bool multi = j < n_flag && sm.fcnt[j] >= 2u && sm.frow[j] != diag;
+                        const uint32_t mm = __ballot_sync(FULL, multi);
+                        if (multi) {
+                            const uint32_t at = n_multi + __popc(mm & lt);
+                            if (at < (uint32_t)PH_MULTI) {
+                                sm.mrow[at] = sm.frow[j];
+                                sm.mcnt[at] = sm.fcnt[j];
+                                sm.mcard[at] = sm.fcard[j];
+                            }
+                        }
+                        n_multi += __popc(mm);
+                    }
+                    n_flag = 0u;
+                    __syncwarp();
+                    return !__ballot_sync(FULL, bad) && n_multi <= (uint32_t)PH_MULTI;
+                };
+                // ---- 1. the rows of every list through the filter: list by list, lanes stride the list, four loads in flight
+                bool ok = true;
+                for (uint32_t i = 0; i < cq && ok; ++i) {
+                    const uint32_t ls = __shfl_sync(FULL, s, (int)i), ll = __shfl_sync(FULL, len, (int)i);
+                    const uint2* lp = p.post + ls;
+                    for (uint32_t t0 = 0; t0 < ll && ok; t0 += 128u) {
+                        uint32_t row[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t t = t0 + (uint32_t)j * 32u + (uint32_t)lane;
+                            row[j] = t < ll ? lp[t].x : NONE;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (t0 + (uint32_t)j * 32u >= ll) break;   // warp-uniform
+                            bool fl = false;
+                            if (row[j] != NONE) {
+                                // two bits of one filter word per row (a blocked Bloom filter: one ATOMS)
+                                const uint32_t h = row[j] * 2654435761u;
+                                const uint32_t mask = (1u << ((h >> 18) & 31u)) | (1u << ((h >> 13) & 31u));
+                                fl = (atomicOr(&sm.bm[h >> 23], mask) & mask) == mask;
+                            }
+                            const uint32_t fm = __ballot_sync(FULL, fl);
+                            if (fm) {
+                                const uint32_t slot = n_flag + __popc(fm & lt);
+                                if (fl && slot < (uint32_t)PH_FLAG) sm.frow[slot] = row[j];
+                                n_flag += __popc(fm);
+                            }
+                        }
+                        // noted rows are resolved in batches; a group of 128 postings that notes more than the buffer has
+                        // room for (a saturated filter, a pool full of repeats) sends the query to the next stage
+                        if (n_flag > (uint32_t)PH_FLAG) ok = false;
+                        else if (n_flag > (uint32_t)PH_FLAG / 2u) ok = resolve();
+                    }
+                }
+                if (ok && n_flag != 0u) ok = resolve();
+                if (!ok) {
+                    hand_over(q);
+                    continue;
+                }
+            }
+            // ---- 3. heads: (|pool set| << 32 | row) keys, ascending = best first; lanes 0..15 carry the merged list
+            unsigned long long cur = DEAD;
+            bool depleted = false;
+            for (uint32_t i = 0; i < cq; ++i) {
+                const int32_t hid = __shfl_sync(FULL, id, (int)i);
+                const uint32_t hlen = __shfl_sync(FULL, len, (int)i);
+                const uint2 e = p.best[(int64_t)hid * PJ_BEST + lane];
+                bool alive = e.x != NONE && e.x != diag;
+                for (uint32_t j = 0; j < n_multi; ++j)   // multi-hit rows are ranked on their own below
+                    if (sm.mrow[j] == e.x) alive = false;
+                const uint32_t am = __ballot_sync(FULL, alive);
+                if (__popc(am) < p.k && hlen > (uint32_t)PJ_BEST) {
+                    depleted = true;
+                    break;
+                }
+                unsigned long long key = alive ? (((unsigned long long)e.y << 32) | (unsigned long long)e.x) : DEAD;
+                if (am & (am + 1u)) {   // holes: the t-th survivor moves to lane t (the order is kept)
+                    const uint32_t src = __fns(am, 0u, lane + 1);
+                    const unsigned long long moved = __shfl_sync(FULL, key, (int)(src & 31u));
+                    key = src < 32u ? moved : DEAD;
+                }
+                if (i == 0u) {
+                    cur = key;
+                } else {
+                    const unsigned long long rev = __shfl_sync(FULL, key, 31 - lane);   // lanes 16..31: the new list, worst first
+                    unsigned long long v = lane < PH_K ? cur : rev;
+#pragma unroll
+                    for (int j2 = 16; j2 > 0; j2 >>= 1) {
+                        const unsigned long long o = __shfl_xor_sync(FULL, v, j2);
+                        v = ((lane & j2) == 0) ? min(v, o) : max(v, o);
+                    }
+                    cur = v;
+                }
+            }
+            if (depleted) {
+                hand_over(q);
+                continue;
+            }
+            WarpTopK<PEntry> tk;
+            tk.init(p.k);
+            if (lane < p.k && cur != DEAD)
+                tk.mine = PEntry{1u, cq + (uint32_t)(cur >> 32) - 1u, (int32_t)(p.pool_base + (int64_t)(uint32_t)cur)};
+            tk.refresh_kth();
+            for (uint32_t j = 0; j < n_multi; ++j) {
+                const uint32_t c = sm.mcnt[j];
+                const PEntry cnd{c, cq + sm.mcard[j] - c, (int32_t)(p.pool_base + (int64_t)sm.mrow[j])};
+                if (__ballot_sync(FULL, lane < p.k && tk.mine.idx == cnd.idx)) continue;   // noted twice
+                tk.insert(cnd);
+            }
+            pj_finish(tk, p, q, cq, packed, staged ? sm.obuf : nullptr, qi, n_here);
+        }
+        if (staged) {
+            // rows of handed-over queries hold stale words here; the later stages rewrite them
+            __syncwarp();
+            pj_flush_chunk(p, sm.obuf, q0, n_here, packed, skip);
+            __syncwarp();
+        }
+    }
 }
 
 constexpr int PJ_HWIN_SHIFT = PJ_WIN_SHIFT_MAX;   // the heavy kernel walks the pool 32 768 rows at a time (several index windows)
@@ -1309,7 +1624,9 @@ static int postings_topk_impl(const int32_t* q_ids, const int64_t* q_off, int64_
     prm.out_qcard = q_card;
     // workspace: counters [64] | list A [nq] | list B [nq]
     //   counters[0] work of the first stage, [1] entries of list A, [2] work of the heavy kernel,
-    //   counters[3] work of the second (hash-table) stage, [4] entries of list B
+    //   counters[3] work of the hash-table stage, [4] entries of list B, [5] work of the register stage behind the head
+    //   kernel, [6] entries of list A when it is filled a second time, [7] long queries listed for the head kernel, [8] its
+    //   work counter over them
     uint32_t* counters = reinterpret_cast<uint32_t*>(workspace);
     uint32_t* list_a = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(workspace) + 256);
     uint32_t* list_b = list_a + nq;
@@ -1322,16 +1639,21 @@ static int postings_topk_impl(const int32_t* q_ids, const int64_t* q_off, int64_
         const double per_query = (double)(q_nnz > 0 ? q_nnz : 0) / (double)nq * ((double)nnz / (double)n_bits);
         const bool large = options().postings_log_t == PJ_LOG_T_LARGE ||
                            (options().postings_log_t != PJ_LOG_T_SMALL && per_query > 4.0 * pj_cap(PJ_LOG_T_SMALL));
-        // label-like sets (the small-table regime) take the register-resident kernel; option "postings_kernel" = 1
-        // keeps the hash-table kernel for them too (comparison point)
-        const bool reg = !large && options().postings_kernel != 1;
         const bool packed = q_card != nullptr;
-        static SmemOptIn opt_in[4];
-        const size_t smem = reg ? sizeof(PRWarpSmem) * PR_WARPS
+        // label-like sets (the small-table regime) take the head kernel first (k <= 16, best lists in use) and the
+        // register-resident kernel for what it hands over; option "postings_kernel": 1 = hash-table kernel first
+        // (comparison point), 2 = register kernel first (no head kernel)
+        const bool reg = !large && options().postings_kernel != 1;
+        const bool head = reg && options().postings_kernel != 2 && prm.best != nullptr && k <= PH_K;
+        static SmemOptIn opt_in[6];
+        const size_t smem_reg = sizeof(PRWarpSmem) * PR_WARPS;
+        const size_t smem = head ? sizeof(PHWarpSmem) * PH_WARPS
+                          : reg ? smem_reg
                                 : (large ? sizeof(PJWarpSmem<PJ_LOG_T_LARGE>) : sizeof(PJWarpSmem<PJ_LOG_T_SMALL>)) * PJ_LIGHT_WARPS;
-        void (*kern)(const PJParams) = reg ? (packed ? postings_reg_kernel<true> : postings_reg_kernel<false>)
+        void (*kern)(const PJParams) = head ? (packed ? postings_head_kernel<true> : postings_head_kernel<false>)
+                                     : reg ? (packed ? postings_reg_kernel<true> : postings_reg_kernel<false>)
                                            : (large ? postings_light_kernel<PJ_LOG_T_LARGE> : postings_light_kernel<PJ_LOG_T_SMALL>);
-        if (int rc = ensure_dyn_smem(kern, smem, opt_in[reg ? (packed ? 3 : 2) : (large ? 1 : 0)])) return rc;
+        if (int rc = ensure_dyn_smem(kern, smem, opt_in[head ? (packed ? 5 : 4) : reg ? (packed ? 3 : 2) : (large ? 1 : 0)])) return rc;
         // every warp should find several grabs of work: small calls take fewer queries per grab
         const int64_t cap = (int64_t)num_sms() * (reg ? 6 : (large ? 2 : 4));   // resident CTAs per SM (shared memory / registers)
         int64_t chunk = nq / (cap * PJ_LIGHT_WARPS * 4);
@@ -1356,42 +1678,71 @@ static int postings_topk_impl(const int32_t* q_ids, const int64_t* q_off, int64_
         prm.hand_list = list_a;
         prm.hand_count = counters + 1;
         prof_begin(PROF_JACCARD_POSTINGS, st);
+        if (head) {
+            // the long queries of the call, listed (in list B, which the later stages reuse) so that the head kernel starts them first
+            prm.big_list = list_b;
+            prm.big_count = counters + 7;
+            prm.big_work = counters + 8;
+            prm.big_ids = PH_BIG_IDS;
+            int64_t gb = (nq + 255) / 256;
+            if (gb > (int64_t)num_sms() * 4) gb = (int64_t)num_sms() * 4;
+            postings_big_scan_kernel<<<(unsigned)gb, 256, 0, st>>>(q_off, nq, PH_BIG_IDS, list_b, counters + 7); note_launch();
+        }
         kern<<<(unsigned)grid, PJ_LIGHT_WARPS * 32, smem, st>>>(prm); note_launch();
-        if (reg) {   // the 8-slot body for pools with hot (id, window) buckets; exits at once otherwise (and vice versa)
+        prm.big_list = nullptr;   // (the later stages copy prm)
+        // the lists ping-pong between the stages: each stage reads the list its predecessor filled and fills the other
+        // (whose earlier contents are consumed by then), with its own counter
+        const uint32_t* cur_list = list_a;
+        const uint32_t* cur_count = counters + 1;
+        if (reg) {
+            // register-resident kernels: the first stage without the head kernel, else the stage for its hand-overs.  The
+            // 8-slot body serves pools with hot (id, window) buckets; one of the two launches exits at once.
+            PJParams pr = prm;
+            if (head) {
+                pr.in_list = list_a;
+                pr.in_count = counters + 1;
+                pr.work = counters + 5;
+                pr.hand_list = list_b;
+                pr.hand_count = counters + 4;
+                cur_list = list_b;
+                cur_count = counters + 4;
+                void (*kern_s)(const PJParams) = packed ? postings_reg_kernel<true> : postings_reg_kernel<false>;
+                if (int rc = ensure_dyn_smem(kern_s, smem_reg, opt_in[packed ? 3 : 2])) return rc;
+                kern_s<<<(unsigned)grid, PR_WARPS * 32, smem_reg, st>>>(pr); note_launch();
+            }
             static SmemOptIn opt_in_l[2];
             void (*kern_l)(const PJParams) = packed ? postings_reg_large_kernel<true> : postings_reg_large_kernel<false>;
-            if (int rc = ensure_dyn_smem(kern_l, smem, opt_in_l[packed ? 1 : 0])) return rc;
+            if (int rc = ensure_dyn_smem(kern_l, smem_reg, opt_in_l[packed ? 1 : 0])) return rc;
             const int64_t cap_l = (int64_t)num_sms() * 4;
-            kern_l<<<(unsigned)(grid > cap_l ? cap_l : grid), PR_WARPS * 32, smem, st>>>(prm); note_launch();
+            kern_l<<<(unsigned)(grid > cap_l ? cap_l : grid), PR_WARPS * 32, smem_reg, st>>>(pr); note_launch();
         }
         prof_end(PROF_JACCARD_POSTINGS, st);
-        const uint32_t* heavy_in = list_a;
-        const uint32_t* heavy_count = counters + 1;
         if (reg) {
-            // second stage: the register kernel's hand-overs (a row window with more postings than its registers hold)
-            // are served by the hash-table kernel, whose 512-slot tables take several times as many per pass;
-            // what even that cannot serve goes to list B.  An empty list A costs one idle launch (~3 us).
+            // next stage: the register kernel's hand-overs (a row window with more postings than its registers hold, more
+            // than 32 ids) are served by the hash-table kernel, whose 512-slot tables take several times as many per
+            // pass; what even that cannot serve goes on to the heavy kernel.  An empty list costs one idle launch (~3 us).
             static SmemOptIn opt_in2;
             const size_t smem2 = sizeof(PJWarpSmem<PJ_LOG_T_SMALL>) * PJ_LIGHT_WARPS;
             if (int rc = ensure_dyn_smem(postings_light_kernel<PJ_LOG_T_SMALL>, smem2, opt_in2)) return rc;
+            const bool from_a = cur_list == list_a;
             PJParams p2 = prm;
-            p2.in_list = list_a;
-            p2.in_count = counters + 1;
+            p2.in_list = cur_list;
+            p2.in_count = cur_count;
             p2.work = counters + 3;
-            p2.hand_list = list_b;
-            p2.hand_count = counters + 4;
+            p2.hand_list = from_a ? list_b : list_a;
+            p2.hand_count = counters + (from_a ? 4 : 6);
             int64_t grid2 = (int64_t)num_sms() * 2;
             if (grid2 > (nq + PJ_LIGHT_WARPS - 1) / PJ_LIGHT_WARPS) grid2 = (nq + PJ_LIGHT_WARPS - 1) / PJ_LIGHT_WARPS;
             postings_light_kernel<PJ_LOG_T_SMALL><<<(unsigned)grid2, PJ_LIGHT_WARPS * 32, smem2, st>>>(p2); note_launch();
-            heavy_in = list_b;
-            heavy_count = counters + 4;
+            cur_list = p2.hand_list;
+            cur_count = p2.hand_count;
         }
         static SmemOptIn opt_in_h;
         const size_t smem_h = sizeof(PJHeavySmem);
         if (int rc = ensure_dyn_smem(postings_heavy_kernel, smem_h, opt_in_h)) return rc;
         PJParams ph = prm;
-        ph.in_list = heavy_in;
-        ph.in_count = heavy_count;
+        ph.in_list = cur_list;
+        ph.in_count = cur_count;
         ph.work = counters + 2;
         ph.hand_list = nullptr;
         ph.hand_count = nullptr;

@@ -225,9 +225,36 @@ def test_register_kernel_repeats_and_passes(npool, n_bits, mean, nq, k, self_que
     ti, tu, tx, bp, index = run_postings(q, p, n_bits, k, zero_diag=zero_diag)
     oi, ou, ox = jo.c_topk(*to_csr(q), *to_csr(p), k, zero_diag=zero_diag)
     assert np.array_equal(tx, ox) and np.array_equal(ti, oi) and np.array_equal(tu, ou)
-    prev = _lib.set_option("postings_kernel", 1)          # the hash-table kernel on the same call
-    try:
-        hi, hu, hx, _, _ = run_postings(q, p, n_bits, k, zero_diag=zero_diag)
-    finally:
-        _lib.set_option("postings_kernel", prev)
-    assert np.array_equal(hx, tx) and np.array_equal(hi, ti) and np.array_equal(hu, tu)
+    for first_stage in (1, 2):        # the hash-table kernel / the register kernel as first stage of the same call
+        prev = _lib.set_option("postings_kernel", first_stage)
+        try:
+            hi, hu, hx, _, _ = run_postings(q, p, n_bits, k, zero_diag=zero_diag)
+        finally:
+            _lib.set_option("postings_kernel", prev)
+        assert np.array_equal(hx, tx) and np.array_equal(hi, ti) and np.array_equal(hu, tu), first_stage
+
+
+def test_head_kernel_hand_overs_and_kills():
+    """The head kernel (first stage for label-like sets, k <= 16): list heads that lose entries to multi-hit rows and
+    to the forced-zero row, heads depleted below k (hand-over), more noted rows than it resolves (hand-over), long
+    lists of a tiny vocabulary (many false positives of the filter), every k the merge network serves."""
+    rng = np.random.default_rng(77)
+    n_bits = 400
+    # ids 0 (X) and 1 (Y): 40 rows {X, Y} head X's list (smallest sets) -> all of X's head is multi-hit for {X, Y}
+    p = [[0, 1] for _ in range(40)]
+    p += [[0, 5 + i % 300, 6 + i % 290] for i in range(400)]          # 400 more rows with X (3 ids each)
+    p += [[1, 7 + i % 200] for i in range(25)]                        # a few more rows with Y
+    p += random_sets(rng, 3000, n_bits, mean=3, p_empty=0.05, dup=True)
+    q = [[0, 1], [0], [1], [0, 1, 5], [1, 0, 0, 1], [0, 399], [2, 3, 4, 5, 6, 7, 8], list(range(2, 34)), []]
+    q += random_sets(rng, 200, n_bits, mean=3, p_empty=0.05, dup=True)
+    for k in (1, 3, 10, 16):
+        check(q, p, n_bits, k)
+    # > 64 rows hold both ids of the query: more noted rows than the kernel resolves
+    p2 = [[10, 11] for _ in range(150)] + random_sets(rng, 2000, n_bits, mean=2.2)
+    check([[10, 11], [10], [11, 12], [10, 11, 12, 13]], p2, n_bits, 10)
+    # forced-zero rows inside the heads, long lists (vocabulary of 50 ids: ~200 postings per id)
+    p3 = random_sets(rng, 5000, 50, mean=2, p_empty=0.02, dup=True)
+    check([list(x) for x in p3[:400]], p3, 50, 10, zero_diag=True)
+    check([list(x) for x in p3[1000:1300]], p3, 50, 16, zero_diag=True, query_base=1000)
+    # sharded pool: global indices and a diagonal that lies outside / inside the shard
+    check([list(x) for x in p3[:300]], p3[200:], 50, 10, zero_diag=True, query_base=0, pool_base=200)
