@@ -62,7 +62,10 @@ int r4d_device_ok(void);
  *   "kernel_timing"     [0]  record CUDA events around the dominant kernels (see r4d_profile_read)
  *   "stripe_interleave" [0]  dense pair kernel: 1 = stripe s owns pool tiles s, s+S, s+2S, ... (measured: same
  *                            time, 1.7x the DRAM reads), 0 = contiguous stripes
- *   "postings_log_t"    [0]  postings path: 0 = automatic, 9 / 10 = force 512- / 1 024-slot per-warp hash tables */
+ *   "postings_log_t"    [0]  postings path: 0 = automatic, 9 / 10 = force 512- / 1 024-slot per-warp hash tables
+ *   "postings_kernel"   [0]  postings path, label-like sets: first stage 0 = head kernel (k <= 16), 1 = hash-table kernel,
+ *                            2 = register-resident kernel (comparison points; results are identical)
+ *   "postings_relay"    [1]  packed lists bound for pinned host memory leave in whole 64-query blocks (0 = per chunk) */
 int r4d_set_option(const char* key, int value);
 
 /* Measurement aid for the roofline figures (bench.py): after r4d_set_option("kernel_timing", 1) the library brackets
@@ -162,7 +165,12 @@ int r4d_jaccard_topk_postings(const int32_t* q_ids, const int64_t* q_off, int64_
  * entry instead of 12.  top_pair[q][j] = inter << 16 | |pool set| (both <= 65 535 because n_bits is), top_idx as above,
  * q_card[q] = |query set| (distinct valid ids of the row).  The consumer recovers union = q_card + |pool set| - inter, so
  * the score inter / union (retrieval_data_annotation.py:18) is the same rational; a padding entry (idx R4D_IDX_NONE)
- * packs as 0 and stands for (0, 1).  Same kernels, same order, same exactness as r4d_jaccard_topk_postings. */
+ * packs as 0 and stands for (0, 1).  Same kernels, same order, same exactness as r4d_jaccard_topk_postings.
+ * When top_pair / top_idx / q_card are pinned HOST buffers (device-addressable, 128-byte aligned) and the workspace is
+ * r4d_jaccard_topk_postings_workspace_bytes(nq) + r4d_jaccard_topk_postings_relay_bytes(nq, k) bytes or more, the lists
+ * are staged in that extra room and leave for the host in whole 64-query blocks of full 128-byte PCIe writes (writes
+ * from an SM are bound by their number, not their bytes); with the smaller workspace the kernels store chunk by chunk. */
+size_t r4d_jaccard_topk_postings_relay_bytes(int64_t nq, int32_t k);
 int r4d_jaccard_topk_postings_packed(const int32_t* q_ids, const int64_t* q_off, int64_t nq, int64_t q_nnz, const void* index,
                                      const uint32_t* pcard, int64_t np, int32_t n_bits, int64_t nnz, int32_t k,
                                      int32_t zero_diag, int64_t query_base, int64_t pool_base, uint32_t* top_pair,

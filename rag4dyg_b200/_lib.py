@@ -49,6 +49,7 @@ PROTOTYPES = {
     "r4d_jaccard_topk_postings_workspace_bytes": (_sz, [_i64]),
     "r4d_jaccard_topk_postings": (_c.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _i64, _i32, _i64, _i32, _i32, _i64, _i64, _vp,
                                              _vp, _vp, _vp, _sz, _vp]),
+    "r4d_jaccard_topk_postings_relay_bytes": (_sz, [_i64, _i32]),
     "r4d_jaccard_topk_postings_packed": (_c.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _i64, _i32, _i64, _i32, _i32, _i64, _i64, _vp,
                                                     _vp, _vp, _vp, _sz, _vp]),
     "r4d_jaccard_topk_postings_scatter": (_c.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _i64, _i32, _i64, _i32, _i32, _i64, _i64,

@@ -290,6 +290,14 @@ struct PJParams {
     const uint32_t* big_count;
     uint32_t* big_work;
     int32_t big_ids;
+    // Head kernel, packed lists bound for pinned HOST memory (relay_done != nullptr): out_inter / out_idx / out_qcard point
+    // at a staging copy in HBM, and the warp that completes a block of PJ_RELAY queries (relay_done[block] counts them)
+    // copies the block to its final place with full 128-byte stores — PCIe writes from an SM are bound by their NUMBER
+    // (~400 per us, measured: tools/probe_host_store.cu), so 40-byte rows or 320-byte chunks waste most of the link.
+    uint32_t* relay_pair;
+    int32_t* relay_idx;
+    uint32_t* relay_qcard;
+    uint32_t* relay_done;
     PeerOut peers;
     int64_t q_out_off, nq_total;   // fused exchange: row offset / rows of the whole call
     int32_t chunk;                 // queries a light warp takes per grab of the work counter (<= PJ_CHUNK)
@@ -402,6 +410,54 @@ __device__ __forceinline__ void pj_flush_chunk(const PJParams& p, const uint32_t
     if (packed && lane < n_here && !((skip >> lane) & 1u)) p.out_qcard[q0 + lane] = stage[n_words + lane];
 }
 
+// Relay of finished blocks (see PJParams::relay_done).  `cnt` queries of block q0 / PJ_RELAY are final in the staging copy
+// (a chunk never straddles two blocks: PJ_RELAY is a multiple of every chunk size); the warp whose count completes the
+// block copies it out.  A block's words are contiguous and 128-byte aligned in every plane (PJ_RELAY * k * 4 = 256 k bytes).
+constexpr int PJ_RELAY = 64;
+__device__ __noinline__ void pj_relay_copy(const uint32_t* __restrict__ src_pair, const int32_t* __restrict__ src_idx,
+                                           const uint32_t* __restrict__ src_qcard, uint32_t* __restrict__ dst_pair,
+                                           int32_t* __restrict__ dst_idx, uint32_t* __restrict__ dst_qcard, int64_t first,
+                                           int bn, int k) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w0 = first * k;
+    const int nw = bn * k;
+    for (int i0 = 0; i0 < nw; i0 += 128) {   // four lines per plane in flight
+        uint32_t a[4], c[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = i0 + j * 32 + lane;
+            if (i < nw) {
+                a[j] = __ldcg(src_pair + w0 + i);
+                c[j] = (uint32_t)__ldcg(src_idx + w0 + i);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = i0 + j * 32 + lane;
+            if (i < nw) {
+                dst_pair[w0 + i] = a[j];
+                dst_idx[w0 + i] = (int32_t)c[j];
+            }
+        }
+    }
+    for (int i = lane; i < bn; i += 32) dst_qcard[first + i] = __ldcg(src_qcard + first + i);
+}
+__device__ __forceinline__ void pj_relay(const PJParams& p, int64_t q0, uint32_t cnt) {
+    if (cnt == 0u) return;   // warp-uniform
+    const int lane = threadIdx.x & 31;
+    const int64_t b = q0 / PJ_RELAY;
+    __threadfence();   // this warp's staging stores before the count
+    __syncwarp();
+    uint32_t old = 0u;
+    if (lane == 0) old = atomicAdd(p.relay_done + b, cnt);
+    old = __shfl_sync(0xffffffffu, old, 0);
+    const int64_t first = b * PJ_RELAY;
+    const uint32_t bn = (uint32_t)min((int64_t)PJ_RELAY, p.nq - first);
+    if (old + cnt != bn) return;
+    __threadfence();   // the other warps' staging stores after their counts
+    pj_relay_copy(p.out_inter, p.out_idx, p.out_qcard, p.relay_pair, p.relay_idx, p.relay_qcard, first, (int)bn, p.k);
+}
+
 constexpr unsigned long long PJ_EMPTY = 0xffffffffffffffffull;
 constexpr int PJ_OBUF_K = 12;   // lists up to this width are staged per chunk (wider ones are stored row by row)
 constexpr int PJ_OWN = 16;   // table slots a lane may claim per pass before the pass falls back to scanning the whole table
@@ -452,11 +508,12 @@ __global__ void __launch_bounds__(PJ_LIGHT_WARPS * 32, LOG_T == PJ_LOG_T_SMALL ?
     auto hand_over = [&](int64_t q) {   // the heavy kernel serves this query
         if (lane == 0) p.hand_list[atomicAdd(p.hand_count, 1u)] = (uint32_t)q;
     };
-    clear_table();
-    bool table_clean = true;
     // second stage of a chain: the queries are the ones the register kernel handed over, one per grab
     const bool listed = p.in_list != nullptr;
     const int64_t n_work = listed ? (int64_t)*p.in_count : p.nq;
+    if (n_work == 0) return;   // (an empty list: no table to clear, no grab)
+    clear_table();
+    bool table_clean = true;
     const int chunk = listed ? 1 : p.chunk;
     for (;;) {
         int64_t q0 = 0;
@@ -720,11 +777,12 @@ __device__ __forceinline__ void postings_reg_body(const PJParams& p) {
     auto hand_over = [&](int64_t q) {   // the heavy kernel serves this query
         if (lane == 0) p.hand_list[atomicAdd(p.hand_count, 1u)] = (uint32_t)q;
     };
-    clear_filter();
-    bool filter_clean = true;
     // later stage of a chain: the queries are the ones the head kernel handed over, one per grab
     const bool listed = p.in_list != nullptr;
     const int64_t n_work = listed ? (int64_t)*p.in_count : p.nq;
+    if (n_work == 0) return;   // (an empty list: no filter to clear, no grab)
+    clear_filter();
+    bool filter_clean = true;
     const int chunk = listed ? 1 : p.chunk;
     for (;;) {
         int64_t q0 = 0;
@@ -1320,6 +1378,8 @@ __global__ void __launch_bounds__(PH_WARPS * 32, 6) postings_head_kernel(const P
             pj_flush_chunk(p, sm.obuf, q0, n_here, packed, skip);
             __syncwarp();
         }
+        // (a handed-over query counts too: its rows are rewritten by a later stage, after this kernel's relays)
+        if (p.relay_done != nullptr) pj_relay(p, q0, (uint32_t)n_here - (uint32_t)__popc(skip));
     }
 }
 
@@ -1344,6 +1404,7 @@ __global__ void __launch_bounds__(PJ_HEAVY_THREADS) postings_heavy_kernel(const 
     constexpr int NW = PJ_HEAVY_THREADS / 32;
     static_assert(PJ_HEAVY_THREADS == SCAN_THREADS, "block_excl_scan is written for SCAN_THREADS threads");
     const uint32_t n_heavy = *p.in_count;
+    if (n_heavy == 0u) return;
     constexpr int HW_ROWS = 1 << PJ_HWIN_SHIFT;
     const int wins_per_hw = 1 << (PJ_HWIN_SHIFT - p.win_shift);
     const int n_hwin = (p.n_win + wins_per_hw - 1) / wins_per_hw;
@@ -1578,6 +1639,14 @@ size_t r4d_jaccard_topk_postings_workspace_bytes(int64_t nq) {
     return 256 + (size_t)(nq > 0 ? nq : 0) * 8;   // counters + two hand-over lists
 }
 
+static size_t relay_done_bytes(int64_t nq) { return (((size_t)((nq + r4d::PJ_RELAY - 1) / r4d::PJ_RELAY) * 4 + 255) / 256) * 256; }
+static size_t relay_plane_bytes(int64_t nq, int32_t k) { return (((size_t)nq * (size_t)k * 4 + 255) / 256) * 256; }
+
+size_t r4d_jaccard_topk_postings_relay_bytes(int64_t nq, int32_t k) {
+    if (nq <= 0 || k <= 0) return 0;
+    return 256 + relay_done_bytes(nq) + 2 * relay_plane_bytes(nq, k) + (((size_t)nq * 4 + 255) / 256) * 256;
+}
+
 static int postings_topk_impl(const int32_t* q_ids, const int64_t* q_off, int64_t nq, int64_t q_nnz, const void* index,
                               const uint32_t* pcard, int64_t np, int32_t n_bits, int64_t nnz, int32_t k, int32_t zero_diag,
                               int64_t query_base, int64_t pool_base, uint32_t* top_inter, uint32_t* top_union,
@@ -1634,6 +1703,11 @@ static int postings_topk_impl(const int32_t* q_ids, const int64_t* q_off, int64_
     prm.q_out_off = 0;
     prm.nq_total = nq;
     R4D_CUDA(cudaMemsetAsync(workspace, 0, 256, st));
+    // room behind the lists for the relay of packed lists to pinned host memory (r4d_jaccard_topk_postings_relay_bytes)
+    uint8_t* relay_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(list_b + nq) + 255) & ~(uintptr_t)255);
+    const bool relay_room = q_card != nullptr &&
+                            relay_base + r4d_jaccard_topk_postings_relay_bytes(nq, k) - 256 <=
+                                reinterpret_cast<uint8_t*>(workspace) + workspace_bytes;
     {
         // table size: expected postings per query = (ids per query) x (postings per id), both known on the host
         const double per_query = (double)(q_nnz > 0 ? q_nnz : 0) / (double)nq * ((double)nnz / (double)n_bits);
@@ -1657,17 +1731,28 @@ static int postings_topk_impl(const int32_t* q_ids, const int64_t* q_off, int64_
         // every warp should find several grabs of work: small calls take fewer queries per grab
         const int64_t cap = (int64_t)num_sms() * (reg ? 6 : (large ? 2 : 4));   // resident CTAs per SM (shared memory / registers)
         int64_t chunk = nq / (cap * PJ_LIGHT_WARPS * 4);
+        bool to_host = false;
         if (top_idx != nullptr && peers.world == 0 && k <= PJ_OBUF_K) {
             // results going straight to pinned HOST memory: the largest chunks make the fewest, widest PCIe writes
             cudaPointerAttributes attr{};
             if (cudaPointerGetAttributes(&attr, top_idx) == cudaSuccess) {
-                if (attr.type == cudaMemoryTypeHost) chunk = PJ_CHUNK;
+                if (attr.type == cudaMemoryTypeHost) {
+                    chunk = PJ_CHUNK;
+                    to_host = true;
+                }
             } else {
                 (void)cudaGetLastError();
             }
         }
+        // packed lists bound for the host leave the head kernel in whole 64-query blocks (see PJParams::relay_done)
+        const bool relay = head && to_host && packed && relay_room && options().postings_relay != 0 &&
+                           (reinterpret_cast<uintptr_t>(top_inter) & 127) == 0 && (reinterpret_cast<uintptr_t>(top_idx) & 127) == 0;
         if (options().postings_chunk > 0) chunk = options().postings_chunk;
         chunk = chunk < 1 ? 1 : (chunk > PJ_CHUNK ? PJ_CHUNK : chunk);
+        if (relay) {   // a chunk must not straddle two relay blocks: a power of two
+            if (options().postings_chunk <= 0) chunk = 2;
+            while (chunk & (chunk - 1)) chunk &= chunk - 1;
+        }
         prm.chunk = (int32_t)chunk;
         int64_t grid = (nq + PJ_LIGHT_WARPS * chunk - 1) / (PJ_LIGHT_WARPS * chunk);
         if (grid > cap) grid = cap;
@@ -1688,7 +1773,22 @@ static int postings_topk_impl(const int32_t* q_ids, const int64_t* q_off, int64_
             if (gb > (int64_t)num_sms() * 4) gb = (int64_t)num_sms() * 4;
             postings_big_scan_kernel<<<(unsigned)gb, 256, 0, st>>>(q_off, nq, PH_BIG_IDS, list_b, counters + 7); note_launch();
         }
-        kern<<<(unsigned)grid, PJ_LIGHT_WARPS * 32, smem, st>>>(prm); note_launch();
+        {
+            PJParams first = prm;
+            if (relay) {
+                uint32_t* done = reinterpret_cast<uint32_t*>(relay_base);
+                uint8_t* at = relay_base + relay_done_bytes(nq);
+                R4D_CUDA(cudaMemsetAsync(done, 0, relay_done_bytes(nq), st));
+                first.relay_pair = top_inter;
+                first.relay_idx = top_idx;
+                first.relay_qcard = q_card;
+                first.relay_done = done;
+                first.out_inter = reinterpret_cast<uint32_t*>(at);
+                first.out_idx = reinterpret_cast<int32_t*>(at + relay_plane_bytes(nq, k));
+                first.out_qcard = reinterpret_cast<uint32_t*>(at + 2 * relay_plane_bytes(nq, k));
+            }
+            kern<<<(unsigned)grid, PJ_LIGHT_WARPS * 32, smem, st>>>(first); note_launch();
+        }
         prm.big_list = nullptr;   // (the later stages copy prm)
         // the lists ping-pong between the stages: each stage reads the list its predecessor filled and fills the other
         // (whose earlier contents are consumed by then), with its own counter

@@ -30,6 +30,7 @@ struct Options {
     int postings_best = 1;      // postings path: single-id queries read their top-K from the per-id best lists
     int postings_kernel = 0;    // postings path, label-like sets: 0 = register-resident kernel, 1 = hash-table kernel
     int postings_chunk = 0;     // postings path: queries per grab of the work counter (0 = automatic, <= 8)
+    int postings_relay = 1;     // postings path: packed lists bound for pinned host memory leave in whole 64-query blocks
     int postings_log_t = 0;     // postings path: 0 = automatic, 9 / 10 = force 512 / 1 024-slot hash tables
 };
 Options& options();  // process-wide knobs (r4d_set_option); environment variables R4D_* give the initial values

@@ -186,6 +186,7 @@ int r4d_set_option(const char* key, int value) {
     else if (!strcmp(key, "postings_chunk")) slot = &o.postings_chunk;
     else if (!strcmp(key, "postings_kernel")) slot = &o.postings_kernel;
     else if (!strcmp(key, "postings_best")) slot = &o.postings_best;
+    else if (!strcmp(key, "postings_relay")) slot = &o.postings_relay;
     if (!slot || (slot == &o.jaccard_warps && value != 8 && value != 16)) {
         r4d::set_error("r4d_set_option: unknown key or bad value (%s = %d)", key, value);
         return R4D_E_ARG;

@@ -46,10 +46,13 @@ class JaccardPool:
     def device(self):
         return self.bits.bits.device
 
-    def workspace(self, nq, k):
+    def workspace(self, nq, k, relay=False):
+        """relay=True adds the staging room that lets packed lists leave for pinned host memory in whole blocks."""
         lib = _lib.load()
         need = (lib.r4d_jaccard_topk_postings_workspace_bytes(nq) if self.index is not None
                 else lib.r4d_jaccard_topk_workspace_bytes(nq, self.n_rows, k))
+        if relay and self.index is not None:
+            need += lib.r4d_jaccard_topk_postings_relay_bytes(nq, k)
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty((need,), dtype=torch.uint8, device=self.device)
         return self._ws
@@ -78,9 +81,10 @@ class JaccardPool:
         if self.index is None:
             raise R4DError("topk_packed needs the postings path (a pool with an index)")
         nq = q_off.numel() - 1
+        to_host = out is not None and not out[0].is_cuda
         return engine.jaccard_topk_postings_packed(q_ids, q_off, self.index, k, zero_diag=zero_diag, query_base=query_base,
-                                                   pool_base=self.pool_base, workspace=self.workspace(nq, k), out=out,
-                                                   q_nnz=q_nnz)
+                                                   pool_base=self.pool_base, workspace=self.workspace(nq, k, relay=to_host),
+                                                   out=out, q_nnz=q_nnz)
 
 
 class GraphTopK:

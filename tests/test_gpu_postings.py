@@ -180,6 +180,43 @@ def test_packed_results_from_every_kernel_of_the_chain():
     check([[], [1]], [[], [], [2]], n_bits, 3)
 
 
+def test_packed_lists_relayed_to_host_in_blocks():
+    """Packed lists bound for pinned host memory leave the head kernel in whole 64-query blocks (relay through a
+    staging copy in HBM): a last partial block, long queries served first, queries handed to the later stages (which
+    write straight to the host after the relays), the forced-zero diagonal — equal to the device-resident call, with
+    the relay on and off."""
+    from rag4dyg_b200 import _lib
+    from rag4dyg_b200.jaccard_pool import JaccardPool
+    rng = np.random.default_rng(41)
+    n_bits, npool, k = 3000, 20000, 10
+    p = random_sets(rng, npool, n_bits, mean=2.5, max_len=40, p_empty=0.03, dup=True)
+    for i in range(0, 3000, 2):
+        p[i] = p[i] + [7]                       # a hot (id, window) bucket: probes of id 7 hand the query over
+    for nq, zero_diag in ((1000 + 37, False), (64, False), (5, False), (2000, True)):
+        q = [list(x) for x in p[:nq]] if zero_diag else random_sets(rng, nq, n_bits, mean=2.5, max_len=40, p_empty=0.03, dup=True)
+        if not zero_diag:
+            q[3] = list(rng.choice(n_bits, 60, replace=False))      # > 32 ids: handed over
+            q[4] = [7, 8, 9]
+            q[-1] = list(rng.choice(n_bits, 20, replace=False))     # a long query (served first)
+        pool = JaccardPool.from_csr(*to_csr(q and p), n_bits)
+        qi, qo = to_csr(q)
+        dq, do = torch.as_tensor(qi).cuda(), torch.as_tensor(qo).cuda()
+        ref = pool.topk(dq, do, k, zero_diag=zero_diag)
+        oi, ou, ox = jo.c_topk(qi, qo, *to_csr(p), k, zero_diag=zero_diag)
+        assert np.array_equal(ref[2].cpu().numpy(), ox) and np.array_equal(ref[0].cpu().numpy(), oi)
+        for relay in (1, 0):
+            prev = _lib.set_option("postings_relay", relay)
+            try:
+                host = (torch.full((nq, k), -1, dtype=torch.int32).pin_memory(), torch.full((nq, k), -1, dtype=torch.int32).pin_memory(),
+                        torch.full((nq,), -1, dtype=torch.int32).pin_memory())
+                pool.topk_packed(dq, do, k, zero_diag=zero_diag, out=host)
+                torch.cuda.synchronize()
+            finally:
+                _lib.set_option("postings_relay", prev)
+            got = engine.unpack_topk(*host)
+            assert all(torch.equal(g, r.cpu()) for g, r in zip(got, ref)), (nq, zero_diag, relay)
+
+
 def test_graph_topk_replays_with_refreshed_queries():
     """GraphTopK: the captured launch sequence re-run on new query CONTENTS (same buffers) equals a plain call."""
     from rag4dyg_b200.jaccard_pool import GraphTopK, JaccardPool
