@@ -284,8 +284,9 @@ struct PJParams {
     uint32_t* work;
     uint32_t* hand_list;
     uint32_t* hand_count;
-    // Head kernel: queries with more than big_ids ids (listed by postings_big_scan_kernel) are served FIRST, one per grab:
-    // they take many times the average query's time, and a long query that starts last is the tail of the launch.
+    // Queries with more than big_ids ids (listed by postings_big_scan_kernel) are served by postings_big_kernel, a whole CTA
+    // per query, before the head kernel (which skips them): one warp takes ~100 us for a 25-id query — alone that is the
+    // length of the whole launch.
     const uint32_t* big_list;
     const uint32_t* big_count;
     uint32_t* big_work;
@@ -1146,7 +1147,6 @@ __global__ void __launch_bounds__(PH_WARPS * 32, 6) postings_head_kernel(const P
     PHWarpSmem& sm = reinterpret_cast<PHWarpSmem*>(pj_smem)[warp];
     const uint32_t lt = (1u << lane) - 1u;
     constexpr uint32_t FULL = 0xffffffffu, NONE = 0xffffffffu;
-    constexpr unsigned long long DEAD = ~0ull;
     auto clear_filter = [&]() {
         uint4* b4 = reinterpret_cast<uint4*>(sm.bm);
 #pragma unroll
@@ -1157,26 +1157,16 @@ __global__ void __launch_bounds__(PH_WARPS * 32, 6) postings_head_kernel(const P
     };
     clear_filter();
     bool filter_clean = true;
-    bool big_phase = p.big_list != nullptr;   // first the long queries, one per grab; then everything else in chunks
+    // head entries are ranked as 32-bit keys |pool set| << key_shift | row
+    const uint32_t key_shift = p.np > 1 ? 32u - (uint32_t)__clz((uint32_t)(p.np - 1)) : 1u;
+    const uint32_t row_mask = (1u << key_shift) - 1u, card_lim = (1u << (32u - key_shift)) - 1u;
+    const int chunk = p.chunk;
+    const bool staged = p.peers.world == 0 && p.k <= PJ_OBUF_K;   // see postings_light_kernel
     for (;;) {
         int64_t q0 = 0;
-        int chunk = p.chunk;
-        if (big_phase) {
-            uint32_t g = 0;
-            if (lane == 0) g = atomicAdd(p.big_work, 1u);
-            g = __shfl_sync(FULL, g, 0);
-            if (g >= *p.big_count) {
-                big_phase = false;
-                continue;
-            }
-            q0 = (int64_t)p.big_list[g];
-            chunk = 1;
-        } else {
-            if (lane == 0) q0 = (int64_t)atomicAdd(p.work, (uint32_t)chunk);
-            q0 = __shfl_sync(FULL, q0, 0);
-            if (q0 >= p.nq) break;
-        }
-        const bool staged = !big_phase && p.peers.world == 0 && p.k <= PJ_OBUF_K;   // see postings_light_kernel
+        if (lane == 0) q0 = (int64_t)atomicAdd(p.work, (uint32_t)chunk);
+        q0 = __shfl_sync(FULL, q0, 0);
+        if (q0 >= p.nq) break;
         int64_t my_off = 0;
         if (lane <= chunk && q0 + lane <= p.nq) my_off = p.q_off[q0 + lane];
         const int n_here = (int)min((int64_t)chunk, p.nq - q0);
@@ -1189,7 +1179,7 @@ __global__ void __launch_bounds__(PH_WARPS * 32, 6) postings_head_kernel(const P
                 hand_over(q);
                 continue;
             }
-            if (!big_phase && p.big_list != nullptr && m_raw > (int64_t)p.big_ids) {   // served in the first phase
+            if (p.big_list != nullptr && m_raw > (int64_t)p.big_ids) {   // served by postings_big_kernel
                 skip |= 1u << qi;
                 continue;
             }
@@ -1321,8 +1311,9 @@ __global__ void __launch_bounds__(PH_WARPS * 32, 6) postings_head_kernel(const P
                     continue;
                 }
             }
-            // ---- 3. heads: (|pool set| << 32 | row) keys, ascending = best first; lanes 0..15 carry the merged list
-            unsigned long long cur = DEAD;
+            // ---- 3. heads: 32-bit keys (|pool set| << key_shift | row), ascending = best first; lanes 0..15 carry the
+            // merged list.  (A |pool set| too large for the key — none among label-like sets — sends the query on.)
+            uint32_t cur = NONE;
             bool depleted = false;
             for (uint32_t i = 0; i < cq; ++i) {
                 const int32_t hid = __shfl_sync(FULL, id, (int)i);
@@ -1332,24 +1323,24 @@ __global__ void __launch_bounds__(PH_WARPS * 32, 6) postings_head_kernel(const P
                 for (uint32_t j = 0; j < n_multi; ++j)   // multi-hit rows are ranked on their own below
                     if (sm.mrow[j] == e.x) alive = false;
                 const uint32_t am = __ballot_sync(FULL, alive);
-                if (__popc(am) < p.k && hlen > (uint32_t)PJ_BEST) {
+                if ((__popc(am) < p.k && hlen > (uint32_t)PJ_BEST) || __ballot_sync(FULL, alive && e.y >= card_lim)) {
                     depleted = true;
                     break;
                 }
-                unsigned long long key = alive ? (((unsigned long long)e.y << 32) | (unsigned long long)e.x) : DEAD;
+                uint32_t key = alive ? ((e.y << key_shift) | e.x) : NONE;
                 if (am & (am + 1u)) {   // holes: the t-th survivor moves to lane t (the order is kept)
                     const uint32_t src = __fns(am, 0u, lane + 1);
-                    const unsigned long long moved = __shfl_sync(FULL, key, (int)(src & 31u));
-                    key = src < 32u ? moved : DEAD;
+                    const uint32_t moved = __shfl_sync(FULL, key, (int)(src & 31u));
+                    key = src < 32u ? moved : NONE;
                 }
                 if (i == 0u) {
                     cur = key;
                 } else {
-                    const unsigned long long rev = __shfl_sync(FULL, key, 31 - lane);   // lanes 16..31: the new list, worst first
-                    unsigned long long v = lane < PH_K ? cur : rev;
+                    const uint32_t rev = __shfl_sync(FULL, key, 31 - lane);   // lanes 16..31: the new list, worst first
+                    uint32_t v = lane < PH_K ? cur : rev;
 #pragma unroll
                     for (int j2 = 16; j2 > 0; j2 >>= 1) {
-                        const unsigned long long o = __shfl_xor_sync(FULL, v, j2);
+                        const uint32_t o = __shfl_xor_sync(FULL, v, j2);
                         v = ((lane & j2) == 0) ? min(v, o) : max(v, o);
                     }
                     cur = v;
@@ -1361,8 +1352,8 @@ __global__ void __launch_bounds__(PH_WARPS * 32, 6) postings_head_kernel(const P
             }
             WarpTopK<PEntry> tk;
             tk.init(p.k);
-            if (lane < p.k && cur != DEAD)
-                tk.mine = PEntry{1u, cq + (uint32_t)(cur >> 32) - 1u, (int32_t)(p.pool_base + (int64_t)(uint32_t)cur)};
+            if (lane < p.k && cur != NONE)
+                tk.mine = PEntry{1u, cq + (cur >> key_shift) - 1u, (int32_t)(p.pool_base + (int64_t)(cur & row_mask))};
             tk.refresh_kth();
             for (uint32_t j = 0; j < n_multi; ++j) {
                 const uint32_t c = sm.mcnt[j];
@@ -1380,6 +1371,216 @@ __global__ void __launch_bounds__(PH_WARPS * 32, 6) postings_head_kernel(const P
         }
         // (a handed-over query counts too: its rows are rewritten by a later stage, after this kernel's relays)
         if (p.relay_done != nullptr) pj_relay(p, q0, (uint32_t)n_here - (uint32_t)__popc(skip));
+    }
+}
+
+// ---------------------------------------------------------------------------- the head kernel's algorithm, one CTA per LONG query
+// A query of 25 ids streams ~2 800 postings; in one warp that is 25 dependent list walks, a per-warp filter that fills
+// up (false positives grow with the square of the postings) and hundreds of bucket probes: ~100 us, as long as the whole
+// head launch for the other 99 000 queries.  Here the eight warps of a CTA share the query: lists are dealt out to the
+// warps, the Bloom filter is CTA wide (131 072 bits: almost no false positives), probes are spread over 256 threads,
+// every warp merges the heads of its lists and warp 0 merges the eight partial rankings.  Exact for the same reasons.
+constexpr int PB_THREADS = 256, PB_WARPS = PB_THREADS / 32;
+constexpr int PB_BM_WORDS = 4096;    // 131 072-bit repeat filter per CTA
+constexpr int PB_FLAG = 512;         // noted rows per query
+constexpr int PB_MULTI = 64;         // multi-hit rows per query
+constexpr int PB_MAX_HITS = 16384;   // postings streamed per query
+
+struct PBSmem {
+    uint32_t bm[PB_BM_WORDS];
+    int32_t ids[32];
+    uint32_t start[32], len[32];
+    uint32_t frow[PB_FLAG], fcnt[PB_FLAG], fcard[PB_FLAG];
+    uint32_t mrow[PB_MULTI], mcnt[PB_MULTI], mcard[PB_MULTI];
+    uint32_t keys[PB_WARPS][PH_K];
+    uint32_t cq, n_flag, n_multi, work, fail;
+};
+
+template <bool PACKED>
+__global__ void __launch_bounds__(PB_THREADS) postings_big_kernel(const PJParams p) {
+    constexpr bool packed = PACKED;
+    __shared__ __align__(16) PBSmem sm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    constexpr uint32_t FULL = 0xffffffffu, NONE = 0xffffffffu;
+    const uint32_t key_shift = p.np > 1 ? 32u - (uint32_t)__clz((uint32_t)(p.np - 1)) : 1u;
+    const uint32_t row_mask = (1u << key_shift) - 1u, card_lim = (1u << (32u - key_shift)) - 1u;
+    const uint32_t n_big = *p.big_count;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) {
+            sm.work = atomicAdd(p.big_work, 1u);
+            sm.n_flag = 0u;
+            sm.n_multi = 0u;
+            sm.fail = 0u;
+        }
+        for (int i = tid; i < PB_BM_WORDS / 4; i += PB_THREADS) reinterpret_cast<uint4*>(sm.bm)[i] = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+        if (sm.work >= n_big) break;
+        const int64_t q = (int64_t)p.big_list[sm.work];
+        if (warp == 0) {
+            // ---- the query's distinct ids, the j-th of them in lane j (the list holds queries of 9 .. 32 ids)
+            const int64_t beg = p.q_off[q], m_raw = p.q_off[q + 1] - beg;
+            int32_t id = -1;
+            if (lane < m_raw) id = p.q_ids[beg + lane];
+            if (id < 0 || id >= p.n_bits) id = -1;
+            const uint32_t same = __match_any_sync(FULL, id);
+            if (id >= 0 && (__ffs(same) - 1) != lane) id = -1;
+            const uint32_t act = __ballot_sync(FULL, id >= 0);
+            const uint32_t cq = __popc(act);
+            if (id >= 0) sm.ids[__popc(act & lt)] = id;
+            __syncwarp();
+            id = lane < (int)cq ? sm.ids[lane] : -1;
+            uint32_t s = 0, len = 0;
+            if (id >= 0) {
+                s = p.off[(int64_t)id * p.n_win];
+                len = p.off[(int64_t)(id + 1) * p.n_win] - s;
+            }
+            sm.start[lane] = s;
+            sm.len[lane] = len;
+            if (lane == 0) sm.cq = cq;
+            if (__reduce_add_sync(FULL, len) > (uint32_t)PB_MAX_HITS && lane == 0) sm.fail = 1u;
+        }
+        __syncthreads();
+        const uint32_t cq = sm.cq;
+        const int64_t diag_row = p.query_base + q - p.pool_base;   // pool row forced to score 0
+        const uint32_t diag = (p.zero_diag != 0 && diag_row >= 0 && diag_row < p.np) ? (uint32_t)diag_row : NONE;
+        // ---- 1. rows through the CTA's filter: list i is walked by warp i % 8
+        if (sm.fail == 0u) {
+            for (uint32_t i = warp; i < cq; i += PB_WARPS) {
+                const uint32_t ll = sm.len[i];
+                const uint2* lp = p.post + sm.start[i];
+                for (uint32_t t0 = 0; t0 < ll; t0 += 128u) {
+                    uint32_t row[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t t = t0 + (uint32_t)j * 32u + (uint32_t)lane;
+                        row[j] = t < ll ? lp[t].x : NONE;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (row[j] != NONE) {
+                            const uint32_t h = row[j] * 2654435761u;
+                            const uint32_t mask = (1u << ((h >> 15) & 31u)) | (1u << ((h >> 10) & 31u));
+                            if ((atomicOr(&sm.bm[h >> 20], mask) & mask) == mask) {
+                                const uint32_t slot = atomicAdd(&sm.n_flag, 1u);
+                                if (slot < (uint32_t)PB_FLAG) sm.frow[slot] = row[j];
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t n_flag = sm.n_flag;
+        if (n_flag > (uint32_t)PB_FLAG && tid == 0) sm.fail = 1u;
+        // ---- 2. the noted rows, counted exactly: thread <-> (row j, id i)
+        for (uint32_t j = tid; j < n_flag && j < (uint32_t)PB_FLAG; j += PB_THREADS) sm.fcnt[j] = 0u;
+        __syncthreads();
+        if (sm.fail == 0u && n_flag != 0u) {
+            const uint32_t n_probe = n_flag * cq, inv = ph_inv[cq];
+            for (uint32_t t = tid; t < n_probe; t += PB_THREADS) {
+                const uint32_t j = __umulhi(t, inv), i = t - j * cq;
+                const uint32_t r = sm.frow[j];
+                const int64_t b = (int64_t)sm.ids[i] * p.n_win + (int64_t)(r >> p.win_shift);
+                const uint32_t bs = p.off[b], be = p.off[b + 1];
+                if (be - bs > (uint32_t)PH_MAX_BUCKET) {
+                    sm.fail = 1u;   // a hot bucket
+                } else {
+                    for (uint32_t u = bs; u < be; ++u) {
+                        const uint2 v = p.post[u];
+                        if (v.x == r) {
+                            atomicAdd(&sm.fcnt[j], 1u);
+                            sm.fcard[j] = v.y;
+                            break;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (sm.fail == 0u)
+            for (uint32_t j = tid; j < n_flag; j += PB_THREADS)
+                if (sm.fcnt[j] >= 2u && sm.frow[j] != diag) {
+                    const uint32_t at = atomicAdd(&sm.n_multi, 1u);
+                    if (at < (uint32_t)PB_MULTI) {
+                        sm.mrow[at] = sm.frow[j];
+                        sm.mcnt[at] = sm.fcnt[j];
+                        sm.mcard[at] = sm.fcard[j];
+                    }
+                }
+        __syncthreads();
+        const uint32_t n_multi = sm.n_multi;
+        if (n_multi > (uint32_t)PB_MULTI && tid == 0) sm.fail = 1u;
+        // ---- 3. every warp merges the heads of its lists (see postings_head_kernel)
+        uint32_t cur = NONE;
+        if (sm.fail == 0u && n_multi <= (uint32_t)PB_MULTI) {
+            bool have = false;
+            for (uint32_t i = warp; i < cq; i += PB_WARPS) {
+                const uint2 e = p.best[(int64_t)sm.ids[i] * PJ_BEST + lane];
+                bool alive = e.x != NONE && e.x != diag;
+                for (uint32_t j = 0; j < n_multi; ++j)
+                    if (sm.mrow[j] == e.x) alive = false;
+                const uint32_t am = __ballot_sync(FULL, alive);
+                if ((__popc(am) < p.k && sm.len[i] > (uint32_t)PJ_BEST) || __ballot_sync(FULL, alive && e.y >= card_lim)) {
+                    if (lane == 0) sm.fail = 1u;   // a depleted head / a |pool set| too large for the key
+                    break;
+                }
+                uint32_t key = alive ? ((e.y << key_shift) | e.x) : NONE;
+                if (am & (am + 1u)) {
+                    const uint32_t src = __fns(am, 0u, lane + 1);
+                    const uint32_t moved = __shfl_sync(FULL, key, (int)(src & 31u));
+                    key = src < 32u ? moved : NONE;
+                }
+                if (!have) {
+                    cur = key;
+                    have = true;
+                } else {
+                    const uint32_t rev = __shfl_sync(FULL, key, 31 - lane);
+                    uint32_t v = lane < PH_K ? cur : rev;
+#pragma unroll
+                    for (int j2 = 16; j2 > 0; j2 >>= 1) {
+                        const uint32_t o = __shfl_xor_sync(FULL, v, j2);
+                        v = ((lane & j2) == 0) ? min(v, o) : max(v, o);
+                    }
+                    cur = v;
+                }
+            }
+        }
+        if (lane < PH_K) sm.keys[warp][lane] = cur;
+        __syncthreads();
+        if (warp == 0) {
+            if (sm.fail != 0u) {
+                if (lane == 0) p.hand_list[atomicAdd(p.hand_count, 1u)] = (uint32_t)q;
+            } else {
+                cur = lane < PH_K ? sm.keys[0][lane] : NONE;
+                for (int w = 1; w < PB_WARPS; ++w) {
+                    const uint32_t key = lane < PH_K ? sm.keys[w][lane] : NONE;
+                    const uint32_t rev = __shfl_sync(FULL, key, 31 - lane);
+                    uint32_t v = lane < PH_K ? cur : rev;
+#pragma unroll
+                    for (int j2 = 16; j2 > 0; j2 >>= 1) {
+                        const uint32_t o = __shfl_xor_sync(FULL, v, j2);
+                        v = ((lane & j2) == 0) ? min(v, o) : max(v, o);
+                    }
+                    cur = v;
+                }
+                WarpTopK<PEntry> tk;
+                tk.init(p.k);
+                if (lane < p.k && cur != NONE)
+                    tk.mine = PEntry{1u, cq + (cur >> key_shift) - 1u, (int32_t)(p.pool_base + (int64_t)(cur & row_mask))};
+                tk.refresh_kth();
+                for (uint32_t j = 0; j < n_multi; ++j) {
+                    const uint32_t c = sm.mcnt[j];
+                    const PEntry cnd{c, cq + sm.mcard[j] - c, (int32_t)(p.pool_base + (int64_t)sm.mrow[j])};
+                    if (__ballot_sync(FULL, lane < p.k && tk.mine.idx == cnd.idx)) continue;   // noted twice
+                    tk.insert(cnd);
+                }
+                pj_finish(tk, p, q, cq, packed);
+            }
+            // (a handed-over query counts too: a later stage rewrites its rows after the relays)
+            if (p.relay_done != nullptr) pj_relay(p, q, 1u);
+        }
     }
 }
 
@@ -1764,7 +1965,7 @@ static int postings_topk_impl(const int32_t* q_ids, const int64_t* q_off, int64_
         prm.hand_count = counters + 1;
         prof_begin(PROF_JACCARD_POSTINGS, st);
         if (head) {
-            // the long queries of the call, listed (in list B, which the later stages reuse) so that the head kernel starts them first
+            // the long queries of the call, listed (in list B, which the later stages reuse) for postings_big_kernel
             prm.big_list = list_b;
             prm.big_count = counters + 7;
             prm.big_work = counters + 8;
@@ -1786,6 +1987,13 @@ static int postings_topk_impl(const int32_t* q_ids, const int64_t* q_off, int64_
                 first.out_inter = reinterpret_cast<uint32_t*>(at);
                 first.out_idx = reinterpret_cast<int32_t*>(at + relay_plane_bytes(nq, k));
                 first.out_qcard = reinterpret_cast<uint32_t*>(at + 2 * relay_plane_bytes(nq, k));
+            }
+            if (head) {   // the long queries, a CTA each (all CTAs are resident at once; those without a query exit)
+                int64_t gbig = (int64_t)num_sms() * 6;
+                if (gbig > nq) gbig = nq;
+                if (packed) postings_big_kernel<true><<<(unsigned)gbig, PB_THREADS, 0, st>>>(first);
+                else postings_big_kernel<false><<<(unsigned)gbig, PB_THREADS, 0, st>>>(first);
+                note_launch();
             }
             kern<<<(unsigned)grid, PJ_LIGHT_WARPS * 32, smem, st>>>(first); note_launch();
         }

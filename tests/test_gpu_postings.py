@@ -295,3 +295,30 @@ def test_head_kernel_hand_overs_and_kills():
     check([list(x) for x in p3[1000:1300]], p3, 50, 16, zero_diag=True, query_base=1000)
     # sharded pool: global indices and a diagonal that lies outside / inside the shard
     check([list(x) for x in p3[:300]], p3[200:], 50, 10, zero_diag=True, query_base=0, pool_base=200)
+
+
+def test_head_kernel_key_overflow_hands_over():
+    """The head kernel ranks list heads as 32-bit keys |pool set| << bits(rows) | row: in a pool of 2.1 M rows a set of
+    more than 2 046 ids does not fit the key, and the query must travel on to the register kernel — same result."""
+    n_bits, npool, k = 3000, (1 << 21) + 5, 10
+    rng = np.random.default_rng(3)
+    ids = rng.integers(10, n_bits, npool).astype(np.int32)           # one id per row (ids 0..9 stay rare)
+    lens = np.ones(npool, np.int64)
+    big = np.arange(0, 2500, dtype=np.int32)                         # row 7: a set of 2 500 ids, among them the rare ones
+    lens[7] = big.size
+    off = np.zeros(npool + 1, np.int64)
+    np.cumsum(lens, out=off[1:])
+    flat = np.empty(int(off[-1]), np.int32)
+    flat[off[:-1]] = ids
+    flat[off[7]:off[8]] = big
+    few = [11, 12, npool - 3, 100000, 2000000]                       # other rows that hold the rare ids 3 and 4
+    for r in few:
+        flat[off[r]] = 3 if r % 2 else 4
+    bp = set_encoder.encode_csr(torch.as_tensor(flat), torch.as_tensor(off), n_bits)
+    index = engine.build_postings(bp)
+    q = [[3], [4, 3], [3, 2999], [5], [2998, 2997, 4]]
+    qi, qo = to_csr(q)
+    got = engine.jaccard_topk_postings(torch.as_tensor(qi).cuda(), torch.as_tensor(qo).cuda(), index, k)
+    oi, ou, ox = jo.c_topk(qi, qo, flat, off, k)
+    assert np.array_equal(got[2].cpu().numpy(), ox)
+    assert np.array_equal(got[0].cpu().numpy(), oi) and np.array_equal(got[1].cpu().numpy(), ou)
