@@ -1092,7 +1092,8 @@ __global__ void __launch_bounds__(PR_WARPS * 32, 6) postings_reg_kernel(const PJ
 }
 template <bool PACKED>
 __global__ void __launch_bounds__(PR_WARPS * 32, 4) postings_reg_large_kernel(const PJParams p) {
-    if (pr_wants_large(p)) postings_reg_body<PR_SLOTS_LARGE, PACKED>(p);
+    // (behind the head kernel this launch serves every pool: one stage for the few queries handed over, not two)
+    if (p.in_list != nullptr || pr_wants_large(p)) postings_reg_body<PR_SLOTS_LARGE, PACKED>(p);
 }
 
 // ---------------------------------------------------------------------------- first stage for label-like sets: heads + repeat check
@@ -2003,8 +2004,9 @@ static int postings_topk_impl(const int32_t* q_ids, const int64_t* q_off, int64_
         const uint32_t* cur_list = list_a;
         const uint32_t* cur_count = counters + 1;
         if (reg) {
-            // register-resident kernels: the first stage without the head kernel, else the stage for its hand-overs.  The
-            // 8-slot body serves pools with hot (id, window) buckets; one of the two launches exits at once.
+            // register-resident kernels: the first stage without the head kernel (the 8-slot body serves pools with hot
+            // (id, window) buckets; one of the two launches exits at once), else ONE launch of the 8-slot body for the
+            // queries the head kernel handed over.
             PJParams pr = prm;
             if (head) {
                 pr.in_list = list_a;
@@ -2014,9 +2016,6 @@ static int postings_topk_impl(const int32_t* q_ids, const int64_t* q_off, int64_
                 pr.hand_count = counters + 4;
                 cur_list = list_b;
                 cur_count = counters + 4;
-                void (*kern_s)(const PJParams) = packed ? postings_reg_kernel<true> : postings_reg_kernel<false>;
-                if (int rc = ensure_dyn_smem(kern_s, smem_reg, opt_in[packed ? 3 : 2])) return rc;
-                kern_s<<<(unsigned)grid, PR_WARPS * 32, smem_reg, st>>>(pr); note_launch();
             }
             static SmemOptIn opt_in_l[2];
             void (*kern_l)(const PJParams) = packed ? postings_reg_large_kernel<true> : postings_reg_large_kernel<false>;
