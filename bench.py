@@ -458,8 +458,10 @@ def main():
             "bound": "hbm", "achieved": survey_bytes / main_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
             "frac": survey_bytes / main_s / 1e9 / hbm_peak,
             "traffic": dram_traffic("jaccard_postings", queries=nq, pool=n_pool),
-            "kernel": "r4d::postings_reg_kernel (one warp per query: the query's posting lists joined in registers, repeat "
-                      "filter in shared memory, exact counts, warp-level top-K)",
+            "kernel": "r4d::postings_head_kernel (one warp per query: single-hit rows ranked by merging the per-id best lists, "
+                      "multi-hit rows found by streaming the posting rows through a Bloom filter in shared memory + exact bucket "
+                      "probes) + r4d::postings_big_kernel (one CTA per query of more than 8 ids) + the list scan before them and "
+                      "the (idle) register-kernel stage behind them: the launches the library brackets as one",
             "kernel_ms": main_s * 1e3, "launches_timed": int(main_n),
             "algorithmic_bytes": survey_bytes,
             "algorithmic_bytes_what": "SURVEY 8(d): (N + Q) * 4W B of bitsets read once + Q*K*12 B written (W = 625 words) — the "
@@ -469,7 +471,7 @@ def main():
             "own_representation": {
                 "what": "bytes the postings representation itself has to touch per launch: 8 B per posting of every query id "
                         "+ bucket offsets + query CSR + [Q,K] output; the 28 MB index is L2 resident, the kernel is bound by "
-                        "issue slots / L2 latency, not by HBM (ncu: profiles/r2_ncu_postings_reg_benchcfg.txt)",
+                        "issue slots / L2 latency, not by HBM (ncu: profiles/r2_ncu_postings_head_benchcfg.txt)",
                 "bytes": own_bytes, "postings_visited": postings_touched, "achieved_GBps": own_bytes / main_s / 1e9,
                 "frac_hbm": own_bytes / main_s / 1e9 / hbm_peak,
                 "postings_per_s": postings_touched / main_s}}

@@ -13,7 +13,7 @@ out = tuple(torch.empty((nq, 10), dtype=torch.int32, device=dev) for _ in range(
 df = torch.bincount(pi.to(dev).long(), minlength=bench.V_BITS)
 hits = torch.zeros(nq, dtype=torch.int64, device=dev).index_add_(0, torch.repeat_interleave(torch.arange(nq, device=dev), (do[1:] - do[:-1])), df[dq.long()])
 print("hits per query: mean %.0f median %.0f p90 %.0f p99 %.0f max %.0f; >256: %.1f%%  >24600: %.2f%%" % (hits.float().mean(), hits.float().median(), hits.float().quantile(0.9), hits.float().quantile(0.99), hits.max(), 100 * (hits > 256).float().mean(), 100 * (hits > 24600).float().mean()))
-for kern in (1, 0):
+for kern in (2, 0):
     _lib.set_option("postings_kernel", kern)
     for _ in range(3): pool.topk(dq, do, 10, out=out)
     _lib.set_option("kernel_timing", 1); _lib.profile_read("jaccard_postings")
@@ -22,4 +22,5 @@ for kern in (1, 0):
     e1.record(); torch.cuda.synchronize()
     ms, n = _lib.profile_read("jaccard_postings"); _lib.set_option("kernel_timing", 0)
     c = pool._ws[:32].view(torch.int32).cpu().tolist()
-    print(f"postings_kernel={kern}: call {e0.elapsed_time(e1) / 10:.3f} ms, first-stage kernel {ms / n:.3f} ms, handed over {c[1]}, to the heavy kernel {c[4] if kern == 0 else c[1]}", flush=True)
+    print(f"postings_kernel={kern}: call {e0.elapsed_time(e1) / 10:.3f} ms, first stages {ms / n:.3f} ms, counters "
+          f"[work0, listA, heavy_work, light_work, listB, reg_work, listA2, n_big, big_work] = {c[:9]}", flush=True)
