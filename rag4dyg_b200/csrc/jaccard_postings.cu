@@ -9,10 +9,18 @@
 //     post[]   8-byte entries {pool row, |pool set|}, grouped by (node id, row window): bucket b = id * n_win + (row >> win_shift)
 //     off[]    bucket offsets (exclusive scan of the bucket sizes); an id's whole posting list is the contiguous
 //              range off[id * n_win] .. off[(id + 1) * n_win], and any run of windows of it is contiguous too
-//   r4d_jaccard_topk_postings (queries arrive as CSR id lists; duplicates inside a row collapse, like Python's set()):
-//     postings_reg_kernel     label-like sets (the headline): one WARP per query, the pass's <= 256 postings held in
-//                             REGISTERS, repeats of a pool row found with an 8 192-bit filter in shared memory and
-//                             resolved by a warp-wide compare; warp-level sorted top-K list (exact rational compare).
+//     best[]   per id: its 32 postings with the smallest (|pool set|, row), ascending (the head of the id's ranking)
+//   r4d_jaccard_topk_postings (queries arrive as CSR id lists; duplicates inside a row collapse, like Python's set()) — a
+//   chain of kernels, each serving what it can and handing the rest to the next through a list in the workspace:
+//     postings_big_kernel     label-like sets, queries of more than 8 ids: the head kernel's algorithm with a whole CTA
+//                             per query (listed first by postings_big_scan_kernel).
+//     postings_head_kernel    label-like sets (the headline): one WARP per query.  Rows holding ONE of the query's ids are
+//                             ranked by merging the per-id best lists; only rows holding SEVERAL ids need the join: the
+//                             posting rows are streamed through a Bloom filter in shared memory, the few noted rows are
+//                             counted exactly by bucket probes.
+//     postings_reg_kernel     first stage when k > 16 (and the stage behind the head kernel): one WARP per query, the
+//                             pass's <= 256 postings held in REGISTERS, repeats of a pool row found with an 8 192-bit
+//                             filter in shared memory and resolved by a warp-wide compare; warp-level sorted top-K list.
 //     postings_light_kernel   history-like sets (hundreds to thousands of postings per query): one WARP per query.  The
 //                             (<= 64) distinct ids of the query select their posting ranges; every posting is inserted
 //                             into the warp's 512 / 1 024-slot hash table in shared memory (64-bit CAS claims a slot for
@@ -21,7 +29,7 @@
 //                             into the warp-level sorted top-K list.
 //                             Both walk the pool's row windows in several passes when a query has more postings than a
 //                             pass holds (disjoint row ranges => a pair never spans two passes).
-//     postings_heavy_kernel   one CTA per query the light kernels handed over (more than 64 ids, a row window with more
+//     postings_heavy_kernel   one CTA per query the others handed over (more than 64 ids, a row window with more
 //                             postings than a pass holds): the query becomes a bitmap over the ids, every window of the
 //                             pool gets one 16-bit counter per row in shared memory, postings increment them, a scan
 //                             turns non-zero counters into candidates.  Any set size, any skew; slower.

@@ -28,7 +28,7 @@ struct Options {
     int dense_x3_combined = 1;      // dense pair kernel, split precision: hi + lo planes of a k-block in ONE 64 KB stage
     int dense_walker_window = 4;    // dense pair kernel: tiles a walker may lead the slowest walker of its stripe (0 = off)
     int postings_best = 1;      // postings path: single-id queries read their top-K from the per-id best lists
-    int postings_kernel = 0;    // postings path, label-like sets: 0 = register-resident kernel, 1 = hash-table kernel
+    int postings_kernel = 0;    // postings path, label-like sets, first stage: 0 = head kernel, 1 = hash-table, 2 = register kernel
     int postings_chunk = 0;     // postings path: queries per grab of the work counter (0 = automatic, <= 8)
     int postings_relay = 1;     // postings path: packed lists bound for pinned host memory leave in whole 64-query blocks
     int postings_log_t = 0;     // postings path: 0 = automatic, 9 / 10 = force 512 / 1 024-slot hash tables

@@ -63,11 +63,25 @@ def test_committed_bench_line_has_the_contract_shape():
 
 
 def test_committed_scaling_lines_are_weak_and_verified():
-    base = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_n1.json")))
-    for n in (2, 4, 8):
-        d = json.load(open(os.path.join(ROOT, "profiles", f"r2_bench_n{n}.json")))
+    """Two measurement series are kept: the final one (head / big kernels: N = 1, 2 and the Jaccard line at N = 8) and the
+    earlier register-kernel series of this round (N = 1, 2, 4, 8 with the fixed-workload curves).  Each series is
+    compared with its own N = 1 line."""
+    prof = os.path.join(ROOT, "profiles")
+    base = json.load(open(os.path.join(prof, "r2_bench_n1.json")))
+    for n, name in ((2, "r2_bench_n2.json"), (8, "r2_bench_n8_jaccard.json")):
+        d = json.load(open(os.path.join(prof, name)))
         assert d["n_gpus"] == n and d["scaling"] == "weak" and d["verified"] is True
         assert "query-sharded" in d["config"]["parallelism"]
         assert d["value"] / (n * base["value"]) > 0.9                                # weak-scaling efficiency
+        assert d["e2e"]["value"] > base["e2e"]["value"]
+    st = json.load(open(os.path.join(prof, "r2_bench_n2.json")))["strong"]
+    assert st["query_sharded"]["value"] > 0 and st["pool_sharded"]["value"] > 0
+    old = json.load(open(os.path.join(prof, "r2_bench_regkernel_n1.json")))
+    assert old["value"] < base["value"]                                              # the head kernel is the faster one
+    for n in (2, 4, 8):
+        d = json.load(open(os.path.join(prof, f"r2_bench_regkernel_n{n}.json")))
+        assert d["n_gpus"] == n and d["scaling"] == "weak" and d["verified"] is True
+        assert "query-sharded" in d["config"]["parallelism"]
+        assert d["value"] / (n * old["value"]) > 0.9
         st = d["strong"]
         assert st["query_sharded"]["value"] > 0 and st["pool_sharded"]["value"] > 0
