@@ -111,6 +111,9 @@ class GraphTopK:
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 pool.topk(q_ids, q_off, self.k, zero_diag=zero_diag, query_base=query_base, out=self.out)
+            # the captured launches point into the pool's workspace: keep THAT buffer alive even if the pool later moves
+            # to a larger one (a bigger step, the relay room of host-bound packed lists)
+            self._workspace = pool._ws
 
     def replay(self):
         self.graph.replay()
