@@ -164,7 +164,7 @@ int r4d_jaccard_topk_postings(const int32_t* q_ids, const int64_t* q_off, int64_
 /* Packed results — for [nq][k] lists that cross PCIe (HostTopK stores them straight into pinned host memory): 8 bytes per
  * entry instead of 12.  top_pair[q][j] = inter << 16 | |pool set| (both <= 65 535 because n_bits is), top_idx as above,
  * q_card[q] = |query set| (distinct valid ids of the row).  The consumer recovers union = q_card + |pool set| - inter, so
- * the score inter / union (retrieval_data_annotation.py:18) is the same rational; a padding entry (idx R4D_IDX_NONE)
+ * the score inter / union (retrieval_data_annotation.py:12-14) is the same rational; a padding entry (idx R4D_IDX_NONE)
  * packs as 0 and stands for (0, 1).  Same kernels, same order, same exactness as r4d_jaccard_topk_postings.
  * When top_pair / top_idx / q_card are pinned HOST buffers (device-addressable, 128-byte aligned) and the workspace is
  * r4d_jaccard_topk_postings_workspace_bytes(nq) + r4d_jaccard_topk_postings_relay_bytes(nq, k) bytes or more, the lists
