@@ -65,7 +65,12 @@ int r4d_device_ok(void);
  *   "postings_log_t"    [0]  postings path: 0 = automatic, 9 / 10 = force 512- / 1 024-slot per-warp hash tables
  *   "postings_kernel"   [0]  postings path, label-like sets: first stage 0 = head kernel (k <= 16), 1 = hash-table kernel,
  *                            2 = register-resident kernel (comparison points; results are identical)
- *   "postings_relay"    [1]  packed lists bound for pinned host memory leave in whole 64-query blocks (0 = per chunk) */
+ *   "postings_relay"    [1]  packed lists bound for pinned host memory leave in whole 64-query blocks (0 = per chunk)
+ *   "postings_best"     [1]  postings path: use the per-id best lists (0 = every query is joined in full; k > 16 or 0
+ *                            start the chain at the register-resident kernel)
+ *   "postings_chunk"    [0]  postings path: queries a warp takes per grab of the work counter (0 = automatic, <= 8)
+ *   "dense_x3_combined" [1]  dense pair kernel, split precision: hi + lo planes of a k-block share one pipeline stage
+ *   "dense_walker_window" [4] dense pair kernel: tiles a walker may lead the slowest walker of its stripe (0 = off) */
 int r4d_set_option(const char* key, int value);
 
 /* Measurement aid for the roofline figures (bench.py): after r4d_set_option("kernel_timing", 1) the library brackets

@@ -57,3 +57,21 @@ def test_product_code_never_imports_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, fn)).read()
                 assert "oracle" not in src.replace("test oracle", ""), f"{fn} mentions the oracle"
+
+
+def test_documented_options_exist_with_their_defaults(lib):
+    """Every knob include/r4d.h documents for r4d_set_option is known to the library and starts at the documented default;
+    an unknown key is an argument error, not a silent no-op."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "r4d.h")).read()
+    block = hdr[hdr.index("Tuning / measurement knobs"):hdr.index("int r4d_set_option")]
+    knobs = re.findall(r'"(\w+)"\s+\[(-?\d+)\]', block)
+    assert len(knobs) == 17 and ("postings_relay", "1") in knobs
+    for key, default in knobs:
+        if os.environ.get("R4D_" + key.upper()) is not None:
+            continue                                  # (environment variables may override the initial value)
+        prev = lib.r4d_set_option(key.encode(), int(default))
+        assert prev == int(default), f"{key}: header says [{default}], library starts at {prev}"
+    assert lib.r4d_set_option(b"no_such_knob", 1) == _lib.R4D_E_ARG
+    assert b"unknown key" in lib.r4d_last_error()
